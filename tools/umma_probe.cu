@@ -1,0 +1,241 @@
+// umma_probe.cu — hardware bring-up probe for the tcgen05 kernels (run on a B200 via gpurun).
+//
+//   1. tc_rows_kernel<MODE_PLAIN> (K-major A and B, SW128 TMA, TMEM epilogue, TMA store) vs a CPU
+//      double-precision GEMM, at the WIRE shapes (2M = 424 -> nb = 432 split 256+176, K tail).
+//   2. tc_wgrad_kernel (both operands MN-major, lane-pair complex fold, split-K atomics) vs CPU.
+//   3. micro-benchmarks: TF32 tcgen05 issue-rate peak, and tc_rows / tc_wgrad at the 512^2 shape.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o umma_probe umma_probe.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../wire_b200/csrc/tc_launch.cuh"
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                     \
+    }                                                                              \
+  } while (0)
+
+static float tf32_round_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u += 0x1000u;  // round-to-nearest (ties away) on the 13 dropped bits
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+static float frand() { return float(rand()) / float(RAND_MAX) * 2.f - 1.f; }
+
+// ---- MMA issue-rate peak: every CTA loops tcgen05.mma on resident (zero) smem tiles ----
+__global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, int n_cols) {
+  using namespace sm100;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < (16384 + 256 * 128) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, n_cols, false, false);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = make_sdesc_sw128(base + ks * 32, 16, 1024);
+        const uint64_t bd = make_sdesc_sw128(base + 16384 + ks * 32, 16, 1024);
+        umma_tf32(tm, ad, bd, idesc, 1);
+        umma_tf32(tm + 256, ad, bd, idesc, 1);
+      }
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+static int g_sms = 148;
+
+static bool test_rows(int n_rows, int two_m, bool time_it) {
+  const int K = two_m, pitch = wire::round_up(two_m + 1, 32);
+  const int nb = wire::round_up(two_m, 16);
+  std::vector<float> A(size_t(n_rows) * pitch, 0.f), B(size_t(nb) * pitch, 0.f), C(size_t(n_rows) * pitch, -7.f);
+  for (int r = 0; r < n_rows; ++r) {
+    for (int c = 0; c < K; ++c) A[size_t(r) * pitch + c] = tf32_round_host(frand());
+    A[size_t(r) * pitch + K] = 1.0f;  // ones column must NOT leak into the K loop
+  }
+  for (int r = 0; r < two_m; ++r)
+    for (int c = 0; c < K; ++c) B[size_t(r) * pitch + c] = tf32_round_host(frand() * 0.1f);
+  float *dA, *dB, *dC;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dC, C.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dC, C.data(), C.size() * 4, cudaMemcpyHostToDevice));
+
+  wire::RowsParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_rows = n_rows; P.k_cols[0] = K; P.k_cols[1] = 0; P.n_blocks = 1; P.n_cols = two_m;
+  size_t smem = wire::rows_configure(P, nb, nb, 1);
+  if (!smem) { printf("rows_configure failed\n"); return false; }
+  bool ok = sm100_host::make_tmap_2d(&P.a_map[0], dA, n_rows, K, pitch, 128, 32);
+  ok &= sm100_host::make_tmap_2d(&P.a_map[1], dA, n_rows, K, pitch, 128, 32);
+  ok &= sm100_host::make_tmap_2d(&P.b_map, dB, nb, pitch, pitch, P.b_box_rows, 32);
+  ok &= sm100_host::make_tmap_2d(&P.o_map[0], dC, n_rows, two_m, pitch, 32, 32);
+  P.o_map[1] = P.o_map[0]; P.o_map[2] = P.o_map[0];
+  if (!ok) { printf("tensor map creation failed\n"); return false; }
+  printf("[rows] n_rows=%d 2M=%d nb=%d stages=%d smem=%zu\n", n_rows, two_m, nb, P.stages, smem);
+  CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0;
+  long bad = 0;
+  const int check_rows = n_rows < 1024 ? n_rows : 1024;
+  for (int rr = 0; rr < check_rows; ++rr) {
+    const int r = (n_rows <= 1024) ? rr : int((long long)rr * 9973 % n_rows);
+    for (int c = 0; c < two_m; ++c) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += double(A[size_t(r) * pitch + k]) * double(B[size_t(c) * pitch + k]);
+      const double err = fabs(acc - double(C[size_t(r) * pitch + c]));
+      if (err > max_err) max_err = err;
+      if (fabs(acc) > max_ref) max_ref = fabs(acc);
+      if (err > 1e-3) ++bad;
+    }
+    // pad columns must be untouched
+    if (C[size_t(r) * pitch + two_m] != -7.f) ++bad;
+  }
+  printf("[rows] max_abs_err=%.3e (max |ref| %.3f) bad=%ld -> %s\n", max_err, max_ref, bad, bad ? "FAIL" : "PASS");
+  if (time_it && !bad) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0));
+    CK(cudaEventRecord(e0));
+    const int reps = 10;
+    for (int i = 0; i < reps; ++i) CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+    const double flop = 2.0 * n_rows * double(two_m) * K;
+    printf("[rows] %.3f ms  %.1f TFLOP/s (useful)  A+C traffic %.1f GB/s\n", ms, flop / ms * 1e-9,
+           (2.0 * n_rows * two_m * 4) / ms * 1e-6);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  return bad == 0;
+}
+
+static bool test_wgrad(int n_rows, int k_in, int m_out, bool time_it) {
+  const int xc = 2 * k_in + 1, gc = 2 * m_out;
+  const int xp = wire::round_up(xc, 32), gp = wire::round_up(gc + 1, 32);
+  std::vector<float> X(size_t(n_rows) * xp, 0.f), G(size_t(n_rows) * gp, 0.f);
+  for (int r = 0; r < n_rows; ++r) {
+    for (int c = 0; c < 2 * k_in; ++c) X[size_t(r) * xp + c] = tf32_round_host(frand());
+    X[size_t(r) * xp + 2 * k_in] = 1.0f;
+    for (int c = 0; c < gc; ++c) G[size_t(r) * gp + c] = tf32_round_host(frand() * 0.1f);
+  }
+  float *dX, *dG, *dW, *dBias;
+  CK(cudaMalloc(&dX, X.size() * 4)); CK(cudaMalloc(&dG, G.size() * 4));
+  CK(cudaMalloc(&dW, size_t(m_out) * k_in * 2 * 4)); CK(cudaMalloc(&dBias, size_t(m_out) * 2 * 4));
+  CK(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dG, G.data(), G.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dW, 0, size_t(m_out) * k_in * 2 * 4)); CK(cudaMemset(dBias, 0, size_t(m_out) * 2 * 4));
+  wire::WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_rows = n_rows; P.k_in = k_in; P.g_cols = gc; P.n_g = 1;
+  P.gW[0] = dW; P.gB[0] = dBias;
+  size_t smem = wire::wgrad_configure(P, g_sms);
+  bool ok = sm100_host::make_tmap_2d(&P.x_map, dX, n_rows, xc, xp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  ok &= sm100_host::make_tmap_2d(&P.g_map[0], dG, n_rows, gc, gp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  P.g_map[1] = P.g_map[0];
+  if (!ok || !smem) { printf("wgrad setup failed\n"); return false; }
+  printf("[wgrad] n=%d K=%d M=%d m_tiles=%d n_blocks=%d nb=%d splits=%d stages=%d smem=%zu\n", n_rows, k_in, m_out,
+         P.m_tiles, P.n_blocks, P.nb, P.splits, P.stages, smem);
+  CK(wire::launch_wgrad(P, smem, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> W(size_t(m_out) * k_in * 2), Bv(size_t(m_out) * 2);
+  CK(cudaMemcpy(W.data(), dW, W.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(Bv.data(), dBias, Bv.size() * 4, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0; long bad = 0;
+  const int jstep = m_out > 64 ? 7 : 1, kstep = k_in > 64 ? 5 : 1;
+  for (int j = 0; j < m_out; j += jstep) {
+    for (int k = 0; k < k_in; k += kstep) {
+      double re = 0, im = 0;
+      for (int n = 0; n < n_rows; ++n) {
+        const double gr = G[size_t(n) * gp + 2 * j], gi = G[size_t(n) * gp + 2 * j + 1];
+        const double xr = X[size_t(n) * xp + 2 * k], xi = X[size_t(n) * xp + 2 * k + 1];
+        re += gr * xr + gi * xi;   // g * conj(x)
+        im += gi * xr - gr * xi;
+      }
+      const double e = fmax(fabs(re - W[(size_t(j) * k_in + k) * 2]), fabs(im - W[(size_t(j) * k_in + k) * 2 + 1]));
+      if (e > max_err) max_err = e;
+      if (fabs(re) > max_ref) max_ref = fabs(re);
+      if (e > 1e-3 * (1.0 + sqrt(double(n_rows)) * 0.01)) ++bad;
+    }
+    double br = 0, bi = 0;
+    for (int n = 0; n < n_rows; ++n) { br += G[size_t(n) * gp + 2 * j]; bi += G[size_t(n) * gp + 2 * j + 1]; }
+    const double e = fmax(fabs(br - Bv[2 * j]), fabs(bi - Bv[2 * j + 1]));
+    if (e > max_err) max_err = e;
+    if (e > 1e-3 * (1.0 + sqrt(double(n_rows)) * 0.01)) ++bad;
+  }
+  printf("[wgrad] max_abs_err=%.3e (max |ref| %.3f) bad=%ld -> %s\n", max_err, max_ref, bad, bad ? "FAIL" : "PASS");
+  if (time_it && !bad) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(wire::launch_wgrad(P, smem, 0));
+    CK(cudaEventRecord(e0));
+    const int reps = 10;
+    for (int i = 0; i < reps; ++i) CK(wire::launch_wgrad(P, smem, 0));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+    const double flop = 8.0 * n_rows * double(m_out) * k_in;
+    printf("[wgrad] %.3f ms  %.1f TFLOP/s (algorithmic 8MK)  read traffic %.1f GB/s\n", ms, flop / ms * 1e-9,
+           (double(n_rows) * (xc + gc) * 4) / ms * 1e-6);
+  }
+  cudaFree(dX); cudaFree(dG); cudaFree(dW); cudaFree(dBias);
+  return bad == 0;
+}
+
+int main(int argc, char** argv) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  g_sms = prop.multiProcessorCount;
+  printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, g_sms);
+  srand(1234);
+  bool ok = true;
+  ok &= test_rows(256, 64, false);       // single MMA piece, 2 K chunks
+  ok &= test_rows(300, 424, false);      // WIRE width: nb=432 (256+176), K tail of 8, ragged rows
+  ok &= test_rows(1000, 180, false);     // M=90: K tail of 20 columns (not a multiple of 8)
+  ok &= test_wgrad(256, 32, 32, false);
+  ok &= test_wgrad(5000, 212, 212, false);
+  ok &= test_wgrad(777, 90, 90, false);
+  {
+    // ---- peak probe ----
+    CK(cudaFuncSetAttribute(mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 256 * 128 + 2048));
+    for (int n : {256, 224, 128}) {
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      const int iters = 4000;
+      mma_peak_kernel<<<g_sms, 128, 16384 + 256 * 128 + 2048>>>(100, n);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      mma_peak_kernel<<<g_sms, 128, 16384 + 256 * 128 + 2048>>>(iters, n);
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double flop = double(g_sms) * iters * 8 * (2.0 * 128 * n * 8);
+      printf("[peak] tf32 M=128 N=%d K=8 cta_group::1: %.3f ms -> %.1f TFLOP/s\n", n, ms, flop / ms * 1e-9);
+    }
+    test_rows(262144, 424, true);
+    test_wgrad(262144, 212, 212, true);
+    test_rows(262144, 256, true);
+  }
+  printf("PROBE %s\n", ok ? "PASS" : "FAIL");
+  return ok ? 0 : 1;
+}

@@ -1,0 +1,64 @@
+// gabor_math.cuh — the complex Gabor wavelet and its Wirtinger derivative, shared by every kernel.
+//
+// Reference semantics (file:line relative to the reference checkout):
+//   forward   modules/wire.py:88-93     y = exp(1j*omega_0*z - |scale_0*z|^2)
+//             modules/wire2d.py:56-67   y = exp(1j*omega_0*z) * exp(-scale_0^2*(|z|^2+|w|^2))
+//   backward  PyTorch complex autograd of the above:
+//             p = conj(y)*g_y ; g_z = -j*omega_0*p - 2*scale_0^2*z*Re(p) ; g_w = -2*scale_0^2*w*Re(p)
+//             first layer (real z): g_z = omega_0*Im(p) - 2*scale_0^2*z*Re(p)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace wire {
+
+// FAST = true : MUFU ex2/sin/cos with an explicit two-term Cody-Waite reduction (TF32 path)
+// FAST = false: libdevice expf/sincosf (FP32 path)
+template <bool FAST>
+__device__ __forceinline__ void exp_cis(float mag_arg, float phase, float& yr, float& yi) {
+  if constexpr (FAST) {
+    const float k = rintf(phase * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, phase);       // 2*pi hi
+    r = fmaf(-k, -1.7484555314695172e-7f, r);             // 2*pi lo
+    float s, c;
+    __sincosf(r, &s, &c);
+    const float m = __expf(mag_arg);
+    yr = m * c;
+    yi = m * s;
+  } else {
+    float s, c;
+    sincosf(phase, &s, &c);
+    const float m = expf(mag_arg);
+    yr = m * c;
+    yi = m * s;
+  }
+}
+
+// hidden layer: complex z; `extra` = scale^2*|w|^2 for wire2d, 0 for wire
+template <bool FAST>
+__device__ __forceinline__ void gabor_fwd(float zr, float zi, float omega, float s2, float extra,
+                                          float& yr, float& yi) {
+  const float mag_arg = -omega * zi - s2 * (zr * zr + zi * zi) - extra;
+  exp_cis<FAST>(mag_arg, omega * zr, yr, yi);
+}
+
+// g_z for a hidden layer from y, z and the upstream g_y; returns Re(p) for the wire2d g_w term
+__device__ __forceinline__ float gabor_bwd(float yr, float yi, float zr, float zi, float gr, float gi,
+                                           float omega, float s2, float& gzr, float& gzi) {
+  const float pr = yr * gr + yi * gi;   // p = conj(y) * g_y
+  const float pi = yr * gi - yi * gr;
+  const float t = -2.0f * s2 * pr;
+  gzr = fmaf(omega, pi, t * zr);
+  gzi = fmaf(-omega, pr, t * zi);
+  return pr;
+}
+
+// first layer: real z (and real w for wire2d)
+__device__ __forceinline__ float gabor_first_bwd(float yr, float yi, float z, float gr, float gi,
+                                                 float omega, float s2, float& gz) {
+  const float pr = yr * gr + yi * gi;
+  const float pi = yr * gi - yi * gr;
+  gz = fmaf(omega, pi, -2.0f * s2 * pr * z);
+  return pr;
+}
+
+}  // namespace wire

@@ -1,0 +1,96 @@
+// tc_launch.cuh — host-side configuration + launch of the tcgen05 kernels (tensor maps, smem budget).
+#pragma once
+#include <cstring>
+
+#include "tc_rows.cuh"
+#include "tc_wgrad.cuh"
+
+namespace wire {
+
+constexpr size_t kMaxDynSmem = 232448 - 1024;  // 227 KB minus the (1 KB-rounded) static barriers/slots
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Fill in nb-dependent fields and pick the deepest pipeline that fits. Returns dynamic smem bytes
+// (0 if the configuration does not fit).
+inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask) {
+  P.nb = nb;
+  P.nbh = nbh;
+  P.store_mask = store_mask;
+  if (nb <= 256) { P.b_box_rows = nb; P.b_boxes = 1; }
+  else { P.b_box_rows = nb / 2; P.b_boxes = 2; }
+  const int n_out = __builtin_popcount(store_mask);
+  const size_t stage = size_t(kTileRows) * 128 + size_t(nb) * 128;
+  const size_t staging = size_t(4) * n_out * 2 * 4096;
+  const size_t budget = kMaxDynSmem - 1024;
+  if (staging + 2 * stage > budget) return 0;
+  int stages = int((budget - staging) / stage);
+  if (stages > 8) stages = 8;
+  P.stages = stages;
+  return stages * stage + staging + 1024;
+}
+
+template <int MODE>
+inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  tc_rows_kernel<MODE><<<grid, kRowsThreads, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  const int row_tiles = (P.n_rows + kTileRows - 1) / kTileRows;
+  const int items = row_tiles * P.n_blocks;
+  if (items <= 0) return cudaSuccess;
+  const int grid = items < sm_count ? items : sm_count;
+  switch (mode) {
+    case MODE_PLAIN: return launch_rows_mode<MODE_PLAIN>(P, smem, grid, st);
+    case MODE_GABOR_FWD: return launch_rows_mode<MODE_GABOR_FWD>(P, smem, grid, st);
+    case MODE_GABOR2D_FWD: return launch_rows_mode<MODE_GABOR2D_FWD>(P, smem, grid, st);
+    case MODE_GABOR_BWD: return launch_rows_mode<MODE_GABOR_BWD>(P, smem, grid, st);
+    case MODE_GABOR2D_BWD: return launch_rows_mode<MODE_GABOR2D_BWD>(P, smem, grid, st);
+    case MODE_FIRST_BWD: return launch_rows_mode<MODE_FIRST_BWD>(P, smem, grid, st);
+    case MODE_FIRST2D_BWD: return launch_rows_mode<MODE_FIRST2D_BWD>(P, smem, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// wgrad: choose column blocking, K splits (to fill the machine) and pipeline depth
+inline size_t wgrad_configure(WgradParams& P, int sm_count) {
+  const int x_cols = 2 * P.k_in + 1;
+  P.m_tiles = (x_cols + 127) / 128;
+  const int gpad = round_up(P.g_cols, 32);
+  P.n_blocks = (gpad + 447) / 448;
+  P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, 32);
+  const int base = P.m_tiles * P.n_blocks * P.n_g;
+  int splits = sm_count / base;
+  if (splits < 1) splits = 1;
+  const int total_chunks = (P.n_rows + kWgradKC - 1) / kWgradKC;
+  if (splits > total_chunks) splits = total_chunks > 0 ? total_chunks : 1;
+  P.splits = splits;
+  const size_t stage = size_t(4 + P.nb / 32) * kWgradKC * 128;
+  int stages = int((kMaxDynSmem - 1024) / stage);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return 0;
+  P.stages = stages;
+  return stages * stage + 1024;
+}
+
+inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = P.m_tiles * P.n_blocks * P.n_g * P.splits;
+  if (grid <= 0 || P.n_rows <= 0) return cudaSuccess;
+  tc_wgrad_kernel<<<grid, kWgradThreads, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace wire
