@@ -1,0 +1,138 @@
+/* wire_b200.h — C ABI of the B200-native WIRE hot path.
+ *
+ * Drop-in boundary for the forward/backward pass through the complex Gabor stack of
+ * Annatk26/wire.  The reference has no native code, so there is no FFI to mirror: these entry
+ * points replace the *PyTorch op sequences* below (file:line relative to the reference checkout)
+ * and are what a maintainer binds from Python with ctypes:
+ *
+ *   wire_net_forward          <- wire.INR.forward          modules/wire.py:161-165
+ *                                wire2d.INR.forward        modules/wire2d.py:121-125
+ *   wire_net_backward         <- loss.backward() through the same modules (PyTorch complex autograd;
+ *                                closed form in SURVEY.md appendix A.2)
+ *   wire_gabor_layer_forward  <- ComplexGaborLayer.forward   modules/wire.py:88-93
+ *                                ComplexGaborLayer2D.forward modules/wire2d.py:56-67
+ *   wire_gabor_layer_backward <- autograd of the above (used by model.net[i](x), modules/utils.py:251-252)
+ *   wire_final_linear_*       <- nn.Linear(M, out, dtype=cfloat) + .real   modules/wire.py:156-165
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (torch-allocated in the Python host); nothing is allocated, freed or retained;
+ *   - complex tensors are interleaved float pairs (torch.view_as_real of a contiguous complex64),
+ *     weights are [out, in] row-major exactly as nn.Linear stores them;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and never synchronise;
+ *   - every function returns 0 on success, non-zero on failure (wire_b200_last_error() explains);
+ *   - there is NO CPU fallback: on a device that is not sm_100 the calls fail.
+ */
+#ifndef WIRE_B200_H
+#define WIRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WIRE_B200_ABI_VERSION 1
+#define WIRE_B200_MAX_LAYERS 16 /* first layer + hidden layers */
+
+enum { WIRE_PRECISION_TF32 = 0, WIRE_PRECISION_FP32 = 1 };
+
+typedef struct wire_net_desc {
+  int32_t two_d;         /* 0 = wire (modules/wire.py), 1 = wire2d (modules/wire2d.py) */
+  int32_t in_features;   /* coordinate dimensions (1..8) */
+  int32_t width;         /* M: complex hidden features (already int(h/sqrt2) or h/2) */
+  int32_t hidden_layers; /* H: complex Gabor layers after the first one */
+  int32_t out_features;
+  int32_t precision;     /* WIRE_PRECISION_* */
+} wire_net_desc;
+
+typedef struct wire_layer_params {
+  const float* weight;  /* first layer: real [M][in]; hidden: complex [M][M] interleaved */
+  const float* bias;    /* first layer: real [M];     hidden: complex [M] interleaved   */
+  const float* weight2; /* wire2d scale_orth.weight (NULL for wire) */
+  const float* bias2;   /* wire2d scale_orth.bias */
+  const float* omega0;  /* device scalar, the layer's omega_0 parameter (f32[1]) */
+  const float* scale0;  /* device scalar, the layer's scale_0 parameter (f32[1]) */
+} wire_layer_params;
+
+typedef struct wire_net_params {
+  wire_layer_params layer[WIRE_B200_MAX_LAYERS]; /* [0] first, [1..H] hidden */
+  const float* final_weight;                     /* complex [out][M] interleaved */
+  const float* final_bias;                       /* complex [out] interleaved */
+} wire_net_params;
+
+typedef struct wire_layer_grads {
+  float* weight;
+  float* bias;
+  float* weight2;
+  float* bias2;
+} wire_layer_grads;
+
+typedef struct wire_net_grads {
+  wire_layer_grads layer[WIRE_B200_MAX_LAYERS];
+  float* final_weight;
+  float* final_bias;
+} wire_net_grads;
+
+int wire_b200_abi_version(void);
+const char* wire_b200_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x) */
+int wire_b200_device_ok(void);
+int wire_b200_sm_count(void);
+
+/* ---- whole network ------------------------------------------------------------------- */
+
+/* Scratch needed for `n` coordinates. training != 0 keeps what backward needs. */
+size_t wire_net_workspace_bytes(const wire_net_desc* d, int64_t n, int32_t training);
+/* One-time initialisation of a freshly allocated workspace (zero padding, "ones" columns). */
+int wire_net_workspace_init(const wire_net_desc* d, int64_t n, int32_t training, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* out[n][out_features] = Re(final(gabor...(first(coords)))) ; coords is [n][in_features] f32 */
+int wire_net_forward(const wire_net_desc* d, const wire_net_params* p, const float* coords,
+                     int64_t n, float* out, void* workspace, size_t workspace_bytes,
+                     int32_t training, void* stream);
+/* Gradients of sum(out * grad_out) w.r.t. every parameter (OVERWRITES *grads; complex gradients
+ * in PyTorch's convention dL/dRe + j dL/dIm) and optionally w.r.t. coords (grad_coords may be NULL).
+ * Must follow a wire_net_forward(training=1) on the same workspace, coords and params. */
+int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const float* coords,
+                      int64_t n, const float* grad_out, void* workspace, size_t workspace_bytes,
+                      const wire_net_grads* grads, float* grad_coords, void* stream);
+
+/* ---- single layers (model.net[i](x) and per-layer parity) ---------------------------- */
+
+size_t wire_gabor_layer_workspace_bytes(const wire_net_desc* d, int32_t is_first, int32_t in_features,
+                                        int64_t n);
+/* x: first layer real [n][in_features], else complex [n][in_features]; y: complex [n][width].
+ * z_save / w_save (complex [n][width]; first layer: real [n][width]) may be NULL (no_grad). */
+int wire_gabor_layer_forward(const wire_net_desc* d, int32_t is_first, int32_t in_features,
+                             const wire_layer_params* p, const float* x, int64_t n, float* y,
+                             float* z_save, float* w_save, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* grad_x may be NULL. grads are OVERWRITTEN. */
+int wire_gabor_layer_backward(const wire_net_desc* d, int32_t is_first, int32_t in_features,
+                              const wire_layer_params* p, const float* x, const float* z_save,
+                              const float* w_save, const float* grad_y, int64_t n, float* grad_x,
+                              const wire_layer_grads* grads, void* workspace, size_t workspace_bytes,
+                              void* stream);
+/* out[n][out] = Re(h Wf^T + bf) ; h complex [n][width] */
+int wire_final_linear_forward(const wire_net_desc* d, const float* weight, const float* bias,
+                              const float* h, int64_t n, float* out, void* stream);
+/* grad_h complex [n][width] (may be NULL); grad_weight/grad_bias OVERWRITTEN */
+int wire_final_linear_backward(const wire_net_desc* d, const float* weight, const float* h,
+                               const float* grad_out, int64_t n, float* grad_h, float* grad_weight,
+                               float* grad_bias, void* stream);
+
+/* ---- fused optimiser step (torch.optim.Adam semantics on view_as_real parameters) ------ */
+/* p -= lr * m_hat / (sqrt(v_hat) + eps), over `count` floats; `step` is the 1-based step index. */
+int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                   float grad_scale, void* stream);
+/* grad_out[i] = 2*(pred[i]-target[i])/count ; *loss (device scalar, accumulated) += mean sq err */
+int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out,
+                       float* loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WIRE_B200_H */

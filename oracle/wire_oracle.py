@@ -86,6 +86,29 @@ class TorchOracle(nn.Module):
         return self.net(coords).real
 
 
+def deterministic_state(model: nn.Module, seed: int):
+    """Weights independent of torch's RNG/version: U(+-1/sqrt(fan_in)) from numpy, re and im independently
+    (the same distribution nn.Linear's default init produces)."""
+    rs = np.random.RandomState(seed)
+    state = {}
+    for k, v in model.state_dict().items():
+        if k.endswith("omega_0") or k.endswith("scale_0"):
+            state[k] = v.clone()
+            continue
+        fan_in = v.shape[1] if v.dim() == 2 else None
+        if fan_in is None:  # bias: fan_in of the matching weight
+            fan_in = model.state_dict()[k.replace("bias", "weight")].shape[1]
+        b = 1.0 / np.sqrt(fan_in)
+        re = rs.uniform(-b, b, size=tuple(v.shape)).astype(np.float32)
+        if v.is_complex():
+            im = rs.uniform(-b, b, size=tuple(v.shape)).astype(np.float32)
+            state[k] = torch.from_numpy(re + 1j * im).to(torch.complex64)
+        else:
+            state[k] = torch.from_numpy(re)
+    return state
+
+
+
 # --------------------------------------------------------------------------------------------
 # closed form (NumPy, float64/complex128) — SURVEY.md appendix A
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,80 @@
+"""The oracle is only trusted after it reproduces the reference's own outputs (tests/golden/*.npz were
+produced by oracle/make_golden.py running /root/reference/modules/{wire,wire2d}.py in c64 and c128)."""
+import numpy as np
+import pytest
+import torch
+
+import util
+import wire_oracle as O
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_torch_oracle_matches_reference_c64(name):
+    c = util.load_golden(name)
+    g = c["g"]
+    m = util.oracle_model(c)
+    out, grads, gc = util.run_oracle(m, torch.from_numpy(g["coords"]), torch.from_numpy(g["grad_out"]))
+    # same op sequence, same torch build: agree to float32 round-off
+    assert util.rel_err(out.numpy(), g["out_c64"]) < 1e-6
+    assert util.rel_err(gc.numpy(), g["gcoords_c64"]) < 1e-5
+    for k, v in grads.items():
+        a, b = util.golden_grad(c, "c64", k, v.numpy())
+        assert util.rel_err(a, b) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_torch_oracle_matches_reference_c128(name):
+    c = util.load_golden(name)
+    g = c["g"]
+    m = util.oracle_model(c, torch.complex128)
+    out, grads, gc = util.run_oracle(m, torch.from_numpy(g["coords"]).double(), torch.from_numpy(g["grad_out"]).double())
+    assert util.rel_err(out.numpy(), g["out_c128"]) < 1e-13
+    for k, v in grads.items():
+        a, b = util.golden_grad(c, "c128", k, v.numpy())
+        assert util.rel_err(a, b) < 1e-12, k
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_closed_form_matches_reference_c128(name):
+    """Autograd-free NumPy closed form (Wirtinger convention, appendix A.2) vs the reference's autograd."""
+    c = util.load_golden(name)
+    g = c["g"]
+    m = util.oracle_model(c)
+    state = {k: v.numpy().astype(np.complex128 if v.is_complex() else np.float64) for k, v in m.state_dict().items()}
+    out = O.forward_np(state, g["coords"])
+    assert util.rel_err(out, g["out_c128"]) < 1e-12
+    grads = O.backward_np(state, g["coords"], g["grad_out"])
+    assert util.rel_err(grads["coords"], g["gcoords_c128"]) < 1e-11
+    for k in (k for k in g.files if k.startswith("grad_c128.")):
+        key = k[len("grad_c128."):]
+        a, b = util.golden_grad(c, "c128", key, grads[key])
+        assert util.rel_err(a, b) < 1e-11, key
+    # final-layer bias gradient is exactly real
+    last = max(int(k.split(".")[1]) for k in state)
+    assert np.all(grads[f"net.{last}.bias"].imag == 0)
+
+
+def test_layer_outputs_match_reference():
+    c = util.load_golden("wire_small")
+    g = c["g"]
+    m = util.oracle_model(c)
+    x = torch.from_numpy(g["coords"])
+    for i, layer in enumerate(m.net):
+        x = layer(x)
+        assert util.rel_err(x.detach().numpy(), g[f"layer{i}_c64"]) < 1e-6
+
+
+def test_stored_params_equal_deterministic_state():
+    c = util.load_golden("wire2d_small")
+    m = util.oracle_model(c)
+    for k, v in m.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), c["g"][f"param.{k}"])
+
+
+def test_metrics():
+    x = np.linspace(0, 1, 64).reshape(8, 8)
+    assert abs(O.psnr(x, x + 0.1) - 10 * np.log10(1.0 / 0.01)) < 1e-9
+    a = np.zeros((4, 4)); b = np.zeros((4, 4)); a[:2] = 1; b[1:3] = 1
+    assert abs(O.iou(a, b) - 4 / 12) < 1e-12
+    assert tuple(O.image_coords(4, 6).shape) == (1, 24, 2)
+    assert tuple(O.volume_coords(2, 3, 4).shape) == (24, 3)

@@ -88,7 +88,7 @@ static bool test_rows(int n_rows, int two_m, bool time_it) {
 
   wire::RowsParams P;
   memset(&P, 0, sizeof(P));
-  P.n_rows = n_rows; P.k_cols[0] = K; P.k_cols[1] = 0; P.n_blocks = 1; P.n_cols = two_m;
+  P.e.n_rows = n_rows; P.k_cols[0] = K; P.k_cols[1] = 0; P.n_blocks = 1; P.e.n_cols = two_m;
   size_t smem = wire::rows_configure(P, nb, nb, 1);
   if (!smem) { printf("rows_configure failed\n"); return false; }
   bool ok = sm100_host::make_tmap_2d(&P.a_map[0], dA, n_rows, K, pitch, 128, 32);

@@ -1,0 +1,737 @@
+// api.cu — the extern "C" boundary (include/wire_b200.h): workspace layout and kernel sequencing
+// for the WIRE forward/backward pass.  No torch, no allocation, no synchronisation.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/wire_b200.h"
+#include "simt_kernels.cuh"
+#include "simt_rows.cuh"
+#include "tc_launch.cuh"
+
+namespace {
+
+using namespace wire;
+
+thread_local char g_err[512] = "";
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CU_OK(expr)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)          \
+  do {                     \
+    int r_ = (expr);       \
+    if (r_) return r_;     \
+  } while (0)
+
+int g_sm_count = 0;
+int g_cc_major = -1;
+int device_info() {
+  if (g_cc_major >= 0) return 0;
+  int dev = 0;
+  CU_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, dev));
+  g_sm_count = prop.multiProcessorCount;
+  g_cc_major = prop.major;
+  return 0;
+}
+int require_device() {
+  TRY(device_info());
+  if (g_cc_major != 10) return fail("wire_b200 needs an sm_100 (Blackwell B200) device, found compute capability %d.x; there is no fallback path", g_cc_major);
+  return 0;
+}
+
+constexpr int64_t kInferChunk = 1 << 19;  // rows per pass when nothing has to be kept for backward
+constexpr int kRowsPerBlock = 64;
+
+// ------------------------------------------------------------------------------------------
+// column blocking of a row-tile GEMM
+// ------------------------------------------------------------------------------------------
+struct Blocking {
+  int n_blocks, nb, nbh;
+};
+// out_cols = real output columns (2M). two_d_fwd: accumulator holds [z half | w half].
+bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b) {
+  for (int nblk = 1; nblk <= 64; ++nblk) {
+    int per = (out_cols + nblk - 1) / nblk;
+    int nbh = (nblk == 1 && !two_d_fwd) ? round_up(per, 16) : round_up(per, 32);
+    int nb = two_d_fwd ? 2 * nbh : nbh;
+    if (nb > 512) continue;
+    RowsParams tmp;
+    if (rows_configure(tmp, nb, nbh, store_mask) == 0) continue;
+    b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
+    return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------
+struct Layout {
+  int M, H, two_m, P, PR, k_pad, two_d;
+  int64_t rows;
+  int n_act;  // y buffers
+  size_t off_y[WIRE_B200_MAX_LAYERS + 1], off_z[WIRE_B200_MAX_LAYERS + 1], off_w[WIRE_B200_MAX_LAYERS + 1];
+  size_t off_gz[2], off_gw[2], off_gz0, off_gw0;
+  size_t off_bf[WIRE_B200_MAX_LAYERS + 1], off_bd[WIRE_B200_MAX_LAYERS + 1];
+  size_t pack_floats;
+  size_t total;
+  bool fuse_final;
+};
+
+int check_desc(const wire_net_desc* d) {
+  if (!d) return fail("null descriptor");
+  if (d->width < 1 || d->width > 1024) return fail("width %d out of range [1,1024]", d->width);
+  if (d->hidden_layers < 1 || d->hidden_layers >= WIRE_B200_MAX_LAYERS) return fail("hidden_layers %d out of range [1,%d)", d->hidden_layers, WIRE_B200_MAX_LAYERS);
+  if (d->in_features < 1 || d->in_features > kMaxIn) return fail("in_features %d out of range [1,%d]", d->in_features, kMaxIn);
+  if (d->out_features < 1 || d->out_features > kSimtMaxOut) return fail("out_features %d out of range [1,%d]", d->out_features, kSimtMaxOut);
+  if (d->precision != WIRE_PRECISION_TF32 && d->precision != WIRE_PRECISION_FP32) return fail("unknown precision %d", d->precision);
+  return 0;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
+  TRY(check_desc(d));
+  memset(&L, 0, sizeof(L));
+  L.M = d->width; L.H = d->hidden_layers; L.two_m = 2 * d->width; L.two_d = d->two_d;
+  L.P = round_up(L.two_m + 1, 32);
+  L.PR = round_up(L.M, 4);
+  L.k_pad = round_up(L.two_m, 32);
+  L.rows = training ? n : (n < kInferChunk ? n : kInferChunk);
+  if (L.rows < 1) L.rows = 1;
+  Blocking bf;
+  if (!choose_blocking(L.two_m, d->two_d != 0, d->two_d ? 7 : 3, bf)) return fail("no tile configuration for width %d", d->width);
+  L.fuse_final = bf.n_blocks == 1 && d->out_features <= kMaxOut;
+  size_t off = 0;
+  const size_t act = align_up(size_t(L.rows) * L.P * sizeof(float), 1024);
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  if (training) {
+    const int ny = L.fuse_final ? L.H : L.H + 1;
+    for (int l = 0; l < ny; ++l) L.off_y[l] = take(act);
+    L.n_act = ny;
+    for (int l = 1; l <= L.H; ++l) { L.off_z[l] = take(act); if (d->two_d) L.off_w[l] = take(act); }
+    for (int i = 0; i < 2; ++i) { L.off_gz[i] = take(act); if (d->two_d) L.off_gw[i] = take(act); }
+    L.off_gz0 = take(size_t(L.rows) * L.PR * sizeof(float));
+    if (d->two_d) L.off_gw0 = take(size_t(L.rows) * L.PR * sizeof(float));
+  } else {
+    L.off_y[0] = take(act); L.off_y[1] = take(act); L.n_act = 2;
+  }
+  // packed weights: generous bound on rows (blocks are padded to 32) x both K parts
+  L.pack_floats = size_t(2 * L.k_pad + 1024) * size_t(2 * L.k_pad);
+  for (int l = 1; l <= L.H; ++l) {
+    L.off_bf[l] = take(L.pack_floats * sizeof(float));
+    if (training) L.off_bd[l] = take(L.pack_floats * sizeof(float));
+  }
+  L.total = off;
+  return 0;
+}
+
+inline float* at(void* ws, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(ws) + off); }
+
+// ------------------------------------------------------------------------------------------
+// generic row-tile GEMM job -> tcgen05 (TF32) or CUDA-core (FP32) kernel
+// ------------------------------------------------------------------------------------------
+struct RowsJob {
+  int mode;
+  const float* a[2];
+  int a_pitch[2];
+  int k_cols[2];
+  const float* b;
+  int b_rows, b_pitch, k0_pad;
+  Blocking blk;
+  float* o[3];
+  int o_pitch[3];
+  int store_mask;
+  RowsEpi e;
+};
+
+template <int MODE>
+int launch_simt_rows(const SimtRowsParams& S, cudaStream_t st) {
+  const int grid = (S.e.n_rows + 127) / 128;
+  if (grid <= 0) return 0;
+  simt_rows_kernel<MODE><<<grid, 128, 0, st>>>(S);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
+  if (J.e.n_rows <= 0) return 0;
+  if (precision == WIRE_PRECISION_FP32) {
+    SimtRowsParams S;
+    memset(&S, 0, sizeof(S));
+    for (int i = 0; i < 2; ++i) { S.a[i] = J.a[i]; S.a_pitch[i] = J.a_pitch[i]; S.k_cols[i] = J.k_cols[i]; }
+    S.b = J.b; S.b_pitch = J.b_pitch; S.k0_pad = J.k0_pad;
+    for (int i = 0; i < 3; ++i) { S.o[i] = J.o[i]; S.o_pitch[i] = J.o_pitch[i]; }
+    S.n_blocks = J.blk.n_blocks; S.nb = J.blk.nb; S.nbh = J.blk.nbh; S.store_mask = J.store_mask;
+    S.e = J.e;
+    switch (J.mode) {
+      case MODE_PLAIN: return launch_simt_rows<MODE_PLAIN>(S, st);
+      case MODE_GABOR_FWD: return launch_simt_rows<MODE_GABOR_FWD>(S, st);
+      case MODE_GABOR2D_FWD: return launch_simt_rows<MODE_GABOR2D_FWD>(S, st);
+      case MODE_GABOR_BWD: return launch_simt_rows<MODE_GABOR_BWD>(S, st);
+      case MODE_GABOR2D_BWD: return launch_simt_rows<MODE_GABOR2D_BWD>(S, st);
+      case MODE_FIRST_BWD: return launch_simt_rows<MODE_FIRST_BWD>(S, st);
+      case MODE_FIRST2D_BWD: return launch_simt_rows<MODE_FIRST2D_BWD>(S, st);
+    }
+    return fail("bad rows mode %d", J.mode);
+  }
+  RowsParams P;
+  memset(&P, 0, sizeof(P));
+  P.k_cols[0] = J.k_cols[0]; P.k_cols[1] = J.k_cols[1];
+  P.n_blocks = J.blk.n_blocks;
+  P.e = J.e;
+  const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask);
+  if (!smem) return fail("row-tile configuration does not fit shared memory (nb=%d)", J.blk.nb);
+  bool ok = true;
+  for (int i = 0; i < 2; ++i) {
+    const int src = (J.k_cols[i] > 0) ? i : 0;
+    ok &= sm100_host::make_tmap_2d(&P.a_map[i], J.a[src], J.e.n_rows, J.k_cols[src], J.a_pitch[src], 128, 32);
+  }
+  ok &= sm100_host::make_tmap_2d(&P.b_map, J.b, J.b_rows, J.b_pitch, J.b_pitch, P.b_box_rows, 32);
+  int nslot = 0;
+  for (int bit = 0; bit < 3; ++bit)
+    if (J.store_mask & (1 << bit)) {
+      ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32);
+      ++nslot;
+    }
+  for (int s = nslot; s < 3; ++s) P.o_map[s] = P.a_map[0];
+  if (!ok) return fail("cuTensorMapEncodeTiled failed (pointer/pitch alignment?)");
+  CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st));
+  return 0;
+}
+
+int run_pack(const float* W1, const float* W2, int M_out, int K_in, int mode, const Blocking& blk, int k0_pad,
+             int k_pad_total, float* B, int precision, cudaStream_t st) {
+  const int total = blk.n_blocks * blk.nb * k_pad_total;
+  const int grid = (total + 255) / 256;
+  pack_weights_kernel<<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B,
+                                           precision == WIRE_PRECISION_TF32);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+// weight gradient of one complex Linear (x has a ones column at 2*k_in)
+int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const float* g2, int g_pitch, int m_out, int64_t n,
+              float* gW1, float* gB1, float* gW2, float* gB2, int precision, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int n_g = g2 ? 2 : 1;
+  if (precision == WIRE_PRECISION_FP32) {
+    const int x_cols = 2 * k_in + 1, g_cols = 2 * m_out;
+    dim3 grid((x_cols + 63) / 64, (g_cols + 63) / 64, 1);
+    int splits = (4 * g_sm_count) / int(grid.x * grid.y);
+    if (splits < 1) splits = 1;
+    int rps = int((n + splits - 1) / splits);
+    rps = round_up(rps, 16);
+    grid.z = unsigned((n + rps - 1) / rps);
+    simt_wgrad_kernel<<<grid, 256, 0, st>>>(x, x_pitch, k_in, g1, g_pitch, g_cols, int(n), rps, gW1, gB1);
+    if (g2) simt_wgrad_kernel<<<grid, 256, 0, st>>>(x, x_pitch, k_in, g2, g_pitch, g_cols, int(n), rps, gW2, gB2);
+    CU_OK(cudaGetLastError());
+    return 0;
+  }
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_rows = int(n); P.k_in = k_in; P.g_cols = 2 * m_out; P.n_g = n_g;
+  P.gW[0] = gW1; P.gB[0] = gB1; P.gW[1] = gW2; P.gB[1] = gB2;
+  const size_t smem = wgrad_configure(P, g_sm_count);
+  if (!smem) return fail("wgrad configuration does not fit shared memory");
+  bool ok = sm100_host::make_tmap_2d(&P.x_map, x, n, 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  ok &= sm100_host::make_tmap_2d(&P.g_map[0], g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  ok &= sm100_host::make_tmap_2d(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (!ok) return fail("cuTensorMapEncodeTiled failed for wgrad");
+  CU_OK(launch_wgrad(P, smem, st));
+  return 0;
+}
+
+int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const float* coords, int64_t n, int in_f, float* y,
+                  int y_pitch, float* z_out, float* w_out, int zr_pitch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
+  const int round_y = d->precision == WIRE_PRECISION_TF32;
+  if (d->precision == WIRE_PRECISION_TF32)
+    first_fwd_kernel<true><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
+                                                 d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, round_y, z_out, w_out,
+                                                 zr_pitch, kRowsPerBlock);
+  else
+    first_fwd_kernel<false><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
+                                                  d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, round_y, z_out, w_out,
+                                                  zr_pitch, kRowsPerBlock);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const float* Wf, const float* z, const float* w, int zw_pitch,
+                const float* h, int h_pitch, const float* omega, const float* scale, float* gz, float* gw, int g_pitch, float* g_Wf,
+                float* g_bf, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
+  const int round_g = (d->precision == WIRE_PRECISION_TF32) && z;
+  if (d->precision == WIRE_PRECISION_TF32)
+    top_bwd_kernel<true><<<grid, 256, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, h, h_pitch, omega, scale, gz,
+                                               gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+  else
+    top_bwd_kernel<false><<<grid, 256, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, h, h_pitch, omega, scale, gz,
+                                                gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t n, int in_f, int M, float* gW, float* gb, cudaStream_t st) {
+  if (n <= 0 || !gW) return 0;
+  const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
+  first_wgrad_kernel<<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int zero(float* p, size_t floats, cudaStream_t st) {
+  if (p) CU_OK(cudaMemsetAsync(p, 0, floats * sizeof(float), st));
+  return 0;
+}
+
+RowsEpi base_epi(int64_t n, int n_cols, int precision) {
+  RowsEpi e;
+  memset(&e, 0, sizeof(e));
+  e.n_rows = int(n);
+  e.n_cols = n_cols;
+  e.round_out0 = precision == WIRE_PRECISION_TF32;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// whole-network forward for one chunk of rows
+// ------------------------------------------------------------------------------------------
+int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout& L, const float* coords, int64_t n, float* out,
+                  void* ws, int training, cudaStream_t st) {
+  const int M = L.M, H = L.H;
+  float* y_prev = at(ws, L.off_y[0]);
+  TRY(run_first_fwd(d, p->layer[0], coords, n, d->in_features, y_prev, L.P, nullptr, nullptr, 0, st));
+  for (int l = 1; l <= H; ++l) {
+    const bool last = l == H;
+    const bool fuse = last && L.fuse_final;
+    const bool store_y = !fuse;
+    float* y_out = nullptr;
+    if (store_y) y_out = training ? at(ws, L.off_y[l]) : at(ws, L.off_y[l & 1]);
+    int mask = 0;
+    if (store_y) mask |= 1;
+    if (training) { mask |= 2; if (d->two_d) mask |= 4; }
+    Blocking blk;
+    if (!choose_blocking(L.two_m, d->two_d != 0, mask ? mask : 1, blk)) return fail("no tile configuration");
+    float* Bf = at(ws, L.off_bf[l]);
+    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st));
+    RowsJob J;
+    memset(&J, 0, sizeof(J));
+    J.mode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
+    J.a[0] = y_prev; J.a_pitch[0] = L.P; J.k_cols[0] = L.two_m;
+    J.b = Bf; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = L.k_pad; J.k0_pad = L.k_pad;
+    J.blk = blk;
+    int slot = 0;
+    if (mask & 1) { J.o[slot] = y_out; J.o_pitch[slot++] = L.P; }
+    if (mask & 2) { J.o[slot] = at(ws, L.off_z[l]); J.o_pitch[slot++] = L.P; }
+    if (mask & 4) { J.o[slot] = at(ws, L.off_w[l]); J.o_pitch[slot++] = L.P; }
+    J.store_mask = mask;
+    J.e = base_epi(n, L.two_m, d->precision);
+    J.e.bias = p->layer[l].bias; J.e.bias2 = p->layer[l].bias2;
+    J.e.omega = p->layer[l].omega0; J.e.scale = p->layer[l].scale0;
+    if (fuse) {
+      J.e.fuse_final = 1; J.e.wf = p->final_weight; J.e.bf = p->final_bias; J.e.out = out; J.e.out_features = d->out_features;
+    }
+    TRY(run_rows(J, d->precision, st));
+    if (store_y) y_prev = y_out;
+  }
+  if (!L.fuse_final) {
+    const int64_t g64 = (n * 32 + 255) / 256;
+    const int grid = int(g64 > 65535 * 16 ? 65535 * 16 : g64);
+    final_fwd_kernel<<<grid, 256, 0, st>>>(y_prev, L.P, int(n), M, d->out_features, p->final_weight, p->final_bias, out);
+    CU_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+int wire_b200_abi_version(void) { return WIRE_B200_ABI_VERSION; }
+const char* wire_b200_last_error(void) { return g_err; }
+int wire_b200_device_ok(void) { return require_device(); }
+int wire_b200_sm_count(void) { return device_info() ? 0 : g_sm_count; }
+
+size_t wire_net_workspace_bytes(const wire_net_desc* d, int64_t n, int32_t training) {
+  Layout L;
+  if (make_layout(d, n, training, L)) return 0;
+  return L.total;
+}
+
+int wire_net_workspace_init(const wire_net_desc* d, int64_t n, int32_t training, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Layout L;
+  TRY(make_layout(d, n, training, L));
+  if (!workspace || workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
+  CU_OK(cudaMemsetAsync(workspace, 0, L.total, st));
+  // "ones" column (col 2M) of every activation buffer: the bias-gradient row of the wgrad GEMM
+  for (int l = 0; l < L.n_act; ++l) {
+    set_column_kernel<<<int((L.rows + 255) / 256), 256, 0, st>>>(at(workspace, L.off_y[l]), L.P, L.rows, L.two_m, 1.0f);
+  }
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_net_forward(const wire_net_desc* d, const wire_net_params* p, const float* coords, int64_t n, float* out, void* workspace,
+                     size_t workspace_bytes, int32_t training, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!p || !coords || !out) return fail("null argument");
+  if (n <= 0) return 0;
+  Layout L;
+  TRY(make_layout(d, n, training, L));
+  if (!workspace || workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
+  if (training) return forward_chunk(d, p, L, coords, n, out, workspace, 1, st);
+  for (int64_t off = 0; off < n; off += L.rows) {
+    const int64_t m = (n - off) < L.rows ? (n - off) : L.rows;
+    TRY(forward_chunk(d, p, L, coords + off * d->in_features, m, out + off * d->out_features, workspace, 0, st));
+  }
+  return 0;
+}
+
+int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
+                      void* workspace, size_t workspace_bytes, const wire_net_grads* g, float* grad_coords, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!p || !coords || !grad_out || !g) return fail("null argument");
+  Layout L;
+  TRY(make_layout(d, n, 1, L));
+  if (!workspace || workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
+  const int M = L.M, H = L.H, in_f = d->in_features;
+  // gradients are overwritten: clear the accumulation targets
+  TRY(zero(g->final_weight, size_t(d->out_features) * M * 2, st));
+  TRY(zero(g->final_bias, size_t(d->out_features) * 2, st));
+  TRY(zero(g->layer[0].weight, size_t(M) * in_f, st));
+  TRY(zero(g->layer[0].bias, size_t(M), st));
+  if (d->two_d) { TRY(zero(g->layer[0].weight2, size_t(M) * in_f, st)); TRY(zero(g->layer[0].bias2, size_t(M), st)); }
+  for (int l = 1; l <= H; ++l) {
+    TRY(zero(g->layer[l].weight, size_t(M) * M * 2, st));
+    TRY(zero(g->layer[l].bias, size_t(M) * 2, st));
+    if (d->two_d) { TRY(zero(g->layer[l].weight2, size_t(M) * M * 2, st)); TRY(zero(g->layer[l].bias2, size_t(M) * 2, st)); }
+  }
+  if (n <= 0) return 0;
+  if (!g->final_weight || !g->final_bias) return fail("final layer gradient buffers are required");
+
+  int cur = 0;
+  // final Linear backward + Gabor backward of the last hidden layer (h recomputed from z_H)
+  TRY(run_top_bwd(d, grad_out, n, p->final_weight, at(workspace, L.off_z[H]), d->two_d ? at(workspace, L.off_w[H]) : nullptr, L.P, nullptr,
+                  0, p->layer[H].omega0, p->layer[H].scale0, at(workspace, L.off_gz[cur]), d->two_d ? at(workspace, L.off_gw[cur]) : nullptr,
+                  L.P, g->final_weight, g->final_bias, st));
+  for (int l = H; l >= 1; --l) {
+    const float* gz = at(workspace, L.off_gz[cur]);
+    const float* gw = d->two_d ? at(workspace, L.off_gw[cur]) : nullptr;
+    const float* x = at(workspace, L.off_y[l - 1]);
+    if (g->layer[l].weight)
+      TRY(run_wgrad(x, L.P, M, gz, gw, L.P, M, n, g->layer[l].weight, g->layer[l].bias, g->layer[l].weight2, g->layer[l].bias2, d->precision, st));
+    // dgrad of layer l fused with the nonlinearity backward of layer l-1
+    const bool to_first = (l == 1);
+    int mask = to_first ? 0 : (d->two_d ? 3 : 1);
+    Blocking blk;
+    if (!choose_blocking(L.two_m, false, mask ? mask : 1, blk)) return fail("no tile configuration");
+    float* Bd = at(workspace, L.off_bd[l]);
+    const int kparts = d->two_d ? 2 : 1;
+    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st));
+    RowsJob J;
+    memset(&J, 0, sizeof(J));
+    J.a[0] = gz; J.a_pitch[0] = L.P; J.k_cols[0] = L.two_m;
+    if (d->two_d) { J.a[1] = gw; J.a_pitch[1] = L.P; J.k_cols[1] = L.two_m; }
+    J.b = Bd; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = kparts * L.k_pad; J.k0_pad = L.k_pad;
+    J.blk = blk;
+    J.store_mask = mask;
+    J.e = base_epi(n, L.two_m, d->precision);
+    J.e.omega = p->layer[l - 1].omega0; J.e.scale = p->layer[l - 1].scale0;
+    if (!to_first) {
+      J.mode = d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD;
+      J.e.z_src = at(workspace, L.off_z[l - 1]); J.e.w_src = d->two_d ? at(workspace, L.off_w[l - 1]) : nullptr; J.e.zw_pitch = L.P;
+      J.o[0] = at(workspace, L.off_gz[1 - cur]); J.o_pitch[0] = L.P;
+      if (d->two_d) { J.o[1] = at(workspace, L.off_gw[1 - cur]); J.o_pitch[1] = L.P; }
+    } else {
+      J.mode = d->two_d ? MODE_FIRST2D_BWD : MODE_FIRST_BWD;
+      J.e.coords = coords; J.e.in_features = in_f;
+      J.e.w0 = p->layer[0].weight; J.e.b0 = p->layer[0].bias; J.e.w0b = p->layer[0].weight2; J.e.b0b = p->layer[0].bias2;
+      J.e.gz0 = at(workspace, L.off_gz0); J.e.gw0 = d->two_d ? at(workspace, L.off_gw0) : nullptr; J.e.gz0_pitch = L.PR;
+    }
+    TRY(run_rows(J, d->precision, st));
+    cur = 1 - cur;
+  }
+  TRY(run_first_wgrad(at(workspace, L.off_gz0), L.PR, coords, n, in_f, M, g->layer[0].weight, g->layer[0].bias, st));
+  if (d->two_d) TRY(run_first_wgrad(at(workspace, L.off_gw0), L.PR, coords, n, in_f, M, g->layer[0].weight2, g->layer[0].bias2, st));
+  if (grad_coords) {
+    const int grid = int((n * 32 + 255) / 256);
+    grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gz0), L.PR, int(n), in_f, M, p->layer[0].weight, grad_coords, 0);
+    if (d->two_d) grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gw0), L.PR, int(n), in_f, M, p->layer[0].weight2, grad_coords, 1);
+    CU_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// single layers
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct LayerLayout {
+  int P_in, P_out, k_pad_in;
+  size_t off_x, off_y, off_z, off_w, off_g1, off_g2, off_gx, off_b, total;
+};
+void make_layer_layout(const wire_net_desc* d, int in_f, int64_t n, LayerLayout& L) {
+  memset(&L, 0, sizeof(L));
+  L.P_in = round_up(2 * in_f + 1, 32);
+  L.P_out = round_up(2 * d->width + 1, 32);
+  L.k_pad_in = round_up(2 * in_f, 32);
+  const int k_pad_out = round_up(2 * d->width, 32);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t rows = size_t(n < 1 ? 1 : n);
+  L.off_x = take(rows * L.P_in * 4);
+  L.off_y = take(rows * L.P_out * 4);
+  L.off_z = take(rows * L.P_out * 4);
+  L.off_w = take(rows * L.P_out * 4);
+  L.off_g1 = take(rows * L.P_out * 4);
+  L.off_g2 = take(rows * L.P_out * 4);
+  L.off_gx = take(rows * L.P_in * 4);
+  const size_t kp = size_t(L.k_pad_in > k_pad_out ? L.k_pad_in : k_pad_out);
+  L.off_b = take(size_t(2 * kp + 1024) * (2 * kp) * 4);
+  L.total = off;
+}
+int copy2d(const float* src, int sp, float* dst, int dp, int64_t n, int cols, int do_round, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int64_t total = n * cols;
+  int grid = int((total + 255) / 256 > 1184 * 8 ? 1184 * 8 : (total + 255) / 256);
+  copy2d_kernel<<<grid, 256, 0, st>>>(src, sp, dst, dp, n, cols, do_round);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+// element-wise Gabor backward on caller tensors (per-layer API)
+template <bool FAST>
+__global__ void gabor_bwd_ew_kernel(const float* __restrict__ gy, const float* __restrict__ z, const float* __restrict__ w, int64_t n,
+                                    int M, int is_first, const float* __restrict__ omega_p, const float* __restrict__ scale_p,
+                                    float* __restrict__ g1, float* __restrict__ g2, int g_pitch, int do_round) {
+  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  const int64_t total = n * M;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / M;
+    const int k = int(i % M);
+    const float gr = gy[i * 2], gi = gy[i * 2 + 1];
+    if (is_first) {
+      const float zv = z[i], wv = w ? w[i] : 0.f;
+      float yr, yi, gz;
+      gabor_fwd<FAST>(zv, 0.f, omega, s2, s2 * wv * wv, yr, yi);
+      const float pr = gabor_first_bwd(yr, yi, zv, gr, gi, omega, s2, gz);
+      g1[r * g_pitch + k] = gz;
+      if (w) g2[r * g_pitch + k] = -2.0f * s2 * pr * wv;
+    } else {
+      const float zr = z[i * 2], zi = z[i * 2 + 1];
+      const float wr = w ? w[i * 2] : 0.f, wi = w ? w[i * 2 + 1] : 0.f;
+      float yr, yi, gzr, gzi;
+      gabor_fwd<FAST>(zr, zi, omega, s2, s2 * (wr * wr + wi * wi), yr, yi);
+      const float pr = gabor_bwd(yr, yi, zr, zi, gr, gi, omega, s2, gzr, gzi);
+      if (do_round) { gzr = sm100::round_tf32(gzr); gzi = sm100::round_tf32(gzi); }
+      g1[r * g_pitch + 2 * k] = gzr;
+      g1[r * g_pitch + 2 * k + 1] = gzi;
+      if (w) {
+        float a = -2.0f * s2 * pr * wr, b = -2.0f * s2 * pr * wi;
+        if (do_round) { a = sm100::round_tf32(a); b = sm100::round_tf32(b); }
+        g2[r * g_pitch + 2 * k] = a;
+        g2[r * g_pitch + 2 * k + 1] = b;
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+size_t wire_gabor_layer_workspace_bytes(const wire_net_desc* d, int32_t is_first, int32_t in_features, int64_t n) {
+  if (!d) return 0;
+  LayerLayout L;
+  make_layer_layout(d, in_features, n, L);
+  return L.total;
+}
+
+int wire_gabor_layer_forward(const wire_net_desc* d, int32_t is_first, int32_t in_features, const wire_layer_params* p, const float* x,
+                             int64_t n, float* y, float* z_save, float* w_save, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!d || !p || !x || !y) return fail("null argument");
+  if (n <= 0) return 0;
+  const int M = d->width;
+  if (is_first) {
+    if (in_features > kMaxIn) return fail("first layer supports up to %d input features", kMaxIn);
+    wire_net_desc dd = *d;
+    return run_first_fwd(&dd, *p, x, n, in_features, y, 2 * M, z_save, d->two_d ? w_save : nullptr, M, st);
+  }
+  LayerLayout L;
+  make_layer_layout(d, in_features, n, L);
+  if (!workspace || workspace_bytes < L.total) return fail("layer workspace too small: %zu < %zu", workspace_bytes, L.total);
+  const int tf32 = d->precision == WIRE_PRECISION_TF32;
+  float* xp = at(workspace, L.off_x);
+  TRY(copy2d(x, 2 * in_features, xp, L.P_in, n, 2 * in_features, tf32, st));
+  const bool training = z_save != nullptr;
+  int mask = 1;
+  if (training) { mask |= 2; if (d->two_d) mask |= 4; }
+  Blocking blk;
+  if (!choose_blocking(2 * M, d->two_d != 0, mask, blk)) return fail("no tile configuration for width %d", M);
+  float* B = at(workspace, L.off_b);
+  TRY(run_pack(p->weight, d->two_d ? p->weight2 : nullptr, M, in_features, 0, blk, L.k_pad_in, L.k_pad_in, B, d->precision, st));
+  RowsJob J;
+  memset(&J, 0, sizeof(J));
+  J.mode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
+  J.a[0] = xp; J.a_pitch[0] = L.P_in; J.k_cols[0] = 2 * in_features;
+  J.b = B; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = L.k_pad_in; J.k0_pad = L.k_pad_in;
+  J.blk = blk;
+  int slot = 0;
+  J.o[slot] = at(workspace, L.off_y); J.o_pitch[slot++] = L.P_out;
+  if (mask & 2) { J.o[slot] = at(workspace, L.off_z); J.o_pitch[slot++] = L.P_out; }
+  if (mask & 4) { J.o[slot] = at(workspace, L.off_w); J.o_pitch[slot++] = L.P_out; }
+  J.store_mask = mask;
+  J.e = base_epi(n, 2 * M, d->precision);
+  J.e.round_out0 = 0;  // the caller sees y: keep full precision here
+  J.e.bias = p->bias; J.e.bias2 = p->bias2; J.e.omega = p->omega0; J.e.scale = p->scale0;
+  TRY(run_rows(J, d->precision, st));
+  TRY(copy2d(at(workspace, L.off_y), L.P_out, y, 2 * M, n, 2 * M, 0, st));
+  if (z_save) TRY(copy2d(at(workspace, L.off_z), L.P_out, z_save, 2 * M, n, 2 * M, 0, st));
+  if (w_save && d->two_d) TRY(copy2d(at(workspace, L.off_w), L.P_out, w_save, 2 * M, n, 2 * M, 0, st));
+  return 0;
+}
+
+int wire_gabor_layer_backward(const wire_net_desc* d, int32_t is_first, int32_t in_features, const wire_layer_params* p, const float* x,
+                              const float* z_save, const float* w_save, const float* grad_y, int64_t n, float* grad_x,
+                              const wire_layer_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!d || !p || !x || !z_save || !grad_y || !g) return fail("null argument");
+  const int M = d->width, K = in_features;
+  const size_t wsz = is_first ? size_t(M) * K : size_t(M) * K * 2;
+  const size_t bsz = is_first ? size_t(M) : size_t(M) * 2;
+  TRY(zero(g->weight, wsz, st)); TRY(zero(g->bias, bsz, st));
+  if (d->two_d) { TRY(zero(g->weight2, wsz, st)); TRY(zero(g->bias2, bsz, st)); }
+  if (n <= 0) return 0;
+  LayerLayout L;
+  make_layer_layout(d, in_features, n, L);
+  if (!workspace || workspace_bytes < L.total) return fail("layer workspace too small: %zu < %zu", workspace_bytes, L.total);
+  const int tf32 = d->precision == WIRE_PRECISION_TF32;
+  float* g1 = at(workspace, L.off_g1);
+  float* g2 = d->two_d ? at(workspace, L.off_g2) : nullptr;
+  const float* wsv = d->two_d ? w_save : nullptr;
+  const int g_pitch = L.P_out;
+  {
+    int64_t total = n * M;
+    int grid = int((total + 255) / 256 > 1184 * 8 ? 1184 * 8 : (total + 255) / 256);
+    if (tf32) gabor_bwd_ew_kernel<true><<<grid, 256, 0, st>>>(grad_y, z_save, wsv, n, M, is_first, p->omega0, p->scale0, g1, g2, g_pitch, !is_first);
+    else gabor_bwd_ew_kernel<false><<<grid, 256, 0, st>>>(grad_y, z_save, wsv, n, M, is_first, p->omega0, p->scale0, g1, g2, g_pitch, 0);
+    CU_OK(cudaGetLastError());
+  }
+  if (is_first) {
+    TRY(run_first_wgrad(g1, g_pitch, x, n, K, M, g->weight, g->bias, st));
+    if (d->two_d) TRY(run_first_wgrad(g2, g_pitch, x, n, K, M, g->weight2, g->bias2, st));
+    if (grad_x) {
+      const int grid = int((n * 32 + 255) / 256);
+      grad_coords_kernel<<<grid, 256, 0, st>>>(g1, g_pitch, int(n), K, M, p->weight, grad_x, 0);
+      if (d->two_d) grad_coords_kernel<<<grid, 256, 0, st>>>(g2, g_pitch, int(n), K, M, p->weight2, grad_x, 1);
+      CU_OK(cudaGetLastError());
+    }
+    return 0;
+  }
+  // wgrad: x needs the ones column
+  float* xp = at(workspace, L.off_x);
+  TRY(copy2d(x, 2 * K, xp, L.P_in, n, 2 * K, tf32, st));
+  set_column_kernel<<<int((n + 255) / 256), 256, 0, st>>>(xp, L.P_in, n, 2 * K, 1.0f);
+  CU_OK(cudaGetLastError());
+  if (g->weight) TRY(run_wgrad(xp, L.P_in, K, g1, g2, g_pitch, M, n, g->weight, g->bias, g->weight2, g->bias2, d->precision, st));
+  if (grad_x) {
+    Blocking blk;
+    if (!choose_blocking(2 * K, false, 1, blk)) return fail("no tile configuration");
+    float* B = at(workspace, L.off_b);
+    const int k_pad_out = round_up(2 * M, 32);
+    const int kparts = d->two_d ? 2 : 1;
+    TRY(run_pack(p->weight, d->two_d ? p->weight2 : nullptr, M, K, 1, blk, k_pad_out, kparts * k_pad_out, B, d->precision, st));
+    RowsJob J;
+    memset(&J, 0, sizeof(J));
+    J.mode = MODE_PLAIN;
+    J.a[0] = g1; J.a_pitch[0] = g_pitch; J.k_cols[0] = 2 * M;
+    if (d->two_d) { J.a[1] = g2; J.a_pitch[1] = g_pitch; J.k_cols[1] = 2 * M; }
+    J.b = B; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = kparts * k_pad_out; J.k0_pad = k_pad_out;
+    J.blk = blk;
+    J.o[0] = at(workspace, L.off_gx); J.o_pitch[0] = L.P_in;
+    J.store_mask = 1;
+    J.e = base_epi(n, 2 * K, d->precision);
+    J.e.round_out0 = 0;
+    TRY(run_rows(J, d->precision, st));
+    TRY(copy2d(at(workspace, L.off_gx), L.P_in, grad_x, 2 * K, n, 2 * K, 0, st));
+  }
+  return 0;
+}
+
+int wire_final_linear_forward(const wire_net_desc* d, const float* weight, const float* bias, const float* h, int64_t n, float* out,
+                              void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!d || !weight || !bias || !h || !out) return fail("null argument");
+  if (d->out_features > kSimtMaxOut) return fail("out_features %d > %d", d->out_features, kSimtMaxOut);
+  if (n <= 0) return 0;
+  int64_t g64 = (n * 32 + 255) / 256;
+  const int grid = int(g64 > 65535 * 16 ? 65535 * 16 : g64);
+  final_fwd_kernel<<<grid, 256, 0, st>>>(h, 2 * d->width, int(n), d->width, d->out_features, weight, bias, out);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_final_linear_backward(const wire_net_desc* d, const float* weight, const float* h, const float* grad_out, int64_t n, float* grad_h,
+                               float* grad_weight, float* grad_bias, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!d || !weight || !h || !grad_out || !grad_weight || !grad_bias) return fail("null argument");
+  TRY(zero(grad_weight, size_t(d->out_features) * d->width * 2, st));
+  TRY(zero(grad_bias, size_t(d->out_features) * 2, st));
+  return run_top_bwd(d, grad_out, n, weight, nullptr, nullptr, 0, h, 2 * d->width, nullptr, nullptr, grad_h, nullptr, 2 * d->width,
+                     grad_weight, grad_bias, st);
+}
+
+int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count <= 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail("null argument");
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  int64_t g64 = (count + 255) / 256;
+  const int grid = int(g64 > 1184 ? 1184 : g64);
+  adam_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay, float(bc1),
+                                    float(sqrt(bc2)), grad_scale);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out, float* loss, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count <= 0) return 0;
+  if (!pred || !target || !grad_out) return fail("null argument");
+  int64_t g64 = (count + 255) / 256;
+  const int grid = int(g64 > 1184 ? 1184 : g64);
+  mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

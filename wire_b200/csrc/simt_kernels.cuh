@@ -1,0 +1,328 @@
+// simt_kernels.cuh — the CUDA-core kernels of the WIRE hot path: everything that is too skinny for
+// tensor cores (first layer K = 2..3, final layer out = 1..3), weight packing, and the optimiser.
+// All are HBM-bound streaming kernels: coalesced along the feature axis, rows blocked per CTA.
+#pragma once
+#include "gabor_math.cuh"
+#include "sm100.cuh"
+
+namespace wire {
+
+constexpr int kSimtMaxIn = 8;
+constexpr int kSimtMaxOut = 8;
+
+// ---------------------------------------------------------------------------------------------
+// first layer forward (modules/wire.py:88-93 with is_first=True; wire2d.py:56-67):
+//   z = c W0^T + b0 (real) ; [w = c W0b^T + b0b] ; y = exp(j w0 z - s0^2 (z^2 [+ w^2]))  (complex)
+// y: [n][y_pitch] interleaved complex. Optional z_out/w_out (real [n][zr_pitch]) for the per-layer API.
+// ---------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict__ coords, int n, int in_f, int M,
+                                                         const float* __restrict__ W0, const float* __restrict__ b0,
+                                                         const float* __restrict__ W0b, const float* __restrict__ b0b,
+                                                         const float* __restrict__ omega_p, const float* __restrict__ scale_p,
+                                                         float* __restrict__ y, int y_pitch, int round_y,
+                                                         float* __restrict__ z_out, float* __restrict__ w_out, int zr_pitch,
+                                                         int rows_per_block) {
+  __shared__ float sc[64 * kSimtMaxIn];
+  const int row0 = blockIdx.x * rows_per_block;
+  int rows = n - row0;
+  rows = rows > rows_per_block ? rows_per_block : rows;
+  for (int i = threadIdx.x; i < rows * in_f; i += blockDim.x) sc[i] = coords[size_t(row0) * in_f + i];
+  __syncthreads();
+  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    float w[kSimtMaxIn], wb[kSimtMaxIn];
+#pragma unroll
+    for (int d = 0; d < kSimtMaxIn; ++d) {
+      w[d] = d < in_f ? W0[size_t(j) * in_f + d] : 0.f;
+      wb[d] = (W0b && d < in_f) ? W0b[size_t(j) * in_f + d] : 0.f;
+    }
+    const float bj = b0[j], bbj = W0b ? b0b[j] : 0.f;
+    for (int r = 0; r < rows; ++r) {
+      float z = bj, ww = bbj;
+#pragma unroll
+      for (int d = 0; d < kSimtMaxIn; ++d)
+        if (d < in_f) { z = fmaf(sc[r * in_f + d], w[d], z); ww = fmaf(sc[r * in_f + d], wb[d], ww); }
+      float yr, yi;
+      gabor_fwd<FAST>(z, 0.f, omega, s2, W0b ? s2 * ww * ww : 0.f, yr, yi);
+      if (round_y) { yr = sm100::round_tf32(yr); yi = sm100::round_tf32(yi); }
+      *reinterpret_cast<float2*>(y + size_t(row0 + r) * y_pitch + 2 * j) = make_float2(yr, yi);
+      if (z_out) z_out[size_t(row0 + r) * zr_pitch + j] = z;
+      if (w_out) w_out[size_t(row0 + r) * zr_pitch + j] = ww;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: complex W[M_out][K_in] -> real K-major B matrices for tc_rows (TF32-rounded).
+//   mode 0 (forward)  row = output real column (z cols, then w cols per block for wire2d)
+//                     z_re: ( Wre, -Wim)   z_im: ( Wim,  Wre)          z = x W^T
+//   mode 1 (dgrad)    row = real column of g_x ; K runs over g_z columns (then g_w columns)
+//                     gx_re: ( Wre,  Wim)  gx_im: (-Wim,  Wre)         g_x = g_z conj(W)
+// B is [n_blocks*nb][k_pad_total], zero padded.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int M_out, int K_in,
+                                    int mode, int n_blocks, int nb, int nbh, int k0_pad, int k_pad_total,
+                                    float* __restrict__ B, int do_round) {
+  const int total = n_blocks * nb * k_pad_total;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / k_pad_total, kk = idx % k_pad_total;
+    float v = 0.f;
+    if (mode == 0) {
+      const int blk = r / nb, c = r % nb;
+      const float* W = W1;
+      int oc;
+      if (nbh < nb) {  // wire2d forward: [z half | w half]
+        if (c < nbh) oc = blk * nbh + c; else { oc = blk * nbh + (c - nbh); W = W2; }
+      } else oc = blk * nb + c;
+      if (oc < 2 * M_out && kk < 2 * K_in && c < 2 * nbh && W) {
+        const int j = oc >> 1, part = oc & 1, k = kk >> 1, d = kk & 1;
+        const float wr = W[(size_t(j) * K_in + k) * 2], wi = W[(size_t(j) * K_in + k) * 2 + 1];
+        v = part == 0 ? (d == 0 ? wr : -wi) : (d == 0 ? wi : wr);
+      }
+    } else {
+      const int oc = r;  // real column of g_x, blocks are contiguous
+      const float* W = W1;
+      int kq = kk;
+      if (kk >= k0_pad) { W = W2; kq = kk - k0_pad; }
+      if (oc < 2 * K_in && kq < 2 * M_out && W) {
+        const int k = oc >> 1, part = oc & 1, j = kq >> 1, d = kq & 1;
+        const float wr = W[(size_t(j) * K_in + k) * 2], wi = W[(size_t(j) * K_in + k) * 2 + 1];
+        v = part == 0 ? (d == 0 ? wr : wi) : (d == 0 ? -wi : wr);
+      }
+    }
+    B[idx] = do_round ? sm100::round_tf32(v) : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// final Linear forward when it is not fused into the last Gabor epilogue:
+//   out[n][o] = Re( sum_k h[n,k] Wf[o,k] + bf[o] )           (modules/wire.py:156-165)
+// one warp per row, lanes strided over k.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) final_fwd_kernel(const float* __restrict__ h, int h_pitch, int n, int M, int out_f,
+                                                         const float* __restrict__ Wf, const float* __restrict__ bf,
+                                                         float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < n; row += nwarps) {
+    float acc[kSimtMaxOut];
+#pragma unroll
+    for (int o = 0; o < kSimtMaxOut; ++o) acc[o] = 0.f;
+    for (int k = lane; k < M; k += 32) {
+      const float2 hv = *reinterpret_cast<const float2*>(h + size_t(row) * h_pitch + 2 * k);
+#pragma unroll
+      for (int o = 0; o < kSimtMaxOut; ++o)
+        if (o < out_f) {
+          const float2 wv = *reinterpret_cast<const float2*>(Wf + (size_t(o) * M + k) * 2);
+          acc[o] = fmaf(hv.x, wv.x, fmaf(-hv.y, wv.y, acc[o]));
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kSimtMaxOut; ++o)
+      if (o < out_f) {
+        float v = acc[o];
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane == 0) out[size_t(row) * out_f + o] = v + bf[2 * o];
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// top of the backward pass: final Linear backward + Gabor backward of the last hidden layer.
+//   g_h = g_o conj(Wf) ; g_Wf = g_o^T conj(h) ; g_bf = sum g_o (imag = 0)
+//   h = gabor(z_H [, w_H]) is RECOMPUTED from the saved pre-activation; g_z (g_w) are written
+//   TF32-rounded for the dgrad / wgrad GEMMs that consume them.
+// If z == nullptr the kernel is the plain final-linear backward (h given, g_h written).
+// block = 256 threads over the feature axis, `rows_per_block` rows per block.
+// ---------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(256) top_bwd_kernel(const float* __restrict__ g_out, int n, int M, int out_f,
+                                                       const float* __restrict__ Wf,
+                                                       const float* __restrict__ z, const float* __restrict__ w, int zw_pitch,
+                                                       const float* __restrict__ h_in, int h_pitch,
+                                                       const float* __restrict__ omega_p, const float* __restrict__ scale_p,
+                                                       float* __restrict__ gz, float* __restrict__ gw, int g_pitch, int round_g,
+                                                       float* __restrict__ g_Wf, float* __restrict__ g_bf,
+                                                       int rows_per_block) {
+  __shared__ float sgo[64 * kSimtMaxOut];
+  const int row0 = blockIdx.x * rows_per_block;
+  int rows = n - row0;
+  rows = rows > rows_per_block ? rows_per_block : rows;
+  for (int i = threadIdx.x; i < rows * out_f; i += blockDim.x) sgo[i] = g_out[size_t(row0) * out_f + i];
+  __syncthreads();
+  const float omega = omega_p ? __ldg(omega_p) : 0.f;
+  const float s = scale_p ? __ldg(scale_p) : 0.f, s2 = s * s;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    float wr[kSimtMaxOut], wi[kSimtMaxOut], ar[kSimtMaxOut], ai[kSimtMaxOut];
+#pragma unroll
+    for (int o = 0; o < kSimtMaxOut; ++o) {
+      wr[o] = o < out_f ? Wf[(size_t(o) * M + k) * 2] : 0.f;
+      wi[o] = o < out_f ? Wf[(size_t(o) * M + k) * 2 + 1] : 0.f;
+      ar[o] = 0.f; ai[o] = 0.f;
+    }
+    for (int r = 0; r < rows; ++r) {
+      const size_t row = size_t(row0 + r);
+      float gyr = 0.f, gyi = 0.f;
+#pragma unroll
+      for (int o = 0; o < kSimtMaxOut; ++o)
+        if (o < out_f) { gyr = fmaf(sgo[r * out_f + o], wr[o], gyr); gyi = fmaf(-sgo[r * out_f + o], wi[o], gyi); }
+      float yr, yi;
+      if (z) {
+        const float2 zv = *reinterpret_cast<const float2*>(z + row * zw_pitch + 2 * k);
+        float2 wv = make_float2(0.f, 0.f);
+        if (w) wv = *reinterpret_cast<const float2*>(w + row * zw_pitch + 2 * k);
+        gabor_fwd<FAST>(zv.x, zv.y, omega, s2, w ? s2 * (wv.x * wv.x + wv.y * wv.y) : 0.f, yr, yi);
+        float gzr, gzi;
+        const float pr = gabor_bwd(yr, yi, zv.x, zv.y, gyr, gyi, omega, s2, gzr, gzi);
+        if (round_g) { gzr = sm100::round_tf32(gzr); gzi = sm100::round_tf32(gzi); }
+        *reinterpret_cast<float2*>(gz + row * g_pitch + 2 * k) = make_float2(gzr, gzi);
+        if (w) {
+          const float t = -2.0f * s2 * pr;
+          float gwr = t * wv.x, gwi = t * wv.y;
+          if (round_g) { gwr = sm100::round_tf32(gwr); gwi = sm100::round_tf32(gwi); }
+          *reinterpret_cast<float2*>(gw + row * g_pitch + 2 * k) = make_float2(gwr, gwi);
+        }
+      } else {
+        const float2 hv = *reinterpret_cast<const float2*>(h_in + row * h_pitch + 2 * k);
+        yr = hv.x; yi = hv.y;
+        if (gz) *reinterpret_cast<float2*>(gz + row * g_pitch + 2 * k) = make_float2(gyr, gyi);
+      }
+#pragma unroll
+      for (int o = 0; o < kSimtMaxOut; ++o)
+        if (o < out_f) { ar[o] = fmaf(sgo[r * out_f + o], yr, ar[o]); ai[o] = fmaf(-sgo[r * out_f + o], yi, ai[o]); }
+    }
+#pragma unroll
+    for (int o = 0; o < kSimtMaxOut; ++o)
+      if (o < out_f) {
+        atomicAdd(g_Wf + (size_t(o) * M + k) * 2, ar[o]);
+        atomicAdd(g_Wf + (size_t(o) * M + k) * 2 + 1, ai[o]);
+      }
+  }
+  if (threadIdx.x < out_f) {
+    float sacc = 0.f;
+    for (int r = 0; r < rows; ++r) sacc += sgo[r * out_f + threadIdx.x];
+    atomicAdd(g_bf + 2 * threadIdx.x, sacc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// first layer weight gradient: g_W0[j][d] = sum_n gz0[n,j] c[n,d] ; g_b0[j] = sum_n gz0[n,j]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restrict__ gz0, int g_pitch,
+                                                           const float* __restrict__ coords, int n, int in_f, int M,
+                                                           float* __restrict__ gW0, float* __restrict__ gb0,
+                                                           int rows_per_block) {
+  __shared__ float sc[64 * kSimtMaxIn];
+  const int row0 = blockIdx.x * rows_per_block;
+  int rows = n - row0;
+  rows = rows > rows_per_block ? rows_per_block : rows;
+  for (int i = threadIdx.x; i < rows * in_f; i += blockDim.x) sc[i] = coords[size_t(row0) * in_f + i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    float acc[kSimtMaxIn], accb = 0.f;
+#pragma unroll
+    for (int d = 0; d < kSimtMaxIn; ++d) acc[d] = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      const float g = gz0[size_t(row0 + r) * g_pitch + j];
+      accb += g;
+#pragma unroll
+      for (int d = 0; d < kSimtMaxIn; ++d)
+        if (d < in_f) acc[d] = fmaf(g, sc[r * in_f + d], acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < kSimtMaxIn; ++d)
+      if (d < in_f) atomicAdd(gW0 + size_t(j) * in_f + d, acc[d]);
+    atomicAdd(gb0 + j, accb);
+  }
+}
+
+// g_c[n][d] (+)= sum_j gz0[n,j] W0[j,d]   (gradient w.r.t. the coordinates; one warp per row)
+__global__ void __launch_bounds__(256) grad_coords_kernel(const float* __restrict__ gz0, int g_pitch, int n, int in_f, int M,
+                                                           const float* __restrict__ W0, float* __restrict__ gc, int accumulate) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < n; row += nwarps) {
+    float acc[kSimtMaxIn];
+#pragma unroll
+    for (int d = 0; d < kSimtMaxIn; ++d) acc[d] = 0.f;
+    for (int j = lane; j < M; j += 32) {
+      const float g = gz0[size_t(row) * g_pitch + j];
+#pragma unroll
+      for (int d = 0; d < kSimtMaxIn; ++d)
+        if (d < in_f) acc[d] = fmaf(g, W0[size_t(j) * in_f + d], acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < kSimtMaxIn; ++d)
+      if (d < in_f) {
+        float v = acc[d];
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane == 0) {
+          float* dst = gc + size_t(row) * in_f + d;
+          *dst = accumulate ? *dst + v : v;
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strided 2-D copy (pad / unpad rows between caller tensors and the 128 B-aligned workspace)
+// ---------------------------------------------------------------------------------------------
+__global__ void copy2d_kernel(const float* __restrict__ src, int src_pitch, float* __restrict__ dst, int dst_pitch,
+                              int64_t n, int cols, int do_round) {
+  const int64_t total = n * cols;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = int(i % cols);
+    float v = src[r * src_pitch + c];
+    dst[r * dst_pitch + c] = do_round ? sm100::round_tf32(v) : v;
+  }
+}
+// set one column of a pitched matrix (the "ones" column of activation buffers)
+__global__ void set_column_kernel(float* __restrict__ dst, int pitch, int64_t n, int col, float v) {
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x)
+    dst[r * pitch + col] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, amsgrad=False, maximize=False) on a flat fp32 view; complex params are
+// their view_as_real, which is exactly how torch treats them.
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t count, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+// grad = 2 (pred - target) / count ; loss += sum (pred-target)^2 / count
+__global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
+                                float* __restrict__ grad, float* __restrict__ loss) {
+  float local = 0.f;
+  const float inv = 1.0f / float(count);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float d = pred[i] - target[i];
+    grad[i] = 2.0f * d * inv;
+    local = fmaf(d, d, local);
+  }
+  for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
+  __shared__ float ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, v * inv);
+  }
+}
+
+}  // namespace wire

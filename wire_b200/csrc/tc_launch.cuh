@@ -43,7 +43,7 @@ inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int grid, 
 }
 
 inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
-  const int row_tiles = (P.n_rows + kTileRows - 1) / kTileRows;
+  const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
   const int items = row_tiles * P.n_blocks;
   if (items <= 0) return cudaSuccess;
   const int grid = items < sm_count ? items : sm_count;

@@ -2,80 +2,38 @@
 //
 //   ACC[128 coords, nb cols] = A[128 coords, K] (K-major, TMA) x Bpacked[nb cols, K] (K-major, TMA)
 //
-// with TF32 inputs, FP32 accumulation in TMEM, and the layer's point-wise work fused in the
-// epilogue straight out of TMEM.  One kernel template, several epilogues:
-//
-//   MODE_PLAIN        out0 = ACC                                         (probe / tests)
-//   MODE_GABOR_FWD    z = ACC + b ; y = gabor(z)          -> y, z        modules/wire.py:88-93
-//   MODE_GABOR2D_FWD  z,w = ACC halves + b1,b2 ; y = gabor2d(z,w) -> y,z,w   modules/wire2d.py:56-67
-//   MODE_GABOR_BWD    g_y = ACC ; g_z = gabor'(z_saved, g_y)  -> g_z     (autograd of wire.py:88-93)
-//   MODE_GABOR2D_BWD  same + g_w                               -> g_z, g_w
-//   MODE_FIRST_BWD / MODE_FIRST2D_BWD   g_y0 = ACC ; z0 recomputed from coords -> real g_z0 (g_w0)
+// with TF32 inputs, FP32 accumulation in TMEM, and the layer's point-wise work (rows_epilogue.cuh)
+// fused in the epilogue straight out of TMEM; results leave through swizzled staging + TMA stores.
 //
 // A is the complex activation tensor seen as real [N, 2M] (interleaved re,im = torch complex64),
-// Bpacked is the real 2x2-block expansion of the complex weight (see pack kernels), so one real
+// Bpacked is the real 2x2-block expansion of the complex weight (pack_weights_kernel), so one real
 // GEMM of width 2M x 2M *is* the complex GEMM (8*M^2 flop/coord, no de-interleave anywhere).
 //
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
 // warps 2..5 = epilogue (TMEM sub-partition = warp_idx & 3).
 #pragma once
-#include "gabor_math.cuh"
+#include "rows_epilogue.cuh"
 #include "sm100.cuh"
 
 namespace wire {
 
-enum RowsMode : int {
-  MODE_PLAIN = 0,
-  MODE_GABOR_FWD = 1,
-  MODE_GABOR2D_FWD = 2,
-  MODE_GABOR_BWD = 3,
-  MODE_GABOR2D_BWD = 4,
-  MODE_FIRST_BWD = 5,
-  MODE_FIRST2D_BWD = 6,
-};
-
-constexpr int kMaxIn = 8;    // coordinate dimensions supported by the fused first-layer epilogue
-constexpr int kMaxOut = 4;   // output features supported by the fused final Linear
 constexpr int kRowsThreads = 192;
 constexpr int kTileRows = 128;
-constexpr int kChunk = 32;   // fp32 columns per 128-byte swizzle row
+constexpr int kChunk = 32;  // fp32 columns per 128-byte swizzle row
 
 struct RowsParams {
   CUtensorMap a_map[2];  // A parts, box {32 cols, 128 rows}
   CUtensorMap b_map;     // packed B [n_blocks*nb, Kpad], box {32 cols, b_box_rows}
   CUtensorMap o_map[3];  // outputs, box {32 cols, 32 rows}
-  int n_rows;
-  int k_cols[2];   // valid K columns in each A part (part 1 may be 0)
-  int n_blocks;    // column blocks (work item = row tile x block)
-  int nb;          // accumulator columns per block (multiple of 16, <= 512)
-  int nbh;         // 2D fwd: columns of the z half (w half follows); otherwise == nb
-  int n_cols;      // valid real output columns (2M)
+  int k_cols[2];         // valid K columns in each A part (part 1 may be 0)
+  int n_blocks;          // column blocks (work item = row tile x block)
+  int nb;                // accumulator columns per block (multiple of 16, <= 512)
+  int nbh;               // 2D fwd: columns of the z half (w half follows); otherwise == nb
   int b_box_rows, b_boxes;
   int stages;
-  int store_mask;  // which epilogue results are TMA-stored: bit0 = y / g_z / plain, bit1 = z / g_w, bit2 = w;
+  int store_mask;  // which epilogue results are TMA-stored: bit0 = o0, bit1 = o1, bit2 = o2;
                    // o_map[] slots are consumed in bit order
-  int round_out0;  // round output 0 to TF32 (it feeds the next GEMM)
-  const float* bias;
-  const float* bias2;
-  const float* omega;  // device scalars of the layer whose nonlinearity runs in the epilogue
-  const float* scale;
-  const float* z_src;  // saved pre-activations for the backward epilogues
-  const float* w_src;
-  int zw_pitch;
-  const float* coords;  // first-layer backward: z0 is recomputed from the coordinates
-  int in_features;
-  const float* w0;
-  const float* b0;
-  const float* w0b;
-  const float* b0b;
-  float* gz0;
-  float* gw0;
-  int gz0_pitch;
-  const float* wf;  // fused final Linear: [out][M] complex interleaved
-  const float* bf;
-  float* out;
-  int out_features;
-  int fuse_final;
+  RowsEpi e;
 };
 
 __device__ __forceinline__ void stage_row(uint32_t buf, int lane, const float (&v)[32]) {
@@ -87,18 +45,6 @@ __device__ __forceinline__ void stage_row(uint32_t buf, int lane, const float (&
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
                  "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
                  : "memory");
-  }
-}
-
-__device__ __forceinline__ void load_row32(const float* src, bool ok, float (&v)[32]) {
-  const float4* p = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 t = ok ? __ldg(p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    v[4 * j] = t.x;
-    v[4 * j + 1] = t.y;
-    v[4 * j + 2] = t.z;
-    v[4 * j + 3] = t.w;
   }
 }
 
@@ -123,7 +69,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   const int kc0 = (P.k_cols[0] + kChunk - 1) / kChunk;
   const int kc1 = (P.k_cols[1] + kChunk - 1) / kChunk;
   const int kc_total = kc0 + kc1;
-  const int row_tiles = (P.n_rows + kTileRows - 1) / kTileRows;
+  const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
   const int n_items = row_tiles * P.n_blocks;
 
   if (threadIdx.x == 0) {
@@ -215,12 +161,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue warps =====================
+    const RowsEpi& E = P.e;
     const int q = warp & 3;
     const int ew = warp - 2;
     const int n_out = __popc(P.store_mask);
     const uint32_t wbuf = staging_base + ew * (n_out * 2 * 4096);
-    const float omega = (MODE != MODE_PLAIN) ? __ldg(P.omega) : 0.f;
-    const float sc = (MODE != MODE_PLAIN) ? __ldg(P.scale) : 0.f;
+    const float omega = (MODE != MODE_PLAIN) ? __ldg(E.omega) : 0.f;
+    const float sc = (MODE != MODE_PLAIN) ? __ldg(E.scale) : 0.f;
     const float s2 = sc * sc;
     uint32_t tphase = 0;
     uint32_t bufsel = 0;
@@ -228,20 +175,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       const int row0 = (item / P.n_blocks) * kTileRows;
       const int blk = item % P.n_blocks;
       const int row = row0 + q * 32 + lane;
-      const bool row_ok = row < P.n_rows;
-      // columns of this block in output space
-      const int ncol_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;
+      const bool row_ok = row < E.n_rows;
+      const int ncol_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;  // output columns per block
       const int col0 = blk * ncol_blk;
-      int valid = P.n_cols - col0;
+      int valid = E.n_cols - col0;
       valid = valid > ncol_blk ? ncol_blk : valid;
       const int nchunks = (valid + kChunk - 1) / kChunk;
 
       float cin[kMaxIn];
-      if constexpr (MODE == MODE_FIRST_BWD || MODE == MODE_FIRST2D_BWD) {
-#pragma unroll
-        for (int d = 0; d < kMaxIn; ++d)
-          cin[d] = (d < P.in_features && row_ok) ? __ldg(P.coords + size_t(row) * P.in_features + d) : 0.f;
-      }
+      rows_load_coords<MODE>(E, row, row_ok, cin);
       float facc[kMaxOut];
 #pragma unroll
       for (int o = 0; o < kMaxOut; ++o) facc[o] = 0.f;
@@ -253,7 +195,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       for (int ch = 0; ch < nchunks; ++ch) {
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + ch * kChunk;
         uint32_t raw[32];
-        float v2[32];
+        float v[32], v2[32];
         tmem_ld32(taddr, raw);
         if constexpr (MODE == MODE_GABOR2D_FWD) {
           uint32_t raw2[32];
@@ -263,6 +205,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           for (int i = 0; i < 32; ++i) v2[i] = __uint_as_float(raw2[i]);
         } else {
           tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v2[i] = 0.f;
         }
         if (ch == nchunks - 1) {
           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
@@ -270,107 +214,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
         }
-        float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         const int c = col0 + ch * kChunk;  // first real output column of this chunk
 
         float o0[32], o1[32], o2[32];
-        if constexpr (MODE == MODE_PLAIN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o0[i] = v[i];
-        } else if constexpr (MODE == MODE_GABOR_FWD || MODE == MODE_GABOR2D_FWD) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int cc = c + 2 * i;
-            const bool ok = cc < P.n_cols;
-            const float zr = v[2 * i] + (ok ? __ldg(P.bias + cc) : 0.f);
-            const float zi = v[2 * i + 1] + (ok ? __ldg(P.bias + cc + 1) : 0.f);
-            float extra = 0.f;
-            if constexpr (MODE == MODE_GABOR2D_FWD) {
-              const float wr = v2[2 * i] + (ok ? __ldg(P.bias2 + cc) : 0.f);
-              const float wi = v2[2 * i + 1] + (ok ? __ldg(P.bias2 + cc + 1) : 0.f);
-              extra = s2 * (wr * wr + wi * wi);
-              o2[2 * i] = wr;
-              o2[2 * i + 1] = wi;
-            }
-            float yr, yi;
-            gabor_fwd<true>(zr, zi, omega, s2, extra, yr, yi);
-            if (P.fuse_final && ok) {
-              const int k = cc >> 1;
-#pragma unroll
-              for (int o = 0; o < kMaxOut; ++o) {
-                if (o < P.out_features) {
-                  const float2 wv = __ldg(reinterpret_cast<const float2*>(P.wf) + size_t(o) * (P.n_cols >> 1) + k);
-                  facc[o] = fmaf(yr, wv.x, fmaf(-yi, wv.y, facc[o]));
-                }
-              }
-            }
-            if (P.round_out0) { yr = round_tf32(yr); yi = round_tf32(yi); }
-            o0[2 * i] = yr;
-            o0[2 * i + 1] = yi;
-            o1[2 * i] = zr;
-            o1[2 * i + 1] = zi;
-          }
-        } else if constexpr (MODE == MODE_GABOR_BWD || MODE == MODE_GABOR2D_BWD) {
-          float z[32];
-          load_row32(P.z_src + size_t(row) * P.zw_pitch + c, row_ok, z);
-          float w[32];
-          if constexpr (MODE == MODE_GABOR2D_BWD) load_row32(P.w_src + size_t(row) * P.zw_pitch + c, row_ok, w);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float zr = z[2 * i], zi = z[2 * i + 1];
-            float extra = 0.f;
-            if constexpr (MODE == MODE_GABOR2D_BWD) extra = s2 * (w[2 * i] * w[2 * i] + w[2 * i + 1] * w[2 * i + 1]);
-            float yr, yi, gzr, gzi;
-            gabor_fwd<true>(zr, zi, omega, s2, extra, yr, yi);
-            const float pr = gabor_bwd(yr, yi, zr, zi, v[2 * i], v[2 * i + 1], omega, s2, gzr, gzi);
-            o0[2 * i] = round_tf32(gzr);
-            o0[2 * i + 1] = round_tf32(gzi);
-            if constexpr (MODE == MODE_GABOR2D_BWD) {
-              const float t = -2.0f * s2 * pr;
-              o1[2 * i] = round_tf32(t * w[2 * i]);
-              o1[2 * i + 1] = round_tf32(t * w[2 * i + 1]);
-            }
-          }
-        } else {  // MODE_FIRST_BWD / MODE_FIRST2D_BWD: real z0 recomputed from coordinates
-          float gz[16], gw[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int j = (c >> 1) + i;  // complex feature index
-            const bool ok = (2 * j) < P.n_cols;
-            float z0 = ok ? __ldg(P.b0 + j) : 0.f;
-            float w0v = 0.f;
-#pragma unroll
-            for (int d = 0; d < kMaxIn; ++d)
-              if (d < P.in_features && ok) z0 = fmaf(cin[d], __ldg(P.w0 + size_t(j) * P.in_features + d), z0);
-            float extra = 0.f;
-            if constexpr (MODE == MODE_FIRST2D_BWD) {
-              w0v = ok ? __ldg(P.b0b + j) : 0.f;
-#pragma unroll
-              for (int d = 0; d < kMaxIn; ++d)
-                if (d < P.in_features && ok) w0v = fmaf(cin[d], __ldg(P.w0b + size_t(j) * P.in_features + d), w0v);
-              extra = s2 * w0v * w0v;
-            }
-            float yr, yi;
-            gabor_fwd<true>(z0, 0.f, omega, s2, extra, yr, yi);
-            const float pr = gabor_first_bwd(yr, yi, z0, v[2 * i], v[2 * i + 1], omega, s2, gz[i]);
-            gw[i] = -2.0f * s2 * pr * w0v;
-          }
-          if (row_ok) {
-            // 16 real outputs per thread = 64 contiguous bytes (two full sectors): direct stores
-            float4* dst = reinterpret_cast<float4*>(P.gz0 + size_t(row) * P.gz0_pitch + (c >> 1));
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              if ((c >> 1) + 4 * j4 < P.gz0_pitch) dst[j4] = make_float4(gz[4 * j4], gz[4 * j4 + 1], gz[4 * j4 + 2], gz[4 * j4 + 3]);
-            if constexpr (MODE == MODE_FIRST2D_BWD) {
-              float4* dw = reinterpret_cast<float4*>(P.gw0 + size_t(row) * P.gz0_pitch + (c >> 1));
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                if ((c >> 1) + 4 * j4 < P.gz0_pitch) dw[j4] = make_float4(gw[4 * j4], gw[4 * j4 + 1], gw[4 * j4 + 2], gw[4 * j4 + 3]);
-            }
-          }
-        }
+        rows_epilogue_chunk<MODE, true>(E, row, row_ok, c, omega, s2, v, v2, cin, facc, o0, o1, o2);
 
         if (n_out > 0) {
           // staging (double-buffered per warp) -> TMA store; OOB rows/cols are clipped by TMA
@@ -394,14 +243,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           bufsel ^= 1;
         }
       }
-
-      if constexpr (MODE == MODE_GABOR_FWD || MODE == MODE_GABOR2D_FWD) {
-        if (P.fuse_final && row_ok) {
-#pragma unroll
-          for (int o = 0; o < kMaxOut; ++o)
-            if (o < P.out_features) P.out[size_t(row) * P.out_features + o] = facc[o] + __ldg(P.bf + 2 * o);
-        }
-      }
+      rows_store_final<MODE>(E, row, row_ok, facc);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }

@@ -1,0 +1,350 @@
+"""torch.autograd.Function wrappers over the C ABI: the only place where torch tensors become raw pointers.
+
+``wire_net``       — whole stack, replaces ``wire.INR.forward`` (modules/wire.py:161-165) /
+                     ``wire2d.INR.forward`` (modules/wire2d.py:121-125) and their autograd graph
+``gabor_layer``    — one layer, replaces ``ComplexGaborLayer.forward`` (modules/wire.py:88-93) /
+                     ``ComplexGaborLayer2D.forward`` (modules/wire2d.py:56-67)
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic runs in the
+hand-written kernels behind ``libwire_b200.so``.  There is no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LayerGrads, LayerParams, NetDesc, NetGrads, NetParams, WireB200Error, check
+
+_PRECISIONS = {"tf32": _lib.PRECISION_TF32, "fp32": _lib.PRECISION_FP32}
+
+
+def precision_id(name: str) -> int:
+    try:
+        return _PRECISIONS[name]
+    except KeyError:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {name!r}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str, dtype) -> torch.Tensor:
+    if not t.is_cuda:
+        raise WireB200Error(f"{what} must be a CUDA tensor: wire_b200 has no CPU path (got device {t.device})")
+    if t.dtype != dtype:
+        raise WireB200Error(f"{what} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# workspace pool: scratch for activations is checked out per forward and returned when the
+# autograd node dies, so two live graphs never share saved activations.
+# --------------------------------------------------------------------------------------------
+class _Lease:
+    def __init__(self, pool, key, buf):
+        self.pool, self.key, self.buf = pool, key, buf
+
+    def release(self):
+        if self.buf is not None:
+            self.pool._give_back(self.key, self.buf)
+            self.buf = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class WorkspacePool:
+    def __init__(self):
+        self._free: Dict[tuple, List[torch.Tensor]] = {}
+        self._lock = threading.Lock()
+
+    def _give_back(self, key, buf):
+        with self._lock:
+            lst = self._free.setdefault(key, [])
+            if len(lst) < 2:
+                lst.append(buf)
+
+    def lease_net(self, desc: NetDesc, n: int, training: bool, device) -> _Lease:
+        lib = _lib.load()
+        key = ("net", desc.two_d, desc.in_features, desc.width, desc.hidden_layers, desc.out_features,
+               desc.precision, int(n) if training else min(int(n), 1 << 19), bool(training), str(device))
+        with self._lock:
+            lst = self._free.get(key)
+            buf = lst.pop() if lst else None
+        if buf is None:
+            nbytes = lib.wire_net_workspace_bytes(ctypes.byref(desc), n, int(training))
+            if nbytes == 0:
+                check(1, "wire_net_workspace_bytes")
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            check(lib.wire_net_workspace_init(ctypes.byref(desc), n, int(training), buf.data_ptr(), nbytes, _stream()),
+                  "wire_net_workspace_init")
+        return _Lease(self, key, buf)
+
+    def clear(self):
+        with self._lock:
+            self._free.clear()
+
+
+POOL = WorkspacePool()
+
+
+def make_desc(two_d: bool, in_features: int, width: int, hidden_layers: int, out_features: int, precision: str) -> NetDesc:
+    return NetDesc(int(bool(two_d)), int(in_features), int(width), int(hidden_layers), int(out_features),
+                   precision_id(precision))
+
+
+# --------------------------------------------------------------------------------------------
+# whole network
+# --------------------------------------------------------------------------------------------
+# flat parameter order handed to WireNetFn.apply (per layer): weight, bias, [weight2, bias2], omega_0, scale_0 ;
+# then final weight, final bias
+def _per_layer(two_d: bool) -> int:
+    return 6 if two_d else 4
+
+
+def _fill_net_params(desc: NetDesc, tensors: Sequence[torch.Tensor]) -> NetParams:
+    two_d = bool(desc.two_d)
+    per = _per_layer(two_d)
+    n_layers = desc.hidden_layers + 1
+    if len(tensors) != per * n_layers + 2:
+        raise WireB200Error(f"expected {per * n_layers + 2} parameter tensors, got {len(tensors)}")
+    P = NetParams()
+    for l in range(n_layers):
+        t = tensors[l * per:(l + 1) * per]
+        lp = P.layer[l]
+        lp.weight, lp.bias = _ptr(t[0]), _ptr(t[1])
+        if two_d:
+            lp.weight2, lp.bias2, lp.omega0, lp.scale0 = _ptr(t[2]), _ptr(t[3]), _ptr(t[4]), _ptr(t[5])
+        else:
+            lp.weight2, lp.bias2, lp.omega0, lp.scale0 = None, None, _ptr(t[2]), _ptr(t[3])
+    P.final_weight, P.final_bias = _ptr(tensors[-2]), _ptr(tensors[-1])
+    return P
+
+
+def _check_net_tensors(desc: NetDesc, tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    two_d = bool(desc.two_d)
+    per = _per_layer(two_d)
+    M, K0 = desc.width, desc.in_features
+    out: List[torch.Tensor] = []
+    for l in range(desc.hidden_layers + 1):
+        t = tensors[l * per:(l + 1) * per]
+        wd = torch.float32 if l == 0 else torch.complex64
+        wshape = (M, K0) if l == 0 else (M, M)
+        n_w = 4 if two_d else 2
+        for i in range(n_w):
+            x = _require_cuda(t[i], f"layer {l} parameter {i}", wd)
+            exp = wshape if i % 2 == 0 else (M,)
+            if tuple(x.shape) != exp:
+                raise WireB200Error(f"layer {l} parameter {i}: expected shape {exp}, got {tuple(x.shape)}")
+            out.append(x)
+        for i in range(n_w, n_w + 2):
+            out.append(_require_cuda(t[i], f"layer {l} omega_0/scale_0", torch.float32))
+    fw = _require_cuda(tensors[-2], "final weight", torch.complex64)
+    fb = _require_cuda(tensors[-1], "final bias", torch.complex64)
+    if tuple(fw.shape) != (desc.out_features, M) or tuple(fb.shape) != (desc.out_features,):
+        raise WireB200Error("final layer shape mismatch")
+    out += [fw, fb]
+    return out
+
+
+class WireNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, desc: NetDesc, coords: torch.Tensor, *params: torch.Tensor):
+        lib = _lib.load()
+        coords_c = _require_cuda(coords, "coords", torch.float32)
+        if coords_c.shape[-1] != desc.in_features:
+            raise WireB200Error(f"coords last dim {coords_c.shape[-1]} != in_features {desc.in_features}")
+        tensors = _check_net_tensors(desc, params)
+        flat = coords_c.reshape(-1, desc.in_features)
+        n = flat.shape[0]
+        training = any(ctx.needs_input_grad[1:])
+        out = torch.empty((n, desc.out_features), dtype=torch.float32, device=flat.device)
+        P = _fill_net_params(desc, tensors)
+        with torch.cuda.device(flat.device):
+            lease = POOL.lease_net(desc, n, training, flat.device)
+            check(lib.wire_net_forward(ctypes.byref(desc), ctypes.byref(P), flat.data_ptr(), n, out.data_ptr(),
+                                       lease.buf.data_ptr(), lease.buf.numel(), int(training), _stream()),
+                  "wire_net_forward")
+        if training:
+            ctx.desc, ctx.lease, ctx.n = desc, lease, n
+            ctx.coords_shape = coords.shape
+            ctx.save_for_backward(flat, *tensors)
+        else:
+            lease.release()
+        return out.reshape(*coords.shape[:-1], desc.out_features)
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        lib = _lib.load()
+        desc, n = ctx.desc, ctx.n
+        flat, *tensors = ctx.saved_tensors
+        if ctx.lease.buf is None:
+            raise WireB200Error("workspace of this forward pass was already released (backward called twice "
+                                "without retain_graph?)")
+        g = _require_cuda(grad_out, "grad_out", torch.float32).reshape(n, desc.out_features)
+        two_d = bool(desc.two_d)
+        per = _per_layer(two_d)
+        n_w = 4 if two_d else 2
+        # one flat fp32 buffer for every gradient (what a data-parallel all-reduce wants to see)
+        sizes = []
+        for l in range(desc.hidden_layers + 1):
+            for i in range(n_w):
+                t = tensors[l * per + i]
+                sizes.append(t.numel() * (2 if t.is_complex() else 1))
+        sizes += [tensors[-2].numel() * 2, tensors[-1].numel() * 2]
+        # every slot starts on a 16-byte boundary (view_as_complex needs an even offset; kernels like float4)
+        starts, off = [], 0
+        for s in sizes:
+            starts.append(off)
+            off += (s + 3) // 4 * 4
+        flatg = torch.empty(off, dtype=torch.float32, device=flat.device)
+        views = [flatg[o:o + s] for o, s in zip(starts, sizes)]
+        G = NetGrads()
+        vi = 0
+        grads: List[Optional[torch.Tensor]] = []
+        for l in range(desc.hidden_layers + 1):
+            lg = G.layer[l]
+            ptrs = []
+            for i in range(n_w):
+                t = tensors[l * per + i]
+                v = views[vi]
+                vi += 1
+                ptrs.append(v.data_ptr())
+                grads.append(torch.view_as_complex(v.view(*t.shape, 2)) if t.is_complex() else v.view(t.shape))
+            lg.weight, lg.bias = ptrs[0], ptrs[1]
+            if two_d:
+                lg.weight2, lg.bias2 = ptrs[2], ptrs[3]
+            grads += [None, None]  # omega_0, scale_0 (non-trainable in every reference driver)
+        G.final_weight, G.final_bias = views[vi].data_ptr(), views[vi + 1].data_ptr()
+        grads.append(torch.view_as_complex(views[vi].view(*tensors[-2].shape, 2)))
+        grads.append(torch.view_as_complex(views[vi + 1].view(*tensors[-1].shape, 2)))
+        g_coords = None
+        if ctx.needs_input_grad[1]:
+            g_coords = torch.empty_like(flat)
+        P = _fill_net_params(desc, tensors)
+        with torch.cuda.device(flat.device):
+            check(lib.wire_net_backward(ctypes.byref(desc), ctypes.byref(P), flat.data_ptr(), n, g.data_ptr(),
+                                        ctx.lease.buf.data_ptr(), ctx.lease.buf.numel(), ctypes.byref(G),
+                                        _ptr(g_coords), _stream()),
+                  "wire_net_backward")
+        if g_coords is not None:
+            g_coords = g_coords.reshape(ctx.coords_shape)
+        return (None, g_coords, *grads)
+
+
+def wire_net(desc: NetDesc, coords: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    return WireNetFn.apply(desc, coords, *params)
+
+
+# --------------------------------------------------------------------------------------------
+# single layer
+# --------------------------------------------------------------------------------------------
+def _layer_ws(desc: NetDesc, is_first: bool, in_features: int, n: int, device) -> torch.Tensor:
+    lib = _lib.load()
+    nbytes = lib.wire_gabor_layer_workspace_bytes(ctypes.byref(desc), int(is_first), in_features, n)
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _layer_params(two_d, weight, bias, weight2, bias2, omega0, scale0) -> LayerParams:
+    lp = LayerParams()
+    lp.weight, lp.bias = _ptr(weight), _ptr(bias)
+    lp.weight2, lp.bias2 = (_ptr(weight2), _ptr(bias2)) if two_d else (None, None)
+    lp.omega0, lp.scale0 = _ptr(omega0), _ptr(scale0)
+    return lp
+
+
+class GaborLayerFn(torch.autograd.Function):
+    """y = gabor(x W^T + b) for one layer; x real [.., K] (first layer) or complex64 [.., K]."""
+
+    @staticmethod
+    def forward(ctx, desc: NetDesc, is_first: bool, x, weight, bias, weight2, bias2, omega0, scale0):
+        lib = _lib.load()
+        two_d = bool(desc.two_d)
+        xd = torch.float32 if is_first else torch.complex64
+        xc = _require_cuda(x, "layer input", xd)
+        K = xc.shape[-1]
+        M = desc.width
+        weight = _require_cuda(weight, "weight", xd)
+        bias = _require_cuda(bias, "bias", xd)
+        if two_d:
+            weight2 = _require_cuda(weight2, "scale_orth.weight", xd)
+            bias2 = _require_cuda(bias2, "scale_orth.bias", xd)
+        omega0 = _require_cuda(omega0, "omega_0", torch.float32)
+        scale0 = _require_cuda(scale0, "scale_0", torch.float32)
+        if tuple(weight.shape) != (M, K):
+            raise WireB200Error(f"weight shape {tuple(weight.shape)} != {(M, K)}")
+        flat = xc.reshape(-1, K)
+        n = flat.shape[0]
+        training = any(ctx.needs_input_grad)
+        y = torch.empty((n, M), dtype=torch.complex64, device=flat.device)
+        z = w = None
+        if training:
+            z = torch.empty((n, M), dtype=xd, device=flat.device)
+            if two_d:
+                w = torch.empty((n, M), dtype=xd, device=flat.device)
+        ws = _layer_ws(desc, is_first, K, n, flat.device)
+        lp = _layer_params(two_d, weight, bias, weight2, bias2, omega0, scale0)
+        with torch.cuda.device(flat.device):
+            check(lib.wire_gabor_layer_forward(ctypes.byref(desc), int(is_first), K, ctypes.byref(lp), flat.data_ptr(), n,
+                                               y.data_ptr(), _ptr(z), _ptr(w), ws.data_ptr(), ws.numel(), _stream()),
+                  "wire_gabor_layer_forward")
+        if training:
+            ctx.desc, ctx.is_first, ctx.K, ctx.n, ctx.x_shape = desc, is_first, K, n, x.shape
+            ctx.save_for_backward(flat, z, w if two_d else flat.new_empty(0), weight, bias,
+                                  weight2 if two_d else flat.new_empty(0), bias2 if two_d else flat.new_empty(0),
+                                  omega0, scale0)
+        return y.reshape(*x.shape[:-1], M)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        lib = _lib.load()
+        desc, is_first, K, n = ctx.desc, ctx.is_first, ctx.K, ctx.n
+        two_d = bool(desc.two_d)
+        flat, z, w, weight, bias, weight2, bias2, omega0, scale0 = ctx.saved_tensors
+        gy = _require_cuda(grad_y, "grad_y", torch.complex64).reshape(n, desc.width)
+        gW, gb = torch.empty_like(weight), torch.empty_like(bias)
+        gW2 = gb2 = None
+        if two_d:
+            gW2, gb2 = torch.empty_like(weight2), torch.empty_like(bias2)
+        gx = torch.empty_like(flat) if ctx.needs_input_grad[2] else None
+        lg = LayerGrads()
+        lg.weight, lg.bias, lg.weight2, lg.bias2 = _ptr(gW), _ptr(gb), _ptr(gW2), _ptr(gb2)
+        lp = _layer_params(two_d, weight, bias, weight2, bias2, omega0, scale0)
+        ws = _layer_ws(desc, is_first, K, n, flat.device)
+        with torch.cuda.device(flat.device):
+            check(lib.wire_gabor_layer_backward(ctypes.byref(desc), int(is_first), K, ctypes.byref(lp), flat.data_ptr(),
+                                                z.data_ptr(), _ptr(w) if two_d else None, gy.data_ptr(), n, _ptr(gx),
+                                                ctypes.byref(lg), ws.data_ptr(), ws.numel(), _stream()),
+                  "wire_gabor_layer_backward")
+        if gx is not None:
+            gx = gx.reshape(ctx.x_shape)
+        return (None, None, gx, gW, gb, gW2, gb2, None, None)
+
+
+def gabor_layer(desc, is_first, x, weight, bias, weight2, bias2, omega0, scale0):
+    return GaborLayerFn.apply(desc, is_first, x, weight, bias, weight2, bias2, omega0, scale0)
+
+
+def final_linear_real(desc: NetDesc, h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Re(h W^T + b) with the CUDA kernel (no autograd; the fused ``wire_net`` is the training path)."""
+    lib = _lib.load()
+    hc = _require_cuda(h, "h", torch.complex64)
+    flat = hc.reshape(-1, hc.shape[-1])
+    out = torch.empty((flat.shape[0], desc.out_features), dtype=torch.float32, device=flat.device)
+    weight = _require_cuda(weight, "final weight", torch.complex64)
+    bias = _require_cuda(bias, "final bias", torch.complex64)
+    with torch.cuda.device(flat.device):
+        check(lib.wire_final_linear_forward(ctypes.byref(desc), weight.data_ptr(), bias.data_ptr(), flat.data_ptr(),
+                                            flat.shape[0], out.data_ptr(), _stream()), "wire_final_linear_forward")
+    return out.reshape(*h.shape[:-1], desc.out_features)

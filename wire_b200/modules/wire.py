@@ -1,0 +1,140 @@
+"""WIRE with the 1-D complex Gabor wavelet — CUDA-backed counterpart of the reference's ``modules/wire.py``.
+
+Same constructor signatures, attribute names, parameter names/dtypes/shapes and ``state_dict`` keys as
+``ComplexGaborLayer`` (modules/wire.py:44-93) and ``INR`` (modules/wire.py:94-167), so
+``model.net[i]``, ``model.net[0].omega_0``, ``state_dict()``/``load_state_dict()``, ``torch.optim.Adam``
+and ``count_parameters`` keep working.  ``INR.forward`` runs the whole stack through the fused
+sm_100a kernels (``wire_b200.functional.wire_net``); a single layer called on its own
+(``model.net[idx](x)``, modules/utils.py:251-252) runs ``wire_b200.functional.gabor_layer``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import functional as F
+
+DEFAULT_PRECISION = "tf32"
+
+
+class _GaborBase(nn.Module):
+    """Shared plumbing of ComplexGaborLayer / ComplexGaborLayer2D."""
+
+    two_d = False
+
+    def __init__(self, in_features, out_features, bias=True, is_first=False, omega0=10.0, sigma0=40.0,
+                 trainable=False, precision=DEFAULT_PRECISION):
+        super().__init__()
+        self.is_first = is_first
+        self.in_features = in_features
+        self.out_features = out_features
+        self.precision = precision
+        dtype = torch.float if is_first else torch.cfloat
+        # modules/wire.py:80-81: f32[1] Parameters that show up in parameters()/state_dict()
+        self.omega_0 = nn.Parameter(omega0 * torch.ones(1), trainable)
+        self.scale_0 = nn.Parameter(sigma0 * torch.ones(1), trainable)
+        self.linear = nn.Linear(in_features, out_features, bias=bias, dtype=dtype)
+        if self.two_d:
+            self.scale_orth = nn.Linear(in_features, out_features, bias=bias, dtype=dtype)
+
+    def _bias(self, lin: nn.Linear) -> torch.Tensor:
+        if lin.bias is not None:
+            return lin.bias
+        return torch.zeros(self.out_features, dtype=lin.weight.dtype, device=lin.weight.device)
+
+    def _check_trainable(self):
+        if self.omega_0.requires_grad or self.scale_0.requires_grad:
+            raise NotImplementedError(
+                "trainable omega_0/scale_0 (trainable=True) is not implemented by the CUDA path yet; "
+                "every reference driver uses trainable=False (SURVEY.md §8f item 3)")
+
+    def flat_params(self):
+        """Parameter tensors in the order ``functional.wire_net`` expects."""
+        ps = [self.linear.weight, self._bias(self.linear)]
+        if self.two_d:
+            ps += [self.scale_orth.weight, self._bias(self.scale_orth)]
+        return ps + [self.omega_0, self.scale_0]
+
+    def forward(self, input):
+        self._check_trainable()
+        desc = F.make_desc(self.two_d, self.in_features, self.out_features, 1, 1, self.precision)
+        so = self.scale_orth if self.two_d else None
+        return F.gabor_layer(desc, self.is_first, input, self.linear.weight, self._bias(self.linear),
+                             so.weight if so is not None else None, self._bias(so) if so is not None else None,
+                             self.omega_0, self.scale_0)
+
+
+class ComplexGaborLayer(_GaborBase):
+    """exp(1j*omega_0*lin - |scale_0*lin|^2) after a Linear — modules/wire.py:44-93."""
+
+    two_d = False
+
+
+class FinalLinear(nn.Linear):
+    """The complex output Linear (modules/wire.py:156).  Inside ``INR.forward`` it is fused into the last
+    Gabor kernel; called on its own (layer-by-layer evaluation) it returns the complex output like
+    ``nn.Linear`` does, computed by the CUDA kernel when no gradient is required."""
+
+    def forward(self, input):
+        if torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad):
+            return super().forward(input)  # stand-alone training of the bare Linear is not a WIRE code path
+        desc = F.make_desc(False, 1, self.in_features, 1, self.out_features, DEFAULT_PRECISION)
+        re = F.final_linear_real(desc, input, self.weight, self.bias)
+        im = F.final_linear_real(desc, input, self.weight * (-1j), self.bias * (-1j))
+        return torch.complex(re, im)
+
+
+class _INRBase(nn.Module):
+    layer_cls = ComplexGaborLayer
+    two_d = False
+
+    def _build(self, in_features, width, hidden_layers, out_features, first_omega_0, hidden_omega_0, scale, precision):
+        self.complex = True
+        self.wavelet = 'gabor'
+        self.pos_encode = False  # legacy attribute read by modules/utils.py:246
+        self.precision = precision
+        self.in_features, self.width = in_features, width
+        self.hidden_layers, self.out_features = hidden_layers, out_features
+        net = [self.layer_cls(in_features, width, omega0=first_omega_0, sigma0=scale, is_first=True,
+                              trainable=False, precision=precision)]
+        for _ in range(hidden_layers):
+            net.append(self.layer_cls(width, width, omega0=hidden_omega_0, sigma0=scale, precision=precision))
+        net.append(FinalLinear(width, out_features, dtype=torch.cfloat))
+        self.net = nn.Sequential(*net)
+
+    def flat_params(self):
+        ps = []
+        for layer in list(self.net)[:-1]:
+            ps += layer.flat_params()
+        final = self.net[-1]
+        return ps + [final.weight, final.bias]
+
+    def forward(self, coords):
+        layers = list(self.net)
+        if self.hidden_layers < 1 or len(layers) != self.hidden_layers + 2:
+            # no hidden layer (or a user-edited Sequential): compose the per-layer kernels
+            x = coords
+            for layer in layers[:-1]:
+                x = layer(x)
+            desc = F.make_desc(self.two_d, self.in_features, self.width, 1, self.out_features, self.precision)
+            return F.final_linear_real(desc, x, layers[-1].weight, layers[-1].bias)
+        for layer in layers[:-1]:
+            layer._check_trainable()
+        desc = F.make_desc(self.two_d, self.in_features, self.width, self.hidden_layers, self.out_features,
+                           self.precision)
+        return F.wire_net(desc, coords, self.flat_params())
+
+
+class INR(_INRBase):
+    """modules/wire.py:94-167 — same positional signature (incl. the fork's ``scaled_hidden_features``)."""
+
+    def __init__(self, in_features, hidden_features, scaled_hidden_features=None, hidden_layers=1, out_features=1,
+                 outermost_linear=True, first_omega_0=30, hidden_omega_0=30., scale=10.0, scale_tensor=[],
+                 pos_encode=False, multi_scale=False, sidelength=512, fn_samples=None, use_nyquist=True,
+                 precision=DEFAULT_PRECISION):
+        super().__init__()
+        self.nonlin = ComplexGaborLayer
+        # "Since complex numbers are two real numbers, reduce the number of hidden parameters by 2" (:119)
+        width = int(hidden_features / np.sqrt(2))
+        self._build(in_features, width, hidden_layers, out_features, first_omega_0, hidden_omega_0, scale, precision)
