@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — WIRE fwd+bwd(+Adam) coordinates/second on a 512x512 image fit (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference ...                      # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...         # coordinate-sharded data parallel, weak scaling
+
+A step = one full training iteration of wire_image_denoise.py:148-157 on one batch of 262 144 coordinates
+per GPU: forward through the complex Gabor stack, MSE loss, backward, Adam step.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "wire_fwd_bwd_coords_per_sec"
+UNIT = "coords/s"
+# the headline workload: wire_image_denoise.py defaults (hidden 300 -> M = 212, 2 hidden layers, omega0 7, sigma0 6)
+CFG = dict(nonlin="wire", in_features=2, hidden_features=300, hidden_layers=2, out_features=3,
+           first_omega_0=7.0, hidden_omega_0=7.0, scale=6.0)
+LR = 5e-3
+
+
+def flop_per_coord(M, H, in_f, out_f):
+    """F_wire = 24 H M^2 + 12 M out + 4 in M (complex MAC = 8 real flop)."""
+    return 24 * H * M * M + 12 * M * out_f + 4 * in_f * M
+
+
+def synthetic_image(H, W, seed=0):
+    """Band-limited sinusoids + hard-edged discs, normalised to [0,1], plus Gaussian noise."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, H), np.linspace(-1, 1, W), indexing="ij")
+    chans = []
+    for c in range(3):
+        im = np.zeros_like(xx)
+        for _ in range(6):
+            fx, fy, ph = rs.uniform(-6, 6), rs.uniform(-6, 6), rs.uniform(0, 2 * np.pi)
+            im += rs.uniform(0.2, 1.0) * np.sin(fx * xx + fy * yy + ph)
+        for _ in range(3):
+            cx, cy, r = rs.uniform(-0.7, 0.7), rs.uniform(-0.7, 0.7), rs.uniform(0.1, 0.3)
+            im += 1.5 * ((xx - cx) ** 2 + (yy - cy) ** 2 < r * r)
+        chans.append(im)
+    img = np.stack(chans, -1)
+    img = (img - img.min()) / (img.max() - img.min())
+    noisy = img + 0.1 * rs.normal(size=img.shape)
+    return img.astype(np.float32), noisy.astype(np.float32)
+
+
+def image_coords(H, W):
+    x = torch.linspace(-1, 1, W)
+    y = torch.linspace(-1, 1, H)
+    X, Y = torch.meshgrid(x, y, indexing="xy")
+    return torch.hstack((X.reshape(-1, 1), Y.reshape(-1, 1)))[None, ...]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx, self.rows, self.proc = device_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(size, steps, warmup, threads=None):
+    """The reference's CPU path: the oracle port (same op sequence as modules/wire.py) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import wire_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = O.TorchOracle("wire", CFG["in_features"], CFG["hidden_features"], CFG["hidden_layers"], CFG["out_features"],
+                          CFG["first_omega_0"], CFG["hidden_omega_0"], CFG["scale"])
+    _, noisy = synthetic_image(size, size)
+    coords = image_coords(size, size)
+    target = torch.from_numpy(noisy.reshape(1, size * size, 3))
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = model(coords)
+        loss = ((out - target) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    n = size * size
+    return dict(coords_per_s=n / statistics.mean(times), ms_per_step=1e3 * statistics.mean(times), cores=threads,
+                sample=f"{size}x{size} image ({n} coords) full-batch fwd+bwd+Adam, fp32/complex64, {steps} timed steps "
+                       f"after {warmup} warm-up, torch {torch.__version__} CPU")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size = 256  # bounded sample of the 512x512 workload: a quarter of the coordinates per step
+    r = cpu_reference_run(size, args.steps, max(args.warmup, 1))
+    M = int(CFG["hidden_features"] / np.sqrt(2))
+    line = {"impl": "reference", "metric": METRIC, "value": r["coords_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "WIRE image fit, 512x512 RGB, M=212 H=2 (sampled: 256x256 coords per step on CPU)",
+                       "width": M, "hidden_layers": CFG["hidden_layers"]},
+            "cpu_baseline": {"value": r["coords_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["coords_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import wire_b200
+    from wire_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = wire_b200._lib.load()
+    wire_b200._lib.check(lib.wire_b200_device_ok(), "device check")
+
+    size = args.size
+    n = size * size
+    M = int(CFG["hidden_features"] / np.sqrt(2))
+    torch.manual_seed(0)
+    model = wire_b200.get_INR(**CFG, precision=args.precision).to(dev)
+    if world > 1:
+        parallel.broadcast_parameters(model)
+    # weak scaling: every rank fits its own 512x512 tile of a (512*world) x 512 synthetic image
+    _, noisy = synthetic_image(size, size, seed=rank)
+    coords_h = image_coords(size, size).pin_memory()
+    target_h = torch.from_numpy(noisy.reshape(1, n, 3)).pin_memory()
+    coords = coords_h.to(dev)
+    target = target_h.to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def step(c, t):
+        out = model(c)
+        loss = ((out - t) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_gradients(params, world)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(coords, target)
+    barrier()
+
+    # ---------------- timed region: device-resident inputs, CUDA events, max over ranks ----------------
+    lib.wire_b200_prof_enable(0)
+    lib.wire_b200_prof_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(coords, target)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = 0
+    for k in range(lib.wire_b200_prof_kinds()):
+        cnt = ctypes.c_uint64(0)
+        lib.wire_b200_prof_get(k, ctypes.byref(cnt), None)
+        launches += cnt.value
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # ---------------- e2e: host inputs, H2D every step, D2H loss read every step ----------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c = coords_h.to(dev, non_blocking=True)
+        t = target_h.to(dev, non_blocking=True)
+        loss = step(c, t)
+        loss_host = float(loss)  # device->host read of the step's result
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt)
+    e2e = {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": coords_h.numel() * 4 + target_h.numel() * 4,
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3, "final_loss": loss_host}
+
+    # ---------------- per-kernel device time (CUDA events on the launching stream) ----------------
+    roofline, kernels = None, {}
+    if rank == 0:
+        lib.wire_b200_prof_reset()
+        lib.wire_b200_prof_enable(1)
+        torch.cuda.synchronize()
+        for _ in range(args.steps):
+            step(coords, target)
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        for k in range(lib.wire_b200_prof_kinds()):
+            cnt, ms = ctypes.c_uint64(0), ctypes.c_double(0.0)
+            lib.wire_b200_prof_get(k, ctypes.byref(cnt), ctypes.byref(ms))
+            if cnt.value:
+                kernels[lib.wire_b200_prof_name(k).decode()] = {"launches": cnt.value, "ms_total": ms.value,
+                                                                "ms_avg": ms.value / cnt.value}
+                total_ms += ms.value
+        lib.wire_b200_prof_enable(0)
+        lib.wire_b200_prof_reset()
+        peaks, peaks_src = load_peaks()
+        top = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
+        gemm_flop = 8.0 * M * M * n  # one complex M x M GEMM over n coordinates (fwd, dgrad and wgrad alike)
+        alg_bytes = {"tc_rows_gabor_fwd": 3 * 8 * M * n, "tc_rows_dgrad_gabor_bwd": 3 * 8 * M * n, "tc_wgrad": 2 * 8 * M * n,
+                     "tc_rows_dgrad_first_bwd": 8 * M * n + 4 * M * n}
+        if top is not None:
+            tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # TF32 runs at half the BF16 tensor rate
+            ach = gemm_flop / (kernels[top]["ms_avg"] * 1e-3) / 1e12 if top.startswith("tc_") else None
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": (ach / tf32_peak) if ach else None, "traffic": None,
+                        "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained/2 (TF32 = half the BF16 "
+                                       f"tensor rate; kernel timed inside a long step)",
+                        "frac_of_nominal_tf32_1100": (ach / 1100.0) if ach else None,
+                        "algorithmic_flop_per_launch": gemm_flop,
+                        "hbm_achieved_gbs": (alg_bytes.get(top, 0) / (kernels[top]["ms_avg"] * 1e-3) / 1e9) if top in alg_bytes else None,
+                        "hbm_peak_gbs": peaks["hbm_gbs"], "share_of_step": kernels[top]["ms_total"] / total_ms if total_ms else None}
+        step_flop = flop_per_coord(M, CFG["hidden_layers"], CFG["in_features"], CFG["out_features"]) * n
+
+    if rank == 0:
+        cpu = cpu_reference_run(256, 3, 1) if (world == 1 and not args.no_cpu_baseline) else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "config": {"workload": f"WIRE image fit {size}x{size} RGB ({n} coords/GPU full-batch fwd+bwd+Adam), "
+                                       f"wire_image_denoise.py defaults: hidden 300 -> M={M}, H=2, omega0=7, sigma0=6",
+                           "width": M, "hidden_layers": CFG["hidden_layers"], "coords_per_gpu": n,
+                           "parallelism": f"coord-sharded dp{world}" if world > 1 else "single GPU",
+                           "l2": "per-step activation traffic (>5 GB) far exceeds the 126 MB L2; no explicit flush"},
+                "algorithmic_tflops": step_flop / (ms_step * 1e-3) / 1e12 * 1.0,
+                "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels}
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["coords_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                                    "sample": cpu["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,15 @@ const char* wire_b200_last_error(void);
 int wire_b200_device_ok(void);
 int wire_b200_sm_count(void);
 
+/* ---- launch accounting / per-kernel device timing (bench.py) --------------------------- */
+/* Every kernel launch is counted per kind. With timing != 0 each launch is also bracketed by CUDA
+ * events recorded on the launching stream; wire_b200_prof_get() resolves them. */
+int wire_b200_prof_enable(int32_t timing);
+int wire_b200_prof_reset(void);
+int wire_b200_prof_kinds(void);
+const char* wire_b200_prof_name(int32_t kind);
+int wire_b200_prof_get(int32_t kind, uint64_t* launches, double* ms);
+
 /* ---- whole network ------------------------------------------------------------------- */
 
 /* Scratch needed for `n` coordinates. training != 0 keeps what backward needs. */

@@ -46,6 +46,11 @@ SIGNATURES = {
     "wire_b200_last_error": (c_char_p, []),
     "wire_b200_device_ok": (c_int32, []),
     "wire_b200_sm_count": (c_int32, []),
+    "wire_b200_prof_enable": (c_int32, [c_int32]),
+    "wire_b200_prof_reset": (c_int32, []),
+    "wire_b200_prof_kinds": (c_int32, []),
+    "wire_b200_prof_name": (c_char_p, [c_int32]),
+    "wire_b200_prof_get": (c_int32, [c_int32, POINTER(ctypes.c_uint64), POINTER(ctypes.c_double)]),
     "wire_net_workspace_bytes": (c_size_t, [POINTER(NetDesc), c_int64, c_int32]),
     "wire_net_workspace_init": (c_int32, [POINTER(NetDesc), c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "wire_net_forward": (c_int32, [POINTER(NetDesc), POINTER(NetParams), c_void_p, c_int64, c_void_p, c_void_p,

@@ -51,6 +51,49 @@ int require_device() {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// launch accounting: every kernel launch is counted; optionally bracketed by CUDA events recorded
+// on the launching stream (bench.py's per-kernel roofline numbers come from here).
+// ------------------------------------------------------------------------------------------
+enum ProfKind { K_FIRST_FWD = 0, K_PACK, K_ROWS_FWD, K_FINAL_FWD, K_TOP_BWD, K_WGRAD, K_ROWS_BWD, K_ROWS_FIRST_BWD,
+                K_FIRST_WGRAD, K_GRAD_COORDS, K_LAYER_MISC, K_ADAM, K_MSE, K_COUNT };
+const char* kProfNames[K_COUNT] = {"first_fwd", "pack_weights", "tc_rows_gabor_fwd", "final_fwd", "top_bwd", "tc_wgrad",
+                                   "tc_rows_dgrad_gabor_bwd", "tc_rows_dgrad_first_bwd", "first_wgrad", "grad_coords",
+                                   "layer_misc", "adam", "mse_grad"};
+struct ProfPending { int kind; cudaEvent_t e0, e1; };
+struct Prof {
+  int timing = 0;
+  unsigned long long launches[K_COUNT] = {};
+  double ms[K_COUNT] = {};
+  ProfPending pending[4096];
+  int n_pending = 0;
+} g_prof;
+struct ProfScope {
+  int kind; cudaStream_t st; cudaEvent_t e1 = nullptr; bool on = false;
+  ProfScope(int k, cudaStream_t s, int n_launches = 1) : kind(k), st(s) {
+    g_prof.launches[k] += n_launches;
+    if (g_prof.timing && g_prof.n_pending < 4096) {
+      cudaEvent_t e0;
+      if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+        cudaEventRecord(e0, st);
+        g_prof.pending[g_prof.n_pending] = {k, e0, e1};
+        on = true;
+      }
+    }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(e1, st); ++g_prof.n_pending; }
+  }
+};
+int rows_kind(int mode) {
+  switch (mode) {
+    case MODE_GABOR_FWD: case MODE_GABOR2D_FWD: return K_ROWS_FWD;
+    case MODE_GABOR_BWD: case MODE_GABOR2D_BWD: return K_ROWS_BWD;
+    case MODE_FIRST_BWD: case MODE_FIRST2D_BWD: return K_ROWS_FIRST_BWD;
+  }
+  return K_LAYER_MISC;
+}
+
 constexpr int64_t kInferChunk = 1 << 19;  // rows per pass when nothing has to be kept for backward
 constexpr int kRowsPerBlock = 64;
 
@@ -168,6 +211,7 @@ int launch_simt_rows(const SimtRowsParams& S, cudaStream_t st) {
 
 int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   if (J.e.n_rows <= 0) return 0;
+  ProfScope prof(rows_kind(J.mode), st);
   if (precision == WIRE_PRECISION_FP32) {
     SimtRowsParams S;
     memset(&S, 0, sizeof(S));
@@ -216,6 +260,7 @@ int run_pack(const float* W1, const float* W2, int M_out, int K_in, int mode, co
              int k_pad_total, float* B, int precision, cudaStream_t st) {
   const int total = blk.n_blocks * blk.nb * k_pad_total;
   const int grid = (total + 255) / 256;
+  ProfScope prof(K_PACK, st);
   pack_weights_kernel<<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B,
                                            precision == WIRE_PRECISION_TF32);
   CU_OK(cudaGetLastError());
@@ -227,6 +272,7 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
               float* gW1, float* gB1, float* gW2, float* gB2, int precision, cudaStream_t st) {
   if (n <= 0) return 0;
   const int n_g = g2 ? 2 : 1;
+  ProfScope prof(K_WGRAD, st, (precision == WIRE_PRECISION_FP32 && g2) ? 2 : 1);
   if (precision == WIRE_PRECISION_FP32) {
     const int x_cols = 2 * k_in + 1, g_cols = 2 * m_out;
     dim3 grid((x_cols + 63) / 64, (g_cols + 63) / 64, 1);
@@ -259,6 +305,7 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
   if (n <= 0) return 0;
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   const int round_y = d->precision == WIRE_PRECISION_TF32;
+  ProfScope prof(K_FIRST_FWD, st);
   if (d->precision == WIRE_PRECISION_TF32)
     first_fwd_kernel<true><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
                                                  d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, round_y, z_out, w_out,
@@ -277,6 +324,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   if (n <= 0) return 0;
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   const int round_g = (d->precision == WIRE_PRECISION_TF32) && z;
+  ProfScope prof(K_TOP_BWD, st);
   if (d->precision == WIRE_PRECISION_TF32)
     top_bwd_kernel<true><<<grid, 256, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, h, h_pitch, omega, scale, gz,
                                                gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
@@ -290,6 +338,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
 int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t n, int in_f, int M, float* gW, float* gb, cudaStream_t st) {
   if (n <= 0 || !gW) return 0;
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
+  ProfScope prof(K_FIRST_WGRAD, st);
   first_wgrad_kernel<<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
   CU_OK(cudaGetLastError());
   return 0;
@@ -353,6 +402,7 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
   if (!L.fuse_final) {
     const int64_t g64 = (n * 32 + 255) / 256;
     const int grid = int(g64 > 65535 * 16 ? 65535 * 16 : g64);
+    ProfScope prof(K_FINAL_FWD, st);
     final_fwd_kernel<<<grid, 256, 0, st>>>(y_prev, L.P, int(n), M, d->out_features, p->final_weight, p->final_bias, out);
     CU_OK(cudaGetLastError());
   }
@@ -370,6 +420,32 @@ int wire_b200_abi_version(void) { return WIRE_B200_ABI_VERSION; }
 const char* wire_b200_last_error(void) { return g_err; }
 int wire_b200_device_ok(void) { return require_device(); }
 int wire_b200_sm_count(void) { return device_info() ? 0 : g_sm_count; }
+
+int wire_b200_prof_enable(int32_t timing) { g_prof.timing = timing; return 0; }
+int wire_b200_prof_reset(void) {
+  for (int i = 0; i < g_prof.n_pending; ++i) { cudaEventDestroy(g_prof.pending[i].e0); cudaEventDestroy(g_prof.pending[i].e1); }
+  g_prof.n_pending = 0;
+  for (int k = 0; k < K_COUNT; ++k) { g_prof.launches[k] = 0; g_prof.ms[k] = 0.0; }
+  return 0;
+}
+int wire_b200_prof_kinds(void) { return K_COUNT; }
+const char* wire_b200_prof_name(int32_t kind) { return (kind >= 0 && kind < K_COUNT) ? kProfNames[kind] : ""; }
+/* Resolves pending events (synchronises on them) and returns launches + accumulated device ms of one kind. */
+int wire_b200_prof_get(int32_t kind, uint64_t* launches, double* ms) {
+  if (kind < 0 || kind >= K_COUNT) return fail("bad profile kind %d", kind);
+  for (int i = 0; i < g_prof.n_pending; ++i) {
+    float t = 0.f;
+    if (cudaEventSynchronize(g_prof.pending[i].e1) == cudaSuccess &&
+        cudaEventElapsedTime(&t, g_prof.pending[i].e0, g_prof.pending[i].e1) == cudaSuccess)
+      g_prof.ms[g_prof.pending[i].kind] += t;
+    cudaEventDestroy(g_prof.pending[i].e0);
+    cudaEventDestroy(g_prof.pending[i].e1);
+  }
+  g_prof.n_pending = 0;
+  if (launches) *launches = g_prof.launches[kind];
+  if (ms) *ms = g_prof.ms[kind];
+  return 0;
+}
 
 size_t wire_net_workspace_bytes(const wire_net_desc* d, int64_t n, int32_t training) {
   Layout L;
@@ -477,6 +553,7 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
   if (d->two_d) TRY(run_first_wgrad(at(workspace, L.off_gw0), L.PR, coords, n, in_f, M, g->layer[0].weight2, g->layer[0].bias2, st));
   if (grad_coords) {
     const int grid = int((n * 32 + 255) / 256);
+    ProfScope prof(K_GRAD_COORDS, st, d->two_d ? 2 : 1);
     grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gz0), L.PR, int(n), in_f, M, p->layer[0].weight, grad_coords, 0);
     if (d->two_d) grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gw0), L.PR, int(n), in_f, M, p->layer[0].weight2, grad_coords, 1);
     CU_OK(cudaGetLastError());
@@ -518,6 +595,7 @@ int copy2d(const float* src, int sp, float* dst, int dp, int64_t n, int cols, in
   if (n <= 0) return 0;
   int64_t total = n * cols;
   int grid = int((total + 255) / 256 > 1184 * 8 ? 1184 * 8 : (total + 255) / 256);
+  ProfScope prof(K_LAYER_MISC, st);
   copy2d_kernel<<<grid, 256, 0, st>>>(src, sp, dst, dp, n, cols, do_round);
   CU_OK(cudaGetLastError());
   return 0;
@@ -717,6 +795,7 @@ int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const double bc2 = 1.0 - pow(double(beta2), double(step));
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
+  ProfScope prof(K_ADAM, st);
   adam_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay, float(bc1),
                                     float(sqrt(bc2)), grad_scale);
   CU_OK(cudaGetLastError());
@@ -729,6 +808,7 @@ int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, fl
   if (!pred || !target || !grad_out) return fail("null argument");
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
+  ProfScope prof(K_MSE, st);
   mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss);
   CU_OK(cudaGetLastError());
   return 0;
