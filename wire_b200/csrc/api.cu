@@ -104,14 +104,15 @@ struct Blocking {
   int n_blocks, nb, nbh;
 };
 // out_cols = real output columns (2M). two_d_fwd: accumulator holds [z half | w half].
-bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b) {
+bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, int n_in = 0, int mode = MODE_PLAIN,
+                     bool fuse_final = false) {
   for (int nblk = 1; nblk <= 64; ++nblk) {
     int per = (out_cols + nblk - 1) / nblk;
     int nbh = (nblk == 1 && !two_d_fwd) ? round_up(per, 16) : round_up(per, 32);
     int nb = two_d_fwd ? 2 * nbh : nbh;
     if (nb > 512) continue;
     RowsParams tmp;
-    if (rows_configure(tmp, nb, nbh, store_mask) == 0) continue;
+    if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final) == 0) continue;
     b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
     return true;
   }
@@ -155,7 +156,8 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
   L.rows = training ? n : (n < kInferChunk ? n : kInferChunk);
   if (L.rows < 1) L.rows = 1;
   Blocking bf;
-  if (!choose_blocking(L.two_m, d->two_d != 0, d->two_d ? 7 : 3, bf)) return fail("no tile configuration for width %d", d->width);
+  if (!choose_blocking(L.two_m, d->two_d != 0, d->two_d ? 6 : 2, bf, 0, d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, true))
+    return fail("no tile configuration for width %d", d->width);
   L.fuse_final = bf.n_blocks == 1 && d->out_features <= kMaxOut;
   size_t off = 0;
   const size_t act = align_up(size_t(L.rows) * L.P * sizeof(float), 1024);
@@ -199,6 +201,10 @@ struct RowsJob {
   int store_mask;
   RowsEpi e;
 };
+int job_n_in(int mode) { return mode == MODE_GABOR_BWD ? 1 : (mode == MODE_GABOR2D_BWD ? 2 : 0); }
+bool job_blocking(int mode, int out_cols, int store_mask, bool fuse_final, Blocking& b) {
+  return choose_blocking(out_cols, mode == MODE_GABOR2D_FWD, store_mask, b, job_n_in(mode), mode, fuse_final);
+}
 
 template <int MODE>
 int launch_simt_rows(const SimtRowsParams& S, cudaStream_t st) {
@@ -212,6 +218,8 @@ int launch_simt_rows(const SimtRowsParams& S, cudaStream_t st) {
 int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   if (J.e.n_rows <= 0) return 0;
   ProfScope prof(rows_kind(J.mode), st);
+  // the tcgen05 first-layer epilogue keeps a {w0[0..2], b0} table: wider coordinates use the FP32 kernel
+  if ((J.mode == MODE_FIRST_BWD || J.mode == MODE_FIRST2D_BWD) && J.e.in_features > 3) precision = WIRE_PRECISION_FP32;
   if (precision == WIRE_PRECISION_FP32) {
     SimtRowsParams S;
     memset(&S, 0, sizeof(S));
@@ -236,7 +244,7 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.k_cols[0] = J.k_cols[0]; P.k_cols[1] = J.k_cols[1];
   P.n_blocks = J.blk.n_blocks;
   P.e = J.e;
-  const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask);
+  const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0);
   if (!smem) return fail("row-tile configuration does not fit shared memory (nb=%d)", J.blk.nb);
   bool ok = true;
   for (int i = 0; i < 2; ++i) {
@@ -251,6 +259,9 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
       ++nslot;
     }
   for (int s = nslot; s < 3; ++s) P.o_map[s] = P.a_map[0];
+  P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
+  if (P.n_in >= 1) ok &= sm100_host::make_tmap_2d(&P.z_map[0], J.e.z_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32);
+  if (P.n_in >= 2) ok &= sm100_host::make_tmap_2d(&P.z_map[1], J.e.w_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32);
   if (!ok) return fail("cuTensorMapEncodeTiled failed (pointer/pitch alignment?)");
   CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st));
   return 0;
@@ -376,7 +387,8 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     if (store_y) mask |= 1;
     if (training) { mask |= 2; if (d->two_d) mask |= 4; }
     Blocking blk;
-    if (!choose_blocking(L.two_m, d->two_d != 0, mask ? mask : 1, blk)) return fail("no tile configuration");
+    const int fmode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
+    if (!job_blocking(fmode, L.two_m, mask, fuse, blk)) return fail("no tile configuration");
     float* Bf = at(ws, L.off_bf[l]);
     TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st));
     RowsJob J;
@@ -522,7 +534,8 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
     const bool to_first = (l == 1);
     int mask = to_first ? 0 : (d->two_d ? 3 : 1);
     Blocking blk;
-    if (!choose_blocking(L.two_m, false, mask ? mask : 1, blk)) return fail("no tile configuration");
+    const int bmode = to_first ? (d->two_d ? MODE_FIRST2D_BWD : MODE_FIRST_BWD) : (d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD);
+    if (!job_blocking(bmode, L.two_m, mask, false, blk)) return fail("no tile configuration");
     float* Bd = at(workspace, L.off_bd[l]);
     const int kparts = d->two_d ? 2 : 1;
     TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st));
@@ -669,7 +682,7 @@ int wire_gabor_layer_forward(const wire_net_desc* d, int32_t is_first, int32_t i
   int mask = 1;
   if (training) { mask |= 2; if (d->two_d) mask |= 4; }
   Blocking blk;
-  if (!choose_blocking(2 * M, d->two_d != 0, mask, blk)) return fail("no tile configuration for width %d", M);
+  if (!job_blocking(d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, 2 * M, mask, false, blk)) return fail("no tile configuration for width %d", M);
   float* B = at(workspace, L.off_b);
   TRY(run_pack(p->weight, d->two_d ? p->weight2 : nullptr, M, in_features, 0, blk, L.k_pad_in, L.k_pad_in, B, d->precision, st));
   RowsJob J;
@@ -739,7 +752,7 @@ int wire_gabor_layer_backward(const wire_net_desc* d, int32_t is_first, int32_t 
   if (g->weight) TRY(run_wgrad(xp, L.P_in, K, g1, g2, g_pitch, M, n, g->weight, g->bias, g->weight2, g->bias2, d->precision, st));
   if (grad_x) {
     Blocking blk;
-    if (!choose_blocking(2 * K, false, 1, blk)) return fail("no tile configuration");
+    if (!job_blocking(MODE_PLAIN, 2 * K, 1, false, blk)) return fail("no tile configuration");
     float* B = at(workspace, L.off_b);
     const int k_pad_out = round_up(2 * M, 32);
     const int kparts = d->two_d ? 2 : 1;

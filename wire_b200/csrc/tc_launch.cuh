@@ -7,27 +7,41 @@
 
 namespace wire {
 
-constexpr size_t kMaxDynSmem = 232448 - 1024;  // 227 KB minus the (1 KB-rounded) static barriers/slots
-
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+constexpr size_t kMaxDynSmem = 232448 - 6144;  // 227 KB minus the static barriers / exchange buffers
 
 // Fill in nb-dependent fields and pick the deepest pipeline that fits. Returns dynamic smem bytes
 // (0 if the configuration does not fit).
-inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask) {
+// `n_in`   : TMA-prefetched epilogue inputs (z / w tiles of the backward modes)
+// `out_cols`: real output columns (2M) -> size of the shared-memory parameter tables
+// `mode`    : decides which tables exist (bias / fused-final weights / first-layer table)
+inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int n_in = 0, int out_cols = 0,
+                             int mode = MODE_PLAIN, bool fuse_final = false) {
   P.nb = nb;
   P.nbh = nbh;
   P.store_mask = store_mask;
+  P.n_in = n_in;
   if (nb <= 256) { P.b_box_rows = nb; P.b_boxes = 1; }
   else { P.b_box_rows = nb / 2; P.b_boxes = 2; }
   const int n_out = __builtin_popcount(store_mask);
   const size_t stage = size_t(kTileRows) * 128 + size_t(nb) * 128;
-  const size_t staging = size_t(4) * n_out * 2 * 4096;
+  const size_t staging = size_t(kEpiWarps) * (n_out + n_in) * 4096;
+  const int pcols = round_up(out_cols > 0 ? out_cols : 32, 32) + 32;  // +1 chunk: the tail chunk may over-read
+  const bool two_d = (mode == MODE_GABOR2D_FWD || mode == MODE_GABOR2D_BWD || mode == MODE_FIRST2D_BWD);
+  size_t pfloats = 0;
+  if (mode == MODE_GABOR_FWD || mode == MODE_GABOR2D_FWD) pfloats = size_t(two_d ? 2 : 1) * pcols + (fuse_final ? size_t(pcols / 2) * 8 : 0);
+  if (mode == MODE_FIRST_BWD || mode == MODE_FIRST2D_BWD) pfloats = size_t(two_d ? 2 : 1) * (pcols / 2) * 4;
+  const size_t pbytes = (pfloats * sizeof(float) + 127) / 128 * 128;
   const size_t budget = kMaxDynSmem - 1024;
-  if (staging + 2 * stage > budget) return 0;
-  int stages = int((budget - staging) / stage);
+  if (staging + pbytes + 2 * stage > budget) return 0;
+  int stages = int((budget - staging - pbytes) / stage);
   if (stages > 8) stages = 8;
   P.stages = stages;
-  return stages * stage + staging + 1024;
+  P.staging_off = uint32_t(stages * stage);
+  P.param_off = uint32_t(stages * stage + staging);
+  P.param_cols = pcols;
+  return stages * stage + staging + pbytes + 1024;
 }
 
 template <int MODE>

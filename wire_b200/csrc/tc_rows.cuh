@@ -2,22 +2,32 @@
 //
 //   ACC[128 coords, nb cols] = A[128 coords, K] (K-major, TMA) x Bpacked[nb cols, K] (K-major, TMA)
 //
-// with TF32 inputs, FP32 accumulation in TMEM, and the layer's point-wise work (rows_epilogue.cuh)
-// fused in the epilogue straight out of TMEM; results leave through swizzled staging + TMA stores.
+// with TF32 inputs, FP32 accumulation in TMEM, and the layer's point-wise work fused in the
+// epilogue straight out of TMEM; results leave through swizzled staging + TMA stores.
+//
+//   MODE_PLAIN        out0 = ACC                                         (probe / per-layer dgrad)
+//   MODE_GABOR_FWD    z = ACC + b ; y = gabor(z)          -> y, z        modules/wire.py:88-93
+//   MODE_GABOR2D_FWD  z,w = ACC halves + b1,b2 ; y = gabor2d(z,w) -> y,z,w   modules/wire2d.py:56-67
+//   MODE_GABOR_BWD    g_y = ACC ; g_z = gabor'(z_saved, g_y)  -> g_z     (autograd of wire.py:88-93)
+//   MODE_GABOR2D_BWD  same + g_w                               -> g_z, g_w
+//   MODE_FIRST_BWD / MODE_FIRST2D_BWD   g_y0 = ACC ; z0 recomputed from coords -> real g_z0 (g_w0)
 //
 // A is the complex activation tensor seen as real [N, 2M] (interleaved re,im = torch complex64),
 // Bpacked is the real 2x2-block expansion of the complex weight (pack_weights_kernel), so one real
 // GEMM of width 2M x 2M *is* the complex GEMM (8*M^2 flop/coord, no de-interleave anywhere).
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (TMEM sub-partition = warp_idx & 3).
+// Warp roles (320 threads): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+// warps 2..9 = epilogue: TMEM sub-partition = warp & 3, the two warps of a sub-partition take the
+// even / odd 32-column chunks.  Layer constants (bias, final-Linear weights, first-layer weights)
+// live in shared memory; the saved pre-activations of the backward modes are TMA-prefetched.
 #pragma once
 #include "rows_epilogue.cuh"
 #include "sm100.cuh"
 
 namespace wire {
 
-constexpr int kRowsThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kRowsThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileRows = 128;
 constexpr int kChunk = 32;  // fp32 columns per 128-byte swizzle row
 
@@ -25,16 +35,51 @@ struct RowsParams {
   CUtensorMap a_map[2];  // A parts, box {32 cols, 128 rows}
   CUtensorMap b_map;     // packed B [n_blocks*nb, Kpad], box {32 cols, b_box_rows}
   CUtensorMap o_map[3];  // outputs, box {32 cols, 32 rows}
+  CUtensorMap z_map[2];  // saved z (and w) for the backward epilogues, box {32 cols, 32 rows}
   int k_cols[2];         // valid K columns in each A part (part 1 may be 0)
   int n_blocks;          // column blocks (work item = row tile x block)
   int nb;                // accumulator columns per block (multiple of 16, <= 512)
   int nbh;               // 2D fwd: columns of the z half (w half follows); otherwise == nb
   int b_box_rows, b_boxes;
   int stages;
-  int store_mask;  // which epilogue results are TMA-stored: bit0 = o0, bit1 = o1, bit2 = o2;
-                   // o_map[] slots are consumed in bit order
+  int store_mask;  // which epilogue results are TMA-stored: bit0 = o0, bit1 = o1, bit2 = o2
+  int n_in;        // TMA-prefetched epilogue inputs (0, 1 = z, 2 = z and w)
+  uint32_t staging_off;  // byte offsets inside dynamic smem (from the 1 KB aligned base)
+  uint32_t param_off;
+  int param_cols;        // padded column count of the bias tables (multiple of 32)
   RowsEpi e;
 };
+
+// ---- branch-free FTZ fast math for the epilogue ------------------------------------------------
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct GaborConst {
+  float omega, s2;
+  float c_t;     // -s2 * log2(e)
+  float c_zi;    // -omega * log2(e)
+  float c_turn;  // omega / (2 pi)
+};
+__device__ __forceinline__ GaborConst make_gabor_const(float omega, float scale) {
+  GaborConst g;
+  g.omega = omega;
+  g.s2 = scale * scale;
+  g.c_t = -g.s2 * 1.4426950408889634f;
+  g.c_zi = -omega * 1.4426950408889634f;
+  g.c_turn = omega * 0.15915494309189535f;
+  return g;
+}
+// y = exp(j w z - s2 (|z|^2 + wnorm));  phase reduced in turns (exact), magnitude through ex2
+__device__ __forceinline__ void gabor_fast(const GaborConst& g, float zr, float zi, float wnorm, float& yr, float& yi) {
+  const float t = fmaf(zi, zi, fmaf(zr, zr, wnorm));
+  const float m = ex2_ftz(fmaf(g.c_t, t, g.c_zi * zi));
+  float u = zr * g.c_turn;
+  u -= rintf(u);
+  const float r = u * 6.283185307179586f;
+  yr = m * cos_ftz(r);
+  yi = m * sin_ftz(r);
+}
 
 __device__ __forceinline__ void stage_row(uint32_t buf, int lane, const float (&v)[32]) {
   const uint32_t row = buf + lane * 128;
@@ -47,6 +92,30 @@ __device__ __forceinline__ void stage_row(uint32_t buf, int lane, const float (&
                  : "memory");
   }
 }
+__device__ __forceinline__ void unstage_row(uint32_t buf, int lane, float (&v)[32]) {
+  const uint32_t row = buf + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t addr = row + ((j ^ sw) << 4);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
+                 : "r"(addr)
+                 : "memory");
+  }
+}
+
+// waits with back-off for the single-thread producer / MMA roles (they share schedulers with epilogue warps)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  using namespace sm100;
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if ((++spins & 0xff) == 0 && (clock64() - t0) > 4000000000LL) __trap();
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_constant__ RowsParams P) {
@@ -56,21 +125,64 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   __shared__ __align__(8) uint64_t bar_empty[8];
   __shared__ __align__(8) uint64_t bar_tmem_full;
   __shared__ __align__(8) uint64_t bar_tmem_empty;
+  __shared__ __align__(8) uint64_t bar_in[kEpiWarps][2];
+  __shared__ __align__(16) float fin_xchg[2][kTileRows][kMaxOut];
   __shared__ uint32_t tmem_slot;
+
+  constexpr bool kFwd = (MODE == MODE_GABOR_FWD || MODE == MODE_GABOR2D_FWD);
+  constexpr bool kBwd = (MODE == MODE_GABOR_BWD || MODE == MODE_GABOR2D_BWD);
+  constexpr bool kFirst = (MODE == MODE_FIRST_BWD || MODE == MODE_FIRST2D_BWD);
+  constexpr bool k2D = (MODE == MODE_GABOR2D_FWD || MODE == MODE_GABOR2D_BWD || MODE == MODE_FIRST2D_BWD);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_bytes = kTileRows * 128;
   const uint32_t b_bytes = uint32_t(P.nb) * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t staging_base = smem_base + P.stages * stage_bytes;
+  const uint32_t staging_base = smem_base + P.staging_off;
+  float* params = reinterpret_cast<float*>(smem_gen + P.param_off);
+  const RowsEpi& E = P.e;
 
   const int kc0 = (P.k_cols[0] + kChunk - 1) / kChunk;
   const int kc1 = (P.k_cols[1] + kChunk - 1) / kChunk;
   const int kc_total = kc0 + kc1;
-  const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
+  const int row_tiles = (E.n_rows + kTileRows - 1) / kTileRows;
   const int n_items = row_tiles * P.n_blocks;
+  const int n_feat = E.n_cols >> 1;  // complex features M
+
+  // ---- shared parameter tables (zero padded so the epilogue needs no column checks) ----
+  //  fwd : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8]  (wr[4], wi[4]) if fused
+  //  first: tab[(param_cols/2)][4] = {w0[0..2], b0}  | tab2 (2D)              (in_features <= 3)
+  if constexpr (kFwd) {
+    for (int i = threadIdx.x; i < P.param_cols; i += blockDim.x) {
+      params[i] = i < E.n_cols ? E.bias[i] : 0.f;
+      if constexpr (k2D) params[P.param_cols + i] = i < E.n_cols ? E.bias2[i] : 0.f;
+    }
+    if (E.fuse_final) {
+      float* wf = params + (k2D ? 2 : 1) * P.param_cols;
+      for (int i = threadIdx.x; i < (P.param_cols >> 1) * 8; i += blockDim.x) {
+        const int k = i >> 3, j = i & 7, o = j & 3;
+        float v = 0.f;
+        if (k < n_feat && o < E.out_features) v = E.wf[(size_t(o) * n_feat + k) * 2 + (j >> 2)];
+        wf[i] = v;
+      }
+    }
+  }
+  if constexpr (kFirst) {
+    for (int i = threadIdx.x; i < (P.param_cols >> 1) * 4; i += blockDim.x) {
+      const int k = i >> 2, j = i & 3;
+      float v = 0.f, v2 = 0.f;
+      if (k < n_feat) {
+        if (j < 3) {
+          if (j < E.in_features) { v = E.w0[size_t(k) * E.in_features + j]; if constexpr (k2D) v2 = E.w0b[size_t(k) * E.in_features + j]; }
+        } else { v = E.b0[k]; if constexpr (k2D) v2 = E.b0b[k]; }
+      }
+      params[i] = v;
+      if constexpr (k2D) params[(P.param_cols >> 1) * 4 + i] = v2;
+    }
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -78,7 +190,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
-    mbar_init(smem_u32(&bar_tmem_empty), 4);
+    mbar_init(smem_u32(&bar_tmem_empty), kEpiWarps);
+    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&bar_in[w][0]), 1); mbar_init(smem_u32(&bar_in[w][1]), 1); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -103,7 +216,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
         const int row0 = (item / P.n_blocks) * kTileRows;
         const int n0 = (item % P.n_blocks) * P.nb;
         for (int kc = 0; kc < kc_total; ++kc) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, stage_bytes);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
@@ -130,12 +243,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         if (it > 0) {
-          mbar_wait(smem_u32(&bar_tmem_empty), tphase);
+          mbar_wait_backoff(smem_u32(&bar_tmem_empty), tphase);
           tphase ^= 1;
         }
         tc_fence_after();
         for (int kc = 0; kc < kc_total; ++kc) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
           const uint32_t a_base = smem_base + stage * stage_bytes;
           const uint32_t b_base = a_base + a_bytes;
@@ -161,17 +274,24 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue warps =====================
-    const RowsEpi& E = P.e;
-    const int q = warp & 3;
-    const int ew = warp - 2;
+    const int ew = warp - 2;       // 0..7
+    const int q = warp & 3;        // TMEM sub-partition (lanes 32q..32q+31)
+    const int half = ew >> 2;      // takes chunks ch = half, half+2, ...
     const int n_out = __popc(P.store_mask);
-    const uint32_t wbuf = staging_base + ew * (n_out * 2 * 4096);
-    const float omega = (MODE != MODE_PLAIN) ? __ldg(E.omega) : 0.f;
-    const float sc = (MODE != MODE_PLAIN) ? __ldg(E.scale) : 0.f;
-    const float s2 = sc * sc;
+    const int slots = n_out + P.n_in;
+    const uint32_t wbuf = staging_base + ew * (slots * 4096);
+    const uint32_t inbuf = wbuf + n_out * 4096;  // n_in x 4 KB (a tile is copied to registers at once, so one buffer
+                                                  // is enough to keep the next chunk's TMA load in flight)
+    const GaborConst G = (MODE != MODE_PLAIN) ? make_gabor_const(__ldg(E.omega), __ldg(E.scale)) : make_gabor_const(0.f, 0.f);
+    const float* s_bias = params;
+    const float* s_bias2 = params + P.param_cols;
+    const float4* s_wf = reinterpret_cast<const float4*>(params + (k2D ? 2 : 1) * P.param_cols);
+    const float4* s_tab = reinterpret_cast<const float4*>(params);
+    const float4* s_tab2 = reinterpret_cast<const float4*>(params + (P.param_cols >> 1) * 4);
     uint32_t tphase = 0;
-    uint32_t bufsel = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    uint32_t in_phase = 0;
+    int tile_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_it) {
       const int row0 = (item / P.n_blocks) * kTileRows;
       const int blk = item % P.n_blocks;
       const int row = row0 + q * 32 + lane;
@@ -181,21 +301,43 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       int valid = E.n_cols - col0;
       valid = valid > ncol_blk ? ncol_blk : valid;
       const int nchunks = (valid + kChunk - 1) / kChunk;
+      // chunks of this warp: half, half+2, ... ; last one it owns:
+      int my_last = -1;
+      if (nchunks > half) my_last = half + 2 * ((nchunks - 1 - half) >> 1);
 
-      float cin[kMaxIn];
-      rows_load_coords<MODE>(E, row, row_ok, cin);
-      float facc[kMaxOut];
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) facc[o] = 0.f;
+      float cin[3] = {0.f, 0.f, 0.f};
+      if constexpr (kFirst) {
+        if (row_ok) {
+          cin[0] = __ldg(E.coords + size_t(row) * E.in_features);
+          if (E.in_features > 1) cin[1] = __ldg(E.coords + size_t(row) * E.in_features + 1);
+          if (E.in_features > 2) cin[2] = __ldg(E.coords + size_t(row) * E.in_features + 2);
+        }
+      }
+      float facc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+
+      // prefetch the first saved-activation chunk of this tile while the MMAs are still running
+      if constexpr (kBwd) {
+        if (half < nchunks && lane == 0) {
+          const uint32_t bar = smem_u32(&bar_in[ew][0]);
+          mbar_expect_tx(bar, P.n_in * 4096);
+          for (int s = 0; s < P.n_in; ++s)
+            tma_load_2d(inbuf + s * 4096, &P.z_map[s], bar, col0 + half * kChunk, row0 + q * 32);
+        }
+      }
 
       mbar_wait(smem_u32(&bar_tmem_full), tphase);
       tphase ^= 1;
       tc_fence_after();
+      if (my_last < 0) {  // nothing to do in this tile (single-chunk block): just release TMEM
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
+      }
 
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = half; ch < nchunks; ch += 2) {
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + ch * kChunk;
         uint32_t raw[32];
-        float v[32], v2[32];
+        float v2[32];
         tmem_ld32(taddr, raw);
         if constexpr (MODE == MODE_GABOR2D_FWD) {
           uint32_t raw2[32];
@@ -205,45 +347,163 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           for (int i = 0; i < 32; ++i) v2[i] = __uint_as_float(raw2[i]);
         } else {
           tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v2[i] = 0.f;
         }
-        if (ch == nchunks - 1) {
-          // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+        if (ch == my_last) {
+          // all TMEM reads of this warp for this tile are done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
         }
+        float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         const int c = col0 + ch * kChunk;  // first real output column of this chunk
+        const int cl = c;                  // index into the smem tables
 
         float o0[32], o1[32], o2[32];
-        rows_epilogue_chunk<MODE, true>(E, row, row_ok, c, omega, s2, v, v2, cin, facc, o0, o1, o2);
+        if constexpr (MODE == MODE_PLAIN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o0[i] = v[i];
+        } else if constexpr (kFwd) {
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + cl);
+          const float4* b24 = reinterpret_cast<const float4*>(s_bias2 + cl);
+#pragma unroll
+          for (int i2 = 0; i2 < 8; ++i2) {
+            const float4 bb = b4[i2];
+            float4 bb2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (k2D) bb2 = b24[i2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 2 * i2 + h;
+              const float zr = v[2 * i] + (h ? bb.z : bb.x);
+              const float zi = v[2 * i + 1] + (h ? bb.w : bb.y);
+              float wn = 0.f;
+              if constexpr (k2D) {
+                const float wr = v2[2 * i] + (h ? bb2.z : bb2.x);
+                const float wi = v2[2 * i + 1] + (h ? bb2.w : bb2.y);
+                wn = fmaf(wr, wr, wi * wi);
+                o2[2 * i] = wr;
+                o2[2 * i + 1] = wi;
+              }
+              float yr, yi;
+              gabor_fast(G, zr, zi, wn, yr, yi);
+              if (E.fuse_final) {
+                const float4 wr4 = s_wf[((cl >> 1) + i) * 2];
+                const float4 wi4 = s_wf[((cl >> 1) + i) * 2 + 1];
+                facc[0] = fmaf(yr, wr4.x, fmaf(-yi, wi4.x, facc[0]));
+                facc[1] = fmaf(yr, wr4.y, fmaf(-yi, wi4.y, facc[1]));
+                facc[2] = fmaf(yr, wr4.z, fmaf(-yi, wi4.z, facc[2]));
+                facc[3] = fmaf(yr, wr4.w, fmaf(-yi, wi4.w, facc[3]));
+              }
+              if (E.round_out0) { yr = round_tf32(yr); yi = round_tf32(yi); }
+              o0[2 * i] = yr;
+              o0[2 * i + 1] = yi;
+              o1[2 * i] = zr;
+              o1[2 * i + 1] = zi;
+            }
+          }
+        } else if constexpr (kBwd) {
+          // wait for this chunk's z (w) tile, then immediately prefetch the next one into the other buffer
+          float z[32], w[32];
+          mbar_wait(smem_u32(&bar_in[ew][0]), in_phase);
+          in_phase ^= 1;
+          unstage_row(inbuf, lane, z);
+          if constexpr (k2D) unstage_row(inbuf + 4096, lane, w);
+          __syncwarp();
+          if (ch + 2 < nchunks && lane == 0) {
+            const uint32_t bar = smem_u32(&bar_in[ew][0]);
+            mbar_expect_tx(bar, P.n_in * 4096);
+            for (int s = 0; s < P.n_in; ++s)
+              tma_load_2d(inbuf + s * 4096, &P.z_map[s], bar, c + 2 * kChunk, row0 + q * 32);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float zr = z[2 * i], zi = z[2 * i + 1];
+            float wn = 0.f;
+            if constexpr (k2D) wn = fmaf(w[2 * i], w[2 * i], w[2 * i + 1] * w[2 * i + 1]);
+            float yr, yi, gzr, gzi;
+            gabor_fast(G, zr, zi, wn, yr, yi);
+            const float pr = gabor_bwd(yr, yi, zr, zi, v[2 * i], v[2 * i + 1], G.omega, G.s2, gzr, gzi);
+            if (E.round_out0) { gzr = round_tf32(gzr); gzi = round_tf32(gzi); }
+            o0[2 * i] = gzr;
+            o0[2 * i + 1] = gzi;
+            if constexpr (k2D) {
+              const float t = -2.0f * G.s2 * pr;
+              float gwr = t * w[2 * i], gwi = t * w[2 * i + 1];
+              if (E.round_out0) { gwr = round_tf32(gwr); gwi = round_tf32(gwi); }
+              o1[2 * i] = gwr;
+              o1[2 * i + 1] = gwi;
+            }
+          }
+        } else {  // kFirst: real z0 recomputed from the coordinates and the smem weight table
+          float gz[16], gw[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 t = s_tab[(cl >> 1) + i];
+            const float z0 = fmaf(cin[0], t.x, fmaf(cin[1], t.y, fmaf(cin[2], t.z, t.w)));
+            float w0v = 0.f;
+            if constexpr (k2D) {
+              const float4 t2 = s_tab2[(cl >> 1) + i];
+              w0v = fmaf(cin[0], t2.x, fmaf(cin[1], t2.y, fmaf(cin[2], t2.z, t2.w)));
+            }
+            float yr, yi;
+            gabor_fast(G, z0, 0.f, w0v * w0v, yr, yi);
+            const float pr = gabor_first_bwd(yr, yi, z0, v[2 * i], v[2 * i + 1], G.omega, G.s2, gz[i]);
+            gw[i] = -2.0f * G.s2 * pr * w0v;
+          }
+          if (row_ok) {
+            // 16 real outputs per thread = 64 contiguous bytes (two full sectors): direct stores
+            float4* dst = reinterpret_cast<float4*>(E.gz0 + size_t(row) * E.gz0_pitch + (c >> 1));
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              if ((c >> 1) + 4 * j4 < E.gz0_pitch) dst[j4] = make_float4(gz[4 * j4], gz[4 * j4 + 1], gz[4 * j4 + 2], gz[4 * j4 + 3]);
+            if constexpr (k2D) {
+              float4* dw = reinterpret_cast<float4*>(E.gw0 + size_t(row) * E.gz0_pitch + (c >> 1));
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                if ((c >> 1) + 4 * j4 < E.gz0_pitch) dw[j4] = make_float4(gw[4 * j4], gw[4 * j4 + 1], gw[4 * j4 + 2], gw[4 * j4 + 3]);
+            }
+          }
+        }
 
         if (n_out > 0) {
-          // staging (double-buffered per warp) -> TMA store; OOB rows/cols are clipped by TMA
-          if (lane == 0) tma_store_wait_read<1>();
+          // staging -> TMA store; the previous store of this warp must have finished READING smem
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
-          const uint32_t sb = wbuf + bufsel * (n_out * 4096);
           int slot = 0;
-          if (P.store_mask & 1) { stage_row(sb, lane, o0); ++slot; }
-          if constexpr (MODE == MODE_GABOR_FWD || MODE == MODE_GABOR2D_FWD || MODE == MODE_GABOR2D_BWD) {
-            if (P.store_mask & 2) { stage_row(sb + slot * 4096, lane, o1); ++slot; }
+          if (P.store_mask & 1) { stage_row(wbuf, lane, o0); ++slot; }
+          if constexpr (kFwd || MODE == MODE_GABOR2D_BWD) {
+            if (P.store_mask & 2) { stage_row(wbuf + slot * 4096, lane, o1); ++slot; }
           }
           if constexpr (MODE == MODE_GABOR2D_FWD) {
-            if (P.store_mask & 4) { stage_row(sb + slot * 4096, lane, o2); ++slot; }
+            if (P.store_mask & 4) { stage_row(wbuf + slot * 4096, lane, o2); ++slot; }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            for (int s = 0; s < n_out; ++s) tma_store_2d(&P.o_map[s], sb + s * 4096, c, row0 + q * 32);
+            for (int s = 0; s < n_out; ++s) tma_store_2d(&P.o_map[s], wbuf + s * 4096, c, row0 + q * 32);
             tma_store_commit();
           }
-          bufsel ^= 1;
         }
       }
-      rows_store_final<MODE>(E, row, row_ok, facc);
+
+      if constexpr (kFwd) {
+        if (E.fuse_final) {
+          // the two warps of a sub-partition hold partial sums over even / odd chunks
+          const int slot = tile_it & 1;
+          if (half == 1) {
+            *reinterpret_cast<float4*>(&fin_xchg[slot][q * 32 + lane][0]) = make_float4(facc[0], facc[1], facc[2], facc[3]);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          if (half == 0 && row_ok) {
+            const float4 o = *reinterpret_cast<const float4*>(&fin_xchg[slot][q * 32 + lane][0]);
+            const float r[4] = {facc[0] + o.x, facc[1] + o.y, facc[2] + o.z, facc[3] + o.w};
+#pragma unroll
+            for (int oo = 0; oo < kMaxOut; ++oo)
+              if (oo < E.out_features) E.out[size_t(row) * E.out_features + oo] = r[oo] + __ldg(E.bf + 2 * oo);
+          }
+        }
+      }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
