@@ -69,10 +69,11 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, int n_cols)
 }
 
 static int g_sms = 148;
+static int g_cluster = 1;
 
 static bool test_rows(int n_rows, int two_m, bool time_it) {
   const int K = two_m, pitch = wire::round_up(two_m + 1, 32);
-  const int nb = wire::round_up(two_m, 16);
+  const int nb = wire::round_up(two_m, (g_cluster == 2 && two_m > 256) ? 32 : 16);
   std::vector<float> A(size_t(n_rows) * pitch, 0.f), B(size_t(nb) * pitch, 0.f), C(size_t(n_rows) * pitch, -7.f);
   for (int r = 0; r < n_rows; ++r) {
     for (int c = 0; c < K; ++c) A[size_t(r) * pitch + c] = tf32_round_host(frand());
@@ -89,7 +90,7 @@ static bool test_rows(int n_rows, int two_m, bool time_it) {
   wire::RowsParams P;
   memset(&P, 0, sizeof(P));
   P.e.n_rows = n_rows; P.k_cols[0] = K; P.k_cols[1] = 0; P.n_blocks = 1; P.e.n_cols = two_m;
-  size_t smem = wire::rows_configure(P, nb, nb, 1);
+  size_t smem = wire::rows_configure(P, nb, nb, 1, 0, two_m, wire::MODE_PLAIN, false, g_cluster);
   if (!smem) { printf("rows_configure failed\n"); return false; }
   bool ok = sm100_host::make_tmap_2d(&P.a_map[0], dA, n_rows, K, pitch, 128, 32);
   ok &= sm100_host::make_tmap_2d(&P.a_map[1], dA, n_rows, K, pitch, 128, 32);
@@ -97,7 +98,7 @@ static bool test_rows(int n_rows, int two_m, bool time_it) {
   ok &= sm100_host::make_tmap_2d(&P.o_map[0], dC, n_rows, two_m, pitch, 32, 32);
   P.o_map[1] = P.o_map[0]; P.o_map[2] = P.o_map[0];
   if (!ok) { printf("tensor map creation failed\n"); return false; }
-  printf("[rows] n_rows=%d 2M=%d nb=%d stages=%d smem=%zu\n", n_rows, two_m, nb, P.stages, smem);
+  printf("[rows] cluster=%d n_rows=%d 2M=%d nb=%d stages=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.stages, smem);
   CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
@@ -235,6 +236,12 @@ int main(int argc, char** argv) {
     test_rows(262144, 424, true);
     test_wgrad(262144, 212, 212, true);
     test_rows(262144, 256, true);
+    g_cluster = 2;
+    ok &= test_rows(300, 424, false);
+    ok &= test_rows(1000, 180, false);
+    test_rows(262144, 424, true);
+    test_rows(262144, 256, true);
+
   }
   printf("PROBE %s\n", ok ? "PASS" : "FAIL");
   return ok ? 0 : 1;

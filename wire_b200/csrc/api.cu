@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/wire_b200.h"
@@ -94,6 +95,17 @@ int rows_kind(int mode) {
   return K_LAYER_MISC;
 }
 
+// CTAs per cluster sharing weight tiles through TMA multicast (WIRE_B200_CLUSTER=1|2|4 overrides)
+int cluster_size() {
+  static int c = 0;
+  if (c == 0) {
+    const char* e = getenv("WIRE_B200_CLUSTER");
+    c = e ? atoi(e) : 2;
+    if (c != 1 && c != 2) c = 2;
+  }
+  return c;
+}
+
 constexpr int64_t kInferChunk = 1 << 19;  // rows per pass when nothing has to be kept for backward
 constexpr int kRowsPerBlock = 64;
 
@@ -108,11 +120,12 @@ bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, 
                      bool fuse_final = false) {
   for (int nblk = 1; nblk <= 64; ++nblk) {
     int per = (out_cols + nblk - 1) / nblk;
-    int nbh = (nblk == 1 && !two_d_fwd) ? round_up(per, 16) : round_up(per, 32);
+    const int C = cluster_size();
+    int nbh = (nblk == 1 && !two_d_fwd && (C == 1 || per <= 256)) ? round_up(per, 16) : round_up(per, 32);
     int nb = two_d_fwd ? 2 * nbh : nbh;
     if (nb > 512) continue;
     RowsParams tmp;
-    if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final) == 0) continue;
+    if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C) == 0) continue;
     b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
     return true;
   }
@@ -244,7 +257,8 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.k_cols[0] = J.k_cols[0]; P.k_cols[1] = J.k_cols[1];
   P.n_blocks = J.blk.n_blocks;
   P.e = J.e;
-  const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0);
+  const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
+                                     cluster_size());
   if (!smem) return fail("row-tile configuration does not fit shared memory (nb=%d)", J.blk.nb);
   bool ok = true;
   for (int i = 0; i < 2; ++i) {
@@ -317,14 +331,22 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   const int round_y = d->precision == WIRE_PRECISION_TF32;
   ProfScope prof(K_FIRST_FWD, st);
-  if (d->precision == WIRE_PRECISION_TF32)
-    first_fwd_kernel<true><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
-                                                 d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, round_y, z_out, w_out,
-                                                 zr_pitch, kRowsPerBlock);
-  else
-    first_fwd_kernel<false><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
-                                                  d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, round_y, z_out, w_out,
-                                                  zr_pitch, kRowsPerBlock);
+  const float* w2 = d->two_d ? p.weight2 : nullptr;
+  const float* b2 = d->two_d ? p.bias2 : nullptr;
+  if (!z_out && !w_out && (y_pitch % 4) == 0) {  // whole-network path: streaming kernel, 16-byte stores
+    if (d->precision == WIRE_PRECISION_TF32)
+      first_fwd2_kernel<true><<<grid, 128, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, w2, b2, p.omega0, p.scale0, y, y_pitch,
+                                                    round_y, kRowsPerBlock);
+    else
+      first_fwd2_kernel<false><<<grid, 128, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, w2, b2, p.omega0, p.scale0, y, y_pitch,
+                                                     round_y, kRowsPerBlock);
+  } else if (d->precision == WIRE_PRECISION_TF32) {
+    first_fwd_kernel<true><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, w2, b2, p.omega0, p.scale0, y, y_pitch,
+                                                 round_y, z_out, w_out, zr_pitch, kRowsPerBlock);
+  } else {
+    first_fwd_kernel<false><<<grid, 256, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, w2, b2, p.omega0, p.scale0, y, y_pitch,
+                                                  round_y, z_out, w_out, zr_pitch, kRowsPerBlock);
+  }
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -336,12 +358,20 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   const int round_g = (d->precision == WIRE_PRECISION_TF32) && z;
   ProfScope prof(K_TOP_BWD, st);
-  if (d->precision == WIRE_PRECISION_TF32)
+  const bool tf = d->precision == WIRE_PRECISION_TF32;
+  if (z && d->out_features <= 4 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
+    const int M = d->width, of = d->out_features;
+    if (tf && w) top_bwd2_kernel<true, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else if (tf) top_bwd2_kernel<true, false><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else if (w) top_bwd2_kernel<false, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else top_bwd2_kernel<false, false><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+  } else if (tf) {
     top_bwd_kernel<true><<<grid, 256, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, h, h_pitch, omega, scale, gz,
                                                gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
-  else
+  } else {
     top_bwd_kernel<false><<<grid, 256, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, h, h_pitch, omega, scale, gz,
                                                 gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+  }
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -350,7 +380,12 @@ int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t 
   if (n <= 0 || !gW) return 0;
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   ProfScope prof(K_FIRST_WGRAD, st);
-  first_wgrad_kernel<<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
+  if (in_f <= 4 && (g_pitch % 4) == 0) {
+    const int rpb = 128;
+    first_wgrad2_kernel<<<int((n + rpb - 1) / rpb), 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, rpb);
+  } else {
+    first_wgrad_kernel<<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
+  }
   CU_OK(cudaGetLastError());
   return 0;
 }

@@ -326,3 +326,224 @@ __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __r
 }
 
 }  // namespace wire
+
+// =============================================================================================
+// v2 streaming kernels: same math as above, restructured for memory-level parallelism
+// (16-byte accesses, 4 rows in flight per thread) — these are the ones the whole-network path uses.
+// =============================================================================================
+namespace wire {
+
+// first layer forward, 2 complex features (one float4) per thread, rows_per_block rows per block
+template <bool FAST>
+__global__ void __launch_bounds__(128) first_fwd2_kernel(const float* __restrict__ coords, int n, int in_f, int M,
+                                                          const float* __restrict__ W0, const float* __restrict__ b0,
+                                                          const float* __restrict__ W0b, const float* __restrict__ b0b,
+                                                          const float* __restrict__ omega_p, const float* __restrict__ scale_p,
+                                                          float* __restrict__ y, int y_pitch, int round_y, int rows_per_block) {
+  __shared__ float sc[64 * kSimtMaxIn];
+  const int row0 = blockIdx.x * rows_per_block;
+  int rows = n - row0;
+  rows = rows > rows_per_block ? rows_per_block : rows;
+  for (int i = threadIdx.x; i < rows * in_f; i += blockDim.x) sc[i] = coords[size_t(row0) * in_f + i];
+  __syncthreads();
+  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  for (int jp = threadIdx.x; 2 * jp < M; jp += blockDim.x) {
+    const int j0 = 2 * jp, j1 = (2 * jp + 1 < M) ? 2 * jp + 1 : j0;
+    float w0[kSimtMaxIn], w1[kSimtMaxIn], v0[kSimtMaxIn], v1[kSimtMaxIn];
+#pragma unroll
+    for (int d = 0; d < kSimtMaxIn; ++d) {
+      w0[d] = d < in_f ? W0[size_t(j0) * in_f + d] : 0.f;
+      w1[d] = d < in_f ? W0[size_t(j1) * in_f + d] : 0.f;
+      v0[d] = (W0b && d < in_f) ? W0b[size_t(j0) * in_f + d] : 0.f;
+      v1[d] = (W0b && d < in_f) ? W0b[size_t(j1) * in_f + d] : 0.f;
+    }
+    const float bj0 = b0[j0], bj1 = b0[j1];
+    const float bb0 = W0b ? b0b[j0] : 0.f, bb1 = W0b ? b0b[j1] : 0.f;
+    for (int r = 0; r < rows; ++r) {
+      float z0 = bj0, z1 = bj1, u0 = bb0, u1 = bb1;
+#pragma unroll
+      for (int d = 0; d < kSimtMaxIn; ++d)
+        if (d < in_f) {
+          const float c = sc[r * in_f + d];
+          z0 = fmaf(c, w0[d], z0); z1 = fmaf(c, w1[d], z1);
+          u0 = fmaf(c, v0[d], u0); u1 = fmaf(c, v1[d], u1);
+        }
+      float4 o;
+      gabor_fwd<FAST>(z0, 0.f, omega, s2, W0b ? s2 * u0 * u0 : 0.f, o.x, o.y);
+      gabor_fwd<FAST>(z1, 0.f, omega, s2, W0b ? s2 * u1 * u1 : 0.f, o.z, o.w);
+      if (round_y) { o.x = sm100::round_tf32(o.x); o.y = sm100::round_tf32(o.y); o.z = sm100::round_tf32(o.z); o.w = sm100::round_tf32(o.w); }
+      float* dst = y + size_t(row0 + r) * y_pitch + 4 * jp;
+      if (2 * jp + 1 < M) *reinterpret_cast<float4*>(dst) = o;
+      else *reinterpret_cast<float2*>(dst) = make_float2(o.x, o.y);
+    }
+  }
+}
+
+// top of the backward pass (training path): z (and w) pitched with 16-byte aligned rows.
+// One thread = 2 complex features; 4 rows of loads in flight.
+template <bool FAST, bool TWO_D>
+__global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__ g_out, int n, int M, int out_f,
+                                                        const float* __restrict__ Wf, const float* __restrict__ z,
+                                                        const float* __restrict__ w, int zw_pitch,
+                                                        const float* __restrict__ omega_p, const float* __restrict__ scale_p,
+                                                        float* __restrict__ gz, float* __restrict__ gw, int g_pitch, int round_g,
+                                                        float* __restrict__ g_Wf, float* __restrict__ g_bf, int rows_per_block) {
+  __shared__ float sgo[64 * 4];
+  const int row0 = blockIdx.x * rows_per_block;
+  int rows = n - row0;
+  rows = rows > rows_per_block ? rows_per_block : rows;
+  for (int i = threadIdx.x; i < rows_per_block * 4; i += blockDim.x) {
+    const int r = i >> 2, o = i & 3;
+    sgo[i] = (r < rows && o < out_f) ? g_out[size_t(row0 + r) * out_f + o] : 0.f;
+  }
+  __syncthreads();
+  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  for (int kp = threadIdx.x; 2 * kp < M; kp += blockDim.x) {
+    const int k0 = 2 * kp, k1 = (2 * kp + 1 < M) ? 2 * kp + 1 : k0;
+    const bool pair = 2 * kp + 1 < M;
+    float wr0[4], wi0[4], wr1[4], wi1[4], ar0[4], ai0[4], ar1[4], ai1[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      wr0[o] = o < out_f ? Wf[(size_t(o) * M + k0) * 2] : 0.f;
+      wi0[o] = o < out_f ? Wf[(size_t(o) * M + k0) * 2 + 1] : 0.f;
+      wr1[o] = o < out_f ? Wf[(size_t(o) * M + k1) * 2] : 0.f;
+      wi1[o] = o < out_f ? Wf[(size_t(o) * M + k1) * 2 + 1] : 0.f;
+      ar0[o] = ai0[o] = ar1[o] = ai1[o] = 0.f;
+    }
+    for (int rb = 0; rb < rows; rb += 4) {
+      float4 zv[4], wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u < rows ? rb + u : rows - 1;
+        zv[u] = __ldcs(reinterpret_cast<const float4*>(z + size_t(row0 + r) * zw_pitch + 4 * kp));
+        if (TWO_D) wv[u] = __ldcs(reinterpret_cast<const float4*>(w + size_t(row0 + r) * zw_pitch + 4 * kp));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rb + u >= rows) break;
+        const int r = rb + u;
+        const float4 go = *reinterpret_cast<const float4*>(&sgo[r * 4]);
+        const float g4[4] = {go.x, go.y, go.z, go.w};
+        float gyr0 = 0.f, gyi0 = 0.f, gyr1 = 0.f, gyi1 = 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          gyr0 = fmaf(g4[o], wr0[o], gyr0); gyi0 = fmaf(-g4[o], wi0[o], gyi0);
+          gyr1 = fmaf(g4[o], wr1[o], gyr1); gyi1 = fmaf(-g4[o], wi1[o], gyi1);
+        }
+        float yr0, yi0, yr1, yi1;
+        float e0 = 0.f, e1 = 0.f;
+        if (TWO_D) { e0 = s2 * (wv[u].x * wv[u].x + wv[u].y * wv[u].y); e1 = s2 * (wv[u].z * wv[u].z + wv[u].w * wv[u].w); }
+        gabor_fwd<FAST>(zv[u].x, zv[u].y, omega, s2, e0, yr0, yi0);
+        gabor_fwd<FAST>(zv[u].z, zv[u].w, omega, s2, e1, yr1, yi1);
+        float4 gzo;
+        const float pr0 = gabor_bwd(yr0, yi0, zv[u].x, zv[u].y, gyr0, gyi0, omega, s2, gzo.x, gzo.y);
+        const float pr1 = gabor_bwd(yr1, yi1, zv[u].z, zv[u].w, gyr1, gyi1, omega, s2, gzo.z, gzo.w);
+        if (round_g) { gzo.x = sm100::round_tf32(gzo.x); gzo.y = sm100::round_tf32(gzo.y); gzo.z = sm100::round_tf32(gzo.z); gzo.w = sm100::round_tf32(gzo.w); }
+        float* dz = gz + size_t(row0 + r) * g_pitch + 4 * kp;
+        if (pair) *reinterpret_cast<float4*>(dz) = gzo; else *reinterpret_cast<float2*>(dz) = make_float2(gzo.x, gzo.y);
+        if (TWO_D) {
+          const float t0 = -2.0f * s2 * pr0, t1 = -2.0f * s2 * pr1;
+          float4 gwo = make_float4(t0 * wv[u].x, t0 * wv[u].y, t1 * wv[u].z, t1 * wv[u].w);
+          if (round_g) { gwo.x = sm100::round_tf32(gwo.x); gwo.y = sm100::round_tf32(gwo.y); gwo.z = sm100::round_tf32(gwo.z); gwo.w = sm100::round_tf32(gwo.w); }
+          float* dw = gw + size_t(row0 + r) * g_pitch + 4 * kp;
+          if (pair) *reinterpret_cast<float4*>(dw) = gwo; else *reinterpret_cast<float2*>(dw) = make_float2(gwo.x, gwo.y);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          ar0[o] = fmaf(g4[o], yr0, ar0[o]); ai0[o] = fmaf(-g4[o], yi0, ai0[o]);
+          ar1[o] = fmaf(g4[o], yr1, ar1[o]); ai1[o] = fmaf(-g4[o], yi1, ai1[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (o < out_f) {
+        atomicAdd(g_Wf + (size_t(o) * M + k0) * 2, ar0[o]);
+        atomicAdd(g_Wf + (size_t(o) * M + k0) * 2 + 1, ai0[o]);
+        if (pair) {
+          atomicAdd(g_Wf + (size_t(o) * M + k1) * 2, ar1[o]);
+          atomicAdd(g_Wf + (size_t(o) * M + k1) * 2 + 1, ai1[o]);
+        }
+      }
+  }
+  if (threadIdx.x < out_f) {
+    float sacc = 0.f;
+    for (int r = 0; r < rows; ++r) sacc += sgo[r * 4 + threadIdx.x];
+    atomicAdd(g_bf + 2 * threadIdx.x, sacc);
+  }
+}
+
+// first layer weight gradient, float4 (4 features) per thread, 4 row groups per block reduced in smem.
+// block = (64 feature quads) x (4 row groups); rows_per_block rows per block.
+__global__ void __launch_bounds__(256) first_wgrad2_kernel(const float* __restrict__ gz0, int g_pitch,
+                                                            const float* __restrict__ coords, int n, int in_f, int M,
+                                                            float* __restrict__ gW0, float* __restrict__ gb0, int rows_per_block) {
+  __shared__ float sc[128 * 4];
+  __shared__ float red[3][64][4][5];  // row groups 1..3 -> [quad][feature][d(0..3 coords, 4 = bias)]
+  const int tq = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  const int row0 = blockIdx.x * rows_per_block;
+  int rows = n - row0;
+  rows = rows > rows_per_block ? rows_per_block : rows;
+  for (int i = threadIdx.x; i < rows_per_block * 4; i += blockDim.x) {
+    const int r = i >> 2, d = i & 3;
+    sc[i] = (r < rows && d < in_f) ? coords[size_t(row0 + r) * in_f + d] : 0.f;
+  }
+  __syncthreads();
+  for (int q0 = 0; 4 * q0 < M; q0 += 64) {
+    const int q = q0 + tq;
+    float acc[4][5];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+      for (int d = 0; d < 5; ++d) acc[f][d] = 0.f;
+    if (4 * q < g_pitch) {
+      for (int rb = tg; rb < rows; rb += 16) {
+        float4 g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + 4 * u;
+          g[u] = (r < rows) ? __ldcs(reinterpret_cast<const float4*>(gz0 + size_t(row0 + r) * g_pitch + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + 4 * u;
+          if (r >= rows) break;
+          const float4 c = *reinterpret_cast<const float4*>(&sc[r * 4]);
+          const float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            acc[f][0] = fmaf(gv[f], c.x, acc[f][0]);
+            acc[f][1] = fmaf(gv[f], c.y, acc[f][1]);
+            acc[f][2] = fmaf(gv[f], c.z, acc[f][2]);
+            acc[f][3] = fmaf(gv[f], c.w, acc[f][3]);
+            acc[f][4] += gv[f];
+          }
+        }
+      }
+    }
+    if (tg > 0) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int d = 0; d < 5; ++d) red[tg - 1][tq][f][d] = acc[f][d];
+    }
+    __syncthreads();
+    if (tg == 0) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int j = 4 * q + f;
+        if (j < M) {
+#pragma unroll
+          for (int d = 0; d < 5; ++d) {
+            const float v = acc[f][d] + red[0][tq][f][d] + red[1][tq][f][d] + red[2][tq][f][d];
+            if (d < 4) { if (d < in_f) atomicAdd(gW0 + size_t(j) * in_f + d, v); }
+            else atomicAdd(gb0 + j, v);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace wire

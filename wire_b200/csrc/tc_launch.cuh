@@ -16,16 +16,27 @@ constexpr size_t kMaxDynSmem = 232448 - 6144;  // 227 KB minus the static barrie
 // `n_in`   : TMA-prefetched epilogue inputs (z / w tiles of the backward modes)
 // `out_cols`: real output columns (2M) -> size of the shared-memory parameter tables
 // `mode`    : decides which tables exist (bias / fused-final weights / first-layer table)
+// `cluster` : CTAs that share each B tile through TMA multicast; nb must split into 8-row aligned shares
 inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int n_in = 0, int out_cols = 0,
-                             int mode = MODE_PLAIN, bool fuse_final = false) {
+                             int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1) {
   P.nb = nb;
   P.nbh = nbh;
   P.store_mask = store_mask;
   P.n_in = n_in;
-  if (nb <= 256) { P.b_box_rows = nb; P.b_boxes = 1; }
-  else { P.b_box_rows = nb / 2; P.b_boxes = 2; }
+  P.cluster = cluster;
+  if (cluster == 2) {
+    // CTA pair: equal MMA pieces, each CTA stages half of every piece
+    const int n1 = nb > 256 ? nb / 2 : nb;
+    if (n1 % 16 || n1 > 256 || (nb > 256 && nb % 32)) return 0;
+    P.b_box_rows = n1 / 2;
+    P.b_boxes = nb > 256 ? 2 : 1;
+  } else {
+    if (cluster != 1) return 0;
+    if (nb <= 256) { P.b_box_rows = nb; P.b_boxes = 1; }
+    else { if (nb % 16) return 0; P.b_box_rows = nb / 2; P.b_boxes = 2; }
+  }
   const int n_out = __builtin_popcount(store_mask);
-  const size_t stage = size_t(kTileRows) * 128 + size_t(nb) * 128;
+  const size_t stage = size_t(kTileRows) * 128 + size_t(nb / cluster) * 128;
   const size_t staging = size_t(kEpiWarps) * (n_out + n_in) * 4096;
   const int pcols = round_up(out_cols > 0 ? out_cols : 32, 32) + 32;  // +1 chunk: the tail chunk may over-read
   const bool two_d = (mode == MODE_GABOR2D_FWD || mode == MODE_GABOR2D_BWD || mode == MODE_FIRST2D_BWD);
@@ -45,30 +56,55 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
 }
 
 template <int MODE>
-inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int grid, cudaStream_t st) {
+inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  tc_rows_kernel<MODE><<<grid, kRowsThreads, smem, st>>>(P);
-  return cudaGetLastError();
+  const int C = P.cluster;
+  const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
+  const int units = ((row_tiles + C - 1) / C) * P.n_blocks;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kRowsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = C > 1 ? 1 : 0;
+  if (C > 1 && max_clusters[C] == 0) {
+    // how many clusters of this size are co-resident (GPC boundaries strand SMs for larger clusters)
+    cfg.gridDim = dim3(sm_count / C * C);
+    cfg.dynamicSmemBytes = kMaxDynSmem;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
+    (void)cudaGetLastError();
+    max_clusters[C] = nc;
+    cfg.dynamicSmemBytes = smem;
+  }
+  int clusters = C > 1 ? max_clusters[C] : sm_count;
+  if (clusters > units) clusters = units;
+  if (clusters <= 0) return cudaSuccess;
+  cfg.gridDim = dim3(clusters * C);
+  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE>, P);
 }
 
 inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
-  const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
-  const int items = row_tiles * P.n_blocks;
-  if (items <= 0) return cudaSuccess;
-  const int grid = items < sm_count ? items : sm_count;
+  if (P.e.n_rows <= 0) return cudaSuccess;
   switch (mode) {
-    case MODE_PLAIN: return launch_rows_mode<MODE_PLAIN>(P, smem, grid, st);
-    case MODE_GABOR_FWD: return launch_rows_mode<MODE_GABOR_FWD>(P, smem, grid, st);
-    case MODE_GABOR2D_FWD: return launch_rows_mode<MODE_GABOR2D_FWD>(P, smem, grid, st);
-    case MODE_GABOR_BWD: return launch_rows_mode<MODE_GABOR_BWD>(P, smem, grid, st);
-    case MODE_GABOR2D_BWD: return launch_rows_mode<MODE_GABOR2D_BWD>(P, smem, grid, st);
-    case MODE_FIRST_BWD: return launch_rows_mode<MODE_FIRST_BWD>(P, smem, grid, st);
-    case MODE_FIRST2D_BWD: return launch_rows_mode<MODE_FIRST2D_BWD>(P, smem, grid, st);
+    case MODE_PLAIN: return launch_rows_mode<MODE_PLAIN>(P, smem, sm_count, st);
+    case MODE_GABOR_FWD: return launch_rows_mode<MODE_GABOR_FWD>(P, smem, sm_count, st);
+    case MODE_GABOR2D_FWD: return launch_rows_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st);
+    case MODE_GABOR_BWD: return launch_rows_mode<MODE_GABOR_BWD>(P, smem, sm_count, st);
+    case MODE_GABOR2D_BWD: return launch_rows_mode<MODE_GABOR2D_BWD>(P, smem, sm_count, st);
+    case MODE_FIRST_BWD: return launch_rows_mode<MODE_FIRST_BWD>(P, smem, sm_count, st);
+    case MODE_FIRST2D_BWD: return launch_rows_mode<MODE_FIRST2D_BWD>(P, smem, sm_count, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -40,7 +40,9 @@ struct RowsParams {
   int n_blocks;          // column blocks (work item = row tile x block)
   int nb;                // accumulator columns per block (multiple of 16, <= 512)
   int nbh;               // 2D fwd: columns of the z half (w half follows); otherwise == nb
-  int b_box_rows, b_boxes;
+  int b_box_rows, b_boxes;  // each CTA loads b_boxes boxes of b_box_rows rows = its share of the B tile
+  int cluster;              // 1 = one CTA per tile (cta_group::1); 2 = CTA pair (cta_group::2): a 256-row tile, each
+                            // CTA stages its own 128 rows of A and HALF of the B tile, halving the smem fill per flop
   int stages;
   int store_mask;  // which epilogue results are TMA-stored: bit0 = o0, bit1 = o1, bit2 = o2
   int n_in;        // TMA-prefetched epilogue inputs (0, 1 = z, 2 = z and w)
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_bytes = kTileRows * 128;
-  const uint32_t b_bytes = uint32_t(P.nb) * 128;
+  const uint32_t b_bytes = uint32_t(P.nb / P.cluster) * 128;  // this CTA's share of the B tile
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t staging_base = smem_base + P.staging_off;
   float* params = reinterpret_cast<float*>(smem_gen + P.param_off);
@@ -149,8 +151,22 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   const int kc1 = (P.k_cols[1] + kChunk - 1) / kChunk;
   const int kc_total = kc0 + kc1;
   const int row_tiles = (E.n_rows + kTileRows - 1) / kTileRows;
-  const int n_items = row_tiles * P.n_blocks;
   const int n_feat = E.n_cols >> 1;  // complex features M
+  // Work decomposition.  The two CTAs of a pair work on the SAME column block and on two consecutive
+  // row tiles, and every CTA of the grid runs the same number of iterations (tiles past the end are
+  // computed on zero-filled rows and their stores are clipped by TMA).
+  const int C = P.cluster;
+  const int crank = int(cluster_ctarank());
+  const int n_clusters = gridDim.x / C;
+  const int my_cluster = blockIdx.x / C;
+  const int row_groups = (row_tiles + C - 1) / C;
+  const int n_units = row_groups * P.n_blocks;                 // cluster-level work units
+  const int n_iters = (n_units + n_clusters - 1) / n_clusters;
+  const bool pair = C == 2;
+  const bool leader = crank == 0;
+  // MMA pieces along N: one instruction covers at most 256 columns
+  const int n1 = pair ? (P.nb > 256 ? P.nb / 2 : P.nb) : (P.nb > 256 ? 256 : P.nb);
+  const int n2 = P.nb - n1;
 
   // ---- shared parameter tables (zero padded so the epilogue needs no column checks) ----
   //  fwd : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8]  (wr[4], wi[4]) if fused
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
-    mbar_init(smem_u32(&bar_tmem_empty), kEpiWarps);
+    mbar_init(smem_u32(&bar_tmem_empty), kEpiWarps * C);  // pair: both CTAs' epilogues release the leader
     for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&bar_in[w][0]), 1); mbar_init(smem_u32(&bar_in[w][1]), 1); }
     fence_barrier_init();
   }
@@ -199,11 +215,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     tma_prefetch_desc(&P.b_map);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_slot), 512);
-    tmem_relinquish();
+    if (pair) { tmem_alloc_2cta(smem_u32(&tmem_slot), 512); tmem_relinquish_2cta(); }
+    else { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();  // the peer's barriers must exist before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -212,36 +229,47 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int row0 = (item / P.n_blocks) * kTileRows;
-        const int n0 = (item % P.n_blocks) * P.nb;
+      for (int it = 0; it < n_iters; ++it) {
+        const int unit = it * n_clusters + my_cluster;
+        const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
+        const int n0 = (unit % P.n_blocks) * P.nb;
         for (int kc = 0; kc < kc_total; ++kc) {
           mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          mbar_expect_tx(full, stage_bytes);
+          const uint32_t full_own = smem_u32(&bar_full[stage]);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const int part = kc < kc0 ? 0 : 1;
           const int kcol = (part ? kc - kc0 : kc) * kChunk;
-          tma_load_2d_hint(a_dst, &P.a_map[part], full, kcol, row0, kEvictFirst);
-          for (int bx = 0; bx < P.b_boxes; ++bx)
-            tma_load_2d_hint(a_dst + a_bytes + bx * P.b_box_rows * 128, &P.b_map, full, kc * kChunk,
-                             n0 + bx * P.b_box_rows, kEvictLast);
+          if (!pair) {
+            mbar_expect_tx(full_own, stage_bytes);
+            tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, kEvictFirst);
+            for (int bx = 0; bx < P.b_boxes; ++bx)
+              tma_load_2d_hint(a_dst + a_bytes + bx * P.b_box_rows * 128, &P.b_map, full_own, kc * kChunk,
+                               n0 + bx * P.b_box_rows, kEvictLast);
+          } else {
+            // both CTAs load into their own smem; all bytes complete on the LEADER's full barrier
+            const uint32_t full_leader = full_own & kPeerBitMask;
+            if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
+            tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, kEvictFirst);
+            // piece i of the MMA covers n_i columns; this CTA stages rows [crank*n_i/2, +n_i/2) of it
+            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kChunk, n0 + crank * (n1 / 2), kEvictLast);
+            if (n2 > 0)
+              tma_load_2d_2cta(a_dst + a_bytes + (n1 / 2) * 128, &P.b_map, full_leader, kc * kChunk,
+                               n0 + n1 + crank * (n2 / 2), kEvictLast);
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const int n1 = P.nb > 256 ? 256 : P.nb;
-      const int n2 = P.nb - n1;
-      const uint32_t idesc1 = make_idesc_tf32(128, n1, false, false);
-      const uint32_t idesc2 = make_idesc_tf32(128, n2 > 0 ? n2 : 16, false, false);
+    if (lane == 0 && (!pair || leader)) {
+      const uint32_t idesc1 = make_idesc_tf32(pair ? 256 : 128, n1, false, false);
+      const uint32_t idesc2 = make_idesc_tf32(pair ? 256 : 128, n2 > 0 ? n2 : 16, false, false);
+      const uint32_t b2_off = uint32_t(pair ? n1 / 2 : n1) * 128;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tphase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int it = 0; it < n_iters; ++it) {
         if (it > 0) {
           mbar_wait_backoff(smem_u32(&bar_tmem_empty), tphase);
           tphase ^= 1;
@@ -260,16 +288,22 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
             const uint32_t acc = (kc | ks) ? 1u : 0u;
             const uint64_t adesc = make_sdesc_sw128(a_base + ks * 32, 16, 1024);
             const uint64_t bdesc = make_sdesc_sw128(b_base + ks * 32, 16, 1024);
-            umma_tf32(tmem_base, adesc, bdesc, idesc1, acc);
-            if (n2 > 0) {
-              const uint64_t bdesc2 = make_sdesc_sw128(b_base + n1 * 128 + ks * 32, 16, 1024);
-              umma_tf32(tmem_base + n1, adesc, bdesc2, idesc2, acc);
+            const uint64_t bdesc2 = make_sdesc_sw128(b_base + b2_off + ks * 32, 16, 1024);
+            if (pair) {
+              umma_tf32_2cta(tmem_base, adesc, bdesc, idesc1, acc);
+              if (n2 > 0) umma_tf32_2cta(tmem_base + n1, adesc, bdesc2, idesc2, acc);
+            } else {
+              umma_tf32(tmem_base, adesc, bdesc, idesc1, acc);
+              if (n2 > 0) umma_tf32(tmem_base + n1, adesc, bdesc2, idesc2, acc);
             }
           }
-          umma_commit(smem_u32(&bar_empty[stage]));
+          // release the smem stage (in both CTAs of a pair) once these MMAs have completed
+          if (pair) umma_commit_2cta_mcast(smem_u32(&bar_empty[stage]), 3);
+          else umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&bar_tmem_full));
+        if (pair) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full), 3);
+        else umma_commit(smem_u32(&bar_tmem_full));
       }
     }
   } else {
@@ -290,10 +324,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     const float4* s_tab2 = reinterpret_cast<const float4*>(params + (P.param_cols >> 1) * 4);
     uint32_t tphase = 0;
     uint32_t in_phase = 0;
-    int tile_it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_it) {
-      const int row0 = (item / P.n_blocks) * kTileRows;
-      const int blk = item % P.n_blocks;
+    for (int tile_it = 0; tile_it < n_iters; ++tile_it) {
+      const int unit = tile_it * n_clusters + my_cluster;
+      const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
+      const int blk = unit % P.n_blocks;
       const int row = row0 + q * 32 + lane;
       const bool row_ok = row < E.n_rows;
       const int ncol_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;  // output columns per block
@@ -331,7 +365,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       if (my_last < 0) {  // nothing to do in this tile (single-chunk block): just release TMEM
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
+        if (lane == 0) { if (pair) mbar_arrive_cluster(smem_u32(&bar_tmem_empty) & kPeerBitMask); else mbar_arrive(smem_u32(&bar_tmem_empty)); }
       }
 
       for (int ch = half; ch < nchunks; ch += 2) {
@@ -352,7 +386,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           // all TMEM reads of this warp for this tile are done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
+          if (lane == 0) { if (pair) mbar_arrive_cluster(smem_u32(&bar_tmem_empty) & kPeerBitMask); else mbar_arrive(smem_u32(&bar_tmem_empty)); }
         }
         float v[32];
 #pragma unroll
@@ -511,9 +545,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   // ===================== teardown =====================
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer still uses the pair's resources
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (pair) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
