@@ -78,3 +78,21 @@ def test_metrics():
     assert abs(O.iou(a, b) - 4 / 12) < 1e-12
     assert tuple(O.image_coords(4, 6).shape) == (1, 24, 2)
     assert tuple(O.volume_coords(2, 3, 4).shape) == (24, 3)
+
+
+@pytest.mark.parametrize("name", ["wire_small", "wire_occ_small", "wire2d_small", "wire_odd_width"])
+def test_c_oracle_matches_reference_c128(name):
+    """oracle/wire_oracle.c (plain C, double) vs the reference's complex128 run."""
+    import c_oracle
+    if not c_oracle.available():
+        pytest.skip("oracle/_build/libwire_oracle_c.so not built (run __graft_entry__.build() or make -C oracle)")
+    c = util.load_golden(name)
+    g = c["g"]
+    m = util.oracle_model(c)
+    state = {k: v.numpy() for k, v in m.state_dict().items()}
+    out, grads, gc = c_oracle.run(state, c["kind"] == "wire2d", g["coords"], g["grad_out"])
+    assert util.rel_err(out.reshape(g["out_c128"].shape), g["out_c128"]) < 1e-12
+    assert util.rel_err(gc.reshape(g["gcoords_c128"].shape), g["gcoords_c128"]) < 1e-11
+    for k in (k for k in g.files if k.startswith("grad_c128.")):
+        key = k[len("grad_c128."):]
+        assert util.rel_err(grads[key], g[k]) < 1e-11, key
