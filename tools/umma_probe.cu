@@ -73,7 +73,7 @@ static int g_cluster = 1;
 
 static bool test_rows(int n_rows, int two_m, bool time_it) {
   const int K = two_m, pitch = wire::round_up(two_m + 1, 32);
-  const int nb = wire::round_up(two_m, (g_cluster == 2 && two_m > 256) ? 32 : 16);
+  const int nb = two_m > 256 ? wire::round_up(two_m, 64) : wire::round_up(two_m, 16);
   std::vector<float> A(size_t(n_rows) * pitch, 0.f), B(size_t(nb) * pitch, 0.f), C(size_t(n_rows) * pitch, -7.f);
   for (int r = 0; r < n_rows; ++r) {
     for (int c = 0; c < K; ++c) A[size_t(r) * pitch + c] = tf32_round_host(frand());
@@ -121,6 +121,21 @@ static bool test_rows(int n_rows, int two_m, bool time_it) {
   printf("[rows] max_abs_err=%.3e (max |ref| %.3f) bad=%ld -> %s\n", max_err, max_ref, bad, bad ? "FAIL" : "PASS");
   if (time_it && !bad) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    {  // stall counters
+      unsigned long long* dd; CK(cudaMalloc(&dd, 8 * 8 * 1024)); CK(cudaMemset(dd, 0, 8 * 8 * 1024));
+      wire::RowsParams Q = P; Q.dbg = dd;
+      CK(wire::launch_rows(wire::MODE_PLAIN, Q, smem, g_sms, 0));
+      CK(cudaDeviceSynchronize());
+      std::vector<unsigned long long> hd(8 * 1024);
+      CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
+      const char* names[8] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in"};
+      for (int k = 0; k < 8; ++k) {
+        double sum = 0; int cnt = 0;
+        for (int b = 0; b < 1024; ++b) if (hd[b * 8 + k]) { sum += double(hd[b * 8 + k]); ++cnt; }
+        printf("   [dbg] %-16s avg %.0f cycles over %d CTAs\n", names[k], cnt ? sum / cnt : 0.0, cnt);
+      }
+      cudaFree(dd);
+    }
     for (int i = 0; i < 3; ++i) CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0));
     CK(cudaEventRecord(e0));
     const int reps = 10;
@@ -133,6 +148,57 @@ static bool test_rows(int n_rows, int two_m, bool time_it) {
   }
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
   return bad == 0;
+}
+
+// timing + stall counters of the fused forward epilogue (no correctness check here: tests/ cover that)
+static void time_rows_gabor(int n_rows, int two_m) {
+  const int K = two_m, pitch = wire::round_up(two_m + 1, 32);
+  const int nb = two_m > 256 ? wire::round_up(two_m, 64) : wire::round_up(two_m, 16);
+  std::vector<float> A(size_t(n_rows) * pitch, 0.f), B(size_t(nb) * pitch, 0.f), bias(two_m, 0.01f);
+  for (auto& v : A) v = tf32_round_host(frand() * 0.5f);
+  for (auto& v : B) v = tf32_round_host(frand() * 0.07f);
+  float *dA, *dB, *dY, *dZ, *dbias, *dom;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dY, A.size() * 4)); CK(cudaMalloc(&dZ, A.size() * 4));
+  CK(cudaMalloc(&dbias, two_m * 4)); CK(cudaMalloc(&dom, 8));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias.data(), two_m * 4, cudaMemcpyHostToDevice));
+  const float os[2] = {7.f, 6.f};
+  CK(cudaMemcpy(dom, os, 8, cudaMemcpyHostToDevice));
+  wire::RowsParams P;
+  memset(&P, 0, sizeof(P));
+  P.e.n_rows = n_rows; P.k_cols[0] = K; P.n_blocks = 1; P.e.n_cols = two_m; P.e.round_out0 = 1;
+  P.e.bias = dbias; P.e.omega = dom; P.e.scale = dom + 1;
+  size_t smem = wire::rows_configure(P, nb, nb, 3, 0, two_m, wire::MODE_GABOR_FWD, false, g_cluster);
+  bool ok = sm100_host::make_tmap_2d(&P.a_map[0], dA, n_rows, K, pitch, 128, 32);
+  P.a_map[1] = P.a_map[0];
+  ok &= sm100_host::make_tmap_2d(&P.b_map, dB, nb, pitch, pitch, P.b_box_rows, 32);
+  ok &= sm100_host::make_tmap_2d(&P.o_map[0], dY, n_rows, two_m, pitch, 32, 32);
+  ok &= sm100_host::make_tmap_2d(&P.o_map[1], dZ, n_rows, two_m, pitch, 32, 32);
+  P.o_map[2] = P.o_map[0]; P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
+  if (!ok || !smem) { printf("gabor setup failed\n"); return; }
+  unsigned long long* dd; CK(cudaMalloc(&dd, 8 * 8 * 1024)); CK(cudaMemset(dd, 0, 8 * 8 * 1024));
+  P.dbg = dd;
+  for (int i = 0; i < 3; ++i) CK(wire::launch_rows(wire::MODE_GABOR_FWD, P, smem, g_sms, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> hd(8 * 1024);
+  CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
+  printf("[gabor_fwd] cluster=%d n_rows=%d 2M=%d nb=%d slices=%d stages=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.slices, P.stages, smem);
+  const char* names[8] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in"};
+  for (int k = 0; k < 8; ++k) {
+    double sum = 0; int cnt = 0;
+    for (int b = 0; b < 1024; ++b) if (hd[b * 8 + k]) { sum += double(hd[b * 8 + k]); ++cnt; }
+    printf("   [dbg] %-16s avg %.0f cycles over %d CTAs\n", names[k], cnt ? sum / cnt : 0.0, cnt);
+  }
+  P.dbg = nullptr;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  const int reps = 10;
+  for (int i = 0; i < reps; ++i) CK(wire::launch_rows(wire::MODE_GABOR_FWD, P, smem, g_sms, 0));
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+  printf("[gabor_fwd] %.3f ms  %.1f TFLOP/s (useful)\n", ms, 2.0 * n_rows * double(two_m) * K / ms * 1e-9);
+  cudaFree(dA); cudaFree(dB); cudaFree(dY); cudaFree(dZ); cudaFree(dbias); cudaFree(dom); cudaFree(dd);
 }
 
 static bool test_wgrad(int n_rows, int k_in, int m_out, bool time_it) {
@@ -154,11 +220,12 @@ static bool test_wgrad(int n_rows, int k_in, int m_out, bool time_it) {
   memset(&P, 0, sizeof(P));
   P.n_rows = n_rows; P.k_in = k_in; P.g_cols = gc; P.n_g = 1;
   P.gW[0] = dW; P.gB[0] = dBias;
-  size_t smem = wire::wgrad_configure(P, g_sms);
+  size_t smem = wire::wgrad_configure(P, g_sms, g_cluster);
   bool ok = sm100_host::make_tmap_2d(&P.x_map, dX, n_rows, xc, xp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   ok &= sm100_host::make_tmap_2d(&P.g_map[0], dG, n_rows, gc, gp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   P.g_map[1] = P.g_map[0];
   if (!ok || !smem) { printf("wgrad setup failed\n"); return false; }
+  printf("[wgrad] cluster=%d ", g_cluster);
   printf("[wgrad] n=%d K=%d M=%d m_tiles=%d n_blocks=%d nb=%d splits=%d stages=%d smem=%zu\n", n_rows, k_in, m_out,
          P.m_tiles, P.n_blocks, P.nb, P.splits, P.stages, smem);
   CK(wire::launch_wgrad(P, smem, 0));
@@ -236,11 +303,18 @@ int main(int argc, char** argv) {
     test_rows(262144, 424, true);
     test_wgrad(262144, 212, 212, true);
     test_rows(262144, 256, true);
+    time_rows_gabor(262144, 424);
     g_cluster = 2;
     ok &= test_rows(300, 424, false);
     ok &= test_rows(1000, 180, false);
     test_rows(262144, 424, true);
     test_rows(262144, 256, true);
+    time_rows_gabor(262144, 424);
+    time_rows_gabor(262144, 256);
+    ok &= test_wgrad(256, 32, 32, false);
+    ok &= test_wgrad(5000, 212, 212, false);
+    ok &= test_wgrad(777, 90, 90, false);
+    test_wgrad(262144, 212, 212, true);
 
   }
   printf("PROBE %s\n", ok ? "PASS" : "FAIL");

@@ -119,11 +119,15 @@ struct Blocking {
 bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, int n_in = 0, int mode = MODE_PLAIN,
                      bool fuse_final = false) {
   for (int nblk = 1; nblk <= 64; ++nblk) {
-    int per = (out_cols + nblk - 1) / nblk;
+    const int per = (out_cols + nblk - 1) / nblk;
     const int C = cluster_size();
-    int nbh = (nblk == 1 && !two_d_fwd && (C == 1 || per <= 256)) ? round_up(per, 16) : round_up(per, 32);
-    int nb = two_d_fwd ? 2 * nbh : nbh;
-    if (nb > 512) continue;
+    int nbh, nb;
+    if (two_d_fwd) { nbh = round_up(per, 32); nb = 2 * nbh; if (nb > 256) continue; }
+    else {
+      nb = round_up(per, nblk == 1 ? 16 : 32);
+      if (nb > 256) nb = round_up(per, 64);
+      nbh = nb;
+    }
     RowsParams tmp;
     if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C) == 0) continue;
     b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
@@ -315,7 +319,7 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
   memset(&P, 0, sizeof(P));
   P.n_rows = int(n); P.k_in = k_in; P.g_cols = 2 * m_out; P.n_g = n_g;
   P.gW[0] = gW1; P.gB[0] = gB1; P.gW[1] = gW2; P.gB[1] = gB2;
-  const size_t smem = wgrad_configure(P, g_sm_count);
+  const size_t smem = wgrad_configure(P, g_sm_count, cluster_size());
   if (!smem) return fail("wgrad configuration does not fit shared memory");
   bool ok = sm100_host::make_tmap_2d(&P.x_map, x, n, 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   ok &= sm100_host::make_tmap_2d(&P.g_map[0], g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -359,8 +363,12 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   const int round_g = (d->precision == WIRE_PRECISION_TF32) && z;
   ProfScope prof(K_TOP_BWD, st);
   const bool tf = d->precision == WIRE_PRECISION_TF32;
-  if (z && d->out_features <= 4 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
+  if (z && d->out_features <= 4 && d->width <= 256 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
     const int M = d->width, of = d->out_features;
+    // few, long-lived blocks: every g_Wf address then sees only `nblk` atomics
+    const int nblk = int(n < int64_t(4 * g_sm_count) * 64 ? (n + 63) / 64 : 4 * g_sm_count);
+    const int kRowsPerBlock = int(((n + nblk - 1) / nblk + 63) / 64 * 64);
+    const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
     if (tf && w) top_bwd2_kernel<true, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
     else if (tf) top_bwd2_kernel<true, false><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
     else if (w) top_bwd2_kernel<false, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
@@ -380,8 +388,9 @@ int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t 
   if (n <= 0 || !gW) return 0;
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   ProfScope prof(K_FIRST_WGRAD, st);
-  if (in_f <= 4 && (g_pitch % 4) == 0) {
-    const int rpb = 128;
+  if (in_f <= 4 && M <= 256 && (g_pitch % 4) == 0) {
+    const int nblk = int(n < int64_t(4 * g_sm_count) * 128 ? (n + 127) / 128 : 4 * g_sm_count);
+    const int rpb = int(((n + nblk - 1) / nblk + 127) / 128 * 128);
     first_wgrad2_kernel<<<int((n + rpb - 1) / rpb), 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, rpb);
   } else {
     first_wgrad_kernel<<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);

@@ -388,28 +388,39 @@ __global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__
                                                         const float* __restrict__ omega_p, const float* __restrict__ scale_p,
                                                         float* __restrict__ gz, float* __restrict__ gw, int g_pitch, int round_g,
                                                         float* __restrict__ g_Wf, float* __restrict__ g_bf, int rows_per_block) {
+  // Each block owns a contiguous range of `rows_per_block` rows and walks it in chunks of 64: the g_W / g_b
+  // partial sums stay in registers for the whole range, so every output address sees only gridDim.x atomics
+  // (same-address atomics serialise in L2; thousands of small blocks made this kernel atomics-bound).
+  // Requires M <= 2 * blockDim.x (one feature pair per thread).
   __shared__ float sgo[64 * 4];
-  const int row0 = blockIdx.x * rows_per_block;
-  int rows = n - row0;
-  rows = rows > rows_per_block ? rows_per_block : rows;
-  for (int i = threadIdx.x; i < rows_per_block * 4; i += blockDim.x) {
-    const int r = i >> 2, o = i & 3;
-    sgo[i] = (r < rows && o < out_f) ? g_out[size_t(row0 + r) * out_f + o] : 0.f;
-  }
-  __syncthreads();
   const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
-  for (int kp = threadIdx.x; 2 * kp < M; kp += blockDim.x) {
-    const int k0 = 2 * kp, k1 = (2 * kp + 1 < M) ? 2 * kp + 1 : k0;
-    const bool pair = 2 * kp + 1 < M;
-    float wr0[4], wi0[4], wr1[4], wi1[4], ar0[4], ai0[4], ar1[4], ai1[4];
+  const int kp = threadIdx.x;
+  const bool active = 2 * kp < M;
+  const int k0 = active ? 2 * kp : 0, k1 = (2 * kp + 1 < M) ? 2 * kp + 1 : k0;
+  const bool pair = 2 * kp + 1 < M;
+  float wr0[4], wi0[4], wr1[4], wi1[4], ar0[4], ai0[4], ar1[4], ai1[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      wr0[o] = o < out_f ? Wf[(size_t(o) * M + k0) * 2] : 0.f;
-      wi0[o] = o < out_f ? Wf[(size_t(o) * M + k0) * 2 + 1] : 0.f;
-      wr1[o] = o < out_f ? Wf[(size_t(o) * M + k1) * 2] : 0.f;
-      wi1[o] = o < out_f ? Wf[(size_t(o) * M + k1) * 2 + 1] : 0.f;
-      ar0[o] = ai0[o] = ar1[o] = ai1[o] = 0.f;
+  for (int o = 0; o < 4; ++o) {
+    wr0[o] = o < out_f ? Wf[(size_t(o) * M + k0) * 2] : 0.f;
+    wi0[o] = o < out_f ? Wf[(size_t(o) * M + k0) * 2 + 1] : 0.f;
+    wr1[o] = o < out_f ? Wf[(size_t(o) * M + k1) * 2] : 0.f;
+    wi1[o] = o < out_f ? Wf[(size_t(o) * M + k1) * 2 + 1] : 0.f;
+    ar0[o] = ai0[o] = ar1[o] = ai1[o] = 0.f;
+  }
+  float bsum = 0.f;
+  const int range0 = blockIdx.x * rows_per_block;
+  int range1 = range0 + rows_per_block;
+  range1 = range1 > n ? n : range1;
+  for (int row0 = range0; row0 < range1; row0 += 64) {
+    const int rows = (range1 - row0) > 64 ? 64 : (range1 - row0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
+      const int r = i >> 2, o = i & 3;
+      sgo[i] = (r < rows && o < out_f) ? g_out[size_t(row0 + r) * out_f + o] : 0.f;
     }
+    __syncthreads();
+    if (threadIdx.x < 4) for (int r = 0; r < rows; ++r) bsum += sgo[r * 4 + threadIdx.x];
+    if (!active) continue;
     for (int rb = 0; rb < rows; rb += 4) {
       float4 zv[4], wv[4];
 #pragma unroll
@@ -455,6 +466,8 @@ __global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__
         }
       }
     }
+  }
+  if (active) {
 #pragma unroll
     for (int o = 0; o < 4; ++o)
       if (o < out_f) {
@@ -466,11 +479,7 @@ __global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__
         }
       }
   }
-  if (threadIdx.x < out_f) {
-    float sacc = 0.f;
-    for (int r = 0; r < rows; ++r) sacc += sgo[r * 4 + threadIdx.x];
-    atomicAdd(g_bf + 2 * threadIdx.x, sacc);
-  }
+  if (threadIdx.x < out_f) atomicAdd(g_bf + 2 * threadIdx.x, bsum);
 }
 
 // first layer weight gradient, float4 (4 features) per thread, 4 row groups per block reduced in smem.
@@ -480,23 +489,28 @@ __global__ void __launch_bounds__(256) first_wgrad2_kernel(const float* __restri
                                                             float* __restrict__ gW0, float* __restrict__ gb0, int rows_per_block) {
   __shared__ float sc[128 * 4];
   __shared__ float red[3][64][4][5];  // row groups 1..3 -> [quad][feature][d(0..3 coords, 4 = bias)]
+  // Each block owns `rows_per_block` rows and walks them in chunks of 128 (few blocks => few same-address atomics).
+  // Requires M <= 256 (one float4 of features per thread column).
   const int tq = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  const int row0 = blockIdx.x * rows_per_block;
-  int rows = n - row0;
-  rows = rows > rows_per_block ? rows_per_block : rows;
-  for (int i = threadIdx.x; i < rows_per_block * 4; i += blockDim.x) {
-    const int r = i >> 2, d = i & 3;
-    sc[i] = (r < rows && d < in_f) ? coords[size_t(row0 + r) * in_f + d] : 0.f;
-  }
-  __syncthreads();
-  for (int q0 = 0; 4 * q0 < M; q0 += 64) {
-    const int q = q0 + tq;
+  const int range0 = blockIdx.x * rows_per_block;
+  int range1 = range0 + rows_per_block;
+  range1 = range1 > n ? n : range1;
+  {
+    const int q = tq;
     float acc[4][5];
 #pragma unroll
     for (int f = 0; f < 4; ++f)
 #pragma unroll
       for (int d = 0; d < 5; ++d) acc[f][d] = 0.f;
-    if (4 * q < g_pitch) {
+    for (int row0 = range0; row0 < range1; row0 += 128) {
+      const int rows = (range1 - row0) > 128 ? 128 : (range1 - row0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) {
+        const int r = i >> 2, d = i & 3;
+        sc[i] = (r < rows && d < in_f) ? coords[size_t(row0 + r) * in_f + d] : 0.f;
+      }
+      __syncthreads();
+      if (4 * q >= g_pitch) continue;
       for (int rb = tg; rb < rows; rb += 16) {
         float4 g[4];
 #pragma unroll
@@ -542,7 +556,6 @@ __global__ void __launch_bounds__(256) first_wgrad2_kernel(const float* __restri
         }
       }
     }
-    __syncthreads();
   }
 }
 

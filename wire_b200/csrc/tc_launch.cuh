@@ -24,19 +24,17 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
   P.store_mask = store_mask;
   P.n_in = n_in;
   P.cluster = cluster;
-  if (cluster == 2) {
-    // CTA pair: equal MMA pieces, each CTA stages half of every piece
-    const int n1 = nb > 256 ? nb / 2 : nb;
-    if (n1 % 16 || n1 > 256 || (nb > 256 && nb % 32)) return 0;
-    P.b_box_rows = n1 / 2;
-    P.b_boxes = nb > 256 ? 2 : 1;
-  } else {
-    if (cluster != 1) return 0;
-    if (nb <= 256) { P.b_box_rows = nb; P.b_boxes = 1; }
-    else { if (nb % 16) return 0; P.b_box_rows = nb / 2; P.b_boxes = 2; }
+  if (cluster != 1 && cluster != 2) return 0;
+  if (nb <= 256) { P.slices = 1; P.ns = nb; P.buf_cols = 256; }
+  else {
+    // two N-slices, each with its own K loop and TMEM buffer (the MMAs of one overlap the epilogue of the other)
+    if (mode == MODE_GABOR2D_FWD || nb % 64 || nb > 512) return 0;
+    P.slices = 2; P.ns = nb / 2; P.buf_cols = nb / 2;
   }
+  if (P.ns % 16 || (P.ns / cluster) % 8) return 0;
+  P.b_box_rows = P.ns / cluster;
   const int n_out = __builtin_popcount(store_mask);
-  const size_t stage = size_t(kTileRows) * 128 + size_t(nb / cluster) * 128;
+  const size_t stage = size_t(kTileRows) * 128 + size_t(P.b_box_rows) * 128;
   const size_t staging = size_t(kEpiWarps) * (n_out + n_in) * 4096;
   const int pcols = round_up(out_cols > 0 ? out_cols : 32, 32) + 32;  // +1 chunk: the tail chunk may over-read
   const bool two_d = (mode == MODE_GABOR2D_FWD || mode == MODE_GABOR2D_BWD || mode == MODE_FIRST2D_BWD);
@@ -55,12 +53,12 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
   return stages * stage + staging + pbytes + 1024;
 }
 
-template <int MODE>
-inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+template <int MODE, bool PAIR>
+inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -83,7 +81,7 @@ inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_cou
     cfg.gridDim = dim3(sm_count / C * C);
     cfg.dynamicSmemBytes = kMaxDynSmem;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE, PAIR>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
     (void)cudaGetLastError();
     max_clusters[C] = nc;
     cfg.dynamicSmemBytes = smem;
@@ -92,7 +90,11 @@ inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_cou
   if (clusters > units) clusters = units;
   if (clusters <= 0) return cudaSuccess;
   cfg.gridDim = dim3(clusters * C);
-  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE>, P);
+  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE, PAIR>, P);
+}
+template <int MODE>
+inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  return P.cluster == 2 ? launch_rows_mode_p<MODE, true>(P, smem, sm_count, st) : launch_rows_mode_p<MODE, false>(P, smem, sm_count, st);
 }
 
 inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
@@ -110,19 +112,22 @@ inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int s
 }
 
 // wgrad: choose column blocking, K splits (to fill the machine) and pipeline depth
-inline size_t wgrad_configure(WgradParams& P, int sm_count) {
+inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2) {
   const int x_cols = 2 * P.k_in + 1;
-  P.m_tiles = (x_cols + 127) / 128;
-  const int gpad = round_up(P.g_cols, 32);
+  P.cluster = cluster;
+  P.m_tiles = (x_cols + 128 * cluster - 1) / (128 * cluster);
+  const int gran = cluster == 2 ? 64 : 32;  // a pair splits every MMA piece in 32-column-aligned halves
+  const int gpad = round_up(P.g_cols, gran);
   P.n_blocks = (gpad + 447) / 448;
-  P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, 32);
+  P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran);
+  if (P.nb > 448) { P.n_blocks += 1; P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran); }
   const int base = P.m_tiles * P.n_blocks * P.n_g;
-  int splits = sm_count / base;
+  int splits = (sm_count / cluster) / base;
   if (splits < 1) splits = 1;
   const int total_chunks = (P.n_rows + kWgradKC - 1) / kWgradKC;
   if (splits > total_chunks) splits = total_chunks > 0 ? total_chunks : 1;
   P.splits = splits;
-  const size_t stage = size_t(4 + P.nb / 32) * kWgradKC * 128;
+  const size_t stage = size_t(4 + P.nb / 32 / cluster) * kWgradKC * 128;
   int stages = int((kMaxDynSmem - 1024) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) return 0;
@@ -130,17 +135,33 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count) {
   return stages * stage + 1024;
 }
 
-inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st) {
+template <bool PAIR>
+inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int grid = P.m_tiles * P.n_blocks * P.n_g * P.splits;
+  const int C = PAIR ? 2 : 1;
+  const int grid = P.m_tiles * P.n_blocks * P.n_g * P.splits * C;
   if (grid <= 0 || P.n_rows <= 0) return cudaSuccess;
-  tc_wgrad_kernel<<<grid, kWgradThreads, smem, st>>>(P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kWgradThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = PAIR ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PAIR>, P);
+}
+inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st) {
+  return P.cluster == 2 ? launch_wgrad_p<true>(P, smem, st) : launch_wgrad_p<false>(P, smem, st);
 }
 
 }  // namespace wire

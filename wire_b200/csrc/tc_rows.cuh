@@ -40,7 +40,11 @@ struct RowsParams {
   int n_blocks;          // column blocks (work item = row tile x block)
   int nb;                // accumulator columns per block (multiple of 16, <= 512)
   int nbh;               // 2D fwd: columns of the z half (w half follows); otherwise == nb
-  int b_box_rows, b_boxes;  // each CTA loads b_boxes boxes of b_box_rows rows = its share of the B tile
+  int slices;               // N-slices per tile (1 or 2): each slice has its own K loop and TMEM accumulator buffer, so
+                            // the MMAs of one slice overlap the epilogue of the previous one (TMEM is double-buffered)
+  int ns;                   // accumulator columns per slice (<= 256; slices * ns == nb)
+  int buf_cols;             // TMEM columns between the two accumulator buffers
+  int b_box_rows;           // rows of the B tile this CTA loads per stage (= ns / cluster)
   int cluster;              // 1 = one CTA per tile (cta_group::1); 2 = CTA pair (cta_group::2): a 256-row tile, each
                             // CTA stages its own 128 rows of A and HALF of the B tile, halving the smem fill per flop
   int stages;
@@ -49,6 +53,7 @@ struct RowsParams {
   uint32_t staging_off;  // byte offsets inside dynamic smem (from the 1 KB aligned base)
   uint32_t param_off;
   int param_cols;        // padded column count of the bias tables (multiple of 32)
+  unsigned long long* dbg;  // optional per-CTA stall counters [8] (tools/umma_probe): see kDbg* below
   RowsEpi e;
 };
 
@@ -119,15 +124,24 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
   }
 }
 
-template <int MODE>
+// stall counters (clock64 cycles), one row of 8 per CTA; compiled in only with -DWIRE_B200_STALL_COUNTERS
+#ifdef WIRE_B200_STALL_COUNTERS
+#define WIRE_CLK() clock64()
+#else
+#define WIRE_CLK() 0ll
+#endif
+enum { kDbgMmaWaitFull = 0, kDbgMmaWaitTmem = 1, kDbgMmaTotal = 2, kDbgEpiWaitAcc = 3, kDbgEpiTotal = 4, kDbgProdWaitEmpty = 5,
+       kDbgProdTotal = 6, kDbgEpiWaitIn = 7 };
+
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_constant__ RowsParams P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8];
   __shared__ __align__(8) uint64_t bar_empty[8];
-  __shared__ __align__(8) uint64_t bar_tmem_full;
-  __shared__ __align__(8) uint64_t bar_tmem_empty;
-  __shared__ __align__(8) uint64_t bar_in[kEpiWarps][2];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ __align__(8) uint64_t bar_in[kEpiWarps];
   __shared__ __align__(16) float fin_xchg[2][kTileRows][kMaxOut];
   __shared__ uint32_t tmem_slot;
 
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_bytes = kTileRows * 128;
-  const uint32_t b_bytes = uint32_t(P.nb / P.cluster) * 128;  // this CTA's share of the B tile
+  const uint32_t b_bytes = uint32_t(P.b_box_rows) * 128;  // this CTA's share of one B slice chunk
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t staging_base = smem_base + P.staging_off;
   float* params = reinterpret_cast<float*>(smem_gen + P.param_off);
@@ -154,7 +168,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   const int n_feat = E.n_cols >> 1;  // complex features M
   // Work decomposition.  The two CTAs of a pair work on the SAME column block and on two consecutive
   // row tiles, and every CTA of the grid runs the same number of iterations (tiles past the end are
-  // computed on zero-filled rows and their stores are clipped by TMA).
+  // computed on zero-filled rows and their stores are clipped by TMA).  A tile is processed as
+  // `slices` jobs; job jb uses TMEM accumulator buffer jb & 1.
   const int C = P.cluster;
   const int crank = int(cluster_ctarank());
   const int n_clusters = gridDim.x / C;
@@ -162,11 +177,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
   const int row_groups = (row_tiles + C - 1) / C;
   const int n_units = row_groups * P.n_blocks;                 // cluster-level work units
   const int n_iters = (n_units + n_clusters - 1) / n_clusters;
-  const bool pair = C == 2;
+  const int n_jobs = n_iters * P.slices;
+  constexpr bool pair = PAIR;
   const bool leader = crank == 0;
-  // MMA pieces along N: one instruction covers at most 256 columns
-  const int n1 = pair ? (P.nb > 256 ? P.nb / 2 : P.nb) : (P.nb > 256 ? 256 : P.nb);
-  const int n2 = P.nb - n1;
+  unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
 
   // ---- shared parameter tables (zero padded so the epilogue needs no column checks) ----
   //  fwd : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8]  (wr[4], wi[4]) if fused
@@ -205,9 +219,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_tmem_full), 1);
-    mbar_init(smem_u32(&bar_tmem_empty), kEpiWarps * C);  // pair: both CTAs' epilogues release the leader
-    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&bar_in[w][0]), 1); mbar_init(smem_u32(&bar_in[w][1]), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tmem_full[b]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[b]), kEpiWarps * C);  // pair: both CTAs' epilogues release the leader
+    }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(smem_u32(&bar_in[w]), 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -229,82 +245,93 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
+      long long t_wait = 0;
+      const long long t_begin = WIRE_CLK();
+      for (int jb = 0; jb < n_jobs; ++jb) {
+        const int it = jb / P.slices, sl = jb % P.slices;
         const int unit = it * n_clusters + my_cluster;
         const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
-        const int n0 = (unit % P.n_blocks) * P.nb;
+        const int brow = (unit % P.n_blocks) * P.nb + sl * P.ns + crank * P.b_box_rows;  // this CTA's B rows
+        // the A tile is read once per slice: keep it in L2 until its last use, then let it go first
+        const uint64_t a_policy = (sl == P.slices - 1 && (unit % P.n_blocks) == P.n_blocks - 1) ? kEvictFirst : kEvictLast;
         for (int kc = 0; kc < kc_total; ++kc) {
+          const long long t0 = WIRE_CLK();
           mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
+          t_wait += WIRE_CLK() - t0;
           const uint32_t full_own = smem_u32(&bar_full[stage]);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const int part = kc < kc0 ? 0 : 1;
           const int kcol = (part ? kc - kc0 : kc) * kChunk;
           if (!pair) {
             mbar_expect_tx(full_own, stage_bytes);
-            tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, kEvictFirst);
-            for (int bx = 0; bx < P.b_boxes; ++bx)
-              tma_load_2d_hint(a_dst + a_bytes + bx * P.b_box_rows * 128, &P.b_map, full_own, kc * kChunk,
-                               n0 + bx * P.b_box_rows, kEvictLast);
+            tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, a_policy);
+            tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kChunk, brow, kEvictLast);
           } else {
             // both CTAs load into their own smem; all bytes complete on the LEADER's full barrier
             const uint32_t full_leader = full_own & kPeerBitMask;
             if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
-            tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, kEvictFirst);
-            // piece i of the MMA covers n_i columns; this CTA stages rows [crank*n_i/2, +n_i/2) of it
-            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kChunk, n0 + crank * (n1 / 2), kEvictLast);
-            if (n2 > 0)
-              tma_load_2d_2cta(a_dst + a_bytes + (n1 / 2) * 128, &P.b_map, full_leader, kc * kChunk,
-                               n0 + n1 + crank * (n2 / 2), kEvictLast);
+            tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, a_policy);
+            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kChunk, brow, kEvictLast);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (dbg) { dbg[kDbgProdWaitEmpty] = t_wait; dbg[kDbgProdTotal] = WIRE_CLK() - t_begin; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && (!pair || leader)) {
-      const uint32_t idesc1 = make_idesc_tf32(pair ? 256 : 128, n1, false, false);
-      const uint32_t idesc2 = make_idesc_tf32(pair ? 256 : 128, n2 > 0 ? n2 : 16, false, false);
-      const uint32_t b2_off = uint32_t(pair ? n1 / 2 : n1) * 128;
+      const uint32_t idesc = make_idesc_tf32(pair ? 256 : 128, P.ns, false, false);
+      // descriptor words are precomputed: only the 14-bit start-address field changes (stage, K-step)
+      const uint32_t desc_hi = uint32_t(make_sdesc_sw128(0, 16, 1024) >> 32);
+      const uint32_t a_lo0 = uint32_t(make_sdesc_sw128(smem_base, 16, 1024));
+      const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
+      const int last0 = ((P.k_cols[0] - (kc0 - 1) * kChunk + 7) >> 3) > 4 ? 4 : ((P.k_cols[0] - (kc0 - 1) * kChunk + 7) >> 3);
+      const int last1 = kc1 > 0 ? (((P.k_cols[1] - (kc1 - 1) * kChunk + 7) >> 3) > 4 ? 4 : ((P.k_cols[1] - (kc1 - 1) * kChunk + 7) >> 3)) : 4;
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t tphase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        if (it > 0) {
-          mbar_wait_backoff(smem_u32(&bar_tmem_empty), tphase);
-          tphase ^= 1;
+      long long w_full = 0, w_tmem = 0;
+      const long long t_begin = WIRE_CLK();
+      for (int jb = 0; jb < n_jobs; ++jb) {
+        const int buf = jb & 1;
+        if (jb >= 2) {
+          const long long t0 = WIRE_CLK();
+          mbar_wait_backoff(smem_u32(&bar_tmem_empty[buf]), ((jb >> 1) & 1) ^ 1);
+          w_tmem += WIRE_CLK() - t0;
         }
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * P.buf_cols;
         for (int kc = 0; kc < kc_total; ++kc) {
+          const long long t1 = WIRE_CLK();
           mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
+          w_full += WIRE_CLK() - t1;
           tc_fence_after();
-          const uint32_t a_base = smem_base + stage * stage_bytes;
-          const uint32_t b_base = a_base + a_bytes;
-          const int part = kc < kc0 ? 0 : 1;
-          const int kcol = (part ? kc - kc0 : kc) * kChunk;
-          int steps = (P.k_cols[part] - kcol + 7) >> 3;
-          steps = steps > 4 ? 4 : steps;
-          for (int ks = 0; ks < steps; ++ks) {
-            const uint32_t acc = (kc | ks) ? 1u : 0u;
-            const uint64_t adesc = make_sdesc_sw128(a_base + ks * 32, 16, 1024);
-            const uint64_t bdesc = make_sdesc_sw128(b_base + ks * 32, 16, 1024);
-            const uint64_t bdesc2 = make_sdesc_sw128(b_base + b2_off + ks * 32, 16, 1024);
-            if (pair) {
-              umma_tf32_2cta(tmem_base, adesc, bdesc, idesc1, acc);
-              if (n2 > 0) umma_tf32_2cta(tmem_base + n1, adesc, bdesc2, idesc2, acc);
-            } else {
-              umma_tf32(tmem_base, adesc, bdesc, idesc1, acc);
-              if (n2 > 0) umma_tf32(tmem_base + n1, adesc, bdesc2, idesc2, acc);
-            }
+          const uint32_t a_lo = a_lo0 + stage * stage_units;
+          const uint32_t b_lo = a_lo + b_units;
+          const int steps = (kc == kc0 - 1) ? last0 : ((kc == kc_total - 1) ? last1 : 4);
+          auto mma = [&](int ks, uint32_t acc) {
+            const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 2 * ks);
+            const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + 2 * ks);
+            if (pair) umma_tf32_2cta(d_tmem, adesc, bdesc, idesc, acc);
+            else umma_tf32(d_tmem, adesc, bdesc, idesc, acc);
+          };
+          if (steps == 4) {
+            mma(0, kc ? 1u : 0u);
+            mma(1, 1u);
+            mma(2, 1u);
+            mma(3, 1u);
+          } else {
+            for (int ks = 0; ks < steps; ++ks) mma(ks, (kc | ks) ? 1u : 0u);
           }
           // release the smem stage (in both CTAs of a pair) once these MMAs have completed
           if (pair) umma_commit_2cta_mcast(smem_u32(&bar_empty[stage]), 3);
           else umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        if (pair) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full), 3);
-        else umma_commit(smem_u32(&bar_tmem_full));
+        if (pair) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full[buf]), 3);
+        else umma_commit(smem_u32(&bar_tmem_full[buf]));
       }
+      if (dbg) { dbg[kDbgMmaWaitFull] = w_full; dbg[kDbgMmaWaitTmem] = w_tmem; dbg[kDbgMmaTotal] = WIRE_CLK() - t_begin; }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -322,54 +349,68 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     const float4* s_wf = reinterpret_cast<const float4*>(params + (k2D ? 2 : 1) * P.param_cols);
     const float4* s_tab = reinterpret_cast<const float4*>(params);
     const float4* s_tab2 = reinterpret_cast<const float4*>(params + (P.param_cols >> 1) * 4);
-    uint32_t tphase = 0;
+    const uint32_t empty_addr0 = pair ? (smem_u32(&bar_tmem_empty[0]) & kPeerBitMask) : smem_u32(&bar_tmem_empty[0]);
+    const uint32_t empty_addr1 = pair ? (smem_u32(&bar_tmem_empty[1]) & kPeerBitMask) : smem_u32(&bar_tmem_empty[1]);
+    const int out_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;  // output columns per column block
+    const int out_ns = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.ns;   // output columns per slice
     uint32_t in_phase = 0;
-    for (int tile_it = 0; tile_it < n_iters; ++tile_it) {
-      const int unit = tile_it * n_clusters + my_cluster;
+    long long e_wait = 0, e_wait_in = 0;
+    const long long e_begin = WIRE_CLK();
+    float cin[3] = {0.f, 0.f, 0.f};
+    float facc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+    for (int jb = 0; jb < n_jobs; ++jb) {
+      const int it = jb / P.slices, sl = jb % P.slices;
+      const int buf = jb & 1;
+      const int unit = it * n_clusters + my_cluster;
       const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
       const int blk = unit % P.n_blocks;
       const int row = row0 + q * 32 + lane;
       const bool row_ok = row < E.n_rows;
-      const int ncol_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;  // output columns per block
-      const int col0 = blk * ncol_blk;
+      const int col0 = blk * out_blk + sl * out_ns;  // first output column of this slice
       int valid = E.n_cols - col0;
-      valid = valid > ncol_blk ? ncol_blk : valid;
-      const int nchunks = (valid + kChunk - 1) / kChunk;
+      valid = valid > out_ns ? out_ns : valid;
+      const int nchunks = valid > 0 ? (valid + kChunk - 1) / kChunk : 0;
       // chunks of this warp: half, half+2, ... ; last one it owns:
       int my_last = -1;
       if (nchunks > half) my_last = half + 2 * ((nchunks - 1 - half) >> 1);
 
-      float cin[3] = {0.f, 0.f, 0.f};
-      if constexpr (kFirst) {
-        if (row_ok) {
-          cin[0] = __ldg(E.coords + size_t(row) * E.in_features);
-          if (E.in_features > 1) cin[1] = __ldg(E.coords + size_t(row) * E.in_features + 1);
-          if (E.in_features > 2) cin[2] = __ldg(E.coords + size_t(row) * E.in_features + 2);
+      if (sl == 0) {
+        if constexpr (kFirst) {
+          cin[0] = cin[1] = cin[2] = 0.f;
+          if (row_ok) {
+            cin[0] = __ldg(E.coords + size_t(row) * E.in_features);
+            if (E.in_features > 1) cin[1] = __ldg(E.coords + size_t(row) * E.in_features + 1);
+            if (E.in_features > 2) cin[2] = __ldg(E.coords + size_t(row) * E.in_features + 2);
+          }
         }
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) facc[o] = 0.f;
       }
-      float facc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
 
-      // prefetch the first saved-activation chunk of this tile while the MMAs are still running
+      // prefetch the first saved-activation chunk of this job while its MMAs are still running
       if constexpr (kBwd) {
         if (half < nchunks && lane == 0) {
-          const uint32_t bar = smem_u32(&bar_in[ew][0]);
+          const uint32_t bar = smem_u32(&bar_in[ew]);
           mbar_expect_tx(bar, P.n_in * 4096);
           for (int s = 0; s < P.n_in; ++s)
             tma_load_2d(inbuf + s * 4096, &P.z_map[s], bar, col0 + half * kChunk, row0 + q * 32);
         }
       }
 
-      mbar_wait(smem_u32(&bar_tmem_full), tphase);
-      tphase ^= 1;
+      {
+        const long long t0 = WIRE_CLK();
+        mbar_wait(smem_u32(&bar_tmem_full[buf]), (jb >> 1) & 1);
+        e_wait += WIRE_CLK() - t0;
+      }
       tc_fence_after();
-      if (my_last < 0) {  // nothing to do in this tile (single-chunk block): just release TMEM
+      if (my_last < 0) {  // nothing to read in this job: just release the accumulator buffer
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (pair) mbar_arrive_cluster(smem_u32(&bar_tmem_empty) & kPeerBitMask); else mbar_arrive(smem_u32(&bar_tmem_empty)); }
+        if (lane == 0) { if (pair) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0); else mbar_arrive(buf ? empty_addr1 : empty_addr0); }
       }
 
       for (int ch = half; ch < nchunks; ch += 2) {
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + ch * kChunk;
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * P.buf_cols + ch * kChunk;
         uint32_t raw[32];
         float v2[32];
         tmem_ld32(taddr, raw);
@@ -383,24 +424,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           tmem_wait_ld();
         }
         if (ch == my_last) {
-          // all TMEM reads of this warp for this tile are done: hand the accumulator back
+          // all TMEM reads of this warp for this job are done: hand the accumulator buffer back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { if (pair) mbar_arrive_cluster(smem_u32(&bar_tmem_empty) & kPeerBitMask); else mbar_arrive(smem_u32(&bar_tmem_empty)); }
+          if (lane == 0) { if (pair) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0); else mbar_arrive(buf ? empty_addr1 : empty_addr0); }
         }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const int c = col0 + ch * kChunk;  // first real output column of this chunk
-        const int cl = c;                  // index into the smem tables
+        const int c = col0 + ch * kChunk;  // first real output column of this chunk (also the smem table index)
 
         float o0[32], o1[32], o2[32];
         if constexpr (MODE == MODE_PLAIN) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o0[i] = v[i];
         } else if constexpr (kFwd) {
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + cl);
-          const float4* b24 = reinterpret_cast<const float4*>(s_bias2 + cl);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
+          const float4* b24 = reinterpret_cast<const float4*>(s_bias2 + c);
 #pragma unroll
           for (int i2 = 0; i2 < 8; ++i2) {
             const float4 bb = b4[i2];
@@ -422,8 +462,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
               float yr, yi;
               gabor_fast(G, zr, zi, wn, yr, yi);
               if (E.fuse_final) {
-                const float4 wr4 = s_wf[((cl >> 1) + i) * 2];
-                const float4 wi4 = s_wf[((cl >> 1) + i) * 2 + 1];
+                const float4 wr4 = s_wf[((c >> 1) + i) * 2];
+                const float4 wi4 = s_wf[((c >> 1) + i) * 2 + 1];
                 facc[0] = fmaf(yr, wr4.x, fmaf(-yi, wi4.x, facc[0]));
                 facc[1] = fmaf(yr, wr4.y, fmaf(-yi, wi4.y, facc[1]));
                 facc[2] = fmaf(yr, wr4.z, fmaf(-yi, wi4.z, facc[2]));
@@ -437,15 +477,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
             }
           }
         } else if constexpr (kBwd) {
-          // wait for this chunk's z (w) tile, then immediately prefetch the next one into the other buffer
+          // wait for this chunk's z (w) tile, then immediately prefetch the next one into the same buffer
           float z[32], w[32];
-          mbar_wait(smem_u32(&bar_in[ew][0]), in_phase);
+          {
+            const long long t0 = WIRE_CLK();
+            mbar_wait(smem_u32(&bar_in[ew]), in_phase);
+            e_wait_in += WIRE_CLK() - t0;
+          }
           in_phase ^= 1;
           unstage_row(inbuf, lane, z);
           if constexpr (k2D) unstage_row(inbuf + 4096, lane, w);
           __syncwarp();
           if (ch + 2 < nchunks && lane == 0) {
-            const uint32_t bar = smem_u32(&bar_in[ew][0]);
+            const uint32_t bar = smem_u32(&bar_in[ew]);
             mbar_expect_tx(bar, P.n_in * 4096);
             for (int s = 0; s < P.n_in; ++s)
               tma_load_2d(inbuf + s * 4096, &P.z_map[s], bar, c + 2 * kChunk, row0 + q * 32);
@@ -473,11 +517,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           float gz[16], gw[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float4 t = s_tab[(cl >> 1) + i];
+            const float4 t = s_tab[(c >> 1) + i];
             const float z0 = fmaf(cin[0], t.x, fmaf(cin[1], t.y, fmaf(cin[2], t.z, t.w)));
             float w0v = 0.f;
             if constexpr (k2D) {
-              const float4 t2 = s_tab2[(cl >> 1) + i];
+              const float4 t2 = s_tab2[(c >> 1) + i];
               w0v = fmaf(cin[0], t2.x, fmaf(cin[1], t2.y, fmaf(cin[2], t2.z, t2.w)));
             }
             float yr, yi;
@@ -522,9 +566,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       }
 
       if constexpr (kFwd) {
-        if (E.fuse_final) {
-          // the two warps of a sub-partition hold partial sums over even / odd chunks
-          const int slot = tile_it & 1;
+        if (E.fuse_final && sl == P.slices - 1) {
+          // the two warps of a sub-partition hold partial sums over even / odd chunks (of every slice)
+          const int slot = it & 1;
           if (half == 1) {
             *reinterpret_cast<float4*>(&fin_xchg[slot][q * 32 + lane][0]) = make_float4(facc[0], facc[1], facc[2], facc[3]);
           }
@@ -540,6 +584,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       }
     }
     if (lane == 0) tma_store_wait_all<0>();
+    if (dbg && ew == 0 && lane == 0) { dbg[kDbgEpiWaitAcc] = e_wait; dbg[kDbgEpiTotal] = WIRE_CLK() - e_begin; dbg[kDbgEpiWaitIn] = e_wait_in; }
   }
 
   // ===================== teardown =====================

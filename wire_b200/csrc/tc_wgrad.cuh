@@ -11,7 +11,8 @@
 //     Re g_W[j,k] = G[2k,2j] + G[2k+1,2j+1]       Im g_W[j,k] = G[2k,2j+1] - G[2k+1,2j]
 // and accumulates split-K partials with fp32 red.global.add into the (pre-zeroed) flat gradient.
 //
-// Work item = (K split, g matrix, column block, 128-row M tile); one item per CTA.
+// Work item = (K split, g matrix, column block, M tile of 128 x-columns per CTA); one item per CTA, or per CTA
+// pair (cta_group::2: 256 x-columns, each CTA stages its own x tile and HALF of the g tile).
 #pragma once
 #include "sm100.cuh"
 
@@ -27,7 +28,8 @@ struct WgradParams {
   int k_in;      // complex input features K (x has 2K+1 meaningful columns)
   int g_cols;    // 2M
   int n_g;       // 1 = wire, 2 = wire2d (linear + scale_orth)
-  int m_tiles;   // ceil((2K+1)/128)
+  int cluster;   // 1 = cta_group::1 (128 x-columns per tile); 2 = CTA pair (256 x-columns per tile, g tile split)
+  int m_tiles;   // ceil((2K+1) / (128 * cluster))
   int n_blocks;  // column blocks per g matrix
   int nb;        // columns per block (multiple of 32, <= 448)
   int splits;
@@ -36,6 +38,7 @@ struct WgradParams {
   float* gB[2];  // [M][2]
 };
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -44,16 +47,22 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
   __shared__ __align__(8) uint64_t bar_tmem_full;
   __shared__ uint32_t tmem_slot;
 
+  constexpr int C = PAIR ? 2 : 1;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = PAIR ? int(cluster_ctarank()) : 0;
+  const bool leader = crank == 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t blk_bytes = kWgradKC * 128;  // one 32-column block of one stage
   const uint32_t a_bytes = 4 * blk_bytes;
-  const uint32_t b_bytes = uint32_t(P.nb / 32) * blk_bytes;
+  // MMA pieces along N (g columns): n1 + n2 = nb ; a pair splits each piece in halves (multiples of 32 columns)
+  int nvalid = P.g_cols;  // per column block below
+  const int nbb_cta = P.nb / 32 / C;          // g blocks this CTA stages per chunk
+  const uint32_t b_bytes = uint32_t(nbb_cta) * blk_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
 
-  // decode the work item
-  int item = blockIdx.x;
+  // decode the work item (all CTAs of a pair share it)
+  int item = blockIdx.x / C;
   const int mt = item % P.m_tiles;  item /= P.m_tiles;
   const int nblk = item % P.n_blocks;  item /= P.n_blocks;
   const int gi = item % P.n_g;  item /= P.n_g;
@@ -64,6 +73,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
   int ch_end = ch_begin + cps;
   ch_end = ch_end > total_chunks ? total_chunks : ch_end;
   const int n_chunks = ch_end > ch_begin ? ch_end - ch_begin : 0;
+  nvalid = P.g_cols - nblk * P.nb;
+  nvalid = nvalid > P.nb ? P.nb : nvalid;
+  // single CTA: pieces rounded to the UMMA N granularity; pair: fixed 64-column-aligned pieces of the padded block
+  const int np = PAIR ? P.nb : ((nvalid + 15) & ~15);
+  const int n1 = np > 256 ? 256 : np;
+  const int n2 = np - n1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -74,11 +89,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_slot), 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_2cta(smem_u32(&tmem_slot), 512); tmem_relinquish_2cta(); }
+    else { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -87,61 +103,77 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const int nbb = P.nb / 32;
+        const int x_col0 = (mt * C + crank) * 128;
         for (int ch = ch_begin; ch < ch_end; ++ch) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          mbar_expect_tx(full, stage_bytes);
+          const uint32_t full_own = smem_u32(&bar_full[stage]);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const int r0 = ch * kWgradKC;
-          for (int b = 0; b < 4; ++b)
-            tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full, mt * 128 + b * 32, r0);
-          for (int b = 0; b < nbb; ++b)
-            tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full, nblk * P.nb + b * 32, r0);
+          if (!PAIR) {
+            mbar_expect_tx(full_own, stage_bytes);
+            for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * 32, r0);
+            for (int b = 0; b < nbb_cta; ++b)
+              tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_own, nblk * P.nb + b * 32, r0);
+          } else {
+            const uint32_t full_leader = full_own & kPeerBitMask;
+            if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
+            for (int b = 0; b < 4; ++b)
+              tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * 32, r0, kEvictNormal);
+            // piece 1: columns [crank*n1/2, +n1/2) ; piece 2: columns [n1 + crank*n2/2, +n2/2)
+            const int p1 = n1 / 64, p2 = n2 / 64;
+            for (int b = 0; b < p1; ++b)
+              tma_load_2d_2cta(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_leader,
+                               nblk * P.nb + crank * (n1 / 2) + b * 32, r0, kEvictNormal);
+            for (int b = 0; b < p2; ++b)
+              tma_load_2d_2cta(a_dst + a_bytes + (p1 + b) * blk_bytes, &P.g_map[gi], full_leader,
+                               nblk * P.nb + n1 + crank * (n2 / 2) + b * 32, r0, kEvictNormal);
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        // valid accumulator columns of this block, rounded up to the UMMA N granularity
-        int nvalid = P.g_cols - nblk * P.nb;
-        nvalid = nvalid > P.nb ? P.nb : nvalid;
-        const int np = (nvalid + 15) & ~15;
-        const int n1 = np > 256 ? 256 : np;
-        const int n2 = np - n1;
-        const uint32_t idesc1 = make_idesc_tf32(128, n1, true, true);
-        const uint32_t idesc2 = make_idesc_tf32(128, n2 > 0 ? n2 : 16, true, true);
+      if (lane == 0 && (!PAIR || leader)) {
+        const uint32_t idesc1 = make_idesc_tf32(PAIR ? 256 : 128, n1, true, true);
+        const uint32_t idesc2 = make_idesc_tf32(PAIR ? 256 : 128, n2 > 0 ? n2 : 16, true, true);
+        // descriptor words precomputed; only the start-address field moves (stage, K-step of 8 rows = 1024 B)
+        const uint32_t desc_hi = uint32_t(make_sdesc(0, blk_bytes, 512, kLayoutSW128Base32) >> 32);
+        const uint32_t a_lo0 = uint32_t(make_sdesc(smem_base, blk_bytes, 512, kLayoutSW128Base32));
+        const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
+        const uint32_t b2_units = (uint32_t(PAIR ? n1 / 64 : 8) * blk_bytes) >> 4;
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_chunks; ++i) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
-          const uint32_t a_base = smem_base + stage * stage_bytes;
-          const uint32_t b_base = a_base + a_bytes;
+          const uint32_t a_lo = a_lo0 + stage * stage_units;
+          const uint32_t b_lo = a_lo + b_units;
 #pragma unroll
           for (int ks = 0; ks < kWgradKC / 8; ++ks) {
-            const uint32_t acc = (i | ks) ? 1u : 0u;
-            const uint64_t adesc = make_sdesc(a_base + ks * 1024, blk_bytes, 512, kLayoutSW128Base32);
-            const uint64_t bdesc = make_sdesc(b_base + ks * 1024, blk_bytes, 512, kLayoutSW128Base32);
-            umma_tf32(tmem_base, adesc, bdesc, idesc1, acc);
-            if (n2 > 0) {
-              const uint64_t bdesc2 = make_sdesc(b_base + 8 * blk_bytes + ks * 1024, blk_bytes, 512, kLayoutSW128Base32);
-              umma_tf32(tmem_base + n1, adesc, bdesc2, idesc2, acc);
+            const uint32_t acc = (ks > 0) ? 1u : (i ? 1u : 0u);
+            const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 64 * ks);
+            const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + 64 * ks);
+            const uint64_t bdesc2 = (uint64_t(desc_hi) << 32) | (b_lo + b2_units + 64 * ks);
+            if (PAIR) {
+              umma_tf32_2cta(tmem_base, adesc, bdesc, idesc1, acc);
+              if (n2 > 0) umma_tf32_2cta(tmem_base + n1, adesc, bdesc2, idesc2, acc);
+            } else {
+              umma_tf32(tmem_base, adesc, bdesc, idesc1, acc);
+              if (n2 > 0) umma_tf32(tmem_base + n1, adesc, bdesc2, idesc2, acc);
             }
           }
-          umma_commit(smem_u32(&bar_empty[stage]));
+          if (PAIR) umma_commit_2cta_mcast(smem_u32(&bar_empty[stage]), 3);
+          else umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&bar_tmem_full));
+        if (PAIR) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full), 3);
+        else umma_commit(smem_u32(&bar_tmem_full));
       }
     } else {
       const int q = warp & 3;
-      const int c = mt * 128 + q * 32 + lane;  // row of G = real column of x
+      const int c = (mt * C + crank) * 128 + q * 32 + lane;  // row of G = real column of x
       const int two_k = 2 * P.k_in;
       float* gW = P.gW[gi];
       float* gB = P.gB[gi];
-      int nvalid = P.g_cols - nblk * P.nb;
-      nvalid = nvalid > P.nb ? P.nb : nvalid;
       const int nchunks = (nvalid + 31) / 32;
       mbar_wait(smem_u32(&bar_tmem_full), 0);
       tc_fence_after();
@@ -172,9 +204,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
