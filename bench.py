@@ -160,7 +160,6 @@ def load_peaks():
 def run_ours(args):
     import torch.distributed as dist
     import wire_b200
-    from wire_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,6 +177,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = wire_b200.get_INR(**CFG, precision=args.precision).to(dev)
     if world > 1:
+        from wire_b200 import parallel
         parallel.broadcast_parameters(model)
     # weak scaling: every rank fits its own 512x512 tile of a (512*world) x 512 synthetic image
     _, noisy = synthetic_image(size, size, seed=rank)
@@ -185,48 +185,48 @@ def run_ours(args):
     target_h = torch.from_numpy(noisy.reshape(1, n, 3)).pin_memory()
     coords = coords_h.to(dev)
     target = target_h.to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=LR)
-    params = [p for p in model.parameters() if p.requires_grad]
-
-    def step(c, t):
-        out = model(c)
-        loss = ((out - t) ** 2).mean()
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if world > 1:
-            parallel.allreduce_gradients(params, world)
-        opt.step()
-        return loss
+    # the public training API: one call = forward + MSE + backward (+ gradient all-reduce) + Adam
+    trainer = wire_b200.Trainer(model, lr=LR, graph=not args.no_graph)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(coords, target)
-    barrier()
+    def counters():
+        tot = 0
+        for k in range(lib.wire_b200_prof_kinds()):
+            cnt = ctypes.c_uint64(0)
+            lib.wire_b200_prof_get(k, ctypes.byref(cnt), None)
+            tot += cnt.value
+        return tot
 
-    # ---------------- timed region: device-resident inputs, CUDA events, max over ranks ----------------
-    lib.wire_b200_prof_enable(0)
-    lib.wire_b200_prof_reset()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        trainer.step(coords, target)
+    barrier()
+    # kernels launched by one step (a graph replay re-launches exactly what one eager step launches)
+    lib.wire_b200_prof_enable(0)
+    lib.wire_b200_prof_reset()
+    saved = trainer.use_graph
+    trainer.use_graph = False
+    trainer.step(coords, target)
+    trainer.use_graph = saved
+    barrier()
+    launches_per_step = counters()
+
+    # ---------------- timed region: device-resident inputs, CUDA events, max over ranks ----------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(coords, target)
+        trainer.step(coords, target)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = 0
-    for k in range(lib.wire_b200_prof_kinds()):
-        cnt = ctypes.c_uint64(0)
-        lib.wire_b200_prof_get(k, ctypes.byref(cnt), None)
-        launches += cnt.value
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -234,14 +234,21 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3)
 
-    # ---------------- e2e: host inputs, H2D every step, D2H loss read every step ----------------
+    # ---------------- e2e: pinned host inputs, H2D every step, D2H loss read every step ----------------
+    loss_pin = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    evs = [torch.cuda.Event() for _ in range(args.steps)]
+    losses = []
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        c = coords_h.to(dev, non_blocking=True)
-        t = target_h.to(dev, non_blocking=True)
-        loss = step(c, t)
-        loss_host = float(loss)  # device->host read of the step's result
+    for i in range(args.steps):
+        loss = trainer.step(coords_h, target_h)            # host -> device copies of this step's inputs inside
+        loss_pin[i:i + 1].copy_(loss.reshape(1), non_blocking=True)   # device -> host read of this step's loss
+        evs[i].record()
+        if i > 0:                                            # consume the previous step's loss on the host
+            evs[i - 1].synchronize()
+            losses.append(float(loss_pin[i - 1]))
+    evs[-1].synchronize()
+    losses.append(float(loss_pin[-1]))
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if world > 1:
@@ -249,17 +256,38 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt)
     e2e = {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": coords_h.numel() * 4 + target_h.numel() * 4,
-           "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3, "final_loss": loss_host}
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3, "final_loss": losses[-1],
+           "note": "trainer.step(host pinned coords, host pinned target); loss copied to pinned memory every step and read "
+                   "on the host one step later"}
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + e2e region"
 
-    # ---------------- per-kernel device time (CUDA events on the launching stream) ----------------
+    # ---------------- the nn.Module + torch.optim.Adam route (what the reference drivers call) ----------------
+    module_ms = None
+    if world == 1:
+        opt = torch.optim.Adam(model.parameters(), lr=LR)
+        for _ in range(3):
+            loss = ((model(coords) - target) ** 2).mean(); opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            loss = ((model(coords) - target) ** 2).mean(); opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
+        e1.record()
+        barrier()
+        module_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---------------- per-kernel device time (CUDA events on the launching stream, eager replay of the step) ----
     roofline, kernels = None, {}
     if rank == 0:
         lib.wire_b200_prof_reset()
         lib.wire_b200_prof_enable(1)
+        trainer.use_graph = False
         torch.cuda.synchronize()
         for _ in range(args.steps):
-            step(coords, target)
+            trainer.step(coords, target)
         torch.cuda.synchronize()
+        trainer.use_graph = saved
         total_ms = 0.0
         for k in range(lib.wire_b200_prof_kinds()):
             cnt, ms = ctypes.c_uint64(0), ctypes.c_double(0.0)
@@ -273,34 +301,47 @@ def run_ours(args):
         peaks, peaks_src = load_peaks()
         top = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
         gemm_flop = 8.0 * M * M * n  # one complex M x M GEMM over n coordinates (fwd, dgrad and wgrad alike)
-        alg_bytes = {"tc_rows_gabor_fwd": 3 * 8 * M * n, "tc_rows_dgrad_gabor_bwd": 3 * 8 * M * n, "tc_wgrad": 2 * 8 * M * n,
-                     "tc_rows_dgrad_first_bwd": 8 * M * n + 4 * M * n}
+        unit_b = 8.0 * M * n         # one complex activation tensor [n, M] in HBM
+        alg_bytes = {"tc_rows_gabor_fwd": 3 * unit_b, "tc_rows_dgrad_gabor_bwd": 3 * unit_b, "tc_wgrad": 2 * unit_b,
+                     "tc_rows_dgrad_first_bwd": 1.5 * unit_b, "top_bwd": 2 * unit_b, "first_fwd": unit_b,
+                     "first_wgrad": 0.5 * unit_b}
+        for k, v in kernels.items():
+            if k in alg_bytes:
+                v["hbm_gbs"] = alg_bytes[k] / (v["ms_avg"] * 1e-3) / 1e9
+                v["hbm_frac"] = v["hbm_gbs"] / peaks["hbm_gbs"]
+            if k.startswith("tc_"):
+                v["tflops"] = gemm_flop / (v["ms_avg"] * 1e-3) / 1e12
         if top is not None:
-            tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # TF32 runs at half the BF16 tensor rate
-            ach = gemm_flop / (kernels[top]["ms_avg"] * 1e-3) / 1e12 if top.startswith("tc_") else None
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": (ach / tf32_peak) if ach else None, "traffic": None,
-                        "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained/2 (TF32 = half the BF16 "
-                                       f"tensor rate; kernel timed inside a long step)",
-                        "frac_of_nominal_tf32_1100": (ach / 1100.0) if ach else None,
-                        "algorithmic_flop_per_launch": gemm_flop,
-                        "hbm_achieved_gbs": (alg_bytes.get(top, 0) / (kernels[top]["ms_avg"] * 1e-3) / 1e9) if top in alg_bytes else None,
-                        "hbm_peak_gbs": peaks["hbm_gbs"], "share_of_step": kernels[top]["ms_total"] / total_ms if total_ms else None}
+            # Each hidden-layer kernel must move 3 activation-sized tensors through HBM for 8 M^2 flop/coord
+            # (M/3 flop/B = 71 at M=212, below the TF32 ridge of ~170): the binding roofline is HBM.
+            ach = kernels[top].get("hbm_gbs")
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
+                        "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs",
+                        "algorithmic_bytes_per_launch": alg_bytes.get(top),
+                        "tensor_achieved_tflops": kernels[top].get("tflops"),
+                        "tensor_peak_tflops": peaks["bf16_tflops_sustained"] / 2.0,
+                        "tensor_frac": (kernels[top]["tflops"] / (peaks["bf16_tflops_sustained"] / 2.0)) if "tflops" in kernels[top] else None,
+                        "tensor_peak_source": f"{peaks_src} bf16_tflops_sustained/2 (TF32 issues at half the BF16 rate)",
+                        "share_of_step": kernels[top]["ms_total"] / total_ms if total_ms else None}
         step_flop = flop_per_coord(M, CFG["hidden_layers"], CFG["in_features"], CFG["out_features"]) * n
 
     if rank == 0:
         cpu = cpu_reference_run(256, 3, 1) if (world == 1 and not args.no_cpu_baseline) else None
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
                 "config": {"workload": f"WIRE image fit {size}x{size} RGB ({n} coords/GPU full-batch fwd+bwd+Adam), "
                                        f"wire_image_denoise.py defaults: hidden 300 -> M={M}, H=2, omega0=7, sigma0=6",
                            "width": M, "hidden_layers": CFG["hidden_layers"], "coords_per_gpu": n,
+                           "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if trainer.use_graph and world == 1 else ""),
                            "parallelism": f"coord-sharded dp{world}" if world > 1 else "single GPU",
-                           "l2": "per-step activation traffic (>5 GB) far exceeds the 126 MB L2; no explicit flush"},
-                "algorithmic_tflops": step_flop / (ms_step * 1e-3) / 1e12 * 1.0,
+                           "l2": "per-step activation traffic (>7 GB) far exceeds the 126 MB L2; no explicit flush"},
+                "algorithmic_tflops": step_flop / (ms_step * 1e-3) / 1e12,
                 "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels}
+                "module_api_ms_per_step": module_ms,
+                "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roofline, "kernels": kernels}
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["coords_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}
@@ -312,12 +353,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -137,6 +137,12 @@ int wire_final_linear_backward(const wire_net_desc* d, const float* weight, cons
 int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                    float grad_scale, void* stream);
+/* Same update with the step counter (*step_dev, 0-based count of completed steps, incremented by the kernel) and the
+ * learning rate (*lr_dev) on the device, so a captured CUDA graph of a whole training step can be replayed.
+ * scratch_dev: one zero-initialised uint32 used by the kernel to detect its last block. */
+int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
+                       const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                       int64_t* step_dev, float grad_scale, uint32_t* scratch_dev, void* stream);
 /* grad_out[i] = 2*(pred[i]-target[i])/count ; *loss (device scalar, accumulated) += mean sq err */
 int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out,
                        float* loss, void* stream);

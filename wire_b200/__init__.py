@@ -10,6 +10,7 @@ from ._lib import WireB200Error
 from .modules import models, wire, wire2d
 from .modules.models import get_INR
 from .patch import patch_reference
+from .train import Trainer
 
-__all__ = ["models", "wire", "wire2d", "get_INR", "patch_reference", "WireB200Error", "_lib"]
+__all__ = ["models", "wire", "wire2d", "get_INR", "patch_reference", "Trainer", "WireB200Error", "_lib"]
 __version__ = "0.1.0"

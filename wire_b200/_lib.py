@@ -69,6 +69,8 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p]),
     "wire_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                  c_float, c_float, c_int64, c_float, c_void_p]),
+    "wire_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
+                                     c_float, c_void_p, c_float, c_void_p, c_void_p]),
     "wire_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -859,6 +859,21 @@ int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   return 0;
 }
 
+int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, const float* lr_dev,
+                       float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev, float grad_scale,
+                       uint32_t* scratch_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count <= 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !scratch_dev) return fail("null argument");
+  int64_t g64 = (count + 255) / 256;
+  const int grid = int(g64 > 592 ? 592 : g64);
+  ProfScope prof(K_ADAM, st);
+  adam_dev_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
+                                        reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out, float* loss, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (count <= 0) return 0;

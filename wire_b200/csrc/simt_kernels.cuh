@@ -304,6 +304,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Same update with the step counter and the learning rate living on the device, so a captured CUDA graph can be
+// replayed: *step_ptr is read (1-based step = *step_ptr + 1) by every thread and incremented by one thread at the end.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                int64_t count, const float* __restrict__ lr_ptr, float b1, float b2, float eps, float wd,
+                                long long* __restrict__ step_ptr, float grad_scale, unsigned int* __restrict__ done_counter) {
+  const long long step = *step_ptr + 1;
+  const float lr = *lr_ptr;
+  const float bc1 = 1.0f - powf(b1, float(step));
+  const float bc2_sqrt = sqrtf(1.0f - powf(b2, float(step)));
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+  // the last block to finish bumps the step counter (every block has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) { *step_ptr = step; *done_counter = 0u; }
+  }
+}
+
 // grad = 2 (pred - target) / count ; loss += sum (pred-target)^2 / count
 __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
                                 float* __restrict__ grad, float* __restrict__ loss) {

@@ -1,0 +1,181 @@
+"""Fused training step for a WIRE INR (fused loss + flat Adam + CUDA graph).
+
+Replaces the body of the reference's training loops
+
+    pixelvalues = model(b_coords)
+    loss = ((pixelvalues - gt[:, b_indices, :])**2).mean()
+    optim.zero_grad(); loss.backward(); optim.step()          # wire_image_denoise.py:148-157
+
+with one call, ``loss = trainer.step(coords, target)``:  C-ABI forward → MSE gradient kernel → C-ABI backward
+into ONE flat fp32 gradient buffer → (one NCCL all-reduce of that buffer when data-parallel) → one fused Adam
+kernel over the flat (re,im) parameter buffer — Adam on ``view_as_real`` parameters, exactly what
+``torch.optim.Adam`` does for complex parameters.  The model's ``nn.Parameter``s are re-pointed at views of the
+flat buffer, so ``state_dict()``, ``model(coords)`` and the reference drivers keep seeing the trained weights.
+With ``graph=True`` (default) the whole step is captured once and replayed as a CUDA graph; the step counter and
+the learning rate live on the device (``set_lr`` implements the drivers' ``LambdaLR`` schedules).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import functional as F
+from ._lib import NetGrads, WireB200Error, check
+
+
+class Trainer:
+    def __init__(self, model, lr: float = 5e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 graph: bool = True, process_group=None):
+        self.model = model
+        self.lib = _lib.load()
+        layers = list(model.net)
+        if model.hidden_layers < 1 or len(layers) != model.hidden_layers + 2:
+            raise WireB200Error("Trainer needs the standard WIRE stack (first layer, >=1 hidden layers, final Linear)")
+        for layer in layers[:-1]:
+            layer._check_trainable()
+        self.desc = F.make_desc(model.two_d, model.in_features, model.width, model.hidden_layers, model.out_features,
+                                model.precision)
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = graph
+        dev = layers[0].linear.weight.device
+        if dev.type != "cuda":
+            raise WireB200Error("Trainer needs the model on a CUDA device: wire_b200 has no CPU path")
+        self.device = dev
+
+        # ---- flat parameter / gradient / Adam buffers (16-byte aligned slots) ----
+        two_d = bool(self.desc.two_d)
+        self._train_params: List[torch.nn.Parameter] = []
+        for layer in layers[:-1]:
+            self._train_params += [layer.linear.weight, layer.linear.bias]
+            if two_d:
+                self._train_params += [layer.scale_orth.weight, layer.scale_orth.bias]
+        self._train_params += [layers[-1].weight, layers[-1].bias]
+        if any(p is None for p in self._train_params):
+            raise WireB200Error("Trainer requires bias=True layers")
+        sizes = [p.numel() * (2 if p.is_complex() else 1) for p in self._train_params]
+        self._starts, off = [], 0
+        for s in sizes:
+            self._starts.append(off)
+            off += (s + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self._grad_views = []
+        with torch.no_grad():
+            for p, o, s in zip(self._train_params, self._starts, sizes):
+                view = self.flat[o:o + s]
+                src = torch.view_as_real(p.data).reshape(-1) if p.is_complex() else p.data.reshape(-1)
+                view.copy_(src)
+                p.data = torch.view_as_complex(view.view(*p.shape, 2)) if p.is_complex() else view.view(p.shape)
+                self._grad_views.append(self.flat_grad[o:o + s])
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._n = None
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+
+    # ------------------------------------------------------------------------------------------
+    def set_lr(self, lr: float) -> None:
+        self.lr_dev.fill_(float(lr))
+
+    @property
+    def steps_done(self) -> int:
+        return int(self.step_dev.item())
+
+    def _prepare(self, n: int) -> None:
+        dev, d = self.device, self.desc
+        self._n = n
+        self._graph = None
+        self.coords_buf = torch.empty((n, d.in_features), dtype=torch.float32, device=dev)
+        self.target_buf = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        self.out_buf = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        self.gout_buf = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        nbytes = self.lib.wire_net_workspace_bytes(ctypes.byref(d), n, 1)
+        if nbytes == 0:
+            check(1, "wire_net_workspace_bytes")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(self.lib.wire_net_workspace_init(ctypes.byref(d), n, 1, self.ws.data_ptr(), nbytes, F._stream()),
+              "wire_net_workspace_init")
+        tensors = self.model.flat_params()
+        self._P = F._fill_net_params(d, F._check_net_tensors(d, tensors))
+        self._G = NetGrads()
+        two_d = bool(d.two_d)
+        vi = 0
+        for l in range(d.hidden_layers + 1):
+            lg = self._G.layer[l]
+            lg.weight, lg.bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+            vi += 2
+            if two_d:
+                lg.weight2, lg.bias2 = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+                vi += 2
+        self._G.final_weight, self._G.final_bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+
+    def _fwd_bwd(self) -> None:
+        d, n, st = self.desc, self._n, F._stream()
+        lib = self.lib
+        self.loss_dev.zero_()
+        check(lib.wire_net_forward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.out_buf.data_ptr(),
+                                   self.ws.data_ptr(), self.ws.numel(), 1, st), "wire_net_forward")
+        check(lib.wire_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
+                                     self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_mse_loss_grad")
+        check(lib.wire_net_backward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.gout_buf.data_ptr(),
+                                    self.ws.data_ptr(), self.ws.numel(), ctypes.byref(self._G), None, st), "wire_net_backward")
+
+    def _adam(self) -> None:
+        b1, b2 = self.betas
+        check(self.lib.wire_adam_step_dev(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr_dev.data_ptr(), b1, b2, self.eps,
+                                          self.weight_decay, self.step_dev.data_ptr(), 1.0 / self.world, self.scratch.data_ptr(),
+                                          F._stream()), "wire_adam_step_dev")
+
+    def _whole_step(self) -> None:
+        self._fwd_bwd()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        self._adam()
+
+    def step(self, coords: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """One training iteration on (coords [..., in], target [..., out]); host or device tensors.
+        Returns the mean-squared error of this rank's batch as a device scalar (no host sync)."""
+        d = self.desc
+        n = coords.numel() // d.in_features
+        if coords.dtype != torch.float32 or target.dtype != torch.float32:
+            raise WireB200Error("coords and target must be float32")
+        if target.numel() != n * d.out_features:
+            raise WireB200Error("target does not match coords")
+        with torch.cuda.device(self.device):
+            if n != self._n:
+                self._prepare(n)
+            self.coords_buf.copy_(coords.reshape(n, d.in_features), non_blocking=True)
+            self.target_buf.copy_(target.reshape(n, d.out_features), non_blocking=True)
+            if not self.use_graph or self.world > 1:
+                self._whole_step()
+            else:
+                if self._graph is None:
+                    # one eager step first (lazy one-time setup inside the C ABI must not happen during capture),
+                    # then capture; both count as training steps
+                    self._whole_step()
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream(self.device)
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(g, stream=side):
+                            self._whole_step()
+                    torch.cuda.current_stream().wait_stream(side)
+                    self._graph = g
+                else:
+                    self._graph.replay()
+        return self.loss_dev[0]
+
+    @torch.no_grad()
+    def predict(self, coords: torch.Tensor) -> torch.Tensor:
+        return self.model(coords)
