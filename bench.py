@@ -279,15 +279,16 @@ def run_ours(args):
 
     # ---------------- per-kernel device time (CUDA events on the launching stream, eager replay of the step) ----
     roofline, kernels = None, {}
+    # every rank replays the steps (the data-parallel step contains a collective); rank 0 reports its own kernels
+    lib.wire_b200_prof_reset()
+    lib.wire_b200_prof_enable(1 if rank == 0 else 0)
+    trainer.use_graph = False
+    barrier()
+    for _ in range(args.steps):
+        trainer.step(coords, target)
+    barrier()
+    trainer.use_graph = saved
     if rank == 0:
-        lib.wire_b200_prof_reset()
-        lib.wire_b200_prof_enable(1)
-        trainer.use_graph = False
-        torch.cuda.synchronize()
-        for _ in range(args.steps):
-            trainer.step(coords, target)
-        torch.cuda.synchronize()
-        trainer.use_graph = saved
         total_ms = 0.0
         for k in range(lib.wire_b200_prof_kinds()):
             cnt, ms = ctypes.c_uint64(0), ctypes.c_double(0.0)
@@ -337,8 +338,8 @@ def run_ours(args):
                            "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if trainer.use_graph and world == 1 else ""),
                            "parallelism": f"coord-sharded dp{world}" if world > 1 else "single GPU",
                            "l2": "per-step activation traffic (>7 GB) far exceeds the 126 MB L2; no explicit flush"},
-                "algorithmic_tflops": step_flop / (ms_step * 1e-3) / 1e12,
-                "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,
+                "algorithmic_tflops": world * step_flop / (ms_step * 1e-3) / 1e12,
+                "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,  # per GPU
                 "module_api_ms_per_step": module_ms,
                 "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roofline, "kernels": kernels}

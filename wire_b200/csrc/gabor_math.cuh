@@ -33,12 +33,49 @@ __device__ __forceinline__ void exp_cis(float mag_arg, float phase, float& yr, f
   }
 }
 
+// ---- branch-free FTZ fast path (TF32 mode): phase reduced in turns (u - rint(u) is exact), magnitude via ex2 ----
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct GaborConst {
+  float omega, s2;
+  float c_t;     // -s2 * log2(e)
+  float c_zi;    // -omega * log2(e)
+  float c_turn;  // omega / (2 pi)
+};
+__device__ __forceinline__ GaborConst make_gabor_const(float omega, float scale) {
+  GaborConst g;
+  g.omega = omega;
+  g.s2 = scale * scale;
+  g.c_t = -g.s2 * 1.4426950408889634f;
+  g.c_zi = -omega * 1.4426950408889634f;
+  g.c_turn = omega * 0.15915494309189535f;
+  return g;
+}
+// y = exp(j w z - s2 (|z|^2 + wnorm)), wnorm = |w|^2 for wire2d
+__device__ __forceinline__ void gabor_fast(const GaborConst& g, float zr, float zi, float wnorm, float& yr, float& yi) {
+  const float t = fmaf(zi, zi, fmaf(zr, zr, wnorm));
+  const float m = ex2_ftz(fmaf(g.c_t, t, g.c_zi * zi));
+  float u = zr * g.c_turn;
+  u -= rintf(u);
+  const float r = u * 6.283185307179586f;
+  yr = m * cos_ftz(r);
+  yi = m * sin_ftz(r);
+}
+
 // hidden layer: complex z; `extra` = scale^2*|w|^2 for wire2d, 0 for wire
 template <bool FAST>
 __device__ __forceinline__ void gabor_fwd(float zr, float zi, float omega, float s2, float extra,
                                           float& yr, float& yi) {
   const float mag_arg = -omega * zi - s2 * (zr * zr + zi * zi) - extra;
   exp_cis<FAST>(mag_arg, omega * zr, yr, yi);
+}
+// same with precomputed constants; FAST -> branch-free MUFU path, else libdevice
+template <bool FAST>
+__device__ __forceinline__ void gabor_fwd_c(const GaborConst& g, float zr, float zi, float wnorm, float& yr, float& yi) {
+  if constexpr (FAST) gabor_fast(g, zr, zi, wnorm, yr, yi);
+  else gabor_fwd<false>(zr, zi, g.omega, g.s2, g.s2 * wnorm, yr, yi);
 }
 
 // g_z for a hidden layer from y, z and the upstream g_y; returns Re(p) for the wire2d g_w term

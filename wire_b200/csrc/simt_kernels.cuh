@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) first_fwd2_kernel(const float* __restrict
   rows = rows > rows_per_block ? rows_per_block : rows;
   for (int i = threadIdx.x; i < rows * in_f; i += blockDim.x) sc[i] = coords[size_t(row0) * in_f + i];
   __syncthreads();
-  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  const GaborConst G = make_gabor_const(__ldg(omega_p), __ldg(scale_p));
   for (int jp = threadIdx.x; 2 * jp < M; jp += blockDim.x) {
     const int j0 = 2 * jp, j1 = (2 * jp + 1 < M) ? 2 * jp + 1 : j0;
     float w0[kSimtMaxIn], w1[kSimtMaxIn], v0[kSimtMaxIn], v1[kSimtMaxIn];
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(128) first_fwd2_kernel(const float* __restrict
           u0 = fmaf(c, v0[d], u0); u1 = fmaf(c, v1[d], u1);
         }
       float4 o;
-      gabor_fwd<FAST>(z0, 0.f, omega, s2, W0b ? s2 * u0 * u0 : 0.f, o.x, o.y);
-      gabor_fwd<FAST>(z1, 0.f, omega, s2, W0b ? s2 * u1 * u1 : 0.f, o.z, o.w);
+      gabor_fwd_c<FAST>(G, z0, 0.f, W0b ? u0 * u0 : 0.f, o.x, o.y);
+      gabor_fwd_c<FAST>(G, z1, 0.f, W0b ? u1 * u1 : 0.f, o.z, o.w);
       if (round_y) { o.x = sm100::round_tf32(o.x); o.y = sm100::round_tf32(o.y); o.z = sm100::round_tf32(o.z); o.w = sm100::round_tf32(o.w); }
       float* dst = y + size_t(row0 + r) * y_pitch + 4 * jp;
       if (2 * jp + 1 < M) *reinterpret_cast<float4*>(dst) = o;
@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__
   // (same-address atomics serialise in L2; thousands of small blocks made this kernel atomics-bound).
   // Requires M <= 2 * blockDim.x (one feature pair per thread).
   __shared__ float sgo[64 * 4];
-  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  const GaborConst G = make_gabor_const(__ldg(omega_p), __ldg(scale_p));
+  const float omega = G.omega, s2 = G.s2;
   const int kp = threadIdx.x;
   const bool active = 2 * kp < M;
   const int k0 = active ? 2 * kp : 0, k1 = (2 * kp + 1 < M) ? 2 * kp + 1 : k0;
@@ -472,9 +473,9 @@ __global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__
         }
         float yr0, yi0, yr1, yi1;
         float e0 = 0.f, e1 = 0.f;
-        if (TWO_D) { e0 = s2 * (wv[u].x * wv[u].x + wv[u].y * wv[u].y); e1 = s2 * (wv[u].z * wv[u].z + wv[u].w * wv[u].w); }
-        gabor_fwd<FAST>(zv[u].x, zv[u].y, omega, s2, e0, yr0, yi0);
-        gabor_fwd<FAST>(zv[u].z, zv[u].w, omega, s2, e1, yr1, yi1);
+        if (TWO_D) { e0 = wv[u].x * wv[u].x + wv[u].y * wv[u].y; e1 = wv[u].z * wv[u].z + wv[u].w * wv[u].w; }
+        gabor_fwd_c<FAST>(G, zv[u].x, zv[u].y, e0, yr0, yi0);
+        gabor_fwd_c<FAST>(G, zv[u].z, zv[u].w, e1, yr1, yi1);
         float4 gzo;
         const float pr0 = gabor_bwd(yr0, yi0, zv[u].x, zv[u].y, gyr0, gyi0, omega, s2, gzo.x, gzo.y);
         const float pr1 = gabor_bwd(yr1, yi1, zv[u].z, zv[u].w, gyr1, gyi1, omega, s2, gzo.z, gzo.w);

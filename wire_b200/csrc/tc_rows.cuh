@@ -57,37 +57,6 @@ struct RowsParams {
   RowsEpi e;
 };
 
-// ---- branch-free FTZ fast math for the epilogue ------------------------------------------------
-__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-struct GaborConst {
-  float omega, s2;
-  float c_t;     // -s2 * log2(e)
-  float c_zi;    // -omega * log2(e)
-  float c_turn;  // omega / (2 pi)
-};
-__device__ __forceinline__ GaborConst make_gabor_const(float omega, float scale) {
-  GaborConst g;
-  g.omega = omega;
-  g.s2 = scale * scale;
-  g.c_t = -g.s2 * 1.4426950408889634f;
-  g.c_zi = -omega * 1.4426950408889634f;
-  g.c_turn = omega * 0.15915494309189535f;
-  return g;
-}
-// y = exp(j w z - s2 (|z|^2 + wnorm));  phase reduced in turns (exact), magnitude through ex2
-__device__ __forceinline__ void gabor_fast(const GaborConst& g, float zr, float zi, float wnorm, float& yr, float& yi) {
-  const float t = fmaf(zi, zi, fmaf(zr, zr, wnorm));
-  const float m = ex2_ftz(fmaf(g.c_t, t, g.c_zi * zi));
-  float u = zr * g.c_turn;
-  u -= rintf(u);
-  const float r = u * 6.283185307179586f;
-  yr = m * cos_ftz(r);
-  yi = m * sin_ftz(r);
-}
-
 __device__ __forceinline__ void stage_row(uint32_t buf, int lane, const float (&v)[32]) {
   const uint32_t row = buf + lane * 128;
   const int sw = lane & 7;
