@@ -130,6 +130,42 @@ def cpu_reference_run(size, steps, warmup, threads=None):
                        f"after {warmup} warm-up, torch {torch.__version__} CPU")
 
 
+def gpu_eager_reference_run(size, dev, steps=5, warmup=2):
+    """Like-for-like GPU bar: the same oracle port executed by eager PyTorch on this GPU in complex64
+    with TF32 disabled — i.e. what the reference's own code does after `model.cuda()`."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import wire_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = O.TorchOracle("wire", CFG["in_features"], CFG["hidden_features"], CFG["hidden_layers"], CFG["out_features"],
+                          CFG["first_omega_0"], CFG["hidden_omega_0"], CFG["scale"]).to(dev)
+    _, noisy = synthetic_image(size, size)
+    coords = image_coords(size, size).to(dev)
+    target = torch.from_numpy(noisy.reshape(1, size * size, 3)).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+
+    def step():
+        loss = ((model(coords) - target) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "value": size * size / ms * 1e3, "unit": UNIT, "kind": "port (eager torch complex64 on this GPU, allow_tf32=False)",
+            "sample": f"{size}x{size} full batch, {steps} timed steps"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -317,7 +353,10 @@ def run_ours(args):
             # (M/3 flop/B = 71 at M=212, below the TF32 ridge of ~170): the binding roofline is HBM.
             ach = kernels[top].get("hbm_gbs")
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
+                        "frac": (ach / peaks["hbm_gbs"]) if ach else None,
+                        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this kernel
+                        # (profiles/r01_ncu_full_v6_summary.txt): 530.7 MB + 835.0 MB
+                        "traffic": 1365.6e6 if (top == "tc_rows_gabor_fwd" and size == 512) else None,
                         "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs",
                         "algorithmic_bytes_per_launch": alg_bytes.get(top),
                         "tensor_achieved_tflops": kernels[top].get("tflops"),
@@ -343,6 +382,11 @@ def run_ours(args):
                 "module_api_ms_per_step": module_ms,
                 "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roofline, "kernels": kernels}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_reference_run(size, dev)
+            except Exception as exc:  # e.g. out of memory on a shared box: the headline numbers do not depend on it
+                line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["coords_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}

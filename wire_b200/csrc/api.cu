@@ -366,7 +366,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   if (z && d->out_features <= 4 && d->width <= 256 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
     const int M = d->width, of = d->out_features;
     // few, long-lived blocks: every g_Wf address then sees only `nblk` atomics
-    const int nblk = int(n < int64_t(4 * g_sm_count) * 64 ? (n + 63) / 64 : 4 * g_sm_count);
+    const int nblk = int(n < int64_t(10 * g_sm_count) * 64 ? (n + 63) / 64 : 10 * g_sm_count);
     const int kRowsPerBlock = int(((n + nblk - 1) / nblk + 63) / 64 * 64);
     const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
     if (tf && w) top_bwd2_kernel<true, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
