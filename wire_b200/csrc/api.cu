@@ -215,6 +215,7 @@ struct RowsJob {
   Blocking blk;
   float* o[3];
   int o_pitch[3];
+  int o_half[3];  // this output is an FP16 tensor (saved z / w)
   int store_mask;
   RowsEpi e;
 };
@@ -273,13 +274,17 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   int nslot = 0;
   for (int bit = 0; bit < 3; ++bit)
     if (J.store_mask & (1 << bit)) {
-      ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32);
+      if (J.o_half[nslot])
+        ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE, true);
+      else
+        ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32);
       ++nslot;
     }
   for (int s = nslot; s < 3; ++s) P.o_map[s] = P.a_map[0];
   P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
-  if (P.n_in >= 1) ok &= sm100_host::make_tmap_2d(&P.z_map[0], J.e.z_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32);
-  if (P.n_in >= 2) ok &= sm100_host::make_tmap_2d(&P.z_map[1], J.e.w_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32);
+  const CUtensorMapSwizzle zsw = J.e.z_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (P.n_in >= 1) ok &= sm100_host::make_tmap_2d(&P.z_map[0], J.e.z_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
+  if (P.n_in >= 2) ok &= sm100_host::make_tmap_2d(&P.z_map[1], J.e.w_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
   if (!ok) return fail("cuTensorMapEncodeTiled failed (pointer/pitch alignment?)");
   CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st));
   return 0;
@@ -356,6 +361,7 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
 }
 
 int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const float* Wf, const float* z, const float* w, int zw_pitch,
+                int z_half,
                 const float* h, int h_pitch, const float* omega, const float* scale, float* gz, float* gw, int g_pitch, float* g_Wf,
                 float* g_bf, cudaStream_t st) {
   if (n <= 0) return 0;
@@ -363,16 +369,19 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   const int round_g = (d->precision == WIRE_PRECISION_TF32) && z;
   ProfScope prof(K_TOP_BWD, st);
   const bool tf = d->precision == WIRE_PRECISION_TF32;
-  if (z && d->out_features <= 4 && d->width <= 256 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
+  if (z && d->out_features <= 4 && d->width <= 1024 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
+    const int thr = round_up((d->width + 1) / 2, 32) < 128 ? 128 : round_up((d->width + 1) / 2, 32);  // one feature pair per thread
     const int M = d->width, of = d->out_features;
     // few, long-lived blocks: every g_Wf address then sees only `nblk` atomics
     const int nblk = int(n < int64_t(10 * g_sm_count) * 64 ? (n + 63) / 64 : 10 * g_sm_count);
     const int kRowsPerBlock = int(((n + nblk - 1) / nblk + 63) / 64 * 64);
     const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
-    if (tf && w) top_bwd2_kernel<true, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
-    else if (tf) top_bwd2_kernel<true, false><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
-    else if (w) top_bwd2_kernel<false, true><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
-    else top_bwd2_kernel<false, false><<<grid, 128, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    if (tf && w && z_half) top_bwd2_kernel<true, true, true><<<grid, thr, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else if (tf && z_half) top_bwd2_kernel<true, false, true><<<grid, thr, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else if (tf && w) top_bwd2_kernel<true, true><<<grid, thr, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else if (tf) top_bwd2_kernel<true, false><<<grid, thr, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else if (w) top_bwd2_kernel<false, true><<<grid, thr, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
+    else top_bwd2_kernel<false, false><<<grid, thr, 0, st>>>(g_out, int(n), M, of, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
   } else if (tf) {
     top_bwd_kernel<true><<<grid, 256, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, h, h_pitch, omega, scale, gz,
                                                gw, g_pitch, round_g, g_Wf, g_bf, kRowsPerBlock);
@@ -443,10 +452,12 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     J.blk = blk;
     int slot = 0;
     if (mask & 1) { J.o[slot] = y_out; J.o_pitch[slot++] = L.P; }
-    if (mask & 2) { J.o[slot] = at(ws, L.off_z[l]); J.o_pitch[slot++] = L.P; }
-    if (mask & 4) { J.o[slot] = at(ws, L.off_w[l]); J.o_pitch[slot++] = L.P; }
+    const int zh = d->precision == WIRE_PRECISION_TF32;  // saved z / w in FP16 on the tensor-core path
+    if (mask & 2) { J.o[slot] = at(ws, L.off_z[l]); J.o_half[slot] = zh; J.o_pitch[slot++] = L.P; }
+    if (mask & 4) { J.o[slot] = at(ws, L.off_w[l]); J.o_half[slot] = zh; J.o_pitch[slot++] = L.P; }
     J.store_mask = mask;
     J.e = base_epi(n, L.two_m, d->precision);
+    J.e.z_half = zh;
     J.e.bias = p->layer[l].bias; J.e.bias2 = p->layer[l].bias2;
     J.e.omega = p->layer[l].omega0; J.e.scale = p->layer[l].scale0;
     if (fuse) {
@@ -565,7 +576,8 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
 
   int cur = 0;
   // final Linear backward + Gabor backward of the last hidden layer (h recomputed from z_H)
-  TRY(run_top_bwd(d, grad_out, n, p->final_weight, at(workspace, L.off_z[H]), d->two_d ? at(workspace, L.off_w[H]) : nullptr, L.P, nullptr,
+  TRY(run_top_bwd(d, grad_out, n, p->final_weight, at(workspace, L.off_z[H]), d->two_d ? at(workspace, L.off_w[H]) : nullptr, L.P,
+                  d->precision == WIRE_PRECISION_TF32, nullptr,
                   0, p->layer[H].omega0, p->layer[H].scale0, at(workspace, L.off_gz[cur]), d->two_d ? at(workspace, L.off_gw[cur]) : nullptr,
                   L.P, g->final_weight, g->final_bias, st));
   for (int l = H; l >= 1; --l) {
@@ -595,6 +607,7 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
     if (!to_first) {
       J.mode = d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD;
       J.e.z_src = at(workspace, L.off_z[l - 1]); J.e.w_src = d->two_d ? at(workspace, L.off_w[l - 1]) : nullptr; J.e.zw_pitch = L.P;
+      J.e.z_half = d->precision == WIRE_PRECISION_TF32;
       J.o[0] = at(workspace, L.off_gz[1 - cur]); J.o_pitch[0] = L.P;
       if (d->two_d) { J.o[1] = at(workspace, L.off_gw[1 - cur]); J.o_pitch[1] = L.P; }
     } else {
@@ -839,7 +852,7 @@ int wire_final_linear_backward(const wire_net_desc* d, const float* weight, cons
   if (!d || !weight || !h || !grad_out || !grad_weight || !grad_bias) return fail("null argument");
   TRY(zero(grad_weight, size_t(d->out_features) * d->width * 2, st));
   TRY(zero(grad_bias, size_t(d->out_features) * 2, st));
-  return run_top_bwd(d, grad_out, n, weight, nullptr, nullptr, 0, h, 2 * d->width, nullptr, nullptr, grad_h, nullptr, 2 * d->width,
+  return run_top_bwd(d, grad_out, n, weight, nullptr, nullptr, 0, 0, h, 2 * d->width, nullptr, nullptr, grad_h, nullptr, 2 * d->width,
                      grad_weight, grad_bias, st);
 }
 

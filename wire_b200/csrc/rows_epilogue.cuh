@@ -39,6 +39,8 @@ struct RowsEpi {
   const float* z_src;  // saved pre-activations for the backward epilogues
   const float* w_src;
   int zw_pitch;
+  int z_half;  // tcgen05 path only: the saved z / w tensors are FP16 (same 11-bit significand as TF32, half the HBM bytes);
+               // forward stores them through FP16 tensor maps, backward loads them the same way
   const float* coords;  // first-layer backward: z0 is recomputed from the coordinates
   int in_features;
   const float* w0;

@@ -2,6 +2,8 @@
 // tensor cores (first layer K = 2..3, final layer out = 1..3), weight packing, and the optimiser.
 // All are HBM-bound streaming kernels: coalesced along the feature axis, rows blocked per CTA.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "gabor_math.cuh"
 #include "sm100.cuh"
 
@@ -410,8 +412,17 @@ __global__ void __launch_bounds__(128) first_fwd2_kernel(const float* __restrict
 
 // top of the backward pass (training path): z (and w) pitched with 16-byte aligned rows.
 // One thread = 2 complex features; 4 rows of loads in flight.
-template <bool FAST, bool TWO_D>
-__global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__ g_out, int n, int M, int out_f,
+// ZHALF: z / w are FP16 [n][zw_pitch] (pitch in elements)
+__device__ __forceinline__ float4 load_zw4(const float* base, size_t row, int pitch, int kp, bool zhalf) {
+  if (!zhalf) return __ldcs(reinterpret_cast<const float4*>(base + row * pitch + 4 * kp));
+  const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + row * pitch + 4 * kp));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <bool FAST, bool TWO_D, bool ZHALF = false>
+__global__ void __launch_bounds__(512) top_bwd2_kernel(const float* __restrict__ g_out, int n, int M, int out_f,
                                                         const float* __restrict__ Wf, const float* __restrict__ z,
                                                         const float* __restrict__ w, int zw_pitch,
                                                         const float* __restrict__ omega_p, const float* __restrict__ scale_p,
@@ -456,8 +467,8 @@ __global__ void __launch_bounds__(128) top_bwd2_kernel(const float* __restrict__
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int r = rb + u < rows ? rb + u : rows - 1;
-        zv[u] = __ldcs(reinterpret_cast<const float4*>(z + size_t(row0 + r) * zw_pitch + 4 * kp));
-        if (TWO_D) wv[u] = __ldcs(reinterpret_cast<const float4*>(w + size_t(row0 + r) * zw_pitch + 4 * kp));
+        zv[u] = load_zw4(z, size_t(row0 + r), zw_pitch, kp, ZHALF);
+        if (TWO_D) wv[u] = load_zw4(w, size_t(row0 + r), zw_pitch, kp, ZHALF);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

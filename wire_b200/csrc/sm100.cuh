@@ -350,14 +350,14 @@ inline PFN_encodeTiled get_encode_fn() {
 // 128-byte swizzle (box_cols * 4 must be 128), out-of-bounds elements read as zero / are not written.
 inline bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                          uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols,
-                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool half = false) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+  cuuint64_t strides[1] = {pitch_elems * (half ? 2 : sizeof(float))};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(out, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;

@@ -21,6 +21,8 @@
 // even / odd 32-column chunks.  Layer constants (bias, final-Linear weights, first-layer weights)
 // live in shared memory; the saved pre-activations of the backward modes are TMA-prefetched.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "rows_epilogue.cuh"
 #include "sm100.cuh"
 
@@ -78,6 +80,35 @@ __device__ __forceinline__ void unstage_row(uint32_t buf, int lane, float (&v)[3
                  : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
                  : "r"(addr)
                  : "memory");
+  }
+}
+
+// FP16 tiles (saved z / w): 32 rows x 32 halves = 64 B per row, dense (TMA SWIZZLE_NONE)
+__device__ __forceinline__ void stage_row_half(uint32_t buf, int lane, const float (&v)[32]) {
+  const uint32_t row = buf + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 t = __floats2half2_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+      h[k] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + j * 16), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  }
+}
+__device__ __forceinline__ void unstage_row_half(uint32_t buf, int lane, float (&v)[32]) {
+  const uint32_t row = buf + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t h[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(row + j * 16) : "memory");
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[k]));
+      v[8 * j + 2 * k] = f.x;
+      v[8 * j + 2 * k + 1] = f.y;
+    }
   }
 }
 
@@ -360,7 +391,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
       if constexpr (kBwd) {
         if (half < nchunks && lane == 0) {
           const uint32_t bar = smem_u32(&bar_in[ew]);
-          mbar_expect_tx(bar, P.n_in * 4096);
+          mbar_expect_tx(bar, P.n_in * (E.z_half ? 2048 : 4096));
           for (int s = 0; s < P.n_in; ++s)
             tma_load_2d(inbuf + s * 4096, &P.z_map[s], bar, col0 + half * kChunk, row0 + q * 32);
         }
@@ -454,12 +485,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
             e_wait_in += WIRE_CLK() - t0;
           }
           in_phase ^= 1;
-          unstage_row(inbuf, lane, z);
-          if constexpr (k2D) unstage_row(inbuf + 4096, lane, w);
+          if (E.z_half) {
+            unstage_row_half(inbuf, lane, z);
+            if constexpr (k2D) unstage_row_half(inbuf + 4096, lane, w);
+          } else {
+            unstage_row(inbuf, lane, z);
+            if constexpr (k2D) unstage_row(inbuf + 4096, lane, w);
+          }
           __syncwarp();
           if (ch + 2 < nchunks && lane == 0) {
             const uint32_t bar = smem_u32(&bar_in[ew]);
-            mbar_expect_tx(bar, P.n_in * 4096);
+            mbar_expect_tx(bar, P.n_in * (E.z_half ? 2048 : 4096));
             for (int s = 0; s < P.n_in; ++s)
               tma_load_2d(inbuf + s * 4096, &P.z_map[s], bar, c + 2 * kChunk, row0 + q * 32);
           }
@@ -520,10 +556,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           int slot = 0;
           if (P.store_mask & 1) { stage_row(wbuf, lane, o0); ++slot; }
           if constexpr (kFwd || MODE == MODE_GABOR2D_BWD) {
-            if (P.store_mask & 2) { stage_row(wbuf + slot * 4096, lane, o1); ++slot; }
+            if (P.store_mask & 2) {
+              if (kFwd && E.z_half) stage_row_half(wbuf + slot * 4096, lane, o1); else stage_row(wbuf + slot * 4096, lane, o1);
+              ++slot;
+            }
           }
           if constexpr (MODE == MODE_GABOR2D_FWD) {
-            if (P.store_mask & 4) { stage_row(wbuf + slot * 4096, lane, o2); ++slot; }
+            if (P.store_mask & 4) {
+              if (E.z_half) stage_row_half(wbuf + slot * 4096, lane, o2); else stage_row(wbuf + slot * 4096, lane, o2);
+              ++slot;
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
