@@ -117,7 +117,7 @@ struct Blocking {
 };
 // out_cols = real output columns (2M). two_d_fwd: accumulator holds [z half | w half].
 bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, int n_in = 0, int mode = MODE_PLAIN,
-                     bool fuse_final = false) {
+                     bool fuse_final = false, bool gen = false) {
   for (int nblk = 1; nblk <= 64; ++nblk) {
     const int per = (out_cols + nblk - 1) / nblk;
     const int C = cluster_size();
@@ -129,7 +129,7 @@ bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, 
       nbh = nb;
     }
     RowsParams tmp;
-    if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C) == 0) continue;
+    if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C, gen) == 0) continue;
     b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
     return true;
   }
@@ -217,11 +217,15 @@ struct RowsJob {
   int o_pitch[3];
   int o_half[3];  // this output is an FP16 tensor (saved z / w)
   int store_mask;
+  int gen;        // A operand = first-layer output, generated in place (e.coords / e.w0 ... describe that layer)
+  const float* gen_omega;
+  const float* gen_scale;
+  int gen_two_d;
   RowsEpi e;
 };
 int job_n_in(int mode) { return mode == MODE_GABOR_BWD ? 1 : (mode == MODE_GABOR2D_BWD ? 2 : 0); }
-bool job_blocking(int mode, int out_cols, int store_mask, bool fuse_final, Blocking& b) {
-  return choose_blocking(out_cols, mode == MODE_GABOR2D_FWD, store_mask, b, job_n_in(mode), mode, fuse_final);
+bool job_blocking(int mode, int out_cols, int store_mask, bool fuse_final, Blocking& b, bool gen = false) {
+  return choose_blocking(out_cols, mode == MODE_GABOR2D_FWD, store_mask, b, job_n_in(mode), mode, fuse_final, gen);
 }
 
 template <int MODE>
@@ -263,7 +267,8 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.n_blocks = J.blk.n_blocks;
   P.e = J.e;
   const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
-                                     cluster_size());
+                                     cluster_size(), J.gen != 0);
+  P.gen_omega = J.gen_omega; P.gen_scale = J.gen_scale; P.gen_two_d = J.gen_two_d;
   if (!smem) return fail("row-tile configuration does not fit shared memory (nb=%d)", J.blk.nb);
   bool ok = true;
   for (int i = 0; i < 2; ++i) {
@@ -286,7 +291,8 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   if (P.n_in >= 1) ok &= sm100_host::make_tmap_2d(&P.z_map[0], J.e.z_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
   if (P.n_in >= 2) ok &= sm100_host::make_tmap_2d(&P.z_map[1], J.e.w_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
   if (!ok) return fail("cuTensorMapEncodeTiled failed (pointer/pitch alignment?)");
-  CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st));
+  if (J.gen) CU_OK(launch_rows_gen(J.mode, P, smem, g_sm_count, st));
+  else CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st));
   return 0;
 }
 
@@ -302,8 +308,14 @@ int run_pack(const float* W1, const float* W2, int M_out, int K_in, int mode, co
 }
 
 // weight gradient of one complex Linear (x has a ones column at 2*k_in)
+struct WgradGen {  // first-layer description when x = y0 is generated in place (nullptr coords = load x)
+  const float* coords = nullptr;
+  int in_features = 0;
+  const float *w0 = nullptr, *b0 = nullptr, *w0b = nullptr, *b0b = nullptr, *omega = nullptr, *scale = nullptr;
+  int two_d = 0;
+};
 int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const float* g2, int g_pitch, int m_out, int64_t n,
-              float* gW1, float* gB1, float* gW2, float* gB2, int precision, cudaStream_t st) {
+              float* gW1, float* gB1, float* gW2, float* gB2, int precision, cudaStream_t st, const WgradGen* gen = nullptr) {
   if (n <= 0) return 0;
   const int n_g = g2 ? 2 : 1;
   ProfScope prof(K_WGRAD, st, (precision == WIRE_PRECISION_FP32 && g2) ? 2 : 1);
@@ -324,13 +336,19 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
   memset(&P, 0, sizeof(P));
   P.n_rows = int(n); P.k_in = k_in; P.g_cols = 2 * m_out; P.n_g = n_g;
   P.gW[0] = gW1; P.gB[0] = gB1; P.gW[1] = gW2; P.gB[1] = gB2;
-  const size_t smem = wgrad_configure(P, g_sm_count, cluster_size());
+  const bool use_gen = gen && gen->coords;
+  const size_t smem = wgrad_configure(P, g_sm_count, cluster_size(), use_gen);
   if (!smem) return fail("wgrad configuration does not fit shared memory");
-  bool ok = sm100_host::make_tmap_2d(&P.x_map, x, n, 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (use_gen) {
+    P.coords = gen->coords; P.in_features = gen->in_features; P.w0 = gen->w0; P.b0 = gen->b0; P.w0b = gen->w0b; P.b0b = gen->b0b;
+    P.gen_omega = gen->omega; P.gen_scale = gen->scale; P.gen_two_d = gen->two_d;
+    x = g1; x_pitch = g_pitch; /* x_map is unused by the GEN kernel but must be a valid descriptor */
+  }
+  bool ok = sm100_host::make_tmap_2d(&P.x_map, x, n, use_gen ? 2 * m_out : 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   ok &= sm100_host::make_tmap_2d(&P.g_map[0], g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   ok &= sm100_host::make_tmap_2d(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (!ok) return fail("cuTensorMapEncodeTiled failed for wgrad");
-  CU_OK(launch_wgrad(P, smem, st));
+  CU_OK(launch_wgrad(P, smem, st, use_gen));
   return 0;
 }
 
@@ -429,7 +447,11 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
                   void* ws, int training, cudaStream_t st) {
   const int M = L.M, H = L.H;
   float* y_prev = at(ws, L.off_y[0]);
-  TRY(run_first_fwd(d, p->layer[0], coords, n, d->in_features, y_prev, L.P, nullptr, nullptr, 0, st));
+  // WIRE_B200_GEN=1 (experiment): the first layer's output is generated inside its consumers and never written to HBM.
+  // Correct (parity-green) but slower on B200: four generator warps cannot hide the MUFU latency (fwd 0.25 -> 0.36 ms,
+  // wgrad 0.22 -> 0.55 ms, profiles/r01_bench_v9_gen.json), so the default keeps first_fwd2_kernel.
+  const bool gen0 = d->precision == WIRE_PRECISION_TF32 && d->in_features <= 3 && getenv("WIRE_B200_GEN") != nullptr;
+  if (!gen0) TRY(run_first_fwd(d, p->layer[0], coords, n, d->in_features, y_prev, L.P, nullptr, nullptr, 0, st));
   for (int l = 1; l <= H; ++l) {
     const bool last = l == H;
     const bool fuse = last && L.fuse_final;
@@ -441,7 +463,8 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     if (training) { mask |= 2; if (d->two_d) mask |= 4; }
     Blocking blk;
     const int fmode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
-    if (!job_blocking(fmode, L.two_m, mask, fuse, blk)) return fail("no tile configuration");
+    const bool gen = gen0 && l == 1;
+    if (!job_blocking(fmode, L.two_m, mask, fuse, blk, gen)) return fail("no tile configuration");
     float* Bf = at(ws, L.off_bf[l]);
     TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st));
     RowsJob J;
@@ -460,6 +483,12 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     J.e.z_half = zh;
     J.e.bias = p->layer[l].bias; J.e.bias2 = p->layer[l].bias2;
     J.e.omega = p->layer[l].omega0; J.e.scale = p->layer[l].scale0;
+    if (gen) {
+      J.gen = 1; J.gen_omega = p->layer[0].omega0; J.gen_scale = p->layer[0].scale0; J.gen_two_d = d->two_d;
+      J.e.coords = coords; J.e.in_features = d->in_features;
+      J.e.w0 = p->layer[0].weight; J.e.b0 = p->layer[0].bias; J.e.w0b = p->layer[0].weight2; J.e.b0b = p->layer[0].bias2;
+      J.a[0] = Bf; J.a_pitch[0] = L.k_pad;  // unused by the kernel, but the descriptor must be valid
+    }
     if (fuse) {
       J.e.fuse_final = 1; J.e.wf = p->final_weight; J.e.bf = p->final_bias; J.e.out = out; J.e.out_features = d->out_features;
     }
@@ -584,8 +613,15 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
     const float* gz = at(workspace, L.off_gz[cur]);
     const float* gw = d->two_d ? at(workspace, L.off_gw[cur]) : nullptr;
     const float* x = at(workspace, L.off_y[l - 1]);
+    WgradGen wg;
+    if (l == 1 && d->precision == WIRE_PRECISION_TF32 && in_f <= 3 && getenv("WIRE_B200_GEN") != nullptr) {
+      wg.coords = coords; wg.in_features = in_f; wg.w0 = p->layer[0].weight; wg.b0 = p->layer[0].bias;
+      wg.w0b = p->layer[0].weight2; wg.b0b = p->layer[0].bias2; wg.omega = p->layer[0].omega0; wg.scale = p->layer[0].scale0;
+      wg.two_d = d->two_d;
+    }
     if (g->layer[l].weight)
-      TRY(run_wgrad(x, L.P, M, gz, gw, L.P, M, n, g->layer[l].weight, g->layer[l].bias, g->layer[l].weight2, g->layer[l].bias2, d->precision, st));
+      TRY(run_wgrad(x, L.P, M, gz, gw, L.P, M, n, g->layer[l].weight, g->layer[l].bias, g->layer[l].weight2, g->layer[l].bias2, d->precision, st,
+                    &wg));
     // dgrad of layer l fused with the nonlinearity backward of layer l-1
     const bool to_first = (l == 1);
     int mask = to_first ? 0 : (d->two_d ? 3 : 1);

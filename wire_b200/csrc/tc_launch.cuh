@@ -18,7 +18,7 @@ constexpr size_t kMaxDynSmem = 232448 - 6144;  // 227 KB minus the static barrie
 // `mode`    : decides which tables exist (bias / fused-final weights / first-layer table)
 // `cluster` : CTAs that share each B tile through TMA multicast; nb must split into 8-row aligned shares
 inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int n_in = 0, int out_cols = 0,
-                             int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1) {
+                             int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1, bool gen = false) {
   P.nb = nb;
   P.nbh = nbh;
   P.store_mask = store_mask;
@@ -41,6 +41,8 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
   size_t pfloats = 0;
   if (mode == MODE_GABOR_FWD || mode == MODE_GABOR2D_FWD) pfloats = size_t(two_d ? 2 : 1) * pcols + (fuse_final ? size_t(pcols / 2) * 8 : 0);
   if (mode == MODE_FIRST_BWD || mode == MODE_FIRST2D_BWD) pfloats = size_t(two_d ? 2 : 1) * (pcols / 2) * 4;
+  P.gen_tab_off = uint32_t((pfloats + 3) / 4 * 4);
+  if (gen) pfloats = P.gen_tab_off + size_t(2) * (pcols / 2) * 4;  // generator tables {w0[0..2], b0} (+ scale_orth)
   const size_t pbytes = (pfloats * sizeof(float) + 127) / 128 * 128;
   const size_t budget = kMaxDynSmem - 1024;
   if (staging + pbytes + 2 * stage > budget) return 0;
@@ -53,12 +55,12 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
   return stages * stage + staging + pbytes + 1024;
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, bool GEN = false>
 inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE, PAIR, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -66,7 +68,7 @@ inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_c
   const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
   const int units = ((row_tiles + C - 1) / C) * P.n_blocks;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kRowsThreads);
+  cfg.blockDim = dim3(kRowsThreads + (GEN ? 32 * kGenWarps : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -81,7 +83,7 @@ inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_c
     cfg.gridDim = dim3(sm_count / C * C);
     cfg.dynamicSmemBytes = kMaxDynSmem;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE, PAIR>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE, PAIR, GEN>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
     (void)cudaGetLastError();
     max_clusters[C] = nc;
     cfg.dynamicSmemBytes = smem;
@@ -90,11 +92,22 @@ inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_c
   if (clusters > units) clusters = units;
   if (clusters <= 0) return cudaSuccess;
   cfg.gridDim = dim3(clusters * C);
-  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE, PAIR>, P);
+  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE, PAIR, GEN>, P);
 }
 template <int MODE>
 inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   return P.cluster == 2 ? launch_rows_mode_p<MODE, true>(P, smem, sm_count, st) : launch_rows_mode_p<MODE, false>(P, smem, sm_count, st);
+}
+
+// forward kernels whose A operand (the first layer's output) is generated in place
+inline cudaError_t launch_rows_gen(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  if (P.e.n_rows <= 0) return cudaSuccess;
+  const bool pair = P.cluster == 2;
+  if (mode == MODE_GABOR_FWD)
+    return pair ? launch_rows_mode_p<MODE_GABOR_FWD, true, true>(P, smem, sm_count, st) : launch_rows_mode_p<MODE_GABOR_FWD, false, true>(P, smem, sm_count, st);
+  if (mode == MODE_GABOR2D_FWD)
+    return pair ? launch_rows_mode_p<MODE_GABOR2D_FWD, true, true>(P, smem, sm_count, st) : launch_rows_mode_p<MODE_GABOR2D_FWD, false, true>(P, smem, sm_count, st);
+  return cudaErrorInvalidValue;
 }
 
 inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
@@ -112,7 +125,7 @@ inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int s
 }
 
 // wgrad: choose column blocking, K splits (to fill the machine) and pipeline depth
-inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2) {
+inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, bool gen = false) {
   const int x_cols = 2 * P.k_in + 1;
   P.cluster = cluster;
   P.m_tiles = (x_cols + 128 * cluster - 1) / (128 * cluster);
@@ -128,18 +141,21 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2) {
   if (splits > total_chunks) splits = total_chunks > 0 ? total_chunks : 1;
   P.splits = splits;
   const size_t stage = size_t(4 + P.nb / 32 / cluster) * kWgradKC * 128;
-  int stages = int((kMaxDynSmem - 1024) / stage);
+  P.gen_tab_feats = round_up(P.k_in + 1, 16) + 64 * 4;  // covers every feature index a generator warp may touch
+  const size_t tab_bytes = gen ? size_t(2) * P.gen_tab_feats * 16 : 0;
+  int stages = int((kMaxDynSmem - 1024 - tab_bytes) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) return 0;
   P.stages = stages;
-  return stages * stage + 1024;
+  P.gen_tab_off = uint32_t(stages * stage);
+  return stages * stage + tab_bytes + 1024;
 }
 
-template <bool PAIR>
+template <bool PAIR, bool GEN = false>
 inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<PAIR, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -148,7 +164,7 @@ inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_
   if (grid <= 0 || P.n_rows <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kWgradThreads);
+  cfg.blockDim = dim3(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -158,9 +174,10 @@ inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = PAIR ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PAIR>, P);
+  return cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PAIR, GEN>, P);
 }
-inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st) {
+inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st, bool gen = false) {
+  if (gen) return P.cluster == 2 ? launch_wgrad_p<true, true>(P, smem, st) : launch_wgrad_p<false, true>(P, smem, st);
   return P.cluster == 2 ? launch_wgrad_p<true>(P, smem, st) : launch_wgrad_p<false>(P, smem, st);
 }
 

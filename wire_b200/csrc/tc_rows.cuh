@@ -55,6 +55,13 @@ struct RowsParams {
   uint32_t staging_off;  // byte offsets inside dynamic smem (from the 1 KB aligned base)
   uint32_t param_off;
   int param_cols;        // padded column count of the bias tables (multiple of 32)
+  // GEN kernels: the A operand is not loaded but COMPUTED by four generator warps straight into the swizzled
+  // smem tile: A = y0 = gabor(coords W0^T + b0), the first WIRE layer (K = 2..3), so y0 never exists in HBM.
+  // (coords / w0 / b0 / w0b / b0b / in_features of `e` describe that layer; these are its omega_0, scale_0.)
+  const float* gen_omega;
+  const float* gen_scale;
+  int gen_two_d;
+  uint32_t gen_tab_off;     // float offset of the generator's {w0[0..2], b0} table inside the param area
   unsigned long long* dbg;  // optional per-CTA stall counters [8] (tools/umma_probe): see kDbg* below
   RowsEpi e;
 };
@@ -133,8 +140,10 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 enum { kDbgMmaWaitFull = 0, kDbgMmaWaitTmem = 1, kDbgMmaTotal = 2, kDbgEpiWaitAcc = 3, kDbgEpiTotal = 4, kDbgProdWaitEmpty = 5,
        kDbgProdTotal = 6, kDbgEpiWaitIn = 7 };
 
-template <int MODE, bool PAIR>
-__global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_constant__ RowsParams P) {
+constexpr int kGenWarps = 4;
+
+template <int MODE, bool PAIR, bool GEN = false>
+__global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) tc_rows_kernel(const __grid_constant__ RowsParams P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8];
@@ -214,9 +223,26 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
     }
   }
 
+  if constexpr (GEN) {
+    float* gt = params + P.gen_tab_off;
+    for (int i = threadIdx.x; i < (P.param_cols >> 1) * 4; i += blockDim.x) {
+      const int k = i >> 2, j = i & 3;
+      const int n_in_feat = P.k_cols[0] >> 1;  // complex features of the generated operand
+      float v = 0.f, v2 = 0.f;
+      if (k < n_in_feat) {
+        if (j < 3) {
+          if (j < E.in_features) { v = E.w0[size_t(k) * E.in_features + j]; if (P.gen_two_d) v2 = E.w0b[size_t(k) * E.in_features + j]; }
+        } else { v = E.b0[k]; if (P.gen_two_d) v2 = E.b0b[k]; }
+      }
+      gt[i] = v;
+      gt[(P.param_cols >> 1) * 4 + i] = v2;
+    }
+  }
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
+      // GEN: one arrival from the TMA producer (B tile bytes) + one per generator warp of every CTA of the pair
+      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kGenWarps * C : 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -262,15 +288,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const int part = kc < kc0 ? 0 : 1;
           const int kcol = (part ? kc - kc0 : kc) * kChunk;
+          const uint32_t tx_bytes = GEN ? b_bytes : stage_bytes;  // GEN: the A tile is written by the generator warps
           if (!pair) {
-            mbar_expect_tx(full_own, stage_bytes);
-            tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, a_policy);
+            mbar_expect_tx(full_own, tx_bytes);
+            if (!GEN) tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, a_policy);
             tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kChunk, brow, kEvictLast);
           } else {
             // both CTAs load into their own smem; all bytes complete on the LEADER's full barrier
             const uint32_t full_leader = full_own & kPeerBitMask;
-            if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
-            tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, a_policy);
+            if (leader) mbar_expect_tx(full_own, 2 * tx_bytes);
+            if (!GEN) tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, a_policy);
             tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kChunk, brow, kEvictLast);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -332,6 +359,53 @@ __global__ void __launch_bounds__(kRowsThreads, 1) tc_rows_kernel(const __grid_c
         else umma_commit(smem_u32(&bar_tmem_full[buf]));
       }
       if (dbg) { dbg[kDbgMmaWaitFull] = w_full; dbg[kDbgMmaWaitTmem] = w_tmem; dbg[kDbgMmaTotal] = WIRE_CLK() - t_begin; }
+    }
+  } else if (GEN && warp >= 2 + kEpiWarps) {
+    // ===================== A-operand generator warps (first WIRE layer computed in place) =====================
+    const int gw = warp - (2 + kEpiWarps);  // rows 32*gw .. 32*gw+31 of the tile
+    const GaborConst G0 = make_gabor_const(__ldg(P.gen_omega), __ldg(P.gen_scale));
+    const float4* tab = reinterpret_cast<const float4*>(params + P.gen_tab_off);
+    const float4* tab2 = tab + (P.param_cols >> 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int jb = 0; jb < n_jobs; ++jb) {
+      const int it = jb / P.slices;
+      const int unit = it * n_clusters + my_cluster;
+      const int row = ((unit / P.n_blocks) * C + crank) * kTileRows + gw * 32 + lane;
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (row < E.n_rows) {
+        c0 = __ldg(E.coords + size_t(row) * E.in_features);
+        if (E.in_features > 1) c1 = __ldg(E.coords + size_t(row) * E.in_features + 1);
+        if (E.in_features > 2) c2 = __ldg(E.coords + size_t(row) * E.in_features + 2);
+      }
+      for (int kc = 0; kc < kc_total; ++kc) {
+        if (lane == 0) mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
+        __syncwarp();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 t = tab[kc * 16 + i];
+          const float z0 = fmaf(c0, t.x, fmaf(c1, t.y, fmaf(c2, t.z, t.w)));
+          float wn = 0.f;
+          if (P.gen_two_d) {
+            const float4 t2 = tab2[kc * 16 + i];
+            const float w0v = fmaf(c0, t2.x, fmaf(c1, t2.y, fmaf(c2, t2.z, t2.w)));
+            wn = w0v * w0v;
+          }
+          float yr, yi;
+          gabor_fast(G0, z0, 0.f, wn, yr, yi);
+          v[2 * i] = round_tf32(yr);
+          v[2 * i + 1] = round_tf32(yi);
+        }
+        stage_row(smem_base + stage * stage_bytes + gw * 4096, lane, v);
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t full_own = smem_u32(&bar_full[stage]);
+          if (pair) mbar_arrive_cluster(full_own & kPeerBitMask); else mbar_arrive(full_own);
+        }
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+      }
     }
   } else {
     // ===================== epilogue warps =====================

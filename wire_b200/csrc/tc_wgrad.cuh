@@ -14,11 +14,13 @@
 // Work item = (K split, g matrix, column block, M tile of 128 x-columns per CTA); one item per CTA, or per CTA
 // pair (cta_group::2: 256 x-columns, each CTA stages its own x tile and HALF of the g tile).
 #pragma once
+#include "gabor_math.cuh"
 #include "sm100.cuh"
 
 namespace wire {
 
 constexpr int kWgradThreads = 192;
+constexpr int kWgradGenWarps = 4;  // GEN kernels: x = y0 = gabor(coords W0^T + b0) is computed in place (first hidden layer)
 constexpr int kWgradKC = 32;  // coordinates per pipeline stage
 
 struct WgradParams {
@@ -36,10 +38,22 @@ struct WgradParams {
   int stages;
   float* gW[2];  // [M][K][2] fp32, accumulated
   float* gB[2];  // [M][2]
+  // GEN: first-layer description (x is generated, never loaded)
+  const float* coords;
+  int in_features;
+  const float* w0;
+  const float* b0;
+  const float* w0b;
+  const float* b0b;
+  const float* gen_omega;
+  const float* gen_scale;
+  int gen_two_d;
+  uint32_t gen_tab_off;  // byte offset of the {w0[0..2], b0} tables inside dynamic smem
+  int gen_tab_feats;     // padded feature count of the tables
 };
 
-template <bool PAIR>
-__global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
+template <bool PAIR, bool GEN = false>
+__global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0), 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8];
@@ -80,9 +94,24 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
   const int n1 = np > 256 ? 256 : np;
   const int n2 = np - n1;
 
+  float4* gtab = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.gen_tab_off);
+  if constexpr (GEN) {
+    float* gt = reinterpret_cast<float*>(gtab);
+    for (int i = threadIdx.x; i < P.gen_tab_feats * 4; i += blockDim.x) {
+      const int k = i >> 2, j = i & 3;
+      float v = 0.f, v2 = 0.f;
+      if (k < P.k_in) {
+        if (j < 3) {
+          if (j < P.in_features) { v = P.w0[size_t(k) * P.in_features + j]; if (P.gen_two_d) v2 = P.w0b[size_t(k) * P.in_features + j]; }
+        } else { v = P.b0[k]; if (P.gen_two_d) v2 = P.b0b[k]; }
+      }
+      gt[i] = v;
+      gt[P.gen_tab_feats * 4 + i] = v2;
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
@@ -109,16 +138,18 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
           const uint32_t full_own = smem_u32(&bar_full[stage]);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const int r0 = ch * kWgradKC;
+          const uint32_t tx_bytes = GEN ? b_bytes : stage_bytes;
           if (!PAIR) {
-            mbar_expect_tx(full_own, stage_bytes);
-            for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * 32, r0);
+            mbar_expect_tx(full_own, tx_bytes);
+            if (!GEN) for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * 32, r0);
             for (int b = 0; b < nbb_cta; ++b)
               tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_own, nblk * P.nb + b * 32, r0);
           } else {
             const uint32_t full_leader = full_own & kPeerBitMask;
-            if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
-            for (int b = 0; b < 4; ++b)
-              tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * 32, r0, kEvictNormal);
+            if (leader) mbar_expect_tx(full_own, 2 * tx_bytes);
+            if (!GEN)
+              for (int b = 0; b < 4; ++b)
+                tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * 32, r0, kEvictNormal);
             // piece 1: columns [crank*n1/2, +n1/2) ; piece 2: columns [n1 + crank*n2/2, +n2/2)
             const int p1 = n1 / 64, p2 = n2 / 64;
             for (int b = 0; b < p1; ++b)
@@ -167,6 +198,68 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
         }
         if (PAIR) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full), 3);
         else umma_commit(smem_u32(&bar_tmem_full));
+      }
+    } else if (GEN && warp >= 6) {
+      // ===================== x-operand generator warps =====================
+      // warp b writes column block b (16 complex features) of every stage; lane = coordinate row of the chunk.
+      // MN-major tile, 128B swizzle with 32B atoms: 32-byte chunk index ^= (row & 3).
+      const int b = warp - 6;
+      const GaborConst G0 = make_gabor_const(__ldg(P.gen_omega), __ldg(P.gen_scale));
+      const float4* tab = gtab;
+      const float4* tab2 = gtab + P.gen_tab_feats;
+      const int feat0 = ((mt * C + crank) * 128 + b * 32) >> 1;  // first complex feature of this block
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int row = ch * kWgradKC + lane;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (row < P.n_rows) {
+          c0 = __ldg(P.coords + size_t(row) * P.in_features);
+          if (P.in_features > 1) c1 = __ldg(P.coords + size_t(row) * P.in_features + 1);
+          if (P.in_features > 2) c2 = __ldg(P.coords + size_t(row) * P.in_features + 2);
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = feat0 + i;
+          float yr = 0.f, yi = 0.f;
+          if (row < P.n_rows) {
+            if (j < P.k_in) {
+              const float4 t = tab[j];
+              const float z0 = fmaf(c0, t.x, fmaf(c1, t.y, fmaf(c2, t.z, t.w)));
+              float wn = 0.f;
+              if (P.gen_two_d) {
+                const float4 t2 = tab2[j];
+                const float w0v = fmaf(c0, t2.x, fmaf(c1, t2.y, fmaf(c2, t2.z, t2.w)));
+                wn = w0v * w0v;
+              }
+              gabor_fast(G0, z0, 0.f, wn, yr, yi);
+              yr = round_tf32(yr);
+              yi = round_tf32(yi);
+            } else if (j == P.k_in) {
+              yr = 1.0f;  // the "ones" column: row 2K of G is the bias gradient
+            }
+          }
+          v[2 * i] = yr;
+          v[2 * i + 1] = yi;
+        }
+        if (lane == 0) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+        __syncwarp();
+        const uint32_t rowaddr = smem_base + stage * stage_bytes + b * blk_bytes + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = rowaddr + ((((j >> 1) ^ (lane & 3)) << 5) | ((j & 1) << 4));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t full_own = smem_u32(&bar_full[stage]);
+          if (PAIR) mbar_arrive_cluster(full_own & kPeerBitMask); else mbar_arrive(full_own);
+        }
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     } else {
       const int q = warp & 3;
