@@ -32,6 +32,9 @@ UNIT = "coords/s"
 CFG = dict(nonlin="wire", in_features=2, hidden_features=300, hidden_layers=2, out_features=3,
            first_omega_0=7.0, hidden_omega_0=7.0, scale=6.0)
 LR = 5e-3
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures of this
+# command at the default size (profiles/*_ncu_full_*_summary.txt): (precision, kernel) -> bytes
+NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6}
 
 
 def flop_per_coord(M, H, in_f, out_f):
@@ -338,10 +341,22 @@ def run_ours(args):
         peaks, peaks_src = load_peaks()
         top = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
         gemm_flop = 8.0 * M * M * n  # one complex M x M GEMM over n coordinates (fwd, dgrad and wgrad alike)
-        unit_b = 8.0 * M * n         # one complex activation tensor [n, M] in HBM
-        alg_bytes = {"tc_rows_gabor_fwd": 3 * unit_b, "tc_rows_dgrad_gabor_bwd": 3 * unit_b, "tc_wgrad": 2 * unit_b,
-                     "tc_rows_dgrad_first_bwd": 1.5 * unit_b, "top_bwd": 2 * unit_b, "first_fwd": unit_b,
-                     "first_wgrad": 0.5 * unit_b}
+        unit_b = 8.0 * M * n         # one complex fp32 activation tensor [n, M] in HBM
+        # algorithmic HBM bytes per launch, in units; a = activation y, g = gradient g_z, z = saved pre-activation (FP16 on
+        # both tensor-core paths), real fp32 g_z0 = 0.5.  The forward entry is the average over the H launches (the last
+        # layer's y is never written: the final Linear is fused into its epilogue).
+        H = CFG["hidden_layers"]
+        mixed = args.precision == "mixed16"
+        a_u = 0.5 if mixed else 1.0
+        g_u = 0.5 if mixed else 1.0
+        z_u = 1.0 if args.precision == "fp32" else 0.5
+        alg_units = {"first_fwd": a_u, "tc_rows_gabor_fwd": (H * (a_u + z_u) + (H - 1) * a_u) / H, "top_bwd": z_u + g_u,
+                     "tc_wgrad": a_u + g_u, "tc_rows_dgrad_gabor_bwd": 2 * g_u + z_u, "tc_rows_dgrad_first_bwd": g_u + 0.5,
+                     "first_wgrad": 0.5}
+        alg_bytes = {k: v * unit_b for k, v in alg_units.items()}
+        step_units = (alg_units["first_fwd"] + H * alg_units["tc_rows_gabor_fwd"] + alg_units["top_bwd"] + H * alg_units["tc_wgrad"]
+                      + (H - 1) * alg_units["tc_rows_dgrad_gabor_bwd"] + alg_units["tc_rows_dgrad_first_bwd"] + alg_units["first_wgrad"])
+        tensor_peak = peaks["bf16_tflops_sustained"] / (1.0 if mixed else 2.0)
         for k, v in kernels.items():
             if k in alg_bytes:
                 v["hbm_gbs"] = alg_bytes[k] / (v["ms_avg"] * 1e-3) / 1e9
@@ -356,27 +371,31 @@ def run_ours(args):
                         "frac": (ach / peaks["hbm_gbs"]) if ach else None,
                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this kernel
                         # (profiles/r01_ncu_full_v6_summary.txt): 530.7 MB + 835.0 MB
-                        "traffic": 1365.6e6 if (top == "tc_rows_gabor_fwd" and size == 512) else None,
+                        "traffic": NCU_TRAFFIC.get((args.precision, top)) if size == 512 else None,
                         "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs",
                         "algorithmic_bytes_per_launch": alg_bytes.get(top),
                         "tensor_achieved_tflops": kernels[top].get("tflops"),
-                        "tensor_peak_tflops": peaks["bf16_tflops_sustained"] / 2.0,
-                        "tensor_frac": (kernels[top]["tflops"] / (peaks["bf16_tflops_sustained"] / 2.0)) if "tflops" in kernels[top] else None,
-                        "tensor_peak_source": f"{peaks_src} bf16_tflops_sustained/2 (TF32 issues at half the BF16 rate)",
-                        "share_of_step": kernels[top]["ms_total"] / total_ms if total_ms else None}
+                        "tensor_peak_tflops": tensor_peak,
+                        "tensor_frac": (kernels[top]["tflops"] / tensor_peak) if "tflops" in kernels[top] else None,
+                        "tensor_peak_source": f"{peaks_src} bf16_tflops_sustained" + ("" if mixed else "/2 (TF32 issues at half the BF16 rate)"),
+                        "share_of_step": kernels[top]["ms_total"] / total_ms if total_ms else None,
+                        "step_algorithmic_bytes": step_units * unit_b,
+                        "step_hbm_frac": step_units * unit_b / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         step_flop = flop_per_coord(M, CFG["hidden_layers"], CFG["in_features"], CFG["out_features"]) * n
 
     if rank == 0:
         cpu = cpu_reference_run(256, 3, 1) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "dtype": {"tf32": "tf32", "fp32": "f32", "mixed16": "f16 activations x bf16 gradients, f32 accumulate"}[args.precision],
+                "data": "synthetic",
                 "config": {"workload": f"WIRE image fit {size}x{size} RGB ({n} coords/GPU full-batch fwd+bwd+Adam), "
                                        f"wire_image_denoise.py defaults: hidden 300 -> M={M}, H=2, omega0=7, sigma0=6",
                            "width": M, "hidden_layers": CFG["hidden_layers"], "coords_per_gpu": n,
                            "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if trainer.use_graph and world == 1 else ""),
                            "parallelism": f"coord-sharded dp{world}" if world > 1 else "single GPU",
-                           "l2": "per-step activation traffic (>7 GB) far exceeds the 126 MB L2; no explicit flush"},
+                           "precision": args.precision,
+                           "l2": "per-step activation traffic (>4 GB) far exceeds the 126 MB L2; no explicit flush"},
                 "algorithmic_tflops": world * step_flop / (ms_step * 1e-3) / 1e12,
                 "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,  # per GPU
                 "module_api_ms_per_step": module_ms,
@@ -402,7 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="mixed16", choices=["mixed16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()

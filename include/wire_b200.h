@@ -36,7 +36,14 @@ extern "C" {
 #define WIRE_B200_ABI_VERSION 1
 #define WIRE_B200_MAX_LAYERS 16 /* first layer + hidden layers */
 
-enum { WIRE_PRECISION_TF32 = 0, WIRE_PRECISION_FP32 = 1 };
+/* TF32    : GEMM operands TF32 (10-bit mantissa, fp32 storage), FP32 accumulate, saved pre-activations FP16.
+ * FP32    : FP32 FMAs on the CUDA cores (precision yardstick; same GPU, not a fallback).
+ * MIXED16 : whole-network path with 16-bit tensors in HBM -- activations and forward weights FP16 (the same 11-bit
+ *           significand as TF32), gradients and dgrad/wgrad operands BF16 (FP32's exponent range, so no loss scaling) --
+ *           FP32 accumulate in TMEM; half the activation traffic and twice the tensor-core rate of TF32.  Falls back to
+ *           the TF32 kernels for shapes it does not cover (in_features > 3, out_features > 4) and for the single-layer
+ *           entry points. */
+enum { WIRE_PRECISION_TF32 = 0, WIRE_PRECISION_FP32 = 1, WIRE_PRECISION_MIXED16 = 2 };
 
 typedef struct wire_net_desc {
   int32_t two_d;         /* 0 = wire (modules/wire.py), 1 = wire2d (modules/wire2d.py) */

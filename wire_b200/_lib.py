@@ -13,6 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_si
 MAX_LAYERS = 16
 PRECISION_TF32 = 0
 PRECISION_FP32 = 1
+PRECISION_MIXED16 = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libwire_b200.so")

@@ -141,6 +141,8 @@ bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, 
 // ------------------------------------------------------------------------------------------
 struct Layout {
   int M, H, two_m, P, PR, k_pad, two_d;
+  int prec;                 // effective precision (net_precision)
+  int y_elem, z_elem, g_elem;  // element types of the y / saved z,w / g_z,g_w tensors (sm100_host::ElemType)
   int64_t rows;
   int n_act;  // y buffers
   size_t off_y[WIRE_B200_MAX_LAYERS + 1], off_z[WIRE_B200_MAX_LAYERS + 1], off_w[WIRE_B200_MAX_LAYERS + 1];
@@ -157,9 +159,25 @@ int check_desc(const wire_net_desc* d) {
   if (d->hidden_layers < 1 || d->hidden_layers >= WIRE_B200_MAX_LAYERS) return fail("hidden_layers %d out of range [1,%d)", d->hidden_layers, WIRE_B200_MAX_LAYERS);
   if (d->in_features < 1 || d->in_features > kMaxIn) return fail("in_features %d out of range [1,%d]", d->in_features, kMaxIn);
   if (d->out_features < 1 || d->out_features > kSimtMaxOut) return fail("out_features %d out of range [1,%d]", d->out_features, kSimtMaxOut);
-  if (d->precision != WIRE_PRECISION_TF32 && d->precision != WIRE_PRECISION_FP32) return fail("unknown precision %d", d->precision);
+  if (d->precision != WIRE_PRECISION_TF32 && d->precision != WIRE_PRECISION_FP32 && d->precision != WIRE_PRECISION_MIXED16)
+    return fail("unknown precision %d", d->precision);
   return 0;
 }
+
+// MIXED16 covers the whole-network path for the shapes every reference driver uses (coordinates <= 3-D, <= 4 outputs);
+// anything else, and the single-layer entry points, run the TF32 kernels (same GPU, same data flow, 32-bit operands).
+int net_precision(const wire_net_desc* d) {
+  if (d->precision == WIRE_PRECISION_MIXED16 && (d->in_features > 3 || d->out_features > 4)) return WIRE_PRECISION_TF32;
+  return d->precision;
+}
+wire_net_desc layer_desc(const wire_net_desc* d) {
+  wire_net_desc dd = *d;
+  if (dd.precision == WIRE_PRECISION_MIXED16) dd.precision = WIRE_PRECISION_TF32;
+  return dd;
+}
+using sm100_host::kElemBF16;
+using sm100_host::kElemF16;
+using sm100_host::kElemF32;
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -167,9 +185,14 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
   TRY(check_desc(d));
   memset(&L, 0, sizeof(L));
   L.M = d->width; L.H = d->hidden_layers; L.two_m = 2 * d->width; L.two_d = d->two_d;
+  L.prec = net_precision(d);
+  const bool mixed = L.prec == WIRE_PRECISION_MIXED16;
+  L.y_elem = mixed ? kElemF16 : kElemF32;                               // activations: FP16 (TF32's 11-bit significand)
+  L.z_elem = L.prec == WIRE_PRECISION_FP32 ? kElemF32 : kElemF16;       // saved pre-activations
+  L.g_elem = mixed ? kElemBF16 : kElemF32;                              // gradients: BF16 (FP32's range, no loss scaling)
   L.P = round_up(L.two_m + 1, 32);
   L.PR = round_up(L.M, 4);
-  L.k_pad = round_up(L.two_m, 32);
+  L.k_pad = round_up(L.two_m, mixed ? 64 : 32);
   L.rows = training ? n : (n < kInferChunk ? n : kInferChunk);
   if (L.rows < 1) L.rows = 1;
   Blocking bf;
@@ -177,18 +200,18 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
     return fail("no tile configuration for width %d", d->width);
   L.fuse_final = bf.n_blocks == 1 && d->out_features <= kMaxOut;
   size_t off = 0;
-  const size_t act = align_up(size_t(L.rows) * L.P * sizeof(float), 1024);
+  auto act = [&](int elem) { return align_up(size_t(L.rows) * L.P * sm100_host::elem_bytes(elem), 1024); };
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
   if (training) {
     const int ny = L.fuse_final ? L.H : L.H + 1;
-    for (int l = 0; l < ny; ++l) L.off_y[l] = take(act);
+    for (int l = 0; l < ny; ++l) L.off_y[l] = take(act(L.y_elem));
     L.n_act = ny;
-    for (int l = 1; l <= L.H; ++l) { L.off_z[l] = take(act); if (d->two_d) L.off_w[l] = take(act); }
-    for (int i = 0; i < 2; ++i) { L.off_gz[i] = take(act); if (d->two_d) L.off_gw[i] = take(act); }
+    for (int l = 1; l <= L.H; ++l) { L.off_z[l] = take(act(L.z_elem)); if (d->two_d) L.off_w[l] = take(act(L.z_elem)); }
+    for (int i = 0; i < 2; ++i) { L.off_gz[i] = take(act(L.g_elem)); if (d->two_d) L.off_gw[i] = take(act(L.g_elem)); }
     L.off_gz0 = take(size_t(L.rows) * L.PR * sizeof(float));
     if (d->two_d) L.off_gw0 = take(size_t(L.rows) * L.PR * sizeof(float));
   } else {
-    L.off_y[0] = take(act); L.off_y[1] = take(act); L.n_act = 2;
+    L.off_y[0] = take(act(L.y_elem)); L.off_y[1] = take(act(L.y_elem)); L.n_act = 2;
   }
   // packed weights: generous bound on rows (blocks are padded to 32) x both K parts
   L.pack_floats = size_t(2 * L.k_pad + 1024) * size_t(2 * L.k_pad);
@@ -215,7 +238,8 @@ struct RowsJob {
   Blocking blk;
   float* o[3];
   int o_pitch[3];
-  int o_half[3];  // this output is an FP16 tensor (saved z / w)
+  int o_half[3];  // element type of each output tensor (sm100_host::ElemType; non-zero = 16-bit: FP16 z / y, BF16 g)
+  int a_elem, b_elem;  // element type of the A / packed-B operands (0 = TF32 kernels, FP16 or BF16 = kind::f16 kernels)
   int store_mask;
   int gen;        // A operand = first-layer output, generated in place (e.coords / e.w0 ... describe that layer)
   const float* gen_omega;
@@ -271,16 +295,22 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.gen_omega = J.gen_omega; P.gen_scale = J.gen_scale; P.gen_two_d = J.gen_two_d;
   if (!smem) return fail("row-tile configuration does not fit shared memory (nb=%d)", J.blk.nb);
   bool ok = true;
+  const bool op16 = J.a_elem != kElemF32;
+  if (op16 && (J.b_elem != J.a_elem || J.gen)) return fail("16-bit row-tile GEMM needs A and B in the same format");
+  P.a_fmt = J.a_elem == kElemBF16 ? int(sm100::kFmtBF16) : int(sm100::kFmtF16);
+  P.b_fmt = P.a_fmt;
+  const int kbox = op16 ? 64 : 32;  // one 128-byte swizzle row of K columns
   for (int i = 0; i < 2; ++i) {
     const int src = (J.k_cols[i] > 0) ? i : 0;
-    ok &= sm100_host::make_tmap_2d(&P.a_map[i], J.a[src], J.e.n_rows, J.k_cols[src], J.a_pitch[src], 128, 32);
+    ok &= sm100_host::make_tmap_2d_t(&P.a_map[i], J.a[src], J.e.n_rows, J.k_cols[src], J.a_pitch[src], 128, kbox, CU_TENSOR_MAP_SWIZZLE_128B, J.a_elem);
   }
-  ok &= sm100_host::make_tmap_2d(&P.b_map, J.b, J.b_rows, J.b_pitch, J.b_pitch, P.b_box_rows, 32);
+  ok &= sm100_host::make_tmap_2d_t(&P.b_map, J.b, J.b_rows, J.b_pitch, J.b_pitch, P.b_box_rows, kbox, CU_TENSOR_MAP_SWIZZLE_128B, J.b_elem);
   int nslot = 0;
   for (int bit = 0; bit < 3; ++bit)
     if (J.store_mask & (1 << bit)) {
+      P.o_fmt[nslot] = J.o_half[nslot];
       if (J.o_half[nslot])
-        ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE, true);
+        ok &= sm100_host::make_tmap_2d_t(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE, J.o_half[nslot]);
       else
         ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32);
       ++nslot;
@@ -292,17 +322,23 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   if (P.n_in >= 2) ok &= sm100_host::make_tmap_2d(&P.z_map[1], J.e.w_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
   if (!ok) return fail("cuTensorMapEncodeTiled failed (pointer/pitch alignment?)");
   if (J.gen) CU_OK(launch_rows_gen(J.mode, P, smem, g_sm_count, st));
-  else CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st));
+  else CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st, op16));
   return 0;
 }
 
+// elem: element type of the packed matrix (FP32/TF32 kernels: kElemF32; mixed16: FP16 forward, BF16 dgrad)
 int run_pack(const float* W1, const float* W2, int M_out, int K_in, int mode, const Blocking& blk, int k0_pad,
-             int k_pad_total, float* B, int precision, cudaStream_t st) {
+             int k_pad_total, float* B, int precision, cudaStream_t st, int elem = kElemF32) {
   const int total = blk.n_blocks * blk.nb * k_pad_total;
   const int grid = (total + 255) / 256;
   ProfScope prof(K_PACK, st);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B,
-                                           precision == WIRE_PRECISION_TF32);
+  if (elem == kElemF16)
+    pack_weights_kernel<1><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0);
+  else if (elem == kElemBF16)
+    pack_weights_kernel<2><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0);
+  else
+    pack_weights_kernel<0><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B,
+                                                precision == WIRE_PRECISION_TF32);
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -315,7 +351,8 @@ struct WgradGen {  // first-layer description when x = y0 is generated in place 
   int two_d = 0;
 };
 int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const float* g2, int g_pitch, int m_out, int64_t n,
-              float* gW1, float* gB1, float* gW2, float* gB2, int precision, cudaStream_t st, const WgradGen* gen = nullptr) {
+              float* gW1, float* gB1, float* gW2, float* gB2, int precision, cudaStream_t st, const WgradGen* gen = nullptr,
+              int x_elem = kElemF32, int g_elem = kElemF32) {
   if (n <= 0) return 0;
   const int n_g = g2 ? 2 : 1;
   ProfScope prof(K_WGRAD, st, (precision == WIRE_PRECISION_FP32 && g2) ? 2 : 1);
@@ -336,25 +373,49 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
   memset(&P, 0, sizeof(P));
   P.n_rows = int(n); P.k_in = k_in; P.g_cols = 2 * m_out; P.n_g = n_g;
   P.gW[0] = gW1; P.gB[0] = gB1; P.gW[1] = gW2; P.gB[1] = gB2;
-  const bool use_gen = gen && gen->coords;
-  const size_t smem = wgrad_configure(P, g_sm_count, cluster_size(), use_gen);
+  const bool op16 = g_elem != kElemF32;
+  const bool use_gen = gen && gen->coords && !op16;
+  if (op16) {
+    if (x_elem == kElemF32) return fail("16-bit wgrad needs a 16-bit x operand");
+    P.x_fmt = x_elem == kElemBF16 ? int(sm100::kFmtBF16) : int(sm100::kFmtF16);
+    P.g_fmt = g_elem == kElemBF16 ? int(sm100::kFmtBF16) : int(sm100::kFmtF16);
+    P.x_conv = x_elem != g_elem;
+    if (P.x_conv && !(x_elem == kElemF16 && g_elem == kElemBF16)) return fail("unsupported wgrad operand formats");
+  }
+  const size_t smem = wgrad_configure(P, g_sm_count, cluster_size(), use_gen, op16);
   if (!smem) return fail("wgrad configuration does not fit shared memory");
   if (use_gen) {
     P.coords = gen->coords; P.in_features = gen->in_features; P.w0 = gen->w0; P.b0 = gen->b0; P.w0b = gen->w0b; P.b0b = gen->b0b;
     P.gen_omega = gen->omega; P.gen_scale = gen->scale; P.gen_two_d = gen->two_d;
     x = g1; x_pitch = g_pitch; /* x_map is unused by the GEN kernel but must be a valid descriptor */
   }
-  bool ok = sm100_host::make_tmap_2d(&P.x_map, x, n, use_gen ? 2 * m_out : 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  ok &= sm100_host::make_tmap_2d(&P.g_map[0], g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  ok &= sm100_host::make_tmap_2d(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  bool ok;
+  if (op16) {
+    ok = sm100_host::make_tmap_2d_t(&P.x_map, x, n, 2 * k_in + 1, x_pitch, kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, x_elem);
+    ok &= sm100_host::make_tmap_2d_t(&P.g_map[0], g1, n, 2 * m_out, g_pitch, kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, g_elem);
+    ok &= sm100_host::make_tmap_2d_t(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, g_elem);
+  } else {
+    ok = sm100_host::make_tmap_2d(&P.x_map, x, n, use_gen ? 2 * m_out : 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    ok &= sm100_host::make_tmap_2d(&P.g_map[0], g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    ok &= sm100_host::make_tmap_2d(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  }
   if (!ok) return fail("cuTensorMapEncodeTiled failed for wgrad");
-  CU_OK(launch_wgrad(P, smem, st, use_gen));
+  CU_OK(launch_wgrad(P, smem, st, use_gen, op16));
   return 0;
 }
 
 int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const float* coords, int64_t n, int in_f, float* y,
-                  int y_pitch, float* z_out, float* w_out, int zr_pitch, cudaStream_t st) {
+                  int y_pitch, float* z_out, float* w_out, int zr_pitch, cudaStream_t st, int y_elem = kElemF32) {
   if (n <= 0) return 0;
+  if (y_elem == kElemF16) {  // mixed16 whole-network path: FP16 activations
+    if (z_out || w_out || (y_pitch % 4)) return fail("FP16 first layer: unsupported call");
+    const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
+    ProfScope prof(K_FIRST_FWD, st);
+    first_fwd2_kernel<true, true><<<grid, 128, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
+                                                        d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, 0, kRowsPerBlock);
+    CU_OK(cudaGetLastError());
+    return 0;
+  }
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   const int round_y = d->precision == WIRE_PRECISION_TF32;
   ProfScope prof(K_FIRST_FWD, st);
@@ -381,8 +442,21 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
 int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const float* Wf, const float* z, const float* w, int zw_pitch,
                 int z_half,
                 const float* h, int h_pitch, const float* omega, const float* scale, float* gz, float* gw, int g_pitch, float* g_Wf,
-                float* g_bf, cudaStream_t st) {
+                float* g_bf, cudaStream_t st, int g_elem = kElemF32) {
   if (n <= 0) return 0;
+  if (g_elem == kElemBF16) {  // mixed16 whole-network path: FP16 z in, BF16 g_z out
+    if (!(z && z_half && d->out_features <= 4 && d->width <= 1024 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0))
+      return fail("BF16 top backward: unsupported shape");
+    ProfScope prof(K_TOP_BWD, st);
+    const int thr = round_up((d->width + 1) / 2, 32) < 128 ? 128 : round_up((d->width + 1) / 2, 32);
+    const int nblk = int(n < int64_t(10 * g_sm_count) * 64 ? (n + 63) / 64 : 10 * g_sm_count);
+    const int rpb = int(((n + nblk - 1) / nblk + 63) / 64 * 64);
+    const int grid = int((n + rpb - 1) / rpb);
+    if (w) top_bwd2_kernel<true, true, true, true><<<grid, thr, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, 0, g_Wf, g_bf, rpb);
+    else top_bwd2_kernel<true, false, true, true><<<grid, thr, 0, st>>>(g_out, int(n), d->width, d->out_features, Wf, z, w, zw_pitch, omega, scale, gz, gw, g_pitch, 0, g_Wf, g_bf, rpb);
+    CU_OK(cudaGetLastError());
+    return 0;
+  }
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   const int round_g = (d->precision == WIRE_PRECISION_TF32) && z;
   ProfScope prof(K_TOP_BWD, st);
@@ -451,7 +525,8 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
   // Correct (parity-green) but slower on B200: four generator warps cannot hide the MUFU latency (fwd 0.25 -> 0.36 ms,
   // wgrad 0.22 -> 0.55 ms, profiles/r01_bench_v9_gen.json), so the default keeps first_fwd2_kernel.
   const bool gen0 = d->precision == WIRE_PRECISION_TF32 && d->in_features <= 3 && getenv("WIRE_B200_GEN") != nullptr;
-  if (!gen0) TRY(run_first_fwd(d, p->layer[0], coords, n, d->in_features, y_prev, L.P, nullptr, nullptr, 0, st));
+  const bool mixed = d->precision == WIRE_PRECISION_MIXED16;
+  if (!gen0) TRY(run_first_fwd(d, p->layer[0], coords, n, d->in_features, y_prev, L.P, nullptr, nullptr, 0, st, L.y_elem));
   for (int l = 1; l <= H; ++l) {
     const bool last = l == H;
     const bool fuse = last && L.fuse_final;
@@ -466,18 +541,19 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     const bool gen = gen0 && l == 1;
     if (!job_blocking(fmode, L.two_m, mask, fuse, blk, gen)) return fail("no tile configuration");
     float* Bf = at(ws, L.off_bf[l]);
-    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st));
+    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st, L.y_elem));
     RowsJob J;
     memset(&J, 0, sizeof(J));
     J.mode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
+    J.a_elem = L.y_elem; J.b_elem = L.y_elem;
     J.a[0] = y_prev; J.a_pitch[0] = L.P; J.k_cols[0] = L.two_m;
     J.b = Bf; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = L.k_pad; J.k0_pad = L.k_pad;
     J.blk = blk;
     int slot = 0;
-    if (mask & 1) { J.o[slot] = y_out; J.o_pitch[slot++] = L.P; }
-    const int zh = d->precision == WIRE_PRECISION_TF32;  // saved z / w in FP16 on the tensor-core path
-    if (mask & 2) { J.o[slot] = at(ws, L.off_z[l]); J.o_half[slot] = zh; J.o_pitch[slot++] = L.P; }
-    if (mask & 4) { J.o[slot] = at(ws, L.off_w[l]); J.o_half[slot] = zh; J.o_pitch[slot++] = L.P; }
+    if (mask & 1) { J.o[slot] = y_out; J.o_half[slot] = L.y_elem; J.o_pitch[slot++] = L.P; }
+    const int zh = L.z_elem != kElemF32;  // saved z / w in FP16 on the tensor-core paths
+    if (mask & 2) { J.o[slot] = at(ws, L.off_z[l]); J.o_half[slot] = L.z_elem; J.o_pitch[slot++] = L.P; }
+    if (mask & 4) { J.o[slot] = at(ws, L.off_w[l]); J.o_half[slot] = L.z_elem; J.o_pitch[slot++] = L.P; }
     J.store_mask = mask;
     J.e = base_epi(n, L.two_m, d->precision);
     J.e.z_half = zh;
@@ -499,7 +575,8 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     const int64_t g64 = (n * 32 + 255) / 256;
     const int grid = int(g64 > 65535 * 16 ? 65535 * 16 : g64);
     ProfScope prof(K_FINAL_FWD, st);
-    final_fwd_kernel<<<grid, 256, 0, st>>>(y_prev, L.P, int(n), M, d->out_features, p->final_weight, p->final_bias, out);
+    if (mixed) final_fwd_kernel<true><<<grid, 256, 0, st>>>(y_prev, L.P, int(n), M, d->out_features, p->final_weight, p->final_bias, out);
+    else final_fwd_kernel<false><<<grid, 256, 0, st>>>(y_prev, L.P, int(n), M, d->out_features, p->final_weight, p->final_bias, out);
     CU_OK(cudaGetLastError());
   }
   return 0;
@@ -545,7 +622,7 @@ int wire_b200_prof_get(int32_t kind, uint64_t* launches, double* ms) {
 
 size_t wire_net_workspace_bytes(const wire_net_desc* d, int64_t n, int32_t training) {
   Layout L;
-  if (make_layout(d, n, training, L)) return 0;
+  if (!d || make_layout(d, n, training, L)) return 0;
   return L.total;
 }
 
@@ -557,18 +634,26 @@ int wire_net_workspace_init(const wire_net_desc* d, int64_t n, int32_t training,
   CU_OK(cudaMemsetAsync(workspace, 0, L.total, st));
   // "ones" column (col 2M) of every activation buffer: the bias-gradient row of the wgrad GEMM
   for (int l = 0; l < L.n_act; ++l) {
-    set_column_kernel<<<int((L.rows + 255) / 256), 256, 0, st>>>(at(workspace, L.off_y[l]), L.P, L.rows, L.two_m, 1.0f);
+    if (L.y_elem == kElemF16)
+      set_column16_kernel<<<int((L.rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint16_t*>(at(workspace, L.off_y[l])), L.P, L.rows,
+                                                                      L.two_m, uint16_t(0x3C00));  // FP16 1.0
+    else
+      set_column_kernel<<<int((L.rows + 255) / 256), 256, 0, st>>>(at(workspace, L.off_y[l]), L.P, L.rows, L.two_m, 1.0f);
   }
   CU_OK(cudaGetLastError());
   return 0;
 }
 
-int wire_net_forward(const wire_net_desc* d, const wire_net_params* p, const float* coords, int64_t n, float* out, void* workspace,
+int wire_net_forward(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, float* out, void* workspace,
                      size_t workspace_bytes, int32_t training, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TRY(require_device());
-  if (!p || !coords || !out) return fail("null argument");
+  if (!d_in || !p || !coords || !out) return fail("null argument");
   if (n <= 0) return 0;
+  TRY(check_desc(d_in));
+  wire_net_desc de = *d_in;
+  de.precision = net_precision(d_in);  // from here on `precision` is the one that actually runs
+  const wire_net_desc* d = &de;
   Layout L;
   TRY(make_layout(d, n, training, L));
   if (!workspace || workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
@@ -580,11 +665,15 @@ int wire_net_forward(const wire_net_desc* d, const wire_net_params* p, const flo
   return 0;
 }
 
-int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
+int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
                       void* workspace, size_t workspace_bytes, const wire_net_grads* g, float* grad_coords, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TRY(require_device());
-  if (!p || !coords || !grad_out || !g) return fail("null argument");
+  if (!d_in || !p || !coords || !grad_out || !g) return fail("null argument");
+  TRY(check_desc(d_in));
+  wire_net_desc de = *d_in;
+  de.precision = net_precision(d_in);
+  const wire_net_desc* d = &de;
   Layout L;
   TRY(make_layout(d, n, 1, L));
   if (!workspace || workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
@@ -606,9 +695,9 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
   int cur = 0;
   // final Linear backward + Gabor backward of the last hidden layer (h recomputed from z_H)
   TRY(run_top_bwd(d, grad_out, n, p->final_weight, at(workspace, L.off_z[H]), d->two_d ? at(workspace, L.off_w[H]) : nullptr, L.P,
-                  d->precision == WIRE_PRECISION_TF32, nullptr,
+                  L.z_elem != kElemF32, nullptr,
                   0, p->layer[H].omega0, p->layer[H].scale0, at(workspace, L.off_gz[cur]), d->two_d ? at(workspace, L.off_gw[cur]) : nullptr,
-                  L.P, g->final_weight, g->final_bias, st));
+                  L.P, g->final_weight, g->final_bias, st, L.g_elem));
   for (int l = H; l >= 1; --l) {
     const float* gz = at(workspace, L.off_gz[cur]);
     const float* gw = d->two_d ? at(workspace, L.off_gw[cur]) : nullptr;
@@ -621,7 +710,7 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
     }
     if (g->layer[l].weight)
       TRY(run_wgrad(x, L.P, M, gz, gw, L.P, M, n, g->layer[l].weight, g->layer[l].bias, g->layer[l].weight2, g->layer[l].bias2, d->precision, st,
-                    &wg));
+                    &wg, L.y_elem, L.g_elem));
     // dgrad of layer l fused with the nonlinearity backward of layer l-1
     const bool to_first = (l == 1);
     int mask = to_first ? 0 : (d->two_d ? 3 : 1);
@@ -630,9 +719,11 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
     if (!job_blocking(bmode, L.two_m, mask, false, blk)) return fail("no tile configuration");
     float* Bd = at(workspace, L.off_bd[l]);
     const int kparts = d->two_d ? 2 : 1;
-    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st));
+    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st,
+                 L.g_elem));
     RowsJob J;
     memset(&J, 0, sizeof(J));
+    J.a_elem = L.g_elem; J.b_elem = L.g_elem;
     J.a[0] = gz; J.a_pitch[0] = L.P; J.k_cols[0] = L.two_m;
     if (d->two_d) { J.a[1] = gw; J.a_pitch[1] = L.P; J.k_cols[1] = L.two_m; }
     J.b = Bd; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = kparts * L.k_pad; J.k0_pad = L.k_pad;
@@ -643,9 +734,9 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
     if (!to_first) {
       J.mode = d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD;
       J.e.z_src = at(workspace, L.off_z[l - 1]); J.e.w_src = d->two_d ? at(workspace, L.off_w[l - 1]) : nullptr; J.e.zw_pitch = L.P;
-      J.e.z_half = d->precision == WIRE_PRECISION_TF32;
-      J.o[0] = at(workspace, L.off_gz[1 - cur]); J.o_pitch[0] = L.P;
-      if (d->two_d) { J.o[1] = at(workspace, L.off_gw[1 - cur]); J.o_pitch[1] = L.P; }
+      J.e.z_half = L.z_elem != kElemF32;
+      J.o[0] = at(workspace, L.off_gz[1 - cur]); J.o_pitch[0] = L.P; J.o_half[0] = L.g_elem;
+      if (d->two_d) { J.o[1] = at(workspace, L.off_gw[1 - cur]); J.o_pitch[1] = L.P; J.o_half[1] = L.g_elem; }
     } else {
       J.mode = d->two_d ? MODE_FIRST2D_BWD : MODE_FIRST_BWD;
       J.e.coords = coords; J.e.in_features = in_f;
@@ -753,11 +844,13 @@ size_t wire_gabor_layer_workspace_bytes(const wire_net_desc* d, int32_t is_first
   return L.total;
 }
 
-int wire_gabor_layer_forward(const wire_net_desc* d, int32_t is_first, int32_t in_features, const wire_layer_params* p, const float* x,
+int wire_gabor_layer_forward(const wire_net_desc* d_in, int32_t is_first, int32_t in_features, const wire_layer_params* p, const float* x,
                              int64_t n, float* y, float* z_save, float* w_save, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TRY(require_device());
-  if (!d || !p || !x || !y) return fail("null argument");
+  if (!d_in || !p || !x || !y) return fail("null argument");
+  const wire_net_desc de = layer_desc(d_in);
+  const wire_net_desc* d = &de;
   if (n <= 0) return 0;
   const int M = d->width;
   if (is_first) {
@@ -799,12 +892,14 @@ int wire_gabor_layer_forward(const wire_net_desc* d, int32_t is_first, int32_t i
   return 0;
 }
 
-int wire_gabor_layer_backward(const wire_net_desc* d, int32_t is_first, int32_t in_features, const wire_layer_params* p, const float* x,
+int wire_gabor_layer_backward(const wire_net_desc* d_in, int32_t is_first, int32_t in_features, const wire_layer_params* p, const float* x,
                               const float* z_save, const float* w_save, const float* grad_y, int64_t n, float* grad_x,
                               const wire_layer_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TRY(require_device());
-  if (!d || !p || !x || !z_save || !grad_y || !g) return fail("null argument");
+  if (!d_in || !p || !x || !z_save || !grad_y || !g) return fail("null argument");
+  const wire_net_desc de = layer_desc(d_in);
+  const wire_net_desc* d = &de;
   const int M = d->width, K = in_features;
   const size_t wsz = is_first ? size_t(M) * K : size_t(M) * K * 2;
   const size_t bsz = is_first ? size_t(M) : size_t(M) * 2;
@@ -876,16 +971,18 @@ int wire_final_linear_forward(const wire_net_desc* d, const float* weight, const
   if (n <= 0) return 0;
   int64_t g64 = (n * 32 + 255) / 256;
   const int grid = int(g64 > 65535 * 16 ? 65535 * 16 : g64);
-  final_fwd_kernel<<<grid, 256, 0, st>>>(h, 2 * d->width, int(n), d->width, d->out_features, weight, bias, out);
+  final_fwd_kernel<false><<<grid, 256, 0, st>>>(h, 2 * d->width, int(n), d->width, d->out_features, weight, bias, out);
   CU_OK(cudaGetLastError());
   return 0;
 }
 
-int wire_final_linear_backward(const wire_net_desc* d, const float* weight, const float* h, const float* grad_out, int64_t n, float* grad_h,
+int wire_final_linear_backward(const wire_net_desc* d_in, const float* weight, const float* h, const float* grad_out, int64_t n, float* grad_h,
                                float* grad_weight, float* grad_bias, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TRY(require_device());
-  if (!d || !weight || !h || !grad_out || !grad_weight || !grad_bias) return fail("null argument");
+  if (!d_in || !weight || !h || !grad_out || !grad_weight || !grad_bias) return fail("null argument");
+  const wire_net_desc de = layer_desc(d_in);
+  const wire_net_desc* d = &de;
   TRY(zero(grad_weight, size_t(d->out_features) * d->width * 2, st));
   TRY(zero(grad_bias, size_t(d->out_features) * 2, st));
   return run_top_bwd(d, grad_out, n, weight, nullptr, nullptr, 0, 0, h, 2 * d->width, nullptr, nullptr, grad_h, nullptr, 2 * d->width,

@@ -2,6 +2,7 @@
 // tensor cores (first layer K = 2..3, final layer out = 1..3), weight packing, and the optimiser.
 // All are HBM-bound streaming kernels: coalesced along the feature axis, rows blocked per CTA.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "gabor_math.cuh"
@@ -63,9 +64,11 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
 //                     gx_re: ( Wre,  Wim)  gx_im: (-Wim,  Wre)         g_x = g_z conj(W)
 // B is [n_blocks*nb][k_pad_total], zero padded.
 // ---------------------------------------------------------------------------------------------
+// ELEM (sm100_host::ElemType): 0 = fp32 (TF32-rounded if do_round), 1 = FP16, 2 = BF16 (mixed16 path)
+template <int ELEM>
 __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int M_out, int K_in,
                                     int mode, int n_blocks, int nb, int nbh, int k0_pad, int k_pad_total,
-                                    float* __restrict__ B, int do_round) {
+                                    void* __restrict__ Bv, int do_round) {
   const int total = n_blocks * nb * k_pad_total;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / k_pad_total, kk = idx % k_pad_total;
@@ -93,7 +96,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
         v = part == 0 ? (d == 0 ? wr : wi) : (d == 0 ? -wi : wr);
       }
     }
-    B[idx] = do_round ? sm100::round_tf32(v) : v;
+    if constexpr (ELEM == 0) reinterpret_cast<float*>(Bv)[idx] = do_round ? sm100::round_tf32(v) : v;
+    else if constexpr (ELEM == 1) reinterpret_cast<__half*>(Bv)[idx] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(Bv)[idx] = __float2bfloat16_rn(v);
   }
 }
 
@@ -102,6 +107,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
 //   out[n][o] = Re( sum_k h[n,k] Wf[o,k] + bf[o] )           (modules/wire.py:156-165)
 // one warp per row, lanes strided over k.
 // ---------------------------------------------------------------------------------------------
+// H16: h is an FP16 tensor (mixed16 path), h_pitch in elements
+template <bool H16 = false>
 __global__ void __launch_bounds__(256) final_fwd_kernel(const float* __restrict__ h, int h_pitch, int n, int M, int out_f,
                                                          const float* __restrict__ Wf, const float* __restrict__ bf,
                                                          float* __restrict__ out) {
@@ -112,7 +119,9 @@ __global__ void __launch_bounds__(256) final_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int o = 0; o < kSimtMaxOut; ++o) acc[o] = 0.f;
     for (int k = lane; k < M; k += 32) {
-      const float2 hv = *reinterpret_cast<const float2*>(h + size_t(row) * h_pitch + 2 * k);
+      float2 hv;
+      if constexpr (H16) hv = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(h) + size_t(row) * h_pitch + 2 * k));
+      else hv = *reinterpret_cast<const float2*>(h + size_t(row) * h_pitch + 2 * k);
 #pragma unroll
       for (int o = 0; o < kSimtMaxOut; ++o)
         if (o < out_f) {
@@ -286,6 +295,11 @@ __global__ void set_column_kernel(float* __restrict__ dst, int pitch, int64_t n,
     dst[r * pitch + col] = v;
 }
 
+__global__ void set_column16_kernel(uint16_t* __restrict__ dst, int pitch, int64_t n, int col, uint16_t bits) {
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x)
+    dst[r * pitch + col] = bits;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam, amsgrad=False, maximize=False) on a flat fp32 view; complex params are
 // their view_as_real, which is exactly how torch treats them.
@@ -365,7 +379,8 @@ __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __r
 namespace wire {
 
 // first layer forward, 2 complex features (one float4) per thread, rows_per_block rows per block
-template <bool FAST>
+// OUT16: y is an FP16 tensor (mixed16 path; y_pitch in elements): 8-byte stores of two complex features
+template <bool FAST, bool OUT16 = false>
 __global__ void __launch_bounds__(128) first_fwd2_kernel(const float* __restrict__ coords, int n, int in_f, int M,
                                                           const float* __restrict__ W0, const float* __restrict__ b0,
                                                           const float* __restrict__ W0b, const float* __restrict__ b0b,
@@ -403,9 +418,16 @@ __global__ void __launch_bounds__(128) first_fwd2_kernel(const float* __restrict
       gabor_fwd_c<FAST>(G, z0, 0.f, W0b ? u0 * u0 : 0.f, o.x, o.y);
       gabor_fwd_c<FAST>(G, z1, 0.f, W0b ? u1 * u1 : 0.f, o.z, o.w);
       if (round_y) { o.x = sm100::round_tf32(o.x); o.y = sm100::round_tf32(o.y); o.z = sm100::round_tf32(o.z); o.w = sm100::round_tf32(o.w); }
-      float* dst = y + size_t(row0 + r) * y_pitch + 4 * jp;
-      if (2 * jp + 1 < M) *reinterpret_cast<float4*>(dst) = o;
-      else *reinterpret_cast<float2*>(dst) = make_float2(o.x, o.y);
+      if constexpr (OUT16) {
+        __half* dst = reinterpret_cast<__half*>(y) + size_t(row0 + r) * y_pitch + 4 * jp;
+        const __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+        if (2 * jp + 1 < M) *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        else *reinterpret_cast<__half2*>(dst) = a;
+      } else {
+        float* dst = y + size_t(row0 + r) * y_pitch + 4 * jp;
+        if (2 * jp + 1 < M) *reinterpret_cast<float4*>(dst) = o;
+        else *reinterpret_cast<float2*>(dst) = make_float2(o.x, o.y);
+      }
     }
   }
 }
@@ -421,7 +443,20 @@ __device__ __forceinline__ float4 load_zw4(const float* base, size_t row, int pi
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <bool FAST, bool TWO_D, bool ZHALF = false>
+// GBF16: g_z / g_w are BF16 tensors (mixed16 path; g_pitch in elements)
+__device__ __forceinline__ void store_g4(float* base, size_t row, int pitch, int kp, bool pair, float4 v, bool bf16) {
+  if (!bf16) {
+    float* d = base + row * pitch + 4 * kp;
+    if (pair) *reinterpret_cast<float4*>(d) = v; else *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
+  } else {
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(base) + row * pitch + 4 * kp;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    if (pair) *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    else *reinterpret_cast<__nv_bfloat162*>(d) = a;
+  }
+}
+
+template <bool FAST, bool TWO_D, bool ZHALF = false, bool GBF16 = false>
 __global__ void __launch_bounds__(512) top_bwd2_kernel(const float* __restrict__ g_out, int n, int M, int out_f,
                                                         const float* __restrict__ Wf, const float* __restrict__ z,
                                                         const float* __restrict__ w, int zw_pitch,
@@ -491,14 +526,12 @@ __global__ void __launch_bounds__(512) top_bwd2_kernel(const float* __restrict__
         const float pr0 = gabor_bwd(yr0, yi0, zv[u].x, zv[u].y, gyr0, gyi0, omega, s2, gzo.x, gzo.y);
         const float pr1 = gabor_bwd(yr1, yi1, zv[u].z, zv[u].w, gyr1, gyi1, omega, s2, gzo.z, gzo.w);
         if (round_g) { gzo.x = sm100::round_tf32(gzo.x); gzo.y = sm100::round_tf32(gzo.y); gzo.z = sm100::round_tf32(gzo.z); gzo.w = sm100::round_tf32(gzo.w); }
-        float* dz = gz + size_t(row0 + r) * g_pitch + 4 * kp;
-        if (pair) *reinterpret_cast<float4*>(dz) = gzo; else *reinterpret_cast<float2*>(dz) = make_float2(gzo.x, gzo.y);
+        store_g4(gz, size_t(row0 + r), g_pitch, kp, pair, gzo, GBF16);
         if (TWO_D) {
           const float t0 = -2.0f * s2 * pr0, t1 = -2.0f * s2 * pr1;
           float4 gwo = make_float4(t0 * wv[u].x, t0 * wv[u].y, t1 * wv[u].z, t1 * wv[u].w);
           if (round_g) { gwo.x = sm100::round_tf32(gwo.x); gwo.y = sm100::round_tf32(gwo.y); gwo.z = sm100::round_tf32(gwo.z); gwo.w = sm100::round_tf32(gwo.w); }
-          float* dw = gw + size_t(row0 + r) * g_pitch + 4 * kp;
-          if (pair) *reinterpret_cast<float4*>(dw) = gwo; else *reinterpret_cast<float2*>(dw) = make_float2(gwo.x, gwo.y);
+          store_g4(gw, size_t(row0 + r), g_pitch, kp, pair, gwo, GBF16);
         }
 #pragma unroll
         for (int o = 0; o < 4; ++o) {

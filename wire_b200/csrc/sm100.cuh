@@ -202,6 +202,28 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc,
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16: A and B are FP16 or BF16 (chosen independently in the instruction descriptor), FP32 accumulate; K = 16.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta_mcast(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -280,6 +302,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
          (uint32_t(M >> 4) << 24);
 }
 
+// kind::f16 (16-bit operands, FP32 accumulator): a_format / b_format 0 = F16, 1 = BF16 (independent fields).
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major, uint32_t a_fmt,
+                                                      uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout):
 //   [0,14) addr>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout=2 (SW128)
 // K-major  operand: rows of 128 B (32 tf32 along K); 8 rows = one 1024 B atom; SBO = 1024; LBO unused (1).
@@ -302,6 +332,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
 }
 constexpr uint32_t kLayoutSW128 = 2;
 constexpr uint32_t kLayoutSW128Base32 = 1;
+// 16-bit MN-major operands in 32-element (64-byte) blocks: rows of 64 B, one per K index, 8 K-rows = one 512 B atom
+// (TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3); SBO = 512 (next 8 K-rows), LBO = MN-block stride.
+constexpr uint32_t kLayoutSW64 = 4;
 __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
                                                      uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -359,6 +392,27 @@ inline bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// element types of the 16-bit tensors of the mixed-precision path
+enum ElemType : int { kElemF32 = 0, kElemF16 = 1, kElemBF16 = 2 };
+inline size_t elem_bytes(int t) { return t == kElemF32 ? 4 : 2; }
+
+// general form: element type and swizzle explicit (box_cols * elem_bytes must equal the swizzle span, or be
+// <= 256 B with SWIZZLE_NONE)
+inline bool make_tmap_2d_t(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                           uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle, int elem) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * elem_bytes(elem)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem == kElemF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                               : (elem == kElemF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

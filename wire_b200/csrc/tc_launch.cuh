@@ -55,12 +55,12 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
   return stages * stage + staging + pbytes + 1024;
 }
 
-template <int MODE, bool PAIR, bool GEN = false>
+template <int MODE, bool PAIR, bool GEN = false, bool OP16 = false>
 inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE, PAIR, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE, PAIR, GEN, OP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -83,7 +83,7 @@ inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_c
     cfg.gridDim = dim3(sm_count / C * C);
     cfg.dynamicSmemBytes = kMaxDynSmem;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE, PAIR, GEN>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows_kernel<MODE, PAIR, GEN, OP16>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
     (void)cudaGetLastError();
     max_clusters[C] = nc;
     cfg.dynamicSmemBytes = smem;
@@ -92,10 +92,13 @@ inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_c
   if (clusters > units) clusters = units;
   if (clusters <= 0) return cudaSuccess;
   cfg.gridDim = dim3(clusters * C);
-  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE, PAIR, GEN>, P);
+  return cudaLaunchKernelEx(&cfg, tc_rows_kernel<MODE, PAIR, GEN, OP16>, P);
 }
 template <int MODE>
-inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st, bool op16) {
+  if (op16)
+    return P.cluster == 2 ? launch_rows_mode_p<MODE, true, false, true>(P, smem, sm_count, st)
+                          : launch_rows_mode_p<MODE, false, false, true>(P, smem, sm_count, st);
   return P.cluster == 2 ? launch_rows_mode_p<MODE, true>(P, smem, sm_count, st) : launch_rows_mode_p<MODE, false>(P, smem, sm_count, st);
 }
 
@@ -110,22 +113,23 @@ inline cudaError_t launch_rows_gen(int mode, const RowsParams& P, size_t smem, i
   return cudaErrorInvalidValue;
 }
 
-inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+// op16: A / B are 16-bit tensors (P.a_fmt / P.b_fmt), tensor maps built with 64-column boxes
+inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st, bool op16 = false) {
   if (P.e.n_rows <= 0) return cudaSuccess;
   switch (mode) {
-    case MODE_PLAIN: return launch_rows_mode<MODE_PLAIN>(P, smem, sm_count, st);
-    case MODE_GABOR_FWD: return launch_rows_mode<MODE_GABOR_FWD>(P, smem, sm_count, st);
-    case MODE_GABOR2D_FWD: return launch_rows_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st);
-    case MODE_GABOR_BWD: return launch_rows_mode<MODE_GABOR_BWD>(P, smem, sm_count, st);
-    case MODE_GABOR2D_BWD: return launch_rows_mode<MODE_GABOR2D_BWD>(P, smem, sm_count, st);
-    case MODE_FIRST_BWD: return launch_rows_mode<MODE_FIRST_BWD>(P, smem, sm_count, st);
-    case MODE_FIRST2D_BWD: return launch_rows_mode<MODE_FIRST2D_BWD>(P, smem, sm_count, st);
+    case MODE_PLAIN: return launch_rows_mode<MODE_PLAIN>(P, smem, sm_count, st, op16);
+    case MODE_GABOR_FWD: return launch_rows_mode<MODE_GABOR_FWD>(P, smem, sm_count, st, op16);
+    case MODE_GABOR2D_FWD: return launch_rows_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st, op16);
+    case MODE_GABOR_BWD: return launch_rows_mode<MODE_GABOR_BWD>(P, smem, sm_count, st, op16);
+    case MODE_GABOR2D_BWD: return launch_rows_mode<MODE_GABOR2D_BWD>(P, smem, sm_count, st, op16);
+    case MODE_FIRST_BWD: return launch_rows_mode<MODE_FIRST_BWD>(P, smem, sm_count, st, op16);
+    case MODE_FIRST2D_BWD: return launch_rows_mode<MODE_FIRST2D_BWD>(P, smem, sm_count, st, op16);
   }
   return cudaErrorInvalidValue;
 }
 
 // wgrad: choose column blocking, K splits (to fill the machine) and pipeline depth
-inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, bool gen = false) {
+inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, bool gen = false, bool op16 = false) {
   const int x_cols = 2 * P.k_in + 1;
   P.cluster = cluster;
   P.m_tiles = (x_cols + 128 * cluster - 1) / (128 * cluster);
@@ -137,10 +141,11 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   const int base = P.m_tiles * P.n_blocks * P.n_g;
   int splits = (sm_count / cluster) / base;
   if (splits < 1) splits = 1;
-  const int total_chunks = (P.n_rows + kWgradKC - 1) / kWgradKC;
+  const int kc = op16 ? kWgradKC16 : kWgradKC;
+  const int total_chunks = (P.n_rows + kc - 1) / kc;
   if (splits > total_chunks) splits = total_chunks > 0 ? total_chunks : 1;
   P.splits = splits;
-  const size_t stage = size_t(4 + P.nb / 32 / cluster) * kWgradKC * 128;
+  const size_t stage = size_t(4 + P.nb / 32 / cluster) * 4096;  // 4 KB per 32-column block (x: 4 blocks, g: nb/32 per pair)
   P.gen_tab_feats = round_up(P.k_in + 1, 16) + 64 * 4;  // covers every feature index a generator warp may touch
   const size_t tab_bytes = gen ? size_t(2) * P.gen_tab_feats * 16 : 0;
   int stages = int((kMaxDynSmem - 1024 - tab_bytes) / stage);
@@ -151,11 +156,11 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   return stages * stage + tab_bytes + 1024;
 }
 
-template <bool PAIR, bool GEN = false>
+template <bool PAIR, bool GEN = false, bool OP16 = false>
 inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<PAIR, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<PAIR, GEN, OP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -174,9 +179,10 @@ inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = PAIR ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PAIR, GEN>, P);
+  return cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PAIR, GEN, OP16>, P);
 }
-inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st, bool gen = false) {
+inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st, bool gen = false, bool op16 = false) {
+  if (op16) return P.cluster == 2 ? launch_wgrad_p<true, false, true>(P, smem, st) : launch_wgrad_p<false, false, true>(P, smem, st);
   if (gen) return P.cluster == 2 ? launch_wgrad_p<true, true>(P, smem, st) : launch_wgrad_p<false, true>(P, smem, st);
   return P.cluster == 2 ? launch_wgrad_p<true>(P, smem, st) : launch_wgrad_p<false>(P, smem, st);
 }

@@ -21,6 +21,7 @@
 // even / odd 32-column chunks.  Layer constants (bias, final-Linear weights, first-layer weights)
 // live in shared memory; the saved pre-activations of the backward modes are TMA-prefetched.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "rows_epilogue.cuh"
@@ -51,6 +52,9 @@ struct RowsParams {
                             // CTA stages its own 128 rows of A and HALF of the B tile, halving the smem fill per flop
   int stages;
   int store_mask;  // which epilogue results are TMA-stored: bit0 = o0, bit1 = o1, bit2 = o2
+  int o_fmt[3];    // element type of each STORED output slot (sm100_host::ElemType): f32 tiles are 32x32x4 B with the
+                   // 128 B swizzle, 16-bit tiles (FP16 saved z / y, BF16 gradients) are dense 32x32x2 B
+  int a_fmt, b_fmt;  // OP16 kernels: operand formats of the kind::f16 MMA (sm100::kFmtF16 / kFmtBF16)
   int n_in;        // TMA-prefetched epilogue inputs (0, 1 = z, 2 = z and w)
   uint32_t staging_off;  // byte offsets inside dynamic smem (from the 1 KB aligned base)
   uint32_t param_off;
@@ -104,6 +108,25 @@ __device__ __forceinline__ void stage_row_half(uint32_t buf, int lane, const flo
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + j * 16), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
   }
 }
+__device__ __forceinline__ void stage_row_bf16(uint32_t buf, int lane, const float (&v)[32]) {
+  const uint32_t row = buf + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+      h[k] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + j * 16), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  }
+}
+// stage one output chunk in the element type of its tensor (fmt: sm100_host::ElemType)
+__device__ __forceinline__ void stage_row_fmt(uint32_t buf, int lane, const float (&v)[32], int fmt) {
+  if (fmt == 0) stage_row(buf, lane, v);
+  else if (fmt == 1) stage_row_half(buf, lane, v);
+  else stage_row_bf16(buf, lane, v);
+}
 __device__ __forceinline__ void unstage_row_half(uint32_t buf, int lane, float (&v)[32]) {
   const uint32_t row = buf + lane * 64;
 #pragma unroll
@@ -142,9 +165,14 @@ enum { kDbgMmaWaitFull = 0, kDbgMmaWaitTmem = 1, kDbgMmaTotal = 2, kDbgEpiWaitAc
 
 constexpr int kGenWarps = 4;
 
-template <int MODE, bool PAIR, bool GEN = false>
+// OP16: A and B are 16-bit (FP16 activations / BF16 gradients, formats in P.a_fmt / P.b_fmt), MMA kind::f16.
+// The smem tiles keep their byte geometry (128 B swizzled rows, 32 B per K-step), so a stage covers 64 K columns.
+template <int MODE, bool PAIR, bool GEN = false, bool OP16 = false>
 __global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) tc_rows_kernel(const __grid_constant__ RowsParams P) {
   using namespace sm100;
+  static_assert(!(GEN && OP16), "the in-place generator writes TF32 tiles");
+  constexpr int kKC = OP16 ? 64 : 32;    // K columns per pipeline stage (one 128 B swizzle row)
+  constexpr int kKStep = OP16 ? 16 : 8;  // K columns per tcgen05.mma
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8];
   __shared__ __align__(8) uint64_t bar_empty[8];
@@ -170,8 +198,8 @@ __global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) 
   float* params = reinterpret_cast<float*>(smem_gen + P.param_off);
   const RowsEpi& E = P.e;
 
-  const int kc0 = (P.k_cols[0] + kChunk - 1) / kChunk;
-  const int kc1 = (P.k_cols[1] + kChunk - 1) / kChunk;
+  const int kc0 = (P.k_cols[0] + kKC - 1) / kKC;
+  const int kc1 = (P.k_cols[1] + kKC - 1) / kKC;
   const int kc_total = kc0 + kc1;
   const int row_tiles = (E.n_rows + kTileRows - 1) / kTileRows;
   const int n_feat = E.n_cols >> 1;  // complex features M
@@ -287,18 +315,18 @@ __global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) 
           const uint32_t full_own = smem_u32(&bar_full[stage]);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const int part = kc < kc0 ? 0 : 1;
-          const int kcol = (part ? kc - kc0 : kc) * kChunk;
+          const int kcol = (part ? kc - kc0 : kc) * kKC;
           const uint32_t tx_bytes = GEN ? b_bytes : stage_bytes;  // GEN: the A tile is written by the generator warps
           if (!pair) {
             mbar_expect_tx(full_own, tx_bytes);
             if (!GEN) tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, a_policy);
-            tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kChunk, brow, kEvictLast);
+            tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kKC, brow, kEvictLast);
           } else {
             // both CTAs load into their own smem; all bytes complete on the LEADER's full barrier
             const uint32_t full_leader = full_own & kPeerBitMask;
             if (leader) mbar_expect_tx(full_own, 2 * tx_bytes);
             if (!GEN) tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, a_policy);
-            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kChunk, brow, kEvictLast);
+            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kKC, brow, kEvictLast);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
@@ -308,13 +336,18 @@ __global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && (!pair || leader)) {
-      const uint32_t idesc = make_idesc_tf32(pair ? 256 : 128, P.ns, false, false);
+      const uint32_t idesc = OP16 ? make_idesc_f16(pair ? 256 : 128, P.ns, false, false, uint32_t(P.a_fmt), uint32_t(P.b_fmt))
+                                  : make_idesc_tf32(pair ? 256 : 128, P.ns, false, false);
       // descriptor words are precomputed: only the 14-bit start-address field changes (stage, K-step)
       const uint32_t desc_hi = uint32_t(make_sdesc_sw128(0, 16, 1024) >> 32);
       const uint32_t a_lo0 = uint32_t(make_sdesc_sw128(smem_base, 16, 1024));
       const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
-      const int last0 = ((P.k_cols[0] - (kc0 - 1) * kChunk + 7) >> 3) > 4 ? 4 : ((P.k_cols[0] - (kc0 - 1) * kChunk + 7) >> 3);
-      const int last1 = kc1 > 0 ? (((P.k_cols[1] - (kc1 - 1) * kChunk + 7) >> 3) > 4 ? 4 : ((P.k_cols[1] - (kc1 - 1) * kChunk + 7) >> 3)) : 4;
+      auto tail_steps = [](int cols, int kc) {  // K-steps of the last (possibly partial) stage of an A part
+        const int st = (cols - (kc - 1) * kKC + kKStep - 1) / kKStep;
+        return st > 4 ? 4 : st;
+      };
+      const int last0 = tail_steps(P.k_cols[0], kc0);
+      const int last1 = kc1 > 0 ? tail_steps(P.k_cols[1], kc1) : 4;
       int stage = 0;
       uint32_t phase = 0;
       long long w_full = 0, w_tmem = 0;
@@ -339,8 +372,13 @@ __global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) 
           auto mma = [&](int ks, uint32_t acc) {
             const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 2 * ks);
             const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + 2 * ks);
-            if (pair) umma_tf32_2cta(d_tmem, adesc, bdesc, idesc, acc);
-            else umma_tf32(d_tmem, adesc, bdesc, idesc, acc);
+            if constexpr (OP16) {
+              if (pair) umma_f16_2cta(d_tmem, adesc, bdesc, idesc, acc);
+              else umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+            } else {
+              if (pair) umma_tf32_2cta(d_tmem, adesc, bdesc, idesc, acc);
+              else umma_tf32(d_tmem, adesc, bdesc, idesc, acc);
+            }
           };
           if (steps == 4) {
             mma(0, kc ? 1u : 0u);
@@ -628,18 +666,12 @@ __global__ void __launch_bounds__(kRowsThreads + (GEN ? 32 * kGenWarps : 0), 1) 
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           int slot = 0;
-          if (P.store_mask & 1) { stage_row(wbuf, lane, o0); ++slot; }
+          if (P.store_mask & 1) { stage_row_fmt(wbuf, lane, o0, P.o_fmt[0]); ++slot; }
           if constexpr (kFwd || MODE == MODE_GABOR2D_BWD) {
-            if (P.store_mask & 2) {
-              if (kFwd && E.z_half) stage_row_half(wbuf + slot * 4096, lane, o1); else stage_row(wbuf + slot * 4096, lane, o1);
-              ++slot;
-            }
+            if (P.store_mask & 2) { stage_row_fmt(wbuf + slot * 4096, lane, o1, P.o_fmt[slot]); ++slot; }
           }
           if constexpr (MODE == MODE_GABOR2D_FWD) {
-            if (P.store_mask & 4) {
-              if (E.z_half) stage_row_half(wbuf + slot * 4096, lane, o2); else stage_row(wbuf + slot * 4096, lane, o2);
-              ++slot;
-            }
+            if (P.store_mask & 4) { stage_row_fmt(wbuf + slot * 4096, lane, o2, P.o_fmt[slot]); ++slot; }
           }
           fence_proxy_async_smem();
           __syncwarp();

@@ -14,6 +14,9 @@
 // Work item = (K split, g matrix, column block, M tile of 128 x-columns per CTA); one item per CTA, or per CTA
 // pair (cta_group::2: 256 x-columns, each CTA stages its own x tile and HALF of the g tile).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "gabor_math.cuh"
 #include "sm100.cuh"
 
@@ -21,7 +24,8 @@ namespace wire {
 
 constexpr int kWgradThreads = 192;
 constexpr int kWgradGenWarps = 4;  // GEN kernels: x = y0 = gabor(coords W0^T + b0) is computed in place (first hidden layer)
-constexpr int kWgradKC = 32;  // coordinates per pipeline stage
+constexpr int kWgradKC = 32;    // coordinates per pipeline stage (TF32 operands: 32 rows x 128 B per 32-column block)
+constexpr int kWgradKC16 = 64;  // 16-bit operands: 64 rows x 64 B per 32-column block (same 4 KB blocks, same K-step stride)
 
 struct WgradParams {
   CUtensorMap x_map;     // x [N, 2K+1(+pad)], box {32 cols, 32 rows}, SWIZZLE_128B_ATOM_32B
@@ -38,6 +42,11 @@ struct WgradParams {
   int stages;
   float* gW[2];  // [M][K][2] fp32, accumulated
   float* gB[2];  // [M][2]
+  int x_fmt, g_fmt;  // OP16 kernels: operand formats of x and g in HBM (sm100::kFmtF16 / kFmtBF16)
+  int x_conv;        // OP16: x is stored FP16 but g is BF16.  kind::f16 cannot mix the two (illegal instruction on
+                     // sm_100a, profiles/r01_probe16.log), so the four epilogue warps -- idle during the K loop --
+                     // convert each landed x tile FP16 -> BF16 in place in shared memory (element-wise, so the swizzle
+                     // does not matter); activations are O(1), so BF16's range is not an issue, only its 8-bit mantissa.
   // GEN: first-layer description (x is generated, never loaded)
   const float* coords;
   int in_features;
@@ -52,22 +61,29 @@ struct WgradParams {
   int gen_tab_feats;     // padded feature count of the tables
 };
 
-template <bool PAIR, bool GEN = false>
+// OP16: x is FP16 and g is BF16 (formats in P.x_fmt / P.g_fmt), both still MN-major; tiles are 32-column blocks of
+// 64-byte rows with the 64 B swizzle (layout type SW64), 64 coordinates per stage, MMA kind::f16 (K = 16).
+template <bool PAIR, bool GEN = false, bool OP16 = false>
 __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0), 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
   using namespace sm100;
+  static_assert(!(GEN && OP16), "the in-place generator writes TF32 tiles");
+  constexpr int kKC = OP16 ? kWgradKC16 : kWgradKC;
+  constexpr uint32_t kLayout = OP16 ? kLayoutSW64 : kLayoutSW128Base32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8];
   __shared__ __align__(8) uint64_t bar_empty[8];
   __shared__ __align__(8) uint64_t bar_tmem_full;
+  __shared__ __align__(8) uint64_t bar_x[8];  // x_conv: this CTA's x tile has landed (own barrier; converters wait on it)
   __shared__ uint32_t tmem_slot;
 
   constexpr int C = PAIR ? 2 : 1;
+  const bool conv = OP16 && P.x_conv;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int crank = PAIR ? int(cluster_ctarank()) : 0;
   const bool leader = crank == 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t blk_bytes = kWgradKC * 128;  // one 32-column block of one stage
+  const uint32_t blk_bytes = 4096;  // one 32-column block of one stage (kKC rows of 128 B, or of 64 B for 16-bit operands)
   const uint32_t a_bytes = 4 * blk_bytes;
   // MMA pieces along N (g columns): n1 + n2 = nb ; a pair splits each piece in halves (multiples of 32 columns)
   int nvalid = P.g_cols;  // per column block below
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   const int nblk = item % P.n_blocks;  item /= P.n_blocks;
   const int gi = item % P.n_g;  item /= P.n_g;
   const int split = item;
-  const int total_chunks = (P.n_rows + kWgradKC - 1) / kWgradKC;
+  const int total_chunks = (P.n_rows + kKC - 1) / kKC;
   const int cps = (total_chunks + P.splits - 1) / P.splits;
   const int ch_begin = split * cps;
   int ch_end = ch_begin + cps;
@@ -111,8 +127,9 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : 1);
+      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : (conv ? 1 + 4 * C : 1));
       mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_x[s]), 1);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
     fence_barrier_init();
@@ -137,17 +154,22 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
           const uint32_t full_own = smem_u32(&bar_full[stage]);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
-          const int r0 = ch * kWgradKC;
-          const uint32_t tx_bytes = GEN ? b_bytes : stage_bytes;
+          const int r0 = ch * kKC;
+          const uint32_t tx_bytes = (GEN || conv) ? b_bytes : stage_bytes;
+          if (conv) {  // the x tile completes on this CTA's own barrier: its converter warps pick it up
+            const uint32_t xb = smem_u32(&bar_x[stage]);
+            mbar_expect_tx(xb, a_bytes);
+            for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, xb, x_col0 + b * 32, r0);
+          }
           if (!PAIR) {
             mbar_expect_tx(full_own, tx_bytes);
-            if (!GEN) for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * 32, r0);
+            if (!GEN && !conv) for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * 32, r0);
             for (int b = 0; b < nbb_cta; ++b)
               tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_own, nblk * P.nb + b * 32, r0);
           } else {
             const uint32_t full_leader = full_own & kPeerBitMask;
             if (leader) mbar_expect_tx(full_own, 2 * tx_bytes);
-            if (!GEN)
+            if (!GEN && !conv)
               for (int b = 0; b < 4; ++b)
                 tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * 32, r0, kEvictNormal);
             // piece 1: columns [crank*n1/2, +n1/2) ; piece 2: columns [n1 + crank*n2/2, +n2/2)
@@ -164,11 +186,15 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
       }
     } else if (warp == 1) {
       if (lane == 0 && (!PAIR || leader)) {
-        const uint32_t idesc1 = make_idesc_tf32(PAIR ? 256 : 128, n1, true, true);
-        const uint32_t idesc2 = make_idesc_tf32(PAIR ? 256 : 128, n2 > 0 ? n2 : 16, true, true);
-        // descriptor words precomputed; only the start-address field moves (stage, K-step of 8 rows = 1024 B)
-        const uint32_t desc_hi = uint32_t(make_sdesc(0, blk_bytes, 512, kLayoutSW128Base32) >> 32);
-        const uint32_t a_lo0 = uint32_t(make_sdesc(smem_base, blk_bytes, 512, kLayoutSW128Base32));
+        const uint32_t xf = conv ? uint32_t(P.g_fmt) : uint32_t(P.x_fmt);
+        const uint32_t idesc1 = OP16 ? make_idesc_f16(PAIR ? 256 : 128, n1, true, true, xf, uint32_t(P.g_fmt))
+                                     : make_idesc_tf32(PAIR ? 256 : 128, n1, true, true);
+        const uint32_t idesc2 = OP16 ? make_idesc_f16(PAIR ? 256 : 128, n2 > 0 ? n2 : 16, true, true, xf, uint32_t(P.g_fmt))
+                                     : make_idesc_tf32(PAIR ? 256 : 128, n2 > 0 ? n2 : 16, true, true);
+        // descriptor words precomputed; only the start-address field moves (stage, K-step = 1024 B: 8 rows of 128 B,
+        // or 16 rows of 64 B for 16-bit operands)
+        const uint32_t desc_hi = uint32_t(make_sdesc(0, blk_bytes, 512, kLayout) >> 32);
+        const uint32_t a_lo0 = uint32_t(make_sdesc(smem_base, blk_bytes, 512, kLayout));
         const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
         const uint32_t b2_units = (uint32_t(PAIR ? n1 / 64 : 8) * blk_bytes) >> 4;
         int stage = 0;
@@ -179,12 +205,20 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
           const uint32_t a_lo = a_lo0 + stage * stage_units;
           const uint32_t b_lo = a_lo + b_units;
 #pragma unroll
-          for (int ks = 0; ks < kWgradKC / 8; ++ks) {
+          for (int ks = 0; ks < 4; ++ks) {
             const uint32_t acc = (ks > 0) ? 1u : (i ? 1u : 0u);
             const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 64 * ks);
             const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + 64 * ks);
             const uint64_t bdesc2 = (uint64_t(desc_hi) << 32) | (b_lo + b2_units + 64 * ks);
-            if (PAIR) {
+            if constexpr (OP16) {
+              if (PAIR) {
+                umma_f16_2cta(tmem_base, adesc, bdesc, idesc1, acc);
+                if (n2 > 0) umma_f16_2cta(tmem_base + n1, adesc, bdesc2, idesc2, acc);
+              } else {
+                umma_f16(tmem_base, adesc, bdesc, idesc1, acc);
+                if (n2 > 0) umma_f16(tmem_base + n1, adesc, bdesc2, idesc2, acc);
+              }
+            } else if (PAIR) {
               umma_tf32_2cta(tmem_base, adesc, bdesc, idesc1, acc);
               if (n2 > 0) umma_tf32_2cta(tmem_base + n1, adesc, bdesc2, idesc2, acc);
             } else {
@@ -262,6 +296,37 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     } else {
+      if (conv) {
+        // ===================== x converters (epilogue warps, during the K loop) =====================
+        // warp b converts 32-column block b of every landed x tile FP16 -> BF16 in place: 4 KB = 8 x 16 B per lane
+        const int b = warp - 2;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < n_chunks; ++i) {
+          mbar_wait(smem_u32(&bar_x[stage]), phase);
+          const uint32_t blk = smem_base + stage * stage_bytes + b * blk_bytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = blk + (j * 32 + lane) * 16;
+            uint32_t h[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr) : "memory");
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[k]));
+              const __nv_bfloat162 t = __floats2bfloat162_rn(f.x, f.y);
+              h[k] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t full_own = smem_u32(&bar_full[stage]);
+            if (PAIR) mbar_arrive_cluster(full_own & kPeerBitMask); else mbar_arrive(full_own);
+          }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+      }
       const int q = warp & 3;
       const int c = (mt * C + crank) * 128 + q * 32 + lane;  // row of G = real column of x
       const int two_k = 2 * P.k_in;

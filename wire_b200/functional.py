@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import LayerGrads, LayerParams, NetDesc, NetGrads, NetParams, WireB200Error, check
 
-_PRECISIONS = {"tf32": _lib.PRECISION_TF32, "fp32": _lib.PRECISION_FP32}
+_PRECISIONS = {"tf32": _lib.PRECISION_TF32, "fp32": _lib.PRECISION_FP32, "mixed16": _lib.PRECISION_MIXED16}
 
 
 def precision_id(name: str) -> int:
