@@ -305,18 +305,18 @@ static bool test_rows16(int n_rows, int two_m, int a_elem, int b_elem, int o_ele
   wire::RowsParams P;
   memset(&P, 0, sizeof(P));
   P.e.n_rows = n_rows; P.k_cols[0] = K; P.k_cols[1] = 0; P.n_blocks = 1; P.e.n_cols = two_m;
-  size_t smem = wire::rows_configure(P, nb, nb, 1, 0, two_m, wire::MODE_PLAIN, false, g_cluster);
-  if (!smem) { printf("rows_configure failed\n"); return false; }
+  size_t smem = wire::rows16_configure(P, nb, nb, 1, 0, two_m, wire::MODE_PLAIN, false, g_cluster);
+  if (!smem) { printf("rows16_configure failed\n"); return false; }
   P.a_fmt = a_elem - 1; P.b_fmt = b_elem - 1; P.o_fmt[0] = o_elem;
   bool ok = sm100_host::make_tmap_2d_t(&P.a_map[0], dA, n_rows, K, pitch, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B, a_elem);
   P.a_map[1] = P.a_map[0];
   ok &= sm100_host::make_tmap_2d_t(&P.b_map, dB, nb, kpad, kpad, P.b_box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B, b_elem);
-  if (o_elem == 0) ok &= sm100_host::make_tmap_2d(&P.o_map[0], dC, n_rows, two_m, pitch, 32, 32);
-  else ok &= sm100_host::make_tmap_2d_t(&P.o_map[0], dC, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE, o_elem);
+  if (o_elem == 0) { printf("rows16 stores 16-bit tensors only\n"); return false; }
+  ok &= sm100_host::make_tmap_2d_t(&P.o_map[0], dC, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, o_elem);
   P.o_map[1] = P.o_map[0]; P.o_map[2] = P.o_map[0]; P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
   if (!ok) { printf("tensor map creation failed\n"); return false; }
   printf("[rows16] cluster=%d n_rows=%d 2M=%d nb=%d a=%d b=%d o=%d stages=%d\n", g_cluster, n_rows, two_m, nb, a_elem, b_elem, o_elem, P.stages);
-  CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0, true));
+  CK(wire::launch_rows16(wire::MODE_PLAIN, P, smem, g_sms, 0));
   CK(cudaDeviceSynchronize());
   std::vector<float> C(size_t(n_rows) * pitch);
   if (o_elem == 0) CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
@@ -343,10 +343,10 @@ static bool test_rows16(int n_rows, int two_m, int a_elem, int b_elem, int o_ele
   printf("[rows16] max_abs_err=%.3e (max |ref| %.3f) bad=%ld -> %s\n", max_err, max_ref, bad, bad ? "FAIL" : "PASS");
   if (time_it && !bad) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0, true));
+    for (int i = 0; i < 3; ++i) CK(wire::launch_rows16(wire::MODE_PLAIN, P, smem, g_sms, 0));
     CK(cudaEventRecord(e0));
     const int reps = 10;
-    for (int i = 0; i < reps; ++i) CK(wire::launch_rows(wire::MODE_PLAIN, P, smem, g_sms, 0, true));
+    for (int i = 0; i < reps; ++i) CK(wire::launch_rows16(wire::MODE_PLAIN, P, smem, g_sms, 0));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
     printf("[rows16] %.3f ms  %.1f TFLOP/s (useful)  A+C traffic %.1f GB/s\n", ms, 2.0 * n_rows * double(two_m) * K / ms * 1e-9,
@@ -430,13 +430,68 @@ static bool test_wgrad16(int n_rows, int k_in, int m_out, int x_elem, int g_elem
   return bad == 0;
 }
 
+static void time_rows_gabor16(int n_rows, int two_m, bool fuse_final) {
+  const int K = two_m, pitch = wire::round_up(two_m + 1, 32), kpad = wire::round_up(two_m, 64);
+  const int nb = two_m > 256 ? wire::round_up(two_m, 64) : wire::round_up(two_m, 16);
+  std::vector<uint16_t> A(size_t(n_rows) * pitch, 0), B(size_t(nb) * kpad, 0);
+  for (auto& v : A) v = to16(frand() * 0.5f, 1);
+  for (auto& v : B) v = to16(frand() * 0.07f, 1);
+  std::vector<float> bias(two_m, 0.01f), wf(size_t(3) * two_m, 0.05f);
+  void *dA, *dB, *dY, *dZ; float *dbias, *dom, *dwf, *dout;
+  CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dY, A.size() * 2)); CK(cudaMalloc(&dZ, A.size() * 2));
+  CK(cudaMalloc(&dbias, two_m * 4)); CK(cudaMalloc(&dom, 8)); CK(cudaMalloc(&dwf, wf.size() * 4)); CK(cudaMalloc(&dout, size_t(n_rows) * 3 * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias.data(), two_m * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dwf, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
+  const float os[2] = {7.f, 6.f};
+  CK(cudaMemcpy(dom, os, 8, cudaMemcpyHostToDevice));
+  wire::RowsParams P;
+  memset(&P, 0, sizeof(P));
+  P.e.n_rows = n_rows; P.k_cols[0] = K; P.n_blocks = 1; P.e.n_cols = two_m; P.e.z_half = 1;
+  P.e.bias = dbias; P.e.omega = dom; P.e.scale = dom + 1;
+  if (fuse_final) { P.e.fuse_final = 1; P.e.wf = dwf; P.e.bf = dbias; P.e.out = dout; P.e.out_features = 3; }
+  const int mask = fuse_final ? 2 : 3;
+  size_t smem = wire::rows16_configure(P, nb, nb, mask, 0, two_m, wire::MODE_GABOR_FWD, fuse_final, g_cluster);
+  P.a_fmt = 0; P.b_fmt = 0; P.o_fmt[0] = 1; P.o_fmt[1] = 1;
+  bool ok = sm100_host::make_tmap_2d_t(&P.a_map[0], dA, n_rows, K, pitch, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B, 1);
+  P.a_map[1] = P.a_map[0];
+  ok &= sm100_host::make_tmap_2d_t(&P.b_map, dB, nb, kpad, kpad, P.b_box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B, 1);
+  ok &= sm100_host::make_tmap_2d_t(&P.o_map[0], fuse_final ? dZ : dY, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1);
+  ok &= sm100_host::make_tmap_2d_t(&P.o_map[1], dZ, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1);
+  P.o_map[2] = P.o_map[0]; P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
+  if (!ok || !smem) { printf("gabor16 setup failed\n"); return; }
+  unsigned long long* dd; CK(cudaMalloc(&dd, 8 * 8 * 1024)); CK(cudaMemset(dd, 0, 8 * 8 * 1024));
+  P.dbg = dd;
+  for (int i = 0; i < 3; ++i) CK(wire::launch_rows16(wire::MODE_GABOR_FWD, P, smem, g_sms, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> hd(8 * 1024);
+  CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
+  printf("[gabor_fwd16] cluster=%d n_rows=%d 2M=%d nb=%d slices=%d stages=%d fuse_final=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.slices, P.stages, int(fuse_final), smem);
+  const char* names[8] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in"};
+  for (int k = 0; k < 8; ++k) {
+    double sum = 0; int cnt = 0;
+    for (int b = 0; b < 1024; ++b) if (hd[b * 8 + k]) { sum += double(hd[b * 8 + k]); ++cnt; }
+    printf("   [dbg] %-16s avg %.0f cycles over %d CTAs\n", names[k], cnt ? sum / cnt : 0.0, cnt);
+  }
+  P.dbg = nullptr;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  const int reps = 10;
+  for (int i = 0; i < reps; ++i) CK(wire::launch_rows16(wire::MODE_GABOR_FWD, P, smem, g_sms, 0));
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+  printf("[gabor_fwd16] %.3f ms  %.1f TFLOP/s (useful)\n", ms, 2.0 * n_rows * double(two_m) * K / ms * 1e-9);
+  cudaFree(dA); cudaFree(dB); cudaFree(dY); cudaFree(dZ); cudaFree(dbias); cudaFree(dom); cudaFree(dd); cudaFree(dwf); cudaFree(dout);
+}
+
 static int main16() {
   bool ok = true;
   for (int c : {1, 2}) {
     g_cluster = c;
-    ok &= test_rows16(256, 64, 1, 1, 0, false);      // f16 x f16
-    ok &= test_rows16(300, 424, 1, 1, 0, false);     // WIRE width, ragged rows, K tail (424 = 6*64 + 40)
-    ok &= test_rows16(300, 424, 2, 2, 0, false);     // bf16 x bf16
+    ok &= test_rows16(256, 64, 1, 1, 1, false);      // f16 x f16
+    ok &= test_rows16(300, 424, 1, 1, 1, false);     // WIRE width, ragged rows, K tail (424 = 6*64 + 40)
+    ok &= test_rows16(300, 424, 2, 2, 2, false);     // bf16 x bf16
     // test_rows16(300, 424, 2, 1, 0, false): bf16 A x f16 B in one kind::f16 MMA -> "illegal instruction" on sm_100a
     // (measured, profiles/r01_probe16.log): the two operands must share one format.
     ok &= test_rows16(1000, 180, 1, 1, 1, false);    // f16 output tiles
@@ -463,6 +518,13 @@ int main(int argc, char** argv) {
   printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, g_sms);
   srand(1234);
   if (argc > 1 && !strcmp(argv[1], "16")) return main16();
+  if (argc > 1 && !strcmp(argv[1], "g16")) {
+    g_cluster = 2;
+    time_rows_gabor16(262144, 424, false);
+    time_rows_gabor16(262144, 424, true);
+    test_rows16(262144, 424, 1, 1, 1, true);
+    return 0;
+  }
   bool ok = true;
   ok &= test_rows(256, 64, false);       // single MMA piece, 2 K chunks
   ok &= test_rows(300, 424, false);      // WIRE width: nb=432 (256+176), K tail of 8, ragged rows

@@ -117,7 +117,7 @@ struct Blocking {
 };
 // out_cols = real output columns (2M). two_d_fwd: accumulator holds [z half | w half].
 bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, int n_in = 0, int mode = MODE_PLAIN,
-                     bool fuse_final = false, bool gen = false) {
+                     bool fuse_final = false, bool gen = false, bool op16 = false) {
   for (int nblk = 1; nblk <= 64; ++nblk) {
     const int per = (out_cols + nblk - 1) / nblk;
     const int C = cluster_size();
@@ -129,7 +129,8 @@ bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, 
       nbh = nb;
     }
     RowsParams tmp;
-    if (rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C, gen) == 0) continue;
+    if (op16 ? rows16_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C) == 0
+             : rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C, gen) == 0) continue;
     b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
     return true;
   }
@@ -196,7 +197,7 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
   L.rows = training ? n : (n < kInferChunk ? n : kInferChunk);
   if (L.rows < 1) L.rows = 1;
   Blocking bf;
-  if (!choose_blocking(L.two_m, d->two_d != 0, d->two_d ? 6 : 2, bf, 0, d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, true))
+  if (!choose_blocking(L.two_m, d->two_d != 0, d->two_d ? 6 : 2, bf, 0, d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, true, false, mixed))
     return fail("no tile configuration for width %d", d->width);
   L.fuse_final = bf.n_blocks == 1 && d->out_features <= kMaxOut;
   size_t off = 0;
@@ -248,8 +249,8 @@ struct RowsJob {
   RowsEpi e;
 };
 int job_n_in(int mode) { return mode == MODE_GABOR_BWD ? 1 : (mode == MODE_GABOR2D_BWD ? 2 : 0); }
-bool job_blocking(int mode, int out_cols, int store_mask, bool fuse_final, Blocking& b, bool gen = false) {
-  return choose_blocking(out_cols, mode == MODE_GABOR2D_FWD, store_mask, b, job_n_in(mode), mode, fuse_final, gen);
+bool job_blocking(int mode, int out_cols, int store_mask, bool fuse_final, Blocking& b, bool gen = false, bool op16 = false) {
+  return choose_blocking(out_cols, mode == MODE_GABOR2D_FWD, store_mask, b, job_n_in(mode), mode, fuse_final, gen, op16);
 }
 
 template <int MODE>
@@ -290,12 +291,14 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.k_cols[0] = J.k_cols[0]; P.k_cols[1] = J.k_cols[1];
   P.n_blocks = J.blk.n_blocks;
   P.e = J.e;
-  const size_t smem = rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
-                                     cluster_size(), J.gen != 0);
+  const bool op16 = J.a_elem != kElemF32;
+  const size_t smem = op16 ? rows16_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
+                                              cluster_size())
+                           : rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
+                                            cluster_size(), J.gen != 0);
   P.gen_omega = J.gen_omega; P.gen_scale = J.gen_scale; P.gen_two_d = J.gen_two_d;
   if (!smem) return fail("row-tile configuration does not fit shared memory (nb=%d)", J.blk.nb);
   bool ok = true;
-  const bool op16 = J.a_elem != kElemF32;
   if (op16 && (J.b_elem != J.a_elem || J.gen)) return fail("16-bit row-tile GEMM needs A and B in the same format");
   P.a_fmt = J.a_elem == kElemBF16 ? int(sm100::kFmtBF16) : int(sm100::kFmtF16);
   P.b_fmt = P.a_fmt;
@@ -309,20 +312,24 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   for (int bit = 0; bit < 3; ++bit)
     if (J.store_mask & (1 << bit)) {
       P.o_fmt[nslot] = J.o_half[nslot];
-      if (J.o_half[nslot])
-        ok &= sm100_host::make_tmap_2d_t(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE, J.o_half[nslot]);
+      if (op16 && !J.o_half[nslot]) return fail("16-bit row-tile kernels store 16-bit tensors only");
+      if (J.o_half[nslot])  // 16-bit tiles: dense for the TF32 kernels' saved z, 64 B swizzle for the 16-bit kernels
+        ok &= sm100_host::make_tmap_2d_t(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32,
+                                         op16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, J.o_half[nslot]);
       else
         ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32);
       ++nslot;
     }
   for (int s = nslot; s < 3; ++s) P.o_map[s] = P.a_map[0];
   P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
-  const CUtensorMapSwizzle zsw = J.e.z_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (op16 && P.n_in && !J.e.z_half) return fail("16-bit row-tile kernels read FP16 saved pre-activations");
+  const CUtensorMapSwizzle zsw = op16 ? CU_TENSOR_MAP_SWIZZLE_64B : (J.e.z_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B);
   if (P.n_in >= 1) ok &= sm100_host::make_tmap_2d(&P.z_map[0], J.e.z_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
   if (P.n_in >= 2) ok &= sm100_host::make_tmap_2d(&P.z_map[1], J.e.w_src, J.e.n_rows, J.e.n_cols, J.e.zw_pitch, 32, 32, zsw, J.e.z_half != 0);
   if (!ok) return fail("cuTensorMapEncodeTiled failed (pointer/pitch alignment?)");
   if (J.gen) CU_OK(launch_rows_gen(J.mode, P, smem, g_sm_count, st));
-  else CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st, op16));
+  else if (op16) CU_OK(launch_rows16(J.mode, P, smem, g_sm_count, st));
+  else CU_OK(launch_rows(J.mode, P, smem, g_sm_count, st, false));
   return 0;
 }
 
@@ -539,7 +546,7 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
     Blocking blk;
     const int fmode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
     const bool gen = gen0 && l == 1;
-    if (!job_blocking(fmode, L.two_m, mask, fuse, blk, gen)) return fail("no tile configuration");
+    if (!job_blocking(fmode, L.two_m, mask, fuse, blk, gen, mixed)) return fail("no tile configuration");
     float* Bf = at(ws, L.off_bf[l]);
     TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st, L.y_elem));
     RowsJob J;
@@ -716,7 +723,7 @@ int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const
     int mask = to_first ? 0 : (d->two_d ? 3 : 1);
     Blocking blk;
     const int bmode = to_first ? (d->two_d ? MODE_FIRST2D_BWD : MODE_FIRST_BWD) : (d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD);
-    if (!job_blocking(bmode, L.two_m, mask, false, blk)) return fail("no tile configuration");
+    if (!job_blocking(bmode, L.two_m, mask, false, blk, false, L.g_elem != kElemF32)) return fail("no tile configuration");
     float* Bd = at(workspace, L.off_bd[l]);
     const int kparts = d->two_d ? 2 : 1;
     TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st,

@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "tc_rows.cuh"
+#include "tc_rows16.cuh"
 #include "tc_wgrad.cuh"
 
 namespace wire {
@@ -96,9 +97,7 @@ inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_c
 }
 template <int MODE>
 inline cudaError_t launch_rows_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st, bool op16) {
-  if (op16)
-    return P.cluster == 2 ? launch_rows_mode_p<MODE, true, false, true>(P, smem, sm_count, st)
-                          : launch_rows_mode_p<MODE, false, false, true>(P, smem, sm_count, st);
+  if (op16) return cudaErrorInvalidValue;  // 16-bit operands run tc_rows16_kernel (launch_rows16)
   return P.cluster == 2 ? launch_rows_mode_p<MODE, true>(P, smem, sm_count, st) : launch_rows_mode_p<MODE, false>(P, smem, sm_count, st);
 }
 
@@ -124,6 +123,102 @@ inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int s
     case MODE_GABOR2D_BWD: return launch_rows_mode<MODE_GABOR2D_BWD>(P, smem, sm_count, st, op16);
     case MODE_FIRST_BWD: return launch_rows_mode<MODE_FIRST_BWD>(P, smem, sm_count, st, op16);
     case MODE_FIRST2D_BWD: return launch_rows_mode<MODE_FIRST2D_BWD>(P, smem, sm_count, st, op16);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ---- 16-bit row-tile kernels (tc_rows16.cuh): 16 epilogue warps, 2 KB staging tiles, final-Linear exchange in dynamic smem ----
+inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, int n_in = 0, int out_cols = 0,
+                               int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1) {
+  P.nb = nb;
+  P.nbh = nbh;
+  P.store_mask = store_mask;
+  P.n_in = n_in;
+  P.cluster = cluster;
+  if (cluster != 1 && cluster != 2) return 0;
+  if (nb <= 256) { P.slices = 1; P.ns = nb; P.buf_cols = 256; }
+  else {
+    if (mode == MODE_GABOR2D_FWD || nb % 64 || nb > 512) return 0;
+    P.slices = 2; P.ns = nb / 2; P.buf_cols = nb / 2;
+  }
+  if (P.ns % 16 || (P.ns / cluster) % 8) return 0;
+  P.b_box_rows = P.ns / cluster;
+  const int n_out = __builtin_popcount(store_mask);
+  const size_t stage = size_t(kTileRows) * 128 + size_t(P.b_box_rows) * 128;
+  const size_t staging = size_t(kEpi16Warps) * (n_out + n_in) * kTile16Bytes;
+  const int pcols = round_up(out_cols > 0 ? out_cols : 32, 32) + 32;
+  const bool two_d = (mode == MODE_GABOR2D_FWD || mode == MODE_GABOR2D_BWD || mode == MODE_FIRST2D_BWD);
+  size_t pfloats = 0;
+  if (mode == MODE_GABOR_FWD || mode == MODE_GABOR2D_FWD)
+    pfloats = size_t(two_d ? 2 : 1) * pcols + (fuse_final ? size_t(pcols / 2) * 8 + size_t(2) * (kEpi16Parts - 1) * kTileRows * 4 : 0);
+  if (mode == MODE_FIRST_BWD || mode == MODE_FIRST2D_BWD) pfloats = size_t(two_d ? 2 : 1) * (pcols / 2) * 4;
+  const size_t pbytes = (pfloats * sizeof(float) + 127) / 128 * 128;
+  const size_t budget = kMaxDynSmem - 1024;
+  if (staging + pbytes + 2 * stage > budget) return 0;
+  int stages = int((budget - staging - pbytes) / stage);
+  if (stages > 8) stages = 8;
+  P.stages = stages;
+  P.staging_off = uint32_t(stages * stage);
+  P.param_off = uint32_t(stages * stage + staging);
+  P.param_cols = pcols;
+  return stages * stage + staging + pbytes + 1024;
+}
+
+template <int MODE, bool PAIR, bool FUSE>
+inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_rows16_kernel<MODE, PAIR, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  constexpr int C = PAIR ? 2 : 1;
+  const int row_tiles = (P.e.n_rows + kTileRows - 1) / kTileRows;
+  const int units = ((row_tiles + C - 1) / C) * P.n_blocks;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kRows16Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = C > 1 ? 1 : 0;
+  if (C > 1 && max_clusters == 0) {
+    cfg.gridDim = dim3(sm_count / C * C);
+    cfg.dynamicSmemBytes = kMaxDynSmem;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows16_kernel<MODE, PAIR, FUSE>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
+    (void)cudaGetLastError();
+    max_clusters = nc;
+    cfg.dynamicSmemBytes = smem;
+  }
+  int clusters = C > 1 ? max_clusters : sm_count;
+  if (clusters > units) clusters = units;
+  if (clusters <= 0) return cudaSuccess;
+  cfg.gridDim = dim3(clusters * C);
+  return cudaLaunchKernelEx(&cfg, tc_rows16_kernel<MODE, PAIR, FUSE>, P);
+}
+template <int MODE, bool FUSE = false>
+inline cudaError_t launch_rows16_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  return P.cluster == 2 ? launch_rows16_p<MODE, true, FUSE>(P, smem, sm_count, st) : launch_rows16_p<MODE, false, FUSE>(P, smem, sm_count, st);
+}
+// P configured by rows16_configure; 16-bit tensor maps: A/B boxes of 64 columns (SWIZZLE_128B), output / saved-z tiles
+// of 32x32 elements with SWIZZLE_64B
+inline cudaError_t launch_rows16(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  if (P.e.n_rows <= 0) return cudaSuccess;
+  const bool fuse = P.e.fuse_final != 0;
+  switch (mode) {
+    case MODE_PLAIN: return launch_rows16_mode<MODE_PLAIN>(P, smem, sm_count, st);
+    case MODE_GABOR_FWD: return fuse ? launch_rows16_mode<MODE_GABOR_FWD, true>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR_FWD>(P, smem, sm_count, st);
+    case MODE_GABOR2D_FWD: return fuse ? launch_rows16_mode<MODE_GABOR2D_FWD, true>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st);
+    case MODE_GABOR_BWD: return launch_rows16_mode<MODE_GABOR_BWD>(P, smem, sm_count, st);
+    case MODE_GABOR2D_BWD: return launch_rows16_mode<MODE_GABOR2D_BWD>(P, smem, sm_count, st);
+    case MODE_FIRST_BWD: return launch_rows16_mode<MODE_FIRST_BWD>(P, smem, sm_count, st);
+    case MODE_FIRST2D_BWD: return launch_rows16_mode<MODE_FIRST2D_BWD>(P, smem, sm_count, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -1,0 +1,526 @@
+// tc_rows16.cuh — the row-tile GEMM of the WIRE hot path for 16-bit tensors (mixed16 precision) on tcgen05.
+//
+//   ACC[128 coords, ns cols] = A[128 coords, K] (FP16 or BF16, K-major, TMA) x Bpacked[ns cols, K] (same format)
+//
+// MMA kind::f16, FP32 accumulation in TMEM.  Producer / MMA-issue roles and the TMEM double buffering are those of
+// tc_rows.cuh (a pipeline stage covers 64 K columns instead of 32).  The epilogue is rebuilt for the regime the 16-bit
+// path lives in: with half the operand bytes and twice the MMA rate, the point-wise Gabor work — not HBM, not the
+// tensor pipe — bounded the TF32-style epilogue (profiles/r01_ncu_rows16_v1_*: 8 epilogue warps, issue slots 28 % busy,
+// MMA thread waiting for a free accumulator 52 % of the time).  So here:
+//   * 16 epilogue warps (four per TMEM sub-partition, 576 threads; registers are granted per 4 warps, so 96 per thread), chunks dealt round-robin with a
+//     per-job rotation so the 7 chunks of a 224-column slice balance over 4 warps in the long run;
+//   * results are converted and staged 4 complex features at a time (one 16-byte st.shared per output), so a thread
+//     never holds more than the 32 accumulator registers of its chunk;
+//   * 16-bit staging / saved-z tiles use the 64-byte TMA swizzle (conflict-free 16-byte accesses at a 64-byte pitch);
+//   * layer flags are template parameters (no per-element branches), rint() is the add-magic-constant trick (FRND
+//     shares the 16-lane XU pipe with ex2/sin/cos, which is the binding unit of this epilogue).
+//
+// Modes and math are exactly those of tc_rows.cuh / rows_epilogue.cuh (same reference lines).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "tc_rows.cuh"
+
+namespace wire {
+
+constexpr int kEpi16Warps = 16;
+constexpr int kEpi16Parts = kEpi16Warps / 4;  // warps per TMEM sub-partition
+constexpr int kRows16Threads = 64 + 32 * kEpi16Warps;
+constexpr int kTile16Bytes = 2048;  // one 32 x 32 tile of 16-bit elements
+
+// 32x32 16-bit tile, TMA SWIZZLE_64B: row r at r*64, 16-byte chunk j stored at chunk (j ^ ((r >> 1) & 3))
+__device__ __forceinline__ uint32_t sw64_addr(uint32_t tile, int lane, int j) {
+  return tile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  const __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+// y = exp(j w z - s2 (|z|^2 + wnorm)) with the phase reduced in turns; rint(u) = (u + 1.5*2^23) - 1.5*2^23 (|u| < 2^22)
+__device__ __forceinline__ void gabor16(const GaborConst& g, float zr, float zi, float wnorm, float& yr, float& yi) {
+  const float t = fmaf(zi, zi, fmaf(zr, zr, wnorm));
+  const float m = ex2_ftz(fmaf(g.c_t, t, g.c_zi * zi));
+  const float u = zr * g.c_turn;
+  const float k = __fadd_rn(__fadd_rn(u, 12582912.0f), -12582912.0f);
+  const float r = (u - k) * 6.283185307179586f;
+  yr = m * cos_ftz(r);
+  yi = m * sin_ftz(r);
+}
+
+// FUSE: the final Linear (.real) is accumulated in this epilogue (GABOR_FWD / GABOR2D_FWD only)
+template <int MODE, bool PAIR, bool FUSE = false>
+__global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __grid_constant__ RowsParams P) {
+  using namespace sm100;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[8];
+  __shared__ __align__(8) uint64_t bar_empty[8];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ __align__(8) uint64_t bar_in[kEpi16Warps];
+  __shared__ uint32_t tmem_slot;
+
+  constexpr bool kFwd = (MODE == MODE_GABOR_FWD || MODE == MODE_GABOR2D_FWD);
+  constexpr bool kBwd = (MODE == MODE_GABOR_BWD || MODE == MODE_GABOR2D_BWD);
+  constexpr bool kFirst = (MODE == MODE_FIRST_BWD || MODE == MODE_FIRST2D_BWD);
+  constexpr bool k2D = (MODE == MODE_GABOR2D_FWD || MODE == MODE_GABOR2D_BWD || MODE == MODE_FIRST2D_BWD);
+  static_assert(!FUSE || kFwd, "only the forward modes fuse the final Linear");
+  constexpr int kKC = 64;  // K columns per pipeline stage (one 128 B swizzle row of 16-bit elements)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_bytes = kTileRows * 128;
+  const uint32_t b_bytes = uint32_t(P.b_box_rows) * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t staging_base = smem_base + P.staging_off;
+  float* params = reinterpret_cast<float*>(smem_gen + P.param_off);
+  const RowsEpi& E = P.e;
+
+  const int kc0 = (P.k_cols[0] + kKC - 1) / kKC;
+  const int kc1 = (P.k_cols[1] + kKC - 1) / kKC;
+  const int kc_total = kc0 + kc1;
+  const int row_tiles = (E.n_rows + kTileRows - 1) / kTileRows;
+  const int n_feat = E.n_cols >> 1;
+  const int C = P.cluster;
+  const int crank = int(cluster_ctarank());
+  const int n_clusters = gridDim.x / C;
+  const int my_cluster = blockIdx.x / C;
+  const int row_groups = (row_tiles + C - 1) / C;
+  const int n_units = row_groups * P.n_blocks;
+  const int n_iters = (n_units + n_clusters - 1) / n_clusters;
+  const int n_jobs = n_iters * P.slices;
+  constexpr bool pair = PAIR;
+  const bool leader = crank == 0;
+  unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
+
+  // ---- shared parameter tables (zero padded: the epilogue needs no column checks) ----
+  //  fwd  : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8] (wr[4], wi[4]) | fin exchange (FUSE)
+  //  first: tab[(param_cols/2)][4] = {w0[0..2], b0} | tab2 (2D)
+  if constexpr (kFwd) {
+    for (int i = threadIdx.x; i < P.param_cols; i += blockDim.x) {
+      params[i] = i < E.n_cols ? E.bias[i] : 0.f;
+      if constexpr (k2D) params[P.param_cols + i] = i < E.n_cols ? E.bias2[i] : 0.f;
+    }
+    if constexpr (FUSE) {
+      float* wf = params + (k2D ? 2 : 1) * P.param_cols;
+      for (int i = threadIdx.x; i < (P.param_cols >> 1) * 8; i += blockDim.x) {
+        const int k = i >> 3, j = i & 7, o = j & 3;
+        float v = 0.f;
+        if (k < n_feat && o < E.out_features) v = E.wf[(size_t(o) * n_feat + k) * 2 + (j >> 2)];
+        wf[i] = v;
+      }
+    }
+  }
+  if constexpr (kFirst) {
+    for (int i = threadIdx.x; i < (P.param_cols >> 1) * 4; i += blockDim.x) {
+      const int k = i >> 2, j = i & 3;
+      float v = 0.f, v2 = 0.f;
+      if (k < n_feat) {
+        if (j < 3) {
+          if (j < E.in_features) { v = E.w0[size_t(k) * E.in_features + j]; if constexpr (k2D) v2 = E.w0b[size_t(k) * E.in_features + j]; }
+        } else { v = E.b0[k]; if constexpr (k2D) v2 = E.b0b[k]; }
+      }
+      params[i] = v;
+      if constexpr (k2D) params[(P.param_cols >> 1) * 4 + i] = v2;
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tmem_full[b]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[b]), kEpi16Warps * C);
+    }
+    for (int w = 0; w < kEpi16Warps; ++w) mbar_init(smem_u32(&bar_in[w]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.a_map[0]);
+    tma_prefetch_desc(&P.b_map);
+  }
+  if (warp == 1) {
+    if (pair) { tmem_alloc_2cta(smem_u32(&tmem_slot), 512); tmem_relinquish_2cta(); }
+    else { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (pair) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long t_wait = 0;
+      const long long t_begin = WIRE_CLK();
+      for (int jb = 0; jb < n_jobs; ++jb) {
+        const int it = jb / P.slices, sl = jb % P.slices;
+        const int unit = it * n_clusters + my_cluster;
+        const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
+        const int brow = (unit % P.n_blocks) * P.nb + sl * P.ns + crank * P.b_box_rows;
+        const uint64_t a_policy = (sl == P.slices - 1 && (unit % P.n_blocks) == P.n_blocks - 1) ? kEvictFirst : kEvictLast;
+        for (int kc = 0; kc < kc_total; ++kc) {
+          const long long t0 = WIRE_CLK();
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          t_wait += WIRE_CLK() - t0;
+          const uint32_t full_own = smem_u32(&bar_full[stage]);
+          const uint32_t a_dst = smem_base + stage * stage_bytes;
+          const int part = kc < kc0 ? 0 : 1;
+          const int kcol = (part ? kc - kc0 : kc) * kKC;
+          if (!pair) {
+            mbar_expect_tx(full_own, stage_bytes);
+            tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, a_policy);
+            tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kKC, brow, kEvictLast);
+          } else {
+            const uint32_t full_leader = full_own & kPeerBitMask;
+            if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
+            tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, a_policy);
+            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kKC, brow, kEvictLast);
+          }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (dbg) { dbg[kDbgProdWaitEmpty] = t_wait; dbg[kDbgProdTotal] = WIRE_CLK() - t_begin; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && (!pair || leader)) {
+      const uint32_t idesc = make_idesc_f16(pair ? 256 : 128, P.ns, false, false, uint32_t(P.a_fmt), uint32_t(P.b_fmt));
+      const uint32_t desc_hi = uint32_t(make_sdesc_sw128(0, 16, 1024) >> 32);
+      const uint32_t a_lo0 = uint32_t(make_sdesc_sw128(smem_base, 16, 1024));
+      const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
+      auto tail_steps = [](int cols, int kc) {
+        const int st = (cols - (kc - 1) * kKC + 15) / 16;
+        return st > 4 ? 4 : st;
+      };
+      const int last0 = tail_steps(P.k_cols[0], kc0);
+      const int last1 = kc1 > 0 ? tail_steps(P.k_cols[1], kc1) : 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      long long w_full = 0, w_tmem = 0;
+      const long long t_begin = WIRE_CLK();
+      for (int jb = 0; jb < n_jobs; ++jb) {
+        const int buf = jb & 1;
+        if (jb >= 2) {
+          const long long t0 = WIRE_CLK();
+          mbar_wait(smem_u32(&bar_tmem_empty[buf]), ((jb >> 1) & 1) ^ 1);
+          w_tmem += WIRE_CLK() - t0;
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * P.buf_cols;
+        for (int kc = 0; kc < kc_total; ++kc) {
+          const long long t1 = WIRE_CLK();
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          w_full += WIRE_CLK() - t1;
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + stage * stage_units;
+          const uint32_t b_lo = a_lo + b_units;
+          const int steps = (kc == kc0 - 1) ? last0 : ((kc == kc_total - 1) ? last1 : 4);
+          auto mma = [&](int ks, uint32_t acc) {
+            const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 2 * ks);
+            const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + 2 * ks);
+            if (pair) umma_f16_2cta(d_tmem, adesc, bdesc, idesc, acc);
+            else umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+          };
+          if (steps == 4) {
+            mma(0, kc ? 1u : 0u);
+            mma(1, 1u);
+            mma(2, 1u);
+            mma(3, 1u);
+          } else {
+            for (int ks = 0; ks < steps; ++ks) mma(ks, (kc | ks) ? 1u : 0u);
+          }
+          if (pair) umma_commit_2cta_mcast(smem_u32(&bar_empty[stage]), 3);
+          else umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        if (pair) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full[buf]), 3);
+        else umma_commit(smem_u32(&bar_tmem_full[buf]));
+      }
+      if (dbg) { dbg[kDbgMmaWaitFull] = w_full; dbg[kDbgMmaWaitTmem] = w_tmem; dbg[kDbgMmaTotal] = WIRE_CLK() - t_begin; }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;   // 0..15
+    const int q = warp & 3;    // TMEM sub-partition (lanes 32q..32q+31)
+    const int part = ew >> 2;  // 0..3: which of the sub-partition's four warps
+    const bool st0 = P.store_mask & 1, st1 = P.store_mask & 2, st2 = P.store_mask & 4;
+    const int n_out = int(st0) + int(st1) + int(st2);
+    const int slots = n_out + P.n_in;
+    const uint32_t wbuf = staging_base + ew * (slots * kTile16Bytes);
+    const uint32_t wbuf1 = wbuf + (st0 ? kTile16Bytes : 0);                      // slot of o1
+    const uint32_t wbuf2 = wbuf1 + (st1 ? kTile16Bytes : 0);                     // slot of o2
+    const uint32_t inbuf = wbuf + n_out * kTile16Bytes;                          // saved z (and w) tiles
+    const GaborConst G = (MODE != MODE_PLAIN) ? make_gabor_const(__ldg(E.omega), __ldg(E.scale)) : make_gabor_const(0.f, 0.f);
+    const float4* s_bias4 = reinterpret_cast<const float4*>(params);
+    const float4* s_bias24 = reinterpret_cast<const float4*>(params + P.param_cols);
+    const float4* s_wf = reinterpret_cast<const float4*>(params + (k2D ? 2 : 1) * P.param_cols);
+    // FUSE: partial sums of parts 1..3 travel through [slot 2][part-1][128 rows] float4 after the wf table
+    float4* s_fin = reinterpret_cast<float4*>(params + (k2D ? 2 : 1) * P.param_cols + (P.param_cols >> 1) * 8);
+    const float4* s_tab = reinterpret_cast<const float4*>(params);
+    const float4* s_tab2 = reinterpret_cast<const float4*>(params + (P.param_cols >> 1) * 4);
+    const uint32_t empty_addr0 = pair ? (smem_u32(&bar_tmem_empty[0]) & kPeerBitMask) : smem_u32(&bar_tmem_empty[0]);
+    const uint32_t empty_addr1 = pair ? (smem_u32(&bar_tmem_empty[1]) & kPeerBitMask) : smem_u32(&bar_tmem_empty[1]);
+    const int out_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;
+    const int out_ns = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.ns;
+    uint32_t in_phase = 0;
+    long long e_wait = 0, e_wait_in = 0;
+    const long long e_begin = WIRE_CLK();
+    float cin[3] = {0.f, 0.f, 0.f};
+    float facc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+    auto release = [&](int buf) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (pair) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0); else mbar_arrive(buf ? empty_addr1 : empty_addr0); }
+    };
+    for (int jb = 0; jb < n_jobs; ++jb) {
+      const int it = jb / P.slices, sl = jb % P.slices;
+      const int buf = jb & 1;
+      const int unit = it * n_clusters + my_cluster;
+      const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
+      const int blk = unit % P.n_blocks;
+      const int row = row0 + q * 32 + lane;
+      const bool row_ok = row < E.n_rows;
+      const int col0 = blk * out_blk + sl * out_ns;
+      int valid = E.n_cols - col0;
+      valid = valid > out_ns ? out_ns : valid;
+      const int nchunks = valid > 0 ? (valid + kChunk - 1) / kChunk : 0;
+      // chunks of this warp: ch0, ch0 + 4, ... with a per-job rotation ((ch + jb) % 4 == part)
+      const int ch0 = (part - jb) & (kEpi16Parts - 1);
+      int my_last = -1;
+      if (nchunks > ch0) my_last = ch0 + kEpi16Parts * ((nchunks - 1 - ch0) / kEpi16Parts);
+
+      if (sl == 0) {
+        if constexpr (kFirst) {
+          cin[0] = cin[1] = cin[2] = 0.f;
+          if (row_ok) {
+            cin[0] = __ldg(E.coords + size_t(row) * E.in_features);
+            if (E.in_features > 1) cin[1] = __ldg(E.coords + size_t(row) * E.in_features + 1);
+            if (E.in_features > 2) cin[2] = __ldg(E.coords + size_t(row) * E.in_features + 2);
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) facc[o] = 0.f;
+      }
+
+      if constexpr (kBwd) {  // prefetch the first saved-z tile of this job while its MMAs are still running
+        if (ch0 < nchunks && lane == 0) {
+          const uint32_t bar = smem_u32(&bar_in[ew]);
+          mbar_expect_tx(bar, P.n_in * kTile16Bytes);
+          for (int s = 0; s < P.n_in; ++s)
+            tma_load_2d(inbuf + s * kTile16Bytes, &P.z_map[s], bar, col0 + ch0 * kChunk, row0 + q * 32);
+        }
+      }
+
+      {
+        const long long t0 = WIRE_CLK();
+        mbar_wait(smem_u32(&bar_tmem_full[buf]), (jb >> 1) & 1);
+        e_wait += WIRE_CLK() - t0;
+      }
+      tc_fence_after();
+      if (my_last < 0) release(buf);
+
+      for (int ch = ch0; ch < nchunks; ch += kEpi16Parts) {
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * P.buf_cols + ch * kChunk;
+        const int c = col0 + ch * kChunk;  // first real output column of this chunk (also the smem table index)
+        uint32_t raw[32];
+        float wn[16];
+        if constexpr (MODE == MODE_GABOR2D_FWD) {
+          // w half first: |w|^2 per feature is all the Gabor needs; w itself goes straight to its staging tile
+          tmem_ld32(taddr + P.nbh, raw);
+          tmem_wait_ld();
+          if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0 = s_bias24[(c >> 2) + 2 * g], b1 = s_bias24[(c >> 2) + 2 * g + 1];
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float w8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = __uint_as_float(raw[8 * g + i]) + bb[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wn[4 * g + i] = fmaf(w8[2 * i], w8[2 * i], w8[2 * i + 1] * w8[2 * i + 1]);
+            if (st2) sts128(sw64_addr(wbuf2, lane, g), pack_f16(w8[0], w8[1]), pack_f16(w8[2], w8[3]), pack_f16(w8[4], w8[5]), pack_f16(w8[6], w8[7]));
+          }
+        }
+        tmem_ld32(taddr, raw);
+        tmem_wait_ld();
+        if (ch == my_last) release(buf);  // all TMEM reads of this warp for this job are done
+
+        if constexpr (MODE == MODE_PLAIN) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a = __uint_as_float(raw[8 * g + 2 * i]), b = __uint_as_float(raw[8 * g + 2 * i + 1]);
+              pk[i] = P.o_fmt[0] == 2 ? pack_bf16(a, b) : pack_f16(a, b);
+            }
+            sts128(sw64_addr(wbuf, lane, g), pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else if constexpr (kFwd) {
+          if constexpr (MODE != MODE_GABOR2D_FWD) {
+            if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0 = s_bias4[(c >> 2) + 2 * g], b1 = s_bias4[(c >> 2) + 2 * g + 1];
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float z8[8], y8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z8[i] = __uint_as_float(raw[8 * g + i]) + bb[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              gabor16(G, z8[2 * i], z8[2 * i + 1], k2D ? wn[4 * g + i] : 0.f, y8[2 * i], y8[2 * i + 1]);
+              if constexpr (FUSE) {
+                const float4 wr4 = s_wf[((c >> 1) + 4 * g + i) * 2];
+                const float4 wi4 = s_wf[((c >> 1) + 4 * g + i) * 2 + 1];
+                facc[0] = fmaf(y8[2 * i], wr4.x, fmaf(-y8[2 * i + 1], wi4.x, facc[0]));
+                facc[1] = fmaf(y8[2 * i], wr4.y, fmaf(-y8[2 * i + 1], wi4.y, facc[1]));
+                facc[2] = fmaf(y8[2 * i], wr4.z, fmaf(-y8[2 * i + 1], wi4.z, facc[2]));
+                facc[3] = fmaf(y8[2 * i], wr4.w, fmaf(-y8[2 * i + 1], wi4.w, facc[3]));
+              }
+            }
+            if (st0) sts128(sw64_addr(wbuf, lane, g), pack_f16(y8[0], y8[1]), pack_f16(y8[2], y8[3]), pack_f16(y8[4], y8[5]), pack_f16(y8[6], y8[7]));
+            if (st1) sts128(sw64_addr(wbuf1, lane, g), pack_f16(z8[0], z8[1]), pack_f16(z8[2], z8[3]), pack_f16(z8[4], z8[5]), pack_f16(z8[6], z8[7]));
+          }
+        } else if constexpr (kBwd) {
+          // this chunk's saved z (w) tile: copy the packed halves to registers, then prefetch the next tile into the same buffer
+          uint32_t zp[16], wp[16];
+          {
+            const long long t0 = WIRE_CLK();
+            mbar_wait(smem_u32(&bar_in[ew]), in_phase);
+            e_wait_in += WIRE_CLK() - t0;
+          }
+          in_phase ^= 1;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            lds128(sw64_addr(inbuf, lane, g), zp[4 * g], zp[4 * g + 1], zp[4 * g + 2], zp[4 * g + 3]);
+            if constexpr (k2D) lds128(sw64_addr(inbuf + kTile16Bytes, lane, g), wp[4 * g], wp[4 * g + 1], wp[4 * g + 2], wp[4 * g + 3]);
+          }
+          __syncwarp();
+          if (ch + kEpi16Parts < nchunks && lane == 0) {
+            const uint32_t bar = smem_u32(&bar_in[ew]);
+            mbar_expect_tx(bar, P.n_in * kTile16Bytes);
+            for (int s = 0; s < P.n_in; ++s)
+              tma_load_2d(inbuf + s * kTile16Bytes, &P.z_map[s], bar, c + kEpi16Parts * kChunk, row0 + q * 32);
+          }
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pz[4], pw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 z = unpack_f16(zp[4 * g + i]);
+              float2 w = make_float2(0.f, 0.f);
+              if constexpr (k2D) w = unpack_f16(wp[4 * g + i]);
+              const float wnorm = k2D ? fmaf(w.x, w.x, w.y * w.y) : 0.f;
+              float yr, yi, gzr, gzi;
+              gabor16(G, z.x, z.y, wnorm, yr, yi);
+              const float pr = gabor_bwd(yr, yi, z.x, z.y, __uint_as_float(raw[8 * g + 2 * i]), __uint_as_float(raw[8 * g + 2 * i + 1]),
+                                         G.omega, G.s2, gzr, gzi);
+              pz[i] = pack_bf16(gzr, gzi);
+              if constexpr (k2D) {
+                const float t = -2.0f * G.s2 * pr;
+                pw[i] = pack_bf16(t * w.x, t * w.y);
+              }
+            }
+            if (st0) sts128(sw64_addr(wbuf, lane, g), pz[0], pz[1], pz[2], pz[3]);
+            if constexpr (k2D) { if (st1) sts128(sw64_addr(wbuf1, lane, g), pw[0], pw[1], pw[2], pw[3]); }
+          }
+        } else {  // kFirst: real z0 recomputed from the coordinates and the smem weight table; fp32 direct stores
+          float gz[16], gw[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 t = s_tab[(c >> 1) + i];
+            const float z0 = fmaf(cin[0], t.x, fmaf(cin[1], t.y, fmaf(cin[2], t.z, t.w)));
+            float w0v = 0.f;
+            if constexpr (k2D) {
+              const float4 t2 = s_tab2[(c >> 1) + i];
+              w0v = fmaf(cin[0], t2.x, fmaf(cin[1], t2.y, fmaf(cin[2], t2.z, t2.w)));
+            }
+            float yr, yi;
+            gabor16(G, z0, 0.f, w0v * w0v, yr, yi);
+            const float pr = gabor_first_bwd(yr, yi, z0, __uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]), G.omega, G.s2, gz[i]);
+            gw[i] = -2.0f * G.s2 * pr * w0v;
+          }
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(E.gz0 + size_t(row) * E.gz0_pitch + (c >> 1));
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              if ((c >> 1) + 4 * j4 < E.gz0_pitch) dst[j4] = make_float4(gz[4 * j4], gz[4 * j4 + 1], gz[4 * j4 + 2], gz[4 * j4 + 3]);
+            if constexpr (k2D) {
+              float4* dw = reinterpret_cast<float4*>(E.gw0 + size_t(row) * E.gz0_pitch + (c >> 1));
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                if ((c >> 1) + 4 * j4 < E.gz0_pitch) dw[j4] = make_float4(gw[4 * j4], gw[4 * j4 + 1], gw[4 * j4 + 2], gw[4 * j4 + 3]);
+            }
+          }
+        }
+
+        if (n_out > 0) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            for (int s = 0; s < n_out; ++s) tma_store_2d(&P.o_map[s], wbuf + s * kTile16Bytes, c, row0 + q * 32);
+            tma_store_commit();
+          }
+        }
+      }
+
+      if constexpr (FUSE) {
+        if (sl == P.slices - 1) {
+          // the four warps of a sub-partition hold partial sums over their chunks (of every slice)
+          const int slot = it & 1;
+          if (part > 0) s_fin[(slot * (kEpi16Parts - 1) + (part - 1)) * kTileRows + q * 32 + lane] = make_float4(facc[0], facc[1], facc[2], facc[3]);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kEpi16Parts) : "memory");
+          if (part == 0 && row_ok) {
+            float r[4] = {facc[0], facc[1], facc[2], facc[3]};
+#pragma unroll
+            for (int pp = 0; pp < kEpi16Parts - 1; ++pp) {
+              const float4 o = s_fin[(slot * (kEpi16Parts - 1) + pp) * kTileRows + q * 32 + lane];
+              r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w;
+            }
+#pragma unroll
+            for (int oo = 0; oo < kMaxOut; ++oo)
+              if (oo < E.out_features) E.out[size_t(row) * E.out_features + oo] = r[oo] + __ldg(E.bf + 2 * oo);
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    if (dbg && ew == 0 && lane == 0) { dbg[kDbgEpiWaitAcc] = e_wait; dbg[kDbgEpiTotal] = WIRE_CLK() - e_begin; dbg[kDbgEpiWaitIn] = e_wait_in; }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  __syncthreads();
+  if (pair) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    if (pair) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace wire
