@@ -10,6 +10,7 @@
 #include "simt_kernels.cuh"
 #include "simt_rows.cuh"
 #include "tc_launch.cuh"
+#include "simt16_kernels.cuh"
 
 namespace {
 
@@ -192,7 +193,7 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
   L.z_elem = L.prec == WIRE_PRECISION_FP32 ? kElemF32 : kElemF16;       // saved pre-activations
   L.g_elem = mixed ? kElemBF16 : kElemF32;                              // gradients: BF16 (FP32's range, no loss scaling)
   L.P = round_up(L.two_m + 1, 32);
-  L.PR = round_up(L.M, 4);
+  L.PR = round_up(L.M, mixed ? 8 : 4);   // real g_z0 rows: fp32 (16-byte aligned), or BF16 on the mixed16 path
   L.k_pad = round_up(L.two_m, mixed ? 64 : 32);
   L.rows = training ? n : (n < kInferChunk ? n : kInferChunk);
   if (L.rows < 1) L.rows = 1;
@@ -209,8 +210,8 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
     L.n_act = ny;
     for (int l = 1; l <= L.H; ++l) { L.off_z[l] = take(act(L.z_elem)); if (d->two_d) L.off_w[l] = take(act(L.z_elem)); }
     for (int i = 0; i < 2; ++i) { L.off_gz[i] = take(act(L.g_elem)); if (d->two_d) L.off_gw[i] = take(act(L.g_elem)); }
-    L.off_gz0 = take(size_t(L.rows) * L.PR * sizeof(float));
-    if (d->two_d) L.off_gw0 = take(size_t(L.rows) * L.PR * sizeof(float));
+    L.off_gz0 = take(size_t(L.rows) * L.PR * sm100_host::elem_bytes(L.g_elem));
+    if (d->two_d) L.off_gw0 = take(size_t(L.rows) * L.PR * sm100_host::elem_bytes(L.g_elem));
   } else {
     L.off_y[0] = take(act(L.y_elem)); L.off_y[1] = take(act(L.y_elem)); L.n_act = 2;
   }
@@ -301,6 +302,7 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   bool ok = true;
   if (op16 && (J.b_elem != J.a_elem || J.gen)) return fail("16-bit row-tile GEMM needs A and B in the same format");
   P.a_fmt = J.a_elem == kElemBF16 ? int(sm100::kFmtBF16) : int(sm100::kFmtF16);
+  P.l2_prefetch = getenv("WIRE_B200_L2PF") ? 1 : 0;  // measured: no gain (0.165 vs 0.154 ms), the fill path is L2->SM bound
   P.b_fmt = P.a_fmt;
   const int kbox = op16 ? 64 : 32;  // one 128-byte swizzle row of K columns
   for (int i = 0; i < 2; ++i) {
@@ -416,10 +418,21 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
   if (n <= 0) return 0;
   if (y_elem == kElemF16) {  // mixed16 whole-network path: FP16 activations
     if (z_out || w_out || (y_pitch % 4)) return fail("FP16 first layer: unsupported call");
-    const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
+    if (in_f > 3 || (y_pitch % 8)) return fail("FP16 first layer: unsupported shape");
+    // persistent blocks: 8 per SM, each owns a contiguous row range (the weight table is built once per block)
+    const int nq = (d->width + 3) / 4;
+    const size_t smem = size_t(d->two_d ? 8 : 4) * nq * 16;
+    int nblk = 8 * g_sm_count;
+    if (int64_t(nblk) * 32 > n) nblk = int((n + 31) / 32);
+    const int rpb = int((n + nblk - 1) / nblk);
+    const int grid = int((n + rpb - 1) / rpb);
     ProfScope prof(K_FIRST_FWD, st);
-    first_fwd2_kernel<true, true><<<grid, 128, 0, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, d->two_d ? p.weight2 : nullptr,
-                                                        d->two_d ? p.bias2 : nullptr, p.omega0, p.scale0, y, y_pitch, 0, kRowsPerBlock);
+    if (d->two_d)
+      first_fwd16_kernel<true><<<grid, 256, smem, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, p.weight2, p.bias2, p.omega0, p.scale0,
+                                                         reinterpret_cast<__half*>(y), y_pitch, rpb);
+    else
+      first_fwd16_kernel<false><<<grid, 256, smem, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, nullptr, nullptr, p.omega0, p.scale0,
+                                                          reinterpret_cast<__half*>(y), y_pitch, rpb);
     CU_OK(cudaGetLastError());
     return 0;
   }
@@ -455,6 +468,50 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
     if (!(z && z_half && d->out_features <= 4 && d->width <= 1024 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0))
       return fail("BF16 top backward: unsupported shape");
     ProfScope prof(K_TOP_BWD, st);
+    // TMA-streamed kernel: a row of `g_pitch` columns moves as n_box equal boxes of <= 256 columns (multiples of 8)
+    int n_box = 0;
+    for (int nb = (g_pitch + 255) / 256; nb <= 16 && zw_pitch == g_pitch; ++nb)
+      if (g_pitch % nb == 0 && (g_pitch / nb) % 8 == 0 && g_pitch / nb <= 256) { n_box = nb; break; }
+    const size_t tile_bytes = size_t(g_pitch) * kTopRows * 2;
+    const size_t smem16 = 4 * (w ? 2 : 1) * tile_bytes + 256;
+    if (n_box > 0 && smem16 <= 200 * 1024 && d->width <= 992 && !getenv("WIRE_B200_TOP_SIMT")) {
+      TopBwd16Params T;
+      memset(&T, 0, sizeof(T));
+      T.g_out = g_out; T.Wf = Wf; T.omega = omega; T.scale = scale; T.g_Wf = g_Wf; T.g_bf = g_bf;
+      T.n = int(n); T.M = d->width; T.out_f = d->out_features; T.pitch = g_pitch; T.two_d = w ? 1 : 0;
+      T.bw = g_pitch / n_box; T.n_box = n_box;
+      bool ok = sm100_host::make_tmap_2d_t(&T.z_map[0], z, n, g_pitch, zw_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemF16);
+      ok &= sm100_host::make_tmap_2d_t(&T.z_map[1], w ? w : z, n, g_pitch, zw_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemF16);
+      ok &= sm100_host::make_tmap_2d_t(&T.g_map[0], gz, n, 2 * d->width, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
+      ok &= sm100_host::make_tmap_2d_t(&T.g_map[1], gw ? gw : gz, n, 2 * d->width, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
+      if (!ok) return fail("cuTensorMapEncodeTiled failed for top_bwd16");
+      const int threads = round_up(d->width, 32) + 32;  // compute warps + the I/O warp
+      const int n_tiles = int((n + kTopRows - 1) / kTopRows);
+      int per_sm = int((220 * 1024) / smem16);
+      if (per_sm * threads > 2048) per_sm = 2048 / threads;
+      if (per_sm < 1) per_sm = 1;
+      int grid16 = g_sm_count * per_sm;
+      if (grid16 > n_tiles) grid16 = n_tiles;
+      auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 256);
+        if (e != cudaSuccess) return e;
+        kern<<<grid16, threads, smem16, st>>>(T);
+        return cudaGetLastError();
+      };
+      cudaError_t e = cudaErrorInvalidValue;
+      switch (d->out_features * 2 + (w ? 1 : 0)) {
+        case 2: e = launch(top_bwd16_kernel<false, 1>); break;
+        case 3: e = launch(top_bwd16_kernel<true, 1>); break;
+        case 4: e = launch(top_bwd16_kernel<false, 2>); break;
+        case 5: e = launch(top_bwd16_kernel<true, 2>); break;
+        case 6: e = launch(top_bwd16_kernel<false, 3>); break;
+        case 7: e = launch(top_bwd16_kernel<true, 3>); break;
+        case 8: e = launch(top_bwd16_kernel<false, 4>); break;
+        case 9: e = launch(top_bwd16_kernel<true, 4>); break;
+      }
+      CU_OK(e);
+      return 0;
+    }
     const int thr = round_up((d->width + 1) / 2, 32) < 128 ? 128 : round_up((d->width + 1) / 2, 32);
     const int nblk = int(n < int64_t(10 * g_sm_count) * 64 ? (n + 63) / 64 : 10 * g_sm_count);
     const int rpb = int(((n + nblk - 1) / nblk + 63) / 64 * 64);
@@ -492,16 +549,29 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   return 0;
 }
 
-int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t n, int in_f, int M, float* gW, float* gb, cudaStream_t st) {
+int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t n, int in_f, int M, float* gW, float* gb, cudaStream_t st,
+                    int g_elem = kElemF32) {
   if (n <= 0 || !gW) return 0;
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   ProfScope prof(K_FIRST_WGRAD, st);
+  if (g_elem == kElemBF16) {
+    if (in_f <= 3 && M <= 256 && (g_pitch % 8) == 0) {
+      const int nblk = int(n < int64_t(2 * g_sm_count) * 256 ? (n + 255) / 256 : 2 * g_sm_count);
+      const int rpb = int((n + nblk - 1) / nblk);
+      first_wgrad16_kernel<<<int((n + rpb - 1) / rpb), kFirstWgrad16Threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gz0), g_pitch, coords,
+                                                                                       int(n), in_f, M, gW, gb, rpb);
+    } else {
+      first_wgrad_kernel<true><<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
+    }
+    CU_OK(cudaGetLastError());
+    return 0;
+  }
   if (in_f <= 4 && M <= 256 && (g_pitch % 4) == 0) {
     const int nblk = int(n < int64_t(4 * g_sm_count) * 128 ? (n + 127) / 128 : 4 * g_sm_count);
     const int rpb = int(((n + nblk - 1) / nblk + 127) / 128 * 128);
     first_wgrad2_kernel<<<int((n + rpb - 1) / rpb), 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, rpb);
   } else {
-    first_wgrad_kernel<<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
+    first_wgrad_kernel<false><<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
   }
   CU_OK(cudaGetLastError());
   return 0;
@@ -753,13 +823,21 @@ int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const
     TRY(run_rows(J, d->precision, st));
     cur = 1 - cur;
   }
-  TRY(run_first_wgrad(at(workspace, L.off_gz0), L.PR, coords, n, in_f, M, g->layer[0].weight, g->layer[0].bias, st));
-  if (d->two_d) TRY(run_first_wgrad(at(workspace, L.off_gw0), L.PR, coords, n, in_f, M, g->layer[0].weight2, g->layer[0].bias2, st));
+  TRY(run_first_wgrad(at(workspace, L.off_gz0), L.PR, coords, n, in_f, M, g->layer[0].weight, g->layer[0].bias, st, L.g_elem));
+  if (d->two_d) TRY(run_first_wgrad(at(workspace, L.off_gw0), L.PR, coords, n, in_f, M, g->layer[0].weight2, g->layer[0].bias2, st, L.g_elem));
   if (grad_coords) {
     const int grid = int((n * 32 + 255) / 256);
     ProfScope prof(K_GRAD_COORDS, st, d->two_d ? 2 : 1);
-    grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gz0), L.PR, int(n), in_f, M, p->layer[0].weight, grad_coords, 0);
-    if (d->two_d) grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gw0), L.PR, int(n), in_f, M, p->layer[0].weight2, grad_coords, 1);
+    if (L.g_elem == kElemBF16) {
+      grad_coords16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(at(workspace, L.off_gz0)), L.PR, int(n), in_f, M,
+                                                 p->layer[0].weight, grad_coords, 0);
+      if (d->two_d)
+        grad_coords16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(at(workspace, L.off_gw0)), L.PR, int(n), in_f, M,
+                                                   p->layer[0].weight2, grad_coords, 1);
+    } else {
+      grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gz0), L.PR, int(n), in_f, M, p->layer[0].weight, grad_coords, 0);
+      if (d->two_d) grad_coords_kernel<<<grid, 256, 0, st>>>(at(workspace, L.off_gw0), L.PR, int(n), in_f, M, p->layer[0].weight2, grad_coords, 1);
+    }
     CU_OK(cudaGetLastError());
   }
   return 0;

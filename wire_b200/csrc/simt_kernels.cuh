@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(256) top_bwd_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // first layer weight gradient: g_W0[j][d] = sum_n gz0[n,j] c[n,d] ; g_b0[j] = sum_n gz0[n,j]
 // ---------------------------------------------------------------------------------------------
+// G16: g_z0 is a BF16 tensor (mixed16 path, widths the streaming kernel does not cover)
+template <bool G16 = false>
 __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restrict__ gz0, int g_pitch,
                                                            const float* __restrict__ coords, int n, int in_f, int M,
                                                            float* __restrict__ gW0, float* __restrict__ gb0,
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restric
 #pragma unroll
     for (int d = 0; d < kSimtMaxIn; ++d) acc[d] = 0.f;
     for (int r = 0; r < rows; ++r) {
-      const float g = gz0[size_t(row0 + r) * g_pitch + j];
+      const float g = G16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gz0)[size_t(row0 + r) * g_pitch + j])
+                          : gz0[size_t(row0 + r) * g_pitch + j];
       accb += g;
 #pragma unroll
       for (int d = 0; d < kSimtMaxIn; ++d)

@@ -96,6 +96,12 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const CUtens
       "l"(policy)
       : "memory");
 }
+// pull a box into L2 ahead of its demand load (no smem, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // multicast load: the box lands at the same smem offset in every CTA of `cta_mask` and completes
 // `bytes` on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar,

@@ -178,6 +178,16 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
         const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
         const int brow = (unit % P.n_blocks) * P.nb + sl * P.ns + crank * P.b_box_rows;
         const uint64_t a_policy = (sl == P.slices - 1 && (unit % P.n_blocks) == P.n_blocks - 1) ? kEvictFirst : kEvictLast;
+        if (sl == 0 && P.l2_prefetch && it + 1 < n_iters) {
+          // pull the NEXT work unit's A rows into L2 now: their demand loads then see L2 latency instead of HBM latency
+          // (the pipeline holds only ~5 stages; HBM latency under load starved the MMA thread, mma_wait_full 52 %)
+          const int unit_n = (it + 1) * n_clusters + my_cluster;
+          if ((unit_n % P.n_blocks) == 0) {
+            const int row_n = ((unit_n / P.n_blocks) * C + crank) * kTileRows;
+            for (int kc = 0; kc < kc0; ++kc) tma_prefetch_l2_2d(&P.a_map[0], kc * kKC, row_n);
+            for (int kc = 0; kc < kc1; ++kc) tma_prefetch_l2_2d(&P.a_map[1], kc * kKC, row_n);
+          }
+        }
         for (int kc = 0; kc < kc_total; ++kc) {
           const long long t0 = WIRE_CLK();
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
@@ -449,7 +459,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
             if (st0) sts128(sw64_addr(wbuf, lane, g), pz[0], pz[1], pz[2], pz[3]);
             if constexpr (k2D) { if (st1) sts128(sw64_addr(wbuf1, lane, g), pw[0], pw[1], pw[2], pw[3]); }
           }
-        } else {  // kFirst: real z0 recomputed from the coordinates and the smem weight table; fp32 direct stores
+        } else {  // kFirst: real z0 recomputed from the coordinates and the smem weight table; BF16 direct stores
           float gz[16], gw[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -466,15 +476,21 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
             gw[i] = -2.0f * G.s2 * pr * w0v;
           }
           if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(E.gz0 + size_t(row) * E.gz0_pitch + (c >> 1));
+            // 16 real outputs per thread as BF16 = 32 contiguous bytes (one full sector): two direct 16-byte stores
+            // (gz0_pitch is a multiple of 8 elements; E.gz0 / E.gw0 point at BF16 tensors on this path)
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(E.gz0) + size_t(row) * E.gz0_pitch + (c >> 1);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              if ((c >> 1) + 4 * j4 < E.gz0_pitch) dst[j4] = make_float4(gz[4 * j4], gz[4 * j4 + 1], gz[4 * j4 + 2], gz[4 * j4 + 3]);
+            for (int j8 = 0; j8 < 2; ++j8)
+              if ((c >> 1) + 8 * j8 < E.gz0_pitch)
+                *reinterpret_cast<uint4*>(dst + 8 * j8) = make_uint4(pack_bf16(gz[8 * j8], gz[8 * j8 + 1]), pack_bf16(gz[8 * j8 + 2], gz[8 * j8 + 3]),
+                                                                     pack_bf16(gz[8 * j8 + 4], gz[8 * j8 + 5]), pack_bf16(gz[8 * j8 + 6], gz[8 * j8 + 7]));
             if constexpr (k2D) {
-              float4* dw = reinterpret_cast<float4*>(E.gw0 + size_t(row) * E.gz0_pitch + (c >> 1));
+              __nv_bfloat16* dw = reinterpret_cast<__nv_bfloat16*>(E.gw0) + size_t(row) * E.gz0_pitch + (c >> 1);
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                if ((c >> 1) + 4 * j4 < E.gz0_pitch) dw[j4] = make_float4(gw[4 * j4], gw[4 * j4 + 1], gw[4 * j4 + 2], gw[4 * j4 + 3]);
+              for (int j8 = 0; j8 < 2; ++j8)
+                if ((c >> 1) + 8 * j8 < E.gz0_pitch)
+                  *reinterpret_cast<uint4*>(dw + 8 * j8) = make_uint4(pack_bf16(gw[8 * j8], gw[8 * j8 + 1]), pack_bf16(gw[8 * j8 + 2], gw[8 * j8 + 3]),
+                                                                      pack_bf16(gw[8 * j8 + 4], gw[8 * j8 + 5]), pack_bf16(gw[8 * j8 + 6], gw[8 * j8 + 7]));
             }
           }
         }
