@@ -341,13 +341,14 @@ int run_pack(const float* W1, const float* W2, int M_out, int K_in, int mode, co
   const int total = blk.n_blocks * blk.nb * k_pad_total;
   const int grid = (total + 255) / 256;
   ProfScope prof(K_PACK, st);
+  // 16-bit matrices feed tc_rows16_kernel, whose epilogues expect pair-transposed accumulator columns
   if (elem == kElemF16)
-    pack_weights_kernel<1><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0);
+    pack_weights_kernel<1><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0, 1);
   else if (elem == kElemBF16)
-    pack_weights_kernel<2><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0);
+    pack_weights_kernel<2><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0, 1);
   else
     pack_weights_kernel<0><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B,
-                                                precision == WIRE_PRECISION_TF32);
+                                                precision == WIRE_PRECISION_TF32, 0);
   CU_OK(cudaGetLastError());
   return 0;
 }

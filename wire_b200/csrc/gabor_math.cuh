@@ -11,6 +11,12 @@
 
 namespace wire {
 
+// Accumulator column order of the 16-bit GABOR / FIRST row-tile modes (tc_rows16.cuh): position p holds logical column
+// acc_col_perm(p) — the two low bits swapped, (re A, im A, re B, im B) -> (re A, re B, im A, im B) for features A = 2j,
+// B = 2j+1 — so that packed FP32 math on feature pairs needs no register shuffles.  An involution; applied by
+// pack_weights_kernel to the rows of the packed weight matrices.  MODE_PLAIN is unpermuted.
+__host__ __device__ __forceinline__ int acc_col_perm(int p) { return (p & ~3) | ((p & 1) << 1) | ((p >> 1) & 1); }
+
 // FAST = true : MUFU ex2/sin/cos with an explicit two-term Cody-Waite reduction (TF32 path)
 // FAST = false: libdevice expf/sincosf (FP32 path)
 template <bool FAST>

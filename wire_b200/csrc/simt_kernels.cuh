@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
 template <int ELEM>
 __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int M_out, int K_in,
                                     int mode, int n_blocks, int nb, int nbh, int k0_pad, int k_pad_total,
-                                    void* __restrict__ Bv, int do_round) {
+                                    void* __restrict__ Bv, int do_round, int pair_perm) {
   const int total = n_blocks * nb * k_pad_total;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / k_pad_total, kk = idx % k_pad_total;
@@ -77,16 +77,17 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
       const int blk = r / nb, c = r % nb;
       const float* W = W1;
       int oc;
+      // pair_perm: accumulator columns in pair-transposed order (acc_col_perm; halves / blocks are multiples of 4 columns)
       if (nbh < nb) {  // wire2d forward: [z half | w half]
-        if (c < nbh) oc = blk * nbh + c; else { oc = blk * nbh + (c - nbh); W = W2; }
-      } else oc = blk * nb + c;
+        if (c < nbh) oc = blk * nbh + (pair_perm ? acc_col_perm(c) : c); else { oc = blk * nbh + (pair_perm ? acc_col_perm(c - nbh) : c - nbh); W = W2; }
+      } else oc = blk * nb + (pair_perm ? acc_col_perm(c) : c);
       if (oc < 2 * M_out && kk < 2 * K_in && c < 2 * nbh && W) {
         const int j = oc >> 1, part = oc & 1, k = kk >> 1, d = kk & 1;
         const float wr = W[(size_t(j) * K_in + k) * 2], wi = W[(size_t(j) * K_in + k) * 2 + 1];
         v = part == 0 ? (d == 0 ? wr : -wi) : (d == 0 ? wi : wr);
       }
     } else {
-      const int oc = r;  // real column of g_x, blocks are contiguous
+      const int oc = pair_perm ? acc_col_perm(r) : r;  // real column of g_x, blocks are contiguous
       const float* W = W1;
       int kq = kk;
       if (kk >= k0_pad) { W = W2; kq = kk - k0_pad; }

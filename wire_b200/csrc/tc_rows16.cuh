@@ -13,16 +13,22 @@
 //     never holds more than the 32 accumulator registers of its chunk;
 //   * 16-bit staging / saved-z tiles use the 64-byte TMA swizzle (conflict-free 16-byte accesses at a 64-byte pitch);
 //   * layer flags are template parameters (no per-element branches), rint() is the add-magic-constant trick (FRND
-//     shares the 16-lane XU pipe with ex2/sin/cos, which is the binding unit of this epilogue).
+//     shares the 16-lane XU pipe with ex2/sin/cos);
+//   * the FP32 math runs on PAIRS of features with the packed FFMA2 / FMUL2 / FADD2 instructions (f32x2.cuh).  To make
+//     that free of register shuffles the packed weight matrices of the 16-bit path put their rows in "pair-transposed"
+//     order (acc_col_perm): accumulator columns 4j..4j+3 hold (re A, re B, im A, im B) of features A = 2j, B = 2j+1,
+//     so tcgen05.ld delivers aligned register pairs; tensors in HBM keep torch's interleaved (re, im) order.
 //
 // Modes and math are exactly those of tc_rows.cuh / rows_epilogue.cuh (same reference lines).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "f32x2.cuh"
 #include "tc_rows.cuh"
 
 namespace wire {
+
 
 constexpr int kEpi16Warps = 16;
 constexpr int kEpi16Parts = kEpi16Warps / 4;  // warps per TMEM sub-partition
@@ -110,32 +116,39 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   // ---- shared parameter tables (zero padded: the epilogue needs no column checks) ----
   //  fwd  : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8] (wr[4], wi[4]) | fin exchange (FUSE)
   //  first: tab[(param_cols/2)][4] = {w0[0..2], b0} | tab2 (2D)
+  //  fwd  : bias[param_cols] (pair-transposed order) | bias2 (2D) | wf[pairs][16] | fin exchange (FUSE)
+  //         wf pair P = features (2P, 2P+1): float4 {wr0A,wr0B,wr1A,wr1B} {wr2A,wr2B,wr3A,wr3B} {-wi0A,-wi0B,-wi1A,-wi1B} {-wi2..}
+  //  first: tab[pairs][8] = float4 {w0A,w0B,w1A,w1B} {w2A,w2B,bA,bB} | tab2 (2D)
   if constexpr (kFwd) {
     for (int i = threadIdx.x; i < P.param_cols; i += blockDim.x) {
-      params[i] = i < E.n_cols ? E.bias[i] : 0.f;
-      if constexpr (k2D) params[P.param_cols + i] = i < E.n_cols ? E.bias2[i] : 0.f;
+      const int l = acc_col_perm(i);
+      params[i] = l < E.n_cols ? E.bias[l] : 0.f;
+      if constexpr (k2D) params[P.param_cols + i] = l < E.n_cols ? E.bias2[l] : 0.f;
     }
     if constexpr (FUSE) {
       float* wf = params + (k2D ? 2 : 1) * P.param_cols;
-      for (int i = threadIdx.x; i < (P.param_cols >> 1) * 8; i += blockDim.x) {
-        const int k = i >> 3, j = i & 7, o = j & 3;
+      for (int i = threadIdx.x; i < (P.param_cols >> 2) * 16; i += blockDim.x) {
+        const int pr = i >> 4, qd = (i >> 2) & 3, e = i & 3;
+        const int o = (qd & 1) * 2 + (e >> 1), k = 2 * pr + (e & 1), im = qd >> 1;
         float v = 0.f;
-        if (k < n_feat && o < E.out_features) v = E.wf[(size_t(o) * n_feat + k) * 2 + (j >> 2)];
-        wf[i] = v;
+        if (k < n_feat && o < E.out_features) v = E.wf[(size_t(o) * n_feat + k) * 2 + im];
+        wf[i] = im ? -v : v;
       }
     }
   }
   if constexpr (kFirst) {
-    for (int i = threadIdx.x; i < (P.param_cols >> 1) * 4; i += blockDim.x) {
-      const int k = i >> 2, j = i & 3;
+    for (int i = threadIdx.x; i < (P.param_cols >> 2) * 8; i += blockDim.x) {
+      const int pr = i >> 3, qd = (i >> 2) & 1, e = i & 3;
+      const int k = 2 * pr + (e & 1);
+      const int d = qd * 2 + (e >> 1);  // 0..2 = coordinate weight, 3 = bias
       float v = 0.f, v2 = 0.f;
       if (k < n_feat) {
-        if (j < 3) {
-          if (j < E.in_features) { v = E.w0[size_t(k) * E.in_features + j]; if constexpr (k2D) v2 = E.w0b[size_t(k) * E.in_features + j]; }
+        if (d < 3) {
+          if (d < E.in_features) { v = E.w0[size_t(k) * E.in_features + d]; if constexpr (k2D) v2 = E.w0b[size_t(k) * E.in_features + d]; }
         } else { v = E.b0[k]; if constexpr (k2D) v2 = E.b0b[k]; }
       }
       params[i] = v;
-      if constexpr (k2D) params[(P.param_cols >> 1) * 4 + i] = v2;
+      if constexpr (k2D) params[(P.param_cols >> 2) * 8 + i] = v2;
     }
   }
 
@@ -287,7 +300,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
     // FUSE: partial sums of parts 1..3 travel through [slot 2][part-1][128 rows] float4 after the wf table
     float4* s_fin = reinterpret_cast<float4*>(params + (k2D ? 2 : 1) * P.param_cols + (P.param_cols >> 1) * 8);
     const float4* s_tab = reinterpret_cast<const float4*>(params);
-    const float4* s_tab2 = reinterpret_cast<const float4*>(params + (P.param_cols >> 1) * 4);
+    const float4* s_tab2 = reinterpret_cast<const float4*>(params + (P.param_cols >> 2) * 8);
+    const GaborConst2 G2 = make_gabor_const2(G);
     const uint32_t empty_addr0 = pair ? (smem_u32(&bar_tmem_empty[0]) & kPeerBitMask) : smem_u32(&bar_tmem_empty[0]);
     const uint32_t empty_addr1 = pair ? (smem_u32(&bar_tmem_empty[1]) & kPeerBitMask) : smem_u32(&bar_tmem_empty[1]);
     const int out_blk = (MODE == MODE_GABOR2D_FWD) ? P.nbh : P.nb;
@@ -295,8 +309,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
     uint32_t in_phase = 0;
     long long e_wait = 0, e_wait_in = 0;
     const long long e_begin = WIRE_CLK();
-    float cin[3] = {0.f, 0.f, 0.f};
-    float facc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+    f2 cin2[3] = {0ull, 0ull, 0ull};          // first-layer modes: this row's coordinates, broadcast pairs
+    f2 facc2[kMaxOut] = {0ull, 0ull, 0ull, 0ull};  // FUSE: partial sums of the final Linear over even / odd features
     auto release = [&](int buf) {
       tc_fence_before();
       __syncwarp();
@@ -321,15 +335,16 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
 
       if (sl == 0) {
         if constexpr (kFirst) {
-          cin[0] = cin[1] = cin[2] = 0.f;
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
           if (row_ok) {
-            cin[0] = __ldg(E.coords + size_t(row) * E.in_features);
-            if (E.in_features > 1) cin[1] = __ldg(E.coords + size_t(row) * E.in_features + 1);
-            if (E.in_features > 2) cin[2] = __ldg(E.coords + size_t(row) * E.in_features + 2);
+            c0 = __ldg(E.coords + size_t(row) * E.in_features);
+            if (E.in_features > 1) c1 = __ldg(E.coords + size_t(row) * E.in_features + 1);
+            if (E.in_features > 2) c2 = __ldg(E.coords + size_t(row) * E.in_features + 2);
           }
+          cin2[0] = f2_bcast(c0); cin2[1] = f2_bcast(c1); cin2[2] = f2_bcast(c2);
         }
 #pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) facc[o] = 0.f;
+        for (int o = 0; o < kMaxOut; ++o) facc2[o] = 0ull;
       }
 
       if constexpr (kBwd) {  // prefetch the first saved-z tile of this job while its MMAs are still running
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * P.buf_cols + ch * kChunk;
         const int c = col0 + ch * kChunk;  // first real output column of this chunk (also the smem table index)
         uint32_t raw[32];
-        float wn[16];
+        f2 wn[8];  // 2D fwd: |w|^2 per feature pair
         if constexpr (MODE == MODE_GABOR2D_FWD) {
           // w half first: |w|^2 per feature is all the Gabor needs; w itself goes straight to its staging tile
           tmem_ld32(taddr + P.nbh, raw);
@@ -361,14 +376,17 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
           if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 b0 = s_bias24[(c >> 2) + 2 * g], b1 = s_bias24[(c >> 2) + 2 * g + 1];
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float w8[8];
+            uint32_t pk[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w8[i] = __uint_as_float(raw[8 * g + i]) + bb[i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) wn[4 * g + i] = fmaf(w8[2 * i], w8[2 * i], w8[2 * i + 1] * w8[2 * i + 1]);
-            if (st2) sts128(sw64_addr(wbuf2, lane, g), pack_f16(w8[0], w8[1]), pack_f16(w8[2], w8[3]), pack_f16(w8[4], w8[5]), pack_f16(w8[6], w8[7]));
+            for (int h = 0; h < 2; ++h) {
+              const float4 b = s_bias24[(c >> 2) + 2 * g + h];
+              const f2 wr = f2_add(f2_bits(raw[8 * g + 4 * h], raw[8 * g + 4 * h + 1]), f2_make(b.x, b.y));
+              const f2 wi = f2_add(f2_bits(raw[8 * g + 4 * h + 2], raw[8 * g + 4 * h + 3]), f2_make(b.z, b.w));
+              wn[2 * g + h] = f2_fma(wr, wr, f2_mul(wi, wi));
+              pk[2 * h] = pack_f16(f2_lo(wr), f2_lo(wi));
+              pk[2 * h + 1] = pack_f16(f2_hi(wr), f2_hi(wi));
+            }
+            if (st2) sts128(sw64_addr(wbuf2, lane, g), pk[0], pk[1], pk[2], pk[3]);
           }
         }
         tmem_ld32(taddr, raw);
@@ -394,25 +412,29 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 b0 = s_bias4[(c >> 2) + 2 * g], b1 = s_bias4[(c >> 2) + 2 * g + 1];
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float z8[8], y8[8];
+            uint32_t py[4], pz[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z8[i] = __uint_as_float(raw[8 * g + i]) + bb[i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              gabor16(G, z8[2 * i], z8[2 * i + 1], k2D ? wn[4 * g + i] : 0.f, y8[2 * i], y8[2 * i + 1]);
+            for (int h = 0; h < 2; ++h) {  // two feature pairs per group of 8 accumulator columns
+              const float4 b = s_bias4[(c >> 2) + 2 * g + h];
+              const f2 zr = f2_add(f2_bits(raw[8 * g + 4 * h], raw[8 * g + 4 * h + 1]), f2_make(b.x, b.y));
+              const f2 zi = f2_add(f2_bits(raw[8 * g + 4 * h + 2], raw[8 * g + 4 * h + 3]), f2_make(b.z, b.w));
+              f2 yr, yi;
+              gabor_x2(G2, zr, zi, k2D ? wn[2 * g + h] : 0ull, yr, yi);
               if constexpr (FUSE) {
-                const float4 wr4 = s_wf[((c >> 1) + 4 * g + i) * 2];
-                const float4 wi4 = s_wf[((c >> 1) + 4 * g + i) * 2 + 1];
-                facc[0] = fmaf(y8[2 * i], wr4.x, fmaf(-y8[2 * i + 1], wi4.x, facc[0]));
-                facc[1] = fmaf(y8[2 * i], wr4.y, fmaf(-y8[2 * i + 1], wi4.y, facc[1]));
-                facc[2] = fmaf(y8[2 * i], wr4.z, fmaf(-y8[2 * i + 1], wi4.z, facc[2]));
-                facc[3] = fmaf(y8[2 * i], wr4.w, fmaf(-y8[2 * i + 1], wi4.w, facc[3]));
+                const float4* wq = s_wf + ((c >> 2) + 2 * g + h) * 4;
+                const float4 w0 = wq[0], w1 = wq[1], w2 = wq[2], w3 = wq[3];
+                facc2[0] = f2_fma(yr, f2_make(w0.x, w0.y), f2_fma(yi, f2_make(w2.x, w2.y), facc2[0]));
+                facc2[1] = f2_fma(yr, f2_make(w0.z, w0.w), f2_fma(yi, f2_make(w2.z, w2.w), facc2[1]));
+                facc2[2] = f2_fma(yr, f2_make(w1.x, w1.y), f2_fma(yi, f2_make(w3.x, w3.y), facc2[2]));
+                facc2[3] = f2_fma(yr, f2_make(w1.z, w1.w), f2_fma(yi, f2_make(w3.z, w3.w), facc2[3]));
               }
+              py[2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
+              py[2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
+              pz[2 * h] = pack_f16(f2_lo(zr), f2_lo(zi));
+              pz[2 * h + 1] = pack_f16(f2_hi(zr), f2_hi(zi));
             }
-            if (st0) sts128(sw64_addr(wbuf, lane, g), pack_f16(y8[0], y8[1]), pack_f16(y8[2], y8[3]), pack_f16(y8[4], y8[5]), pack_f16(y8[6], y8[7]));
-            if (st1) sts128(sw64_addr(wbuf1, lane, g), pack_f16(z8[0], z8[1]), pack_f16(z8[2], z8[3]), pack_f16(z8[4], z8[5]), pack_f16(z8[6], z8[7]));
+            if (st0) sts128(sw64_addr(wbuf, lane, g), py[0], py[1], py[2], py[3]);
+            if (st1) sts128(sw64_addr(wbuf1, lane, g), pz[0], pz[1], pz[2], pz[3]);
           }
         } else if constexpr (kBwd) {
           // this chunk's saved z (w) tile: copy the packed halves to registers, then prefetch the next tile into the same buffer
@@ -441,39 +463,52 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
           for (int g = 0; g < 4; ++g) {
             uint32_t pz[4], pw[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 z = unpack_f16(zp[4 * g + i]);
-              float2 w = make_float2(0.f, 0.f);
-              if constexpr (k2D) w = unpack_f16(wp[4 * g + i]);
-              const float wnorm = k2D ? fmaf(w.x, w.x, w.y * w.y) : 0.f;
-              float yr, yi, gzr, gzi;
-              gabor16(G, z.x, z.y, wnorm, yr, yi);
-              const float pr = gabor_bwd(yr, yi, z.x, z.y, __uint_as_float(raw[8 * g + 2 * i]), __uint_as_float(raw[8 * g + 2 * i + 1]),
-                                         G.omega, G.s2, gzr, gzi);
-              pz[i] = pack_bf16(gzr, gzi);
+            for (int h = 0; h < 2; ++h) {
+              const float2 za = unpack_f16(zp[4 * g + 2 * h]), zb = unpack_f16(zp[4 * g + 2 * h + 1]);
+              const f2 zr = f2_make(za.x, zb.x), zi = f2_make(za.y, zb.y);
+              f2 wr = 0ull, wi = 0ull, wnorm = 0ull;
               if constexpr (k2D) {
-                const float t = -2.0f * G.s2 * pr;
-                pw[i] = pack_bf16(t * w.x, t * w.y);
+                const float2 wa = unpack_f16(wp[4 * g + 2 * h]), wb = unpack_f16(wp[4 * g + 2 * h + 1]);
+                wr = f2_make(wa.x, wb.x); wi = f2_make(wa.y, wb.y);
+                wnorm = f2_fma(wr, wr, f2_mul(wi, wi));
+              }
+              const f2 gr = f2_bits(raw[8 * g + 4 * h], raw[8 * g + 4 * h + 1]);
+              const f2 gi = f2_bits(raw[8 * g + 4 * h + 2], raw[8 * g + 4 * h + 3]);
+              f2 yr, yi, gzr, gzi;
+              gabor_x2(G2, zr, zi, wnorm, yr, yi);
+              const f2 pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gr, gi, gzr, gzi);
+              pz[2 * h] = pack_bf16(f2_lo(gzr), f2_lo(gzi));
+              pz[2 * h + 1] = pack_bf16(f2_hi(gzr), f2_hi(gzi));
+              if constexpr (k2D) {
+                const f2 t = f2_mul(G2.m2s2, pr);
+                const f2 gwr = f2_mul(t, wr), gwi = f2_mul(t, wi);
+                pw[2 * h] = pack_bf16(f2_lo(gwr), f2_lo(gwi));
+                pw[2 * h + 1] = pack_bf16(f2_hi(gwr), f2_hi(gwi));
               }
             }
             if (st0) sts128(sw64_addr(wbuf, lane, g), pz[0], pz[1], pz[2], pz[3]);
             if constexpr (k2D) { if (st1) sts128(sw64_addr(wbuf1, lane, g), pw[0], pw[1], pw[2], pw[3]); }
           }
         } else {  // kFirst: real z0 recomputed from the coordinates and the smem weight table; BF16 direct stores
-          float gz[16], gw[16];
+          uint32_t gzp[8], gwp[8];  // 16 real outputs as packed BF16 pairs (features A, B of each pair are adjacent)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 t = s_tab[(c >> 1) + i];
-            const float z0 = fmaf(cin[0], t.x, fmaf(cin[1], t.y, fmaf(cin[2], t.z, t.w)));
-            float w0v = 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 ta = s_tab[((c >> 2) + j) * 2], tb = s_tab[((c >> 2) + j) * 2 + 1];
+            const f2 z0 = f2_fma(cin2[0], f2_make(ta.x, ta.y), f2_fma(cin2[1], f2_make(ta.z, ta.w), f2_fma(cin2[2], f2_make(tb.x, tb.y), f2_make(tb.z, tb.w))));
+            f2 w0v = 0ull, wnorm = 0ull;
             if constexpr (k2D) {
-              const float4 t2 = s_tab2[(c >> 1) + i];
-              w0v = fmaf(cin[0], t2.x, fmaf(cin[1], t2.y, fmaf(cin[2], t2.z, t2.w)));
+              const float4 ua = s_tab2[((c >> 2) + j) * 2], ub = s_tab2[((c >> 2) + j) * 2 + 1];
+              w0v = f2_fma(cin2[0], f2_make(ua.x, ua.y), f2_fma(cin2[1], f2_make(ua.z, ua.w), f2_fma(cin2[2], f2_make(ub.x, ub.y), f2_make(ub.z, ub.w))));
+              wnorm = f2_mul(w0v, w0v);
             }
-            float yr, yi;
-            gabor16(G, z0, 0.f, w0v * w0v, yr, yi);
-            const float pr = gabor_first_bwd(yr, yi, z0, __uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]), G.omega, G.s2, gz[i]);
-            gw[i] = -2.0f * G.s2 * pr * w0v;
+            f2 yr, yi, gz;
+            gabor_real_x2(G2, z0, wnorm, yr, yi);
+            const f2 pr = gabor_first_bwd_x2(G2, yr, yi, z0, f2_bits(raw[4 * j], raw[4 * j + 1]), f2_bits(raw[4 * j + 2], raw[4 * j + 3]), gz);
+            gzp[j] = pack_bf16(f2_lo(gz), f2_hi(gz));
+            if constexpr (k2D) {
+              const f2 gw = f2_mul(f2_mul(G2.m2s2, pr), w0v);
+              gwp[j] = pack_bf16(f2_lo(gw), f2_hi(gw));
+            }
           }
           if (row_ok) {
             // 16 real outputs per thread as BF16 = 32 contiguous bytes (one full sector): two direct 16-byte stores
@@ -482,15 +517,13 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
 #pragma unroll
             for (int j8 = 0; j8 < 2; ++j8)
               if ((c >> 1) + 8 * j8 < E.gz0_pitch)
-                *reinterpret_cast<uint4*>(dst + 8 * j8) = make_uint4(pack_bf16(gz[8 * j8], gz[8 * j8 + 1]), pack_bf16(gz[8 * j8 + 2], gz[8 * j8 + 3]),
-                                                                     pack_bf16(gz[8 * j8 + 4], gz[8 * j8 + 5]), pack_bf16(gz[8 * j8 + 6], gz[8 * j8 + 7]));
+                *reinterpret_cast<uint4*>(dst + 8 * j8) = make_uint4(gzp[4 * j8], gzp[4 * j8 + 1], gzp[4 * j8 + 2], gzp[4 * j8 + 3]);
             if constexpr (k2D) {
               __nv_bfloat16* dw = reinterpret_cast<__nv_bfloat16*>(E.gw0) + size_t(row) * E.gz0_pitch + (c >> 1);
 #pragma unroll
               for (int j8 = 0; j8 < 2; ++j8)
                 if ((c >> 1) + 8 * j8 < E.gz0_pitch)
-                  *reinterpret_cast<uint4*>(dw + 8 * j8) = make_uint4(pack_bf16(gw[8 * j8], gw[8 * j8 + 1]), pack_bf16(gw[8 * j8 + 2], gw[8 * j8 + 3]),
-                                                                      pack_bf16(gw[8 * j8 + 4], gw[8 * j8 + 5]), pack_bf16(gw[8 * j8 + 6], gw[8 * j8 + 7]));
+                  *reinterpret_cast<uint4*>(dw + 8 * j8) = make_uint4(gwp[4 * j8], gwp[4 * j8 + 1], gwp[4 * j8 + 2], gwp[4 * j8 + 3]);
             }
           }
         }
@@ -509,6 +542,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
         if (sl == P.slices - 1) {
           // the four warps of a sub-partition hold partial sums over their chunks (of every slice)
           const int slot = it & 1;
+          const float facc[4] = {f2_lo(facc2[0]) + f2_hi(facc2[0]), f2_lo(facc2[1]) + f2_hi(facc2[1]),
+                                 f2_lo(facc2[2]) + f2_hi(facc2[2]), f2_lo(facc2[3]) + f2_hi(facc2[3])};
           if (part > 0) s_fin[(slot * (kEpi16Parts - 1) + (part - 1)) * kTileRows + q * 32 + lane] = make_float4(facc[0], facc[1], facc[2], facc[3]);
           asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kEpi16Parts) : "memory");
           if (part == 0 && row_ok) {
