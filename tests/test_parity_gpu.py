@@ -380,3 +380,27 @@ def test_fused_trainer_matches_module_plus_torch_adam(kind, graph, precision):
     # the module still sees the trained weights (parameters are views of the trainer's flat buffer)
     with torch.no_grad():
         assert util.rel_err(b(coords).cpu().numpy(), a(coords).cpu().numpy()) < 5e-2
+
+
+@pytest.mark.parametrize("precision", ["tf32", "mixed16"])
+@pytest.mark.parametrize("kind,hidden", [("wire", 300), ("wire", 200), ("wire2d", 256)])
+def test_run_to_run_reproducibility(kind, hidden, precision):
+    """Same inputs twice: outputs must be bit-identical (the forward has no atomics) and gradients may differ only by the
+    order of fp32 atomics in the split-K reductions (~1e-6 relative).  Anything larger is a race (this caught lanes past
+    the last feature storing into feature 0's slot of the TMA-streamed top-of-backward kernel)."""
+    import wire_b200
+    torch.manual_seed(0)
+    m = wire_b200.get_INR(kind, 2, hidden, None, 2, 3, True, 7.0, 7.0, 6.0, precision=precision).cuda()
+    coords = (torch.rand(1, 5000, 2, device="cuda") * 2 - 1)
+    target = torch.rand(1, 5000, 3, device="cuda")
+    outs, grads = [], []
+    for _ in range(4):
+        out = m(coords)
+        g = torch.autograd.grad(((out - target) ** 2).mean(), [p for p in m.parameters() if p.requires_grad])
+        outs.append(out.detach().clone())
+        grads.append([torch.view_as_real(x).clone() if x.is_complex() else x.clone() for x in g])
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    for gs in grads[1:]:
+        for a, b in zip(gs, grads[0]):
+            assert util.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5

@@ -381,8 +381,8 @@ static bool test_wgrad16(int n_rows, int k_in, int m_out, int x_elem, int g_elem
   P.n_rows = n_rows; P.k_in = k_in; P.g_cols = gc; P.n_g = 1;
   P.gW[0] = dW; P.gB[0] = dBias; P.x_fmt = x_elem - 1; P.g_fmt = g_elem - 1; P.x_conv = x_elem != g_elem;
   size_t smem = wire::wgrad_configure(P, g_sms, g_cluster, false, true);
-  bool ok = sm100_host::make_tmap_2d_t(&P.x_map, dX, n_rows, xc, xp, wire::kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, x_elem);
-  ok &= sm100_host::make_tmap_2d_t(&P.g_map[0], dG, n_rows, gc, gp, wire::kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, g_elem);
+  bool ok = sm100_host::make_tmap_2d_t(&P.x_map, dX, n_rows, xc, xp, wire::kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, x_elem);
+  ok &= sm100_host::make_tmap_2d_t(&P.g_map[0], dG, n_rows, gc, gp, wire::kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, g_elem);
   P.g_map[1] = P.g_map[0];
   if (!ok || !smem) { printf("wgrad16 setup failed\n"); return false; }
   printf("[wgrad16] cluster=%d n=%d K=%d M=%d x=%d g=%d m_tiles=%d n_blocks=%d nb=%d splits=%d stages=%d\n", g_cluster, n_rows, k_in, m_out,

@@ -401,9 +401,9 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
   }
   bool ok;
   if (op16) {
-    ok = sm100_host::make_tmap_2d_t(&P.x_map, x, n, 2 * k_in + 1, x_pitch, kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, x_elem);
-    ok &= sm100_host::make_tmap_2d_t(&P.g_map[0], g1, n, 2 * m_out, g_pitch, kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, g_elem);
-    ok &= sm100_host::make_tmap_2d_t(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, kWgradKC16, 32, CU_TENSOR_MAP_SWIZZLE_64B, g_elem);
+    ok = sm100_host::make_tmap_2d_t(&P.x_map, x, n, 2 * k_in + 1, x_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, x_elem);
+    ok &= sm100_host::make_tmap_2d_t(&P.g_map[0], g1, n, 2 * m_out, g_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, g_elem);
+    ok &= sm100_host::make_tmap_2d_t(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, g_elem);
   } else {
     ok = sm100_host::make_tmap_2d(&P.x_map, x, n, use_gen ? 2 * m_out : 2 * k_in + 1, x_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     ok &= sm100_host::make_tmap_2d(&P.g_map[0], g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -500,15 +500,16 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
         return cudaGetLastError();
       };
       cudaError_t e = cudaErrorInvalidValue;
+      const bool small = threads <= 512;
       switch (d->out_features * 2 + (w ? 1 : 0)) {
-        case 2: e = launch(top_bwd16_kernel<false, 1>); break;
-        case 3: e = launch(top_bwd16_kernel<true, 1>); break;
-        case 4: e = launch(top_bwd16_kernel<false, 2>); break;
-        case 5: e = launch(top_bwd16_kernel<true, 2>); break;
-        case 6: e = launch(top_bwd16_kernel<false, 3>); break;
-        case 7: e = launch(top_bwd16_kernel<true, 3>); break;
-        case 8: e = launch(top_bwd16_kernel<false, 4>); break;
-        case 9: e = launch(top_bwd16_kernel<true, 4>); break;
+        case 2: e = small ? launch(top_bwd16_kernel<false, 1, 512>) : launch(top_bwd16_kernel<false, 1, 1024>); break;
+        case 3: e = small ? launch(top_bwd16_kernel<true, 1, 512>) : launch(top_bwd16_kernel<true, 1, 1024>); break;
+        case 4: e = small ? launch(top_bwd16_kernel<false, 2, 512>) : launch(top_bwd16_kernel<false, 2, 1024>); break;
+        case 5: e = small ? launch(top_bwd16_kernel<true, 2, 512>) : launch(top_bwd16_kernel<true, 2, 1024>); break;
+        case 6: e = small ? launch(top_bwd16_kernel<false, 3, 512>) : launch(top_bwd16_kernel<false, 3, 1024>); break;
+        case 7: e = small ? launch(top_bwd16_kernel<true, 3, 512>) : launch(top_bwd16_kernel<true, 3, 1024>); break;
+        case 8: e = small ? launch(top_bwd16_kernel<false, 4, 512>) : launch(top_bwd16_kernel<false, 4, 1024>); break;
+        case 9: e = small ? launch(top_bwd16_kernel<true, 4, 512>) : launch(top_bwd16_kernel<true, 4, 1024>); break;
       }
       CU_OK(e);
       return 0;

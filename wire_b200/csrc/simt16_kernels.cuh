@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restric
     if constexpr (TWO_D) tab2[(k & 3) * nq + (k >> 2)] = t2;
   }
   __syncthreads();
-  const GaborConst G = make_gabor_const(__ldg(omega_p), __ldg(scale_p));
+  const GaborConst2 G2 = make_gabor_const2(make_gabor_const(__ldg(omega_p), __ldg(scale_p)));
   const int items = rows * nq;
   // (r, q) of this thread's first item and the per-step increment, without a division in the loop
   int r = int(threadIdx.x) / nq, q = int(threadIdx.x) - r * nq;
@@ -66,27 +66,29 @@ __global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restric
   for (int item = threadIdx.x; item < items; item += blockDim.x) {
     // the ~nq threads that share a row hit the same L1 line
     const float* cp = coords + size_t(row0 + r) * in_f;
-    const float c0 = __ldg(cp), c1 = in_f > 1 ? __ldg(cp + 1) : 0.f, c2 = in_f > 2 ? __ldg(cp + 2) : 0.f;
-    float yv[8];
+    const f2 c0p = f2_bcast(__ldg(cp)), c1p = f2_bcast(in_f > 1 ? __ldg(cp + 1) : 0.f), c2p = f2_bcast(in_f > 2 ? __ldg(cp + 2) : 0.f);
+    // two feature pairs (f = 0,1 and 2,3), packed FP32 math (f32x2.cuh)
+    uint32_t pp[4];
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const float4 t = tab[f * nq + q];
-      const float z = fmaf(c0, t.x, fmaf(c1, t.y, fmaf(c2, t.z, t.w)));
-      float wn = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const float4 ta = tab[(2 * h) * nq + q], tb = tab[(2 * h + 1) * nq + q];
+      const f2 z = f2_fma(c0p, f2_make(ta.x, tb.x), f2_fma(c1p, f2_make(ta.y, tb.y), f2_fma(c2p, f2_make(ta.z, tb.z), f2_make(ta.w, tb.w))));
+      f2 wn = 0ull;
       if constexpr (TWO_D) {
-        const float4 t2 = tab2[f * nq + q];
-        const float w = fmaf(c0, t2.x, fmaf(c1, t2.y, fmaf(c2, t2.z, t2.w)));
-        wn = w * w;
+        const float4 ua = tab2[(2 * h) * nq + q], ub = tab2[(2 * h + 1) * nq + q];
+        const f2 w = f2_fma(c0p, f2_make(ua.x, ub.x), f2_fma(c1p, f2_make(ua.y, ub.y), f2_fma(c2p, f2_make(ua.z, ub.z), f2_make(ua.w, ub.w))));
+        wn = f2_mul(w, w);
       }
-      gabor16(G, z, 0.f, wn, yv[2 * f], yv[2 * f + 1]);
+      f2 yr, yi;
+      gabor_real_x2(G2, z, wn, yr, yi);
+      pp[2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
+      pp[2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
     }
     __half* dst = y + size_t(row0 + r) * y_pitch + 8 * q;
-    const uint32_t p0 = pack_f16(yv[0], yv[1]), p1 = pack_f16(yv[2], yv[3]), p2 = pack_f16(yv[4], yv[5]), p3 = pack_f16(yv[6], yv[7]);
     if (4 * q + 3 < M) {
-      __stcs(reinterpret_cast<uint4*>(dst), make_uint4(p0, p1, p2, p3));
+      __stcs(reinterpret_cast<uint4*>(dst), make_uint4(pp[0], pp[1], pp[2], pp[3]));
     } else {  // ragged last quad: only the valid features (the ones column follows them)
       uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-      const uint32_t pp[4] = {p0, p1, p2, p3};
 #pragma unroll
       for (int f = 0; f < 4; ++f)
         if (4 * q + f < M) d32[f] = pp[f];
@@ -120,8 +122,9 @@ struct TopBwd16Params {
 // Block = W compute warps (thread k owns complex feature k) + one I/O warp.  No block-wide barrier in the loop: tiles
 // flow through two-deep in / out rings guarded by mbarriers (in_full: TMA bytes + g_out rows staged by the I/O warp;
 // in_empty / out_full: one arrival per compute warp; out_empty: the I/O warp, once the TMA store has read the tile).
-template <bool TWO_D, int OUTF>
-__global__ void __launch_bounds__(1024) top_bwd16_kernel(const __grid_constant__ TopBwd16Params P) {
+// MAXT: launch bound (512 leaves 128 registers per thread for the usual widths; 1024 covers M up to 992)
+template <bool TWO_D, int OUTF, int MAXT>
+__global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__ TopBwd16Params P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t tsm[];
   __shared__ __align__(8) uint64_t in_full[2], in_empty[2], out_full[2], out_empty[2];
@@ -247,10 +250,11 @@ __global__ void __launch_bounds__(1024) top_bwd16_kernel(const __grid_constant__
       float yr, yi, gzr, gzi;
       gabor16(G, z.x, z.y, wnorm, yr, yi);
       const float pr = gabor_bwd(yr, yi, z.x, z.y, gyr, gyi, G.omega, G.s2, gzr, gzi);
-      *reinterpret_cast<uint32_t*>(zout + rr * row_bytes) = pack_bf16(gzr, gzi);
+      // (lanes past the last feature alias feature 0's slot: they compute on it but must not store)
+      if (active) *reinterpret_cast<uint32_t*>(zout + rr * row_bytes) = pack_bf16(gzr, gzi);
       if constexpr (TWO_D) {
         const float t = -2.0f * G.s2 * pr;
-        *reinterpret_cast<uint32_t*>(zout + tile_bytes + rr * row_bytes) = pack_bf16(t * w.x, t * w.y);
+        if (active) *reinterpret_cast<uint32_t*>(zout + tile_bytes + rr * row_bytes) = pack_bf16(t * w.x, t * w.y);
       }
 #pragma unroll
       for (int o = 0; o < OUTF; ++o) { ar[o] = fmaf(g4[o], yr, ar[o]); ai[o] = fmaf(-g4[o], yi, ai[o]); }

@@ -228,11 +228,15 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   const int x_cols = 2 * P.k_in + 1;
   P.cluster = cluster;
   P.m_tiles = (x_cols + 128 * cluster - 1) / (128 * cluster);
-  const int gran = cluster == 2 ? 64 : 32;  // a pair splits every MMA piece in 32-column-aligned halves
+  // a pair splits every MMA piece in block-aligned halves (blocks: 32 columns, or 64 for 16-bit operands); the
+  // accumulator of one work item may use all 512 TMEM columns
+  const int blk_cols = op16 ? 64 : 32;
+  const int gran = cluster == 2 ? 2 * blk_cols : blk_cols;
+  const int nb_max = op16 ? 512 : 448;
   const int gpad = round_up(P.g_cols, gran);
-  P.n_blocks = (gpad + 447) / 448;
+  P.n_blocks = (gpad + nb_max - 1) / nb_max;
   P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran);
-  if (P.nb > 448) { P.n_blocks += 1; P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran); }
+  if (P.nb > nb_max) { P.n_blocks += 1; P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran); }
   const int base = P.m_tiles * P.n_blocks * P.n_g;
   int splits = (sm_count / cluster) / base;
   if (splits < 1) splits = 1;
@@ -240,7 +244,8 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   const int total_chunks = (P.n_rows + kc - 1) / kc;
   if (splits > total_chunks) splits = total_chunks > 0 ? total_chunks : 1;
   P.splits = splits;
-  const size_t stage = size_t(4 + P.nb / 32 / cluster) * 4096;  // 4 KB per 32-column block (x: 4 blocks, g: nb/32 per pair)
+  // x: 128 columns per CTA; g: nb / cluster columns per CTA; one block = blk_cols columns x (32 | 64) rows x (4 | 2) bytes
+  const size_t stage = size_t(128 / blk_cols + P.nb / blk_cols / cluster) * (op16 ? 8192 : 4096);
   P.gen_tab_feats = round_up(P.k_in + 1, 16) + 64 * 4;  // covers every feature index a generator warp may touch
   const size_t tab_bytes = gen ? size_t(2) * P.gen_tab_feats * 16 : 0;
   int stages = int((kMaxDynSmem - 1024 - tab_bytes) / stage);

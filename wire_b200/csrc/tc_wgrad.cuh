@@ -25,7 +25,7 @@ namespace wire {
 constexpr int kWgradThreads = 192;
 constexpr int kWgradGenWarps = 4;  // GEN kernels: x = y0 = gabor(coords W0^T + b0) is computed in place (first hidden layer)
 constexpr int kWgradKC = 32;    // coordinates per pipeline stage (TF32 operands: 32 rows x 128 B per 32-column block)
-constexpr int kWgradKC16 = 64;  // 16-bit operands: 64 rows x 64 B per 32-column block (same 4 KB blocks, same K-step stride)
+constexpr int kWgradKC16 = 64;  // 16-bit operands: 64 rows x 128 B per 64-column block (8 KB blocks, 128 B swizzle)
 
 struct WgradParams {
   CUtensorMap x_map;     // x [N, 2K+1(+pad)], box {32 cols, 32 rows}, SWIZZLE_128B_ATOM_32B
@@ -61,14 +61,20 @@ struct WgradParams {
   int gen_tab_feats;     // padded feature count of the tables
 };
 
-// OP16: x is FP16 and g is BF16 (formats in P.x_fmt / P.g_fmt), both still MN-major; tiles are 32-column blocks of
-// 64-byte rows with the 64 B swizzle (layout type SW64), 64 coordinates per stage, MMA kind::f16 (K = 16).
+// OP16: x is FP16 and g is BF16 (formats in P.x_fmt / P.g_fmt), both still MN-major; tiles are 64-column blocks of
+// 128-byte rows with the 128 B swizzle (UMMA layout SW128; 8 K-rows = one 1024 B atom, SBO = 1024, LBO = block stride),
+// 64 coordinates per stage, MMA kind::f16 (K = 16 = 2048 B per step).  (A first version used 32-column blocks of
+// 64-byte rows: every TMA row request then moved only two sectors and the loads, not the MMAs, set the pace.)
 template <bool PAIR, bool GEN = false, bool OP16 = false>
 __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0), 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
   using namespace sm100;
   static_assert(!(GEN && OP16), "the in-place generator writes TF32 tiles");
   constexpr int kKC = OP16 ? kWgradKC16 : kWgradKC;
-  constexpr uint32_t kLayout = OP16 ? kLayoutSW64 : kLayoutSW128Base32;
+  constexpr uint32_t kLayout = OP16 ? kLayoutSW128 : kLayoutSW128Base32;
+  constexpr int kBlkCols = OP16 ? 64 : 32;       // columns per smem block (one 128-byte swizzle row)
+  constexpr int kXBlocks = 128 / kBlkCols;       // x blocks per CTA (128 x-columns)
+  constexpr uint32_t kSBO = OP16 ? 1024 : 512;
+  constexpr uint32_t kStepUnits = OP16 ? 128 : 64;  // descriptor start-address advance per K-step (bytes >> 4)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8];
   __shared__ __align__(8) uint64_t bar_empty[8];
@@ -83,11 +89,11 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   const int crank = PAIR ? int(cluster_ctarank()) : 0;
   const bool leader = crank == 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t blk_bytes = 4096;  // one 32-column block of one stage (kKC rows of 128 B, or of 64 B for 16-bit operands)
-  const uint32_t a_bytes = 4 * blk_bytes;
+  const uint32_t blk_bytes = uint32_t(kKC) * 128;  // one block of one stage: kKC rows of 128 B
+  const uint32_t a_bytes = kXBlocks * blk_bytes;
   // MMA pieces along N (g columns): n1 + n2 = nb ; a pair splits each piece in halves (multiples of 32 columns)
   int nvalid = P.g_cols;  // per column block below
-  const int nbb_cta = P.nb / 32 / C;          // g blocks this CTA stages per chunk
+  const int nbb_cta = P.nb / kBlkCols / C;    // g blocks this CTA stages per chunk
   const uint32_t b_bytes = uint32_t(nbb_cta) * blk_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
 
@@ -159,27 +165,27 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
           if (conv) {  // the x tile completes on this CTA's own barrier: its converter warps pick it up
             const uint32_t xb = smem_u32(&bar_x[stage]);
             mbar_expect_tx(xb, a_bytes);
-            for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, xb, x_col0 + b * 32, r0);
+            for (int b = 0; b < kXBlocks; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, xb, x_col0 + b * kBlkCols, r0);
           }
           if (!PAIR) {
             mbar_expect_tx(full_own, tx_bytes);
-            if (!GEN && !conv) for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * 32, r0);
+            if (!GEN && !conv) for (int b = 0; b < kXBlocks; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * kBlkCols, r0);
             for (int b = 0; b < nbb_cta; ++b)
-              tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_own, nblk * P.nb + b * 32, r0);
+              tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_own, nblk * P.nb + b * kBlkCols, r0);
           } else {
             const uint32_t full_leader = full_own & kPeerBitMask;
             if (leader) mbar_expect_tx(full_own, 2 * tx_bytes);
             if (!GEN && !conv)
-              for (int b = 0; b < 4; ++b)
-                tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * 32, r0, kEvictNormal);
+              for (int b = 0; b < kXBlocks; ++b)
+                tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * kBlkCols, r0, kEvictNormal);
             // piece 1: columns [crank*n1/2, +n1/2) ; piece 2: columns [n1 + crank*n2/2, +n2/2)
-            const int p1 = n1 / 64, p2 = n2 / 64;
+            const int p1 = n1 / (2 * kBlkCols), p2 = n2 / (2 * kBlkCols);
             for (int b = 0; b < p1; ++b)
               tma_load_2d_2cta(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_leader,
-                               nblk * P.nb + crank * (n1 / 2) + b * 32, r0, kEvictNormal);
+                               nblk * P.nb + crank * (n1 / 2) + b * kBlkCols, r0, kEvictNormal);
             for (int b = 0; b < p2; ++b)
               tma_load_2d_2cta(a_dst + a_bytes + (p1 + b) * blk_bytes, &P.g_map[gi], full_leader,
-                               nblk * P.nb + n1 + crank * (n2 / 2) + b * 32, r0, kEvictNormal);
+                               nblk * P.nb + n1 + crank * (n2 / 2) + b * kBlkCols, r0, kEvictNormal);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
@@ -193,10 +199,10 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
                                      : make_idesc_tf32(PAIR ? 256 : 128, n2 > 0 ? n2 : 16, true, true);
         // descriptor words precomputed; only the start-address field moves (stage, K-step = 1024 B: 8 rows of 128 B,
         // or 16 rows of 64 B for 16-bit operands)
-        const uint32_t desc_hi = uint32_t(make_sdesc(0, blk_bytes, 512, kLayout) >> 32);
-        const uint32_t a_lo0 = uint32_t(make_sdesc(smem_base, blk_bytes, 512, kLayout));
+        const uint32_t desc_hi = uint32_t(make_sdesc(0, blk_bytes, kSBO, kLayout) >> 32);
+        const uint32_t a_lo0 = uint32_t(make_sdesc(smem_base, blk_bytes, kSBO, kLayout));
         const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
-        const uint32_t b2_units = (uint32_t(PAIR ? n1 / 64 : 8) * blk_bytes) >> 4;
+        const uint32_t b2_units = (uint32_t(PAIR ? n1 / (2 * kBlkCols) : n1 / kBlkCols) * blk_bytes) >> 4;
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_chunks; ++i) {
@@ -207,9 +213,9 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t acc = (ks > 0) ? 1u : (i ? 1u : 0u);
-            const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 64 * ks);
-            const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + 64 * ks);
-            const uint64_t bdesc2 = (uint64_t(desc_hi) << 32) | (b_lo + b2_units + 64 * ks);
+            const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + kStepUnits * ks);
+            const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + kStepUnits * ks);
+            const uint64_t bdesc2 = (uint64_t(desc_hi) << 32) | (b_lo + b2_units + kStepUnits * ks);
             if constexpr (OP16) {
               if (PAIR) {
                 umma_f16_2cta(tmem_base, adesc, bdesc, idesc1, acc);
@@ -298,13 +304,13 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
     } else {
       if (conv) {
         // ===================== x converters (epilogue warps, during the K loop) =====================
-        // warp b converts 32-column block b of every landed x tile FP16 -> BF16 in place: 4 KB = 8 x 16 B per lane
+        // warp b converts quarter b (4 KB = 8 x 16 B per lane) of every landed 16 KB x tile FP16 -> BF16 in place
         const int b = warp - 2;
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_chunks; ++i) {
           mbar_wait(smem_u32(&bar_x[stage]), phase);
-          const uint32_t blk = smem_base + stage * stage_bytes + b * blk_bytes;
+          const uint32_t blk = smem_base + stage * stage_bytes + b * 4096;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t addr = blk + (j * 32 + lane) * 16;
