@@ -350,9 +350,10 @@ def run_ours(args):
         a_u = 0.5 if mixed else 1.0
         g_u = 0.5 if mixed else 1.0
         z_u = 1.0 if args.precision == "fp32" else 0.5
+        g0_u = 0.25 if mixed else 0.5   # real g_z0 [n, M]: BF16 on the mixed16 path, fp32 otherwise
         alg_units = {"first_fwd": a_u, "tc_rows_gabor_fwd": (H * (a_u + z_u) + (H - 1) * a_u) / H, "top_bwd": z_u + g_u,
-                     "tc_wgrad": a_u + g_u, "tc_rows_dgrad_gabor_bwd": 2 * g_u + z_u, "tc_rows_dgrad_first_bwd": g_u + 0.5,
-                     "first_wgrad": 0.5}
+                     "tc_wgrad": a_u + g_u, "tc_rows_dgrad_gabor_bwd": 2 * g_u + z_u, "tc_rows_dgrad_first_bwd": g_u + g0_u,
+                     "first_wgrad": g0_u}
         alg_bytes = {k: v * unit_b for k, v in alg_units.items()}
         step_units = (alg_units["first_fwd"] + H * alg_units["tc_rows_gabor_fwd"] + alg_units["top_bwd"] + H * alg_units["tc_wgrad"]
                       + (H - 1) * alg_units["tc_rows_dgrad_gabor_bwd"] + alg_units["tc_rows_dgrad_first_bwd"] + alg_units["first_wgrad"])

@@ -430,7 +430,7 @@ static bool test_wgrad16(int n_rows, int k_in, int m_out, int x_elem, int g_elem
   return bad == 0;
 }
 
-static void time_rows_gabor16(int n_rows, int two_m, bool fuse_final) {
+static void time_rows_gabor16(int n_rows, int two_m, bool fuse_final, int mask_override = -1) {
   const int K = two_m, pitch = wire::round_up(two_m + 1, 32), kpad = wire::round_up(two_m, 64);
   const int nb = two_m > 256 ? wire::round_up(two_m, 64) : wire::round_up(two_m, 16);
   std::vector<uint16_t> A(size_t(n_rows) * pitch, 0), B(size_t(nb) * kpad, 0);
@@ -451,13 +451,13 @@ static void time_rows_gabor16(int n_rows, int two_m, bool fuse_final) {
   P.e.n_rows = n_rows; P.k_cols[0] = K; P.n_blocks = 1; P.e.n_cols = two_m; P.e.z_half = 1;
   P.e.bias = dbias; P.e.omega = dom; P.e.scale = dom + 1;
   if (fuse_final) { P.e.fuse_final = 1; P.e.wf = dwf; P.e.bf = dbias; P.e.out = dout; P.e.out_features = 3; }
-  const int mask = fuse_final ? 2 : 3;
+  const int mask = mask_override >= 0 ? mask_override : (fuse_final ? 2 : 3);
   size_t smem = wire::rows16_configure(P, nb, nb, mask, 0, two_m, wire::MODE_GABOR_FWD, fuse_final, g_cluster);
   P.a_fmt = 0; P.b_fmt = 0; P.o_fmt[0] = 1; P.o_fmt[1] = 1;
   bool ok = sm100_host::make_tmap_2d_t(&P.a_map[0], dA, n_rows, K, pitch, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B, 1);
   P.a_map[1] = P.a_map[0];
   ok &= sm100_host::make_tmap_2d_t(&P.b_map, dB, nb, kpad, kpad, P.b_box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B, 1);
-  ok &= sm100_host::make_tmap_2d_t(&P.o_map[0], fuse_final ? dZ : dY, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1);
+  ok &= sm100_host::make_tmap_2d_t(&P.o_map[0], (mask & 1) ? dY : dZ, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1);
   ok &= sm100_host::make_tmap_2d_t(&P.o_map[1], dZ, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1);
   P.o_map[2] = P.o_map[0]; P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
   if (!ok || !smem) { printf("gabor16 setup failed\n"); return; }
@@ -467,7 +467,7 @@ static void time_rows_gabor16(int n_rows, int two_m, bool fuse_final) {
   CK(cudaDeviceSynchronize());
   std::vector<unsigned long long> hd(8 * 1024);
   CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
-  printf("[gabor_fwd16] cluster=%d n_rows=%d 2M=%d nb=%d slices=%d stages=%d fuse_final=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.slices, P.stages, int(fuse_final), smem);
+  printf("[gabor_fwd16] cluster=%d n_rows=%d 2M=%d nb=%d slices=%d stages=%d fuse_final=%d mask=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.slices, P.stages, int(fuse_final), mask, smem);
   const char* names[8] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in"};
   for (int k = 0; k < 8; ++k) {
     double sum = 0; int cnt = 0;
@@ -521,7 +521,11 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "g16")) {
     g_cluster = 2;
     time_rows_gabor16(262144, 424, false);
+    time_rows_gabor16(262144, 424, false, 1);   // y only
+    time_rows_gabor16(262144, 424, false, 2);   // z only
+    time_rows_gabor16(262144, 424, false, 0);   // no stores at all
     time_rows_gabor16(262144, 424, true);
+    time_rows_gabor16(262144, 424, true, 0);    // fused final, no stores (inference)
     test_rows16(262144, 424, 1, 1, 1, true);
     return 0;
   }

@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary (include/wire_b200.h): workspace layout and kernel sequencing
 // for the WIRE forward/backward pass.  No torch, no allocation, no synchronisation.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -593,6 +594,53 @@ RowsEpi base_epi(int64_t n, int n_cols, int precision) {
   return e;
 }
 
+// tile configuration of hidden layer l's forward / backward row-tile GEMM (the same everywhere it is needed)
+bool fwd_job_blocking(const wire_net_desc* d, const Layout& L, int l, int training, Blocking& blk, int& mask, bool& fuse, bool gen = false) {
+  fuse = (l == L.H) && L.fuse_final;
+  mask = fuse ? 0 : 1;
+  if (training) { mask |= 2; if (d->two_d) mask |= 4; }
+  return job_blocking(d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, L.two_m, mask, fuse, blk, gen, d->precision == WIRE_PRECISION_MIXED16);
+}
+bool bwd_job_blocking(const wire_net_desc* d, const Layout& L, int l, Blocking& blk, int& mask, int& bmode) {
+  const bool to_first = (l == 1);
+  mask = to_first ? 0 : (d->two_d ? 3 : 1);
+  bmode = to_first ? (d->two_d ? MODE_FIRST2D_BWD : MODE_FIRST_BWD) : (d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD);
+  return job_blocking(bmode, L.two_m, mask, false, blk, false, L.g_elem != kElemF32);
+}
+
+// mixed16: every packed weight matrix of the step (forward FP16, and when training the dgrad BF16 ones the backward
+// pass will read from the same workspace) in one launch
+int pack_all16(const wire_net_desc* d, const wire_net_params* p, const Layout& L, void* ws, int training, cudaStream_t st) {
+  PackJobs J;
+  memset(&J, 0, sizeof(J));
+  J.M_out = L.M; J.K_in = L.M;
+  int max_total = 0;
+  for (int l = 1; l <= L.H; ++l) {
+    Blocking blk; int mask; bool fuse;
+    if (!fwd_job_blocking(d, L, l, training, blk, mask, fuse)) return fail("no tile configuration");
+    if (J.n + 2 > kMaxPackJobs) return fail("too many layers for the fused weight packing");
+    PackJob& a = J.job[J.n++];
+    a.W1 = p->layer[l].weight; a.W2 = d->two_d ? p->layer[l].weight2 : nullptr; a.B = at(ws, L.off_bf[l]);
+    a.mode = 0; a.n_blocks = blk.n_blocks; a.nb = blk.nb; a.nbh = blk.nbh; a.k0_pad = L.k_pad; a.k_pad_total = L.k_pad; a.elem = L.y_elem;
+    max_total = std::max(max_total, a.n_blocks * a.nb * a.k_pad_total);
+    if (training) {
+      int bmode;
+      if (!bwd_job_blocking(d, L, l, blk, mask, bmode)) return fail("no tile configuration");
+      PackJob& b = J.job[J.n++];
+      b.W1 = p->layer[l].weight; b.W2 = d->two_d ? p->layer[l].weight2 : nullptr; b.B = at(ws, L.off_bd[l]);
+      b.mode = 1; b.n_blocks = blk.n_blocks; b.nb = blk.nb; b.nbh = blk.nbh; b.k0_pad = L.k_pad; b.k_pad_total = (d->two_d ? 2 : 1) * L.k_pad;
+      b.elem = L.g_elem;
+      max_total = std::max(max_total, b.n_blocks * b.nb * b.k_pad_total);
+    }
+  }
+  ProfScope prof(K_PACK, st);
+  int gx = (max_total + 255) / 256;
+  if (gx > 8 * g_sm_count) gx = 8 * g_sm_count;
+  pack_all16_kernel<<<dim3(gx, J.n), 256, 0, st>>>(J);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // whole-network forward for one chunk of rows
 // ------------------------------------------------------------------------------------------
@@ -605,22 +653,19 @@ int forward_chunk(const wire_net_desc* d, const wire_net_params* p, const Layout
   // wgrad 0.22 -> 0.55 ms, profiles/r01_bench_v9_gen.json), so the default keeps first_fwd2_kernel.
   const bool gen0 = d->precision == WIRE_PRECISION_TF32 && d->in_features <= 3 && getenv("WIRE_B200_GEN") != nullptr;
   const bool mixed = d->precision == WIRE_PRECISION_MIXED16;
+  if (mixed) TRY(pack_all16(d, p, L, ws, training, st));
   if (!gen0) TRY(run_first_fwd(d, p->layer[0], coords, n, d->in_features, y_prev, L.P, nullptr, nullptr, 0, st, L.y_elem));
   for (int l = 1; l <= H; ++l) {
-    const bool last = l == H;
-    const bool fuse = last && L.fuse_final;
+    Blocking blk;
+    int mask;
+    bool fuse;
+    const bool gen = gen0 && l == 1;
+    if (!fwd_job_blocking(d, L, l, training, blk, mask, fuse, gen)) return fail("no tile configuration");
     const bool store_y = !fuse;
     float* y_out = nullptr;
     if (store_y) y_out = training ? at(ws, L.off_y[l]) : at(ws, L.off_y[l & 1]);
-    int mask = 0;
-    if (store_y) mask |= 1;
-    if (training) { mask |= 2; if (d->two_d) mask |= 4; }
-    Blocking blk;
-    const int fmode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
-    const bool gen = gen0 && l == 1;
-    if (!job_blocking(fmode, L.two_m, mask, fuse, blk, gen, mixed)) return fail("no tile configuration");
     float* Bf = at(ws, L.off_bf[l]);
-    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st, L.y_elem));
+    if (!mixed) TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 0, blk, L.k_pad, L.k_pad, Bf, d->precision, st, L.y_elem));
     RowsJob J;
     memset(&J, 0, sizeof(J));
     J.mode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
@@ -792,14 +837,16 @@ int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const
                     &wg, L.y_elem, L.g_elem));
     // dgrad of layer l fused with the nonlinearity backward of layer l-1
     const bool to_first = (l == 1);
-    int mask = to_first ? 0 : (d->two_d ? 3 : 1);
+    int mask, bmode;
     Blocking blk;
-    const int bmode = to_first ? (d->two_d ? MODE_FIRST2D_BWD : MODE_FIRST_BWD) : (d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD);
-    if (!job_blocking(bmode, L.two_m, mask, false, blk, false, L.g_elem != kElemF32)) return fail("no tile configuration");
+    if (!bwd_job_blocking(d, L, l, blk, mask, bmode)) return fail("no tile configuration");
     float* Bd = at(workspace, L.off_bd[l]);
     const int kparts = d->two_d ? 2 : 1;
-    TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st,
-                 L.g_elem));
+    // mixed16: the dgrad matrices were packed by the forward pass of this step (pack_all16); autograd semantics forbid
+    // changing the weights between a forward and its backward
+    if (d->precision != WIRE_PRECISION_MIXED16)
+      TRY(run_pack(p->layer[l].weight, d->two_d ? p->layer[l].weight2 : nullptr, M, M, 1, blk, L.k_pad, kparts * L.k_pad, Bd, d->precision, st,
+                   L.g_elem));
     RowsJob J;
     memset(&J, 0, sizeof(J));
     J.a_elem = L.g_elem; J.b_elem = L.g_elem;

@@ -64,6 +64,59 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
 //                     gx_re: ( Wre,  Wim)  gx_im: (-Wim,  Wre)         g_x = g_z conj(W)
 // B is [n_blocks*nb][k_pad_total], zero padded.
 // ---------------------------------------------------------------------------------------------
+// One element of a packed matrix (see pack_weights_kernel below for the layouts).
+__device__ __forceinline__ float pack_weight_value(const float* __restrict__ W1, const float* __restrict__ W2, int M_out, int K_in, int mode,
+                                                   int nb, int nbh, int k0_pad, int k_pad_total, int pair_perm, int idx) {
+  const int r = idx / k_pad_total, kk = idx % k_pad_total;
+  float v = 0.f;
+  if (mode == 0) {
+    const int blk = r / nb, c = r % nb;
+    const float* W = W1;
+    int oc;
+    if (nbh < nb) {  // wire2d forward: [z half | w half]
+      if (c < nbh) oc = blk * nbh + (pair_perm ? acc_col_perm(c) : c); else { oc = blk * nbh + (pair_perm ? acc_col_perm(c - nbh) : c - nbh); W = W2; }
+    } else oc = blk * nb + (pair_perm ? acc_col_perm(c) : c);
+    if (oc < 2 * M_out && kk < 2 * K_in && c < 2 * nbh && W) {
+      const int j = oc >> 1, part = oc & 1, k = kk >> 1, d = kk & 1;
+      const float wr = W[(size_t(j) * K_in + k) * 2], wi = W[(size_t(j) * K_in + k) * 2 + 1];
+      v = part == 0 ? (d == 0 ? wr : -wi) : (d == 0 ? wi : wr);
+    }
+  } else {
+    const int oc = pair_perm ? acc_col_perm(r) : r;
+    const float* W = W1;
+    int kq = kk;
+    if (kk >= k0_pad) { W = W2; kq = kk - k0_pad; }
+    if (oc < 2 * K_in && kq < 2 * M_out && W) {
+      const int k = oc >> 1, part = oc & 1, j = kq >> 1, d = kq & 1;
+      const float wr = W[(size_t(j) * K_in + k) * 2], wi = W[(size_t(j) * K_in + k) * 2 + 1];
+      v = part == 0 ? (d == 0 ? wr : wi) : (d == 0 ? -wi : wr);
+    }
+  }
+  return v;
+}
+
+// All packed matrices of one training step in ONE launch (mixed16 path): job = blockIdx.y.
+struct PackJob {
+  const float* W1;
+  const float* W2;
+  void* B;
+  int mode, n_blocks, nb, nbh, k0_pad, k_pad_total, elem;
+};
+constexpr int kMaxPackJobs = 32;
+struct PackJobs {
+  PackJob job[kMaxPackJobs];
+  int n, M_out, K_in;
+};
+__global__ void pack_all16_kernel(const __grid_constant__ PackJobs J) {
+  const PackJob& j = J.job[blockIdx.y];
+  const int total = j.n_blocks * j.nb * j.k_pad_total;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const float v = pack_weight_value(j.W1, j.W2, J.M_out, J.K_in, j.mode, j.nb, j.nbh, j.k0_pad, j.k_pad_total, 1, idx);
+    if (j.elem == 1) reinterpret_cast<__half*>(j.B)[idx] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(j.B)[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 // ELEM (sm100_host::ElemType): 0 = fp32 (TF32-rounded if do_round), 1 = FP16, 2 = BF16 (mixed16 path)
 template <int ELEM>
 __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int M_out, int K_in,

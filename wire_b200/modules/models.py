@@ -18,7 +18,7 @@ def get_INR(nonlin, in_features, hidden_features, scaled_hidden_features=None, h
             scale_tensor=[], pos_encode=False, sidelength=512, fn_samples=None, use_nyquist=True, **extra):
     """Same arguments as the reference's ``get_INR``; returns an ``nn.Module`` whose ``forward(coords)``
     maps f32 ``[..., in_features]`` to f32 ``[..., out_features]``.  ``extra`` may carry ``precision``
-    ('tf32' default, 'fp32')."""
+    ('mixed16' default, 'tf32', 'fp32')."""
     if nonlin not in model_dict:
         raise ValueError(f"nonlin={nonlin!r} is outside the WIRE hot path served by wire_b200 "
                          f"(supported: {sorted(model_dict)})")

@@ -15,7 +15,9 @@ from torch import nn
 
 from .. import functional as F
 
-DEFAULT_PRECISION = "tf32"
+# 'mixed16' (default): FP16 activations / BF16 gradients in HBM, FP32 accumulate — the fastest path, parity-tested to the
+# same bars as 'tf32' (FP16 carries TF32's 11-bit significand); 'tf32': 32-bit operands; 'fp32': CUDA-core yardstick.
+DEFAULT_PRECISION = "mixed16"
 
 
 class _GaborBase(nn.Module):
