@@ -34,7 +34,10 @@ CFG = dict(nonlin="wire", in_features=2, hidden_features=300, hidden_layers=2, o
 LR = 5e-3
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures of this
 # command at the default size (profiles/*_ncu_full_*_summary.txt): (precision, kernel) -> bytes
-NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6}
+# tf32: profiles/r01_ncu_full_v6_summary.txt (530.7 MB read + 835.0 MB written, hidden layer 1);
+# mixed16: profiles/r01_ncu_full_v11_mixed16_summary.txt, mean of the two forward launches of a step
+#          (layer 1: 251.4 + 398.4 MB, layer 2 with the fused final Linear: 242.4 + 182.1 MB)
+NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6, ("mixed16", "tc_rows_gabor_fwd"): 537.1e6}
 
 
 def flop_per_coord(M, H, in_f, out_f):
@@ -203,6 +206,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print from C (NCCL's "NCCL version ..." banner) go to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -410,7 +417,10 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["coords_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
