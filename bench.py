@@ -400,8 +400,11 @@ def run_ours(args):
                 "config": {"workload": f"WIRE image fit {size}x{size} RGB ({n} coords/GPU full-batch fwd+bwd+Adam), "
                                        f"wire_image_denoise.py defaults: hidden 300 -> M={M}, H=2, omega0=7, sigma0=6",
                            "width": M, "hidden_layers": CFG["hidden_layers"], "coords_per_gpu": n,
-                           "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if trainer.use_graph and world == 1 else ""),
+                           "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if trainer.use_graph and (world == 1 or trainer.peer is not None) else ""),
                            "parallelism": f"coord-sharded dp{world}" if world > 1 else "single GPU",
+                           "exchange": (None if world == 1 else
+                                        ("flat fp32 gradients summed by the Adam kernel with P2P loads over NVLink (no NCCL call per step)"
+                                         if trainer.peer is not None else "one NCCL all-reduce of the flat fp32 gradient per step")),
                            "precision": args.precision,
                            "l2": "per-step activation traffic (>4 GB) far exceeds the 126 MB L2; no explicit flush"},
                 "algorithmic_tflops": world * step_flop / (ms_step * 1e-3) / 1e12,
@@ -421,6 +424,7 @@ def run_ours(args):
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    trainer.close()
     if world > 1:
         dist.destroy_process_group()
 

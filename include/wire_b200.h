@@ -154,6 +154,28 @@ int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
 int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out,
                        float* loss, void* stream);
 
+/* ---- data-parallel gradient exchange fused with Adam, over NVLink peer memory ----------------
+ * The reference is single-GPU; its chunked loops (wire_occupancy.py:137-154) shard by coordinate batch, and the only
+ * exchange is a SUM of the flat weight gradient.  Every rank allocates one peer buffer
+ *     [ wire_peer_header_bytes() of barrier counters | grad_floats floats ]
+ * with wire_peer_alloc (cudaMalloc + cudaIpc handle), exchanges the 64-byte handles through any host channel, maps the
+ * others with wire_peer_open, and points wire_net_backward's gradient slots into the float area of its OWN buffer.
+ * wire_adam_step_peer then sums all ranks' gradients with P2P loads (rank order, so replicas stay bit-identical) and applies
+ * torch.optim.Adam's update; wire_peer_wait_done must be enqueued before the next kernel that overwrites the gradient
+ * area (it waits until every peer has finished reading).  peer_bases: host array of `world` pointers, [rank] = own buffer.
+ * All ranks must call in lockstep; no NCCL call is involved and the kernels can be captured in a CUDA graph. */
+#define WIRE_B200_IPC_HANDLE_BYTES 64
+#define WIRE_B200_MAX_PEERS 16
+size_t wire_peer_header_bytes(void);
+int wire_peer_alloc(size_t grad_floats, void** base, void* ipc_handle /* WIRE_B200_IPC_HANDLE_BYTES out */);
+int wire_peer_open(const void* ipc_handle, void** base);
+int wire_peer_close(void* base);
+int wire_peer_free(void* base);
+int wire_adam_step_peer(float* param, void* const* peer_bases, int32_t world, int32_t rank, float* exp_avg, float* exp_avg_sq,
+                        int64_t count, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                        int64_t* step_dev, float grad_scale, uint32_t* scratch_dev, void* stream);
+int wire_peer_wait_done(void* const* peer_bases, int32_t world, int32_t rank, const int64_t* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -404,3 +404,70 @@ def test_run_to_run_reproducibility(kind, hidden, precision):
     for gs in grads[1:]:
         for a, b in zip(gs, grads[0]):
             assert util.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+
+
+def test_peer_adam_kernel_single_rank_matches_adam_dev():
+    """wire_adam_step_peer with a world of one (its own peer buffer) == wire_adam_step_dev on the same inputs, and the
+    barrier counters in the buffer header advance with the step counter."""
+    import ctypes
+    import wire_b200
+    from wire_b200 import _lib
+    from wire_b200.parallel import _RawCudaBuffer
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    count = 4 * 12345
+    torch.manual_seed(3)
+    p0 = torch.randn(count, device=dev)
+    handle = ctypes.create_string_buffer(64)
+    base = ctypes.c_void_p()
+    _lib.check(lib.wire_peer_alloc(count, ctypes.byref(base), handle), "wire_peer_alloc")
+    try:
+        hdr = int(lib.wire_peer_header_bytes())
+        raw = _RawCudaBuffer(base.value + hdr, count)
+        grad = torch.as_tensor(raw, device=dev)
+        bases = (ctypes.c_void_p * 1)(base.value)
+        st = torch.cuda.current_stream().cuda_stream
+        state = {}
+        for which in ("peer", "dev"):
+            p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+            step = torch.zeros(1, dtype=torch.int64, device=dev)
+            lr = torch.full((1,), 5e-3, device=dev)
+            scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+            for it in range(5):
+                g = torch.randn(count, device=dev, generator=torch.Generator(device=dev).manual_seed(it)) * 1e-3
+                grad.copy_(g)
+                if which == "peer":
+                    _lib.check(lib.wire_peer_wait_done(bases, 1, 0, step.data_ptr(), st), "wire_peer_wait_done")
+                    _lib.check(lib.wire_adam_step_peer(p.data_ptr(), bases, 1, 0, m.data_ptr(), v.data_ptr(), count, lr.data_ptr(),
+                                                       0.9, 0.999, 1e-8, 0.0, step.data_ptr(), 0.5, scratch.data_ptr(), st), "peer")
+                else:
+                    _lib.check(lib.wire_adam_step_dev(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), count, lr.data_ptr(),
+                                                      0.9, 0.999, 1e-8, 0.0, step.data_ptr(), 0.5, scratch.data_ptr(), st), "dev")
+            torch.cuda.synchronize()
+            assert int(step) == 5
+            state[which] = (p, m, v)
+            if which == "peer":
+                hdr_t = torch.as_tensor(_RawCudaBuffer(base.value, hdr // 4), device=dev).view(torch.int32)
+                assert int(hdr_t[0]) == 5 and int(hdr_t[16]) == 5   # arrive[0], done[0]
+                hdr_t.zero_()
+        for a, b in zip(state["peer"], state["dev"]):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-9)
+    finally:
+        torch.cuda.synchronize()
+        lib.wire_peer_free(base)
+
+
+def test_peer_exchange_two_gpus():
+    """Data-parallel Trainer with the NVLink peer-memory exchange (2 ranks under torchrun): same parameters as the NCCL
+    all-reduce variant, replicas bit-identical (tools/peer_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tools", "peer_check.py")]
+    env = dict(os.environ, PEER_CHECK_N="20000", PEER_CHECK_STEPS="20")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and "PEER_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

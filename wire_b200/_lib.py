@@ -73,6 +73,14 @@ SIGNATURES = {
     "wire_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
                                      c_float, c_void_p, c_float, c_void_p, c_void_p]),
     "wire_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "wire_peer_header_bytes": (c_size_t, []),
+    "wire_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "wire_peer_open": (c_int32, [c_void_p, POINTER(c_void_p)]),
+    "wire_peer_close": (c_int32, [c_void_p]),
+    "wire_peer_free": (c_int32, [c_void_p]),
+    "wire_adam_step_peer": (c_int32, [c_void_p, POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_float, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_void_p]),
+    "wire_peer_wait_done": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -10,8 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libwire_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["sm100.cuh", "gabor_math.cuh", "rows_epilogue.cuh", "tc_rows.cuh", "tc_wgrad.cuh", "tc_launch.cuh",
-           "simt_kernels.cuh", "simt_rows.cuh", os.path.join("..", "..", "include", "wire_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "wire_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--shared", "-Xcompiler", "-fPIC"]
 

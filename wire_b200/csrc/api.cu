@@ -12,6 +12,7 @@
 #include "simt_rows.cuh"
 #include "tc_launch.cuh"
 #include "simt16_kernels.cuh"
+#include "peer_kernels.cuh"
 
 namespace {
 
@@ -59,10 +60,10 @@ int require_device() {
 // on the launching stream (bench.py's per-kernel roofline numbers come from here).
 // ------------------------------------------------------------------------------------------
 enum ProfKind { K_FIRST_FWD = 0, K_PACK, K_ROWS_FWD, K_FINAL_FWD, K_TOP_BWD, K_WGRAD, K_ROWS_BWD, K_ROWS_FIRST_BWD,
-                K_FIRST_WGRAD, K_GRAD_COORDS, K_LAYER_MISC, K_ADAM, K_MSE, K_COUNT };
+                K_FIRST_WGRAD, K_GRAD_COORDS, K_LAYER_MISC, K_ADAM, K_MSE, K_PEER_WAIT, K_COUNT };
 const char* kProfNames[K_COUNT] = {"first_fwd", "pack_weights", "tc_rows_gabor_fwd", "final_fwd", "top_bwd", "tc_wgrad",
                                    "tc_rows_dgrad_gabor_bwd", "tc_rows_dgrad_first_bwd", "first_wgrad", "grad_coords",
-                                   "layer_misc", "adam", "mse_grad"};
+                                   "layer_misc", "adam", "mse_grad", "peer_wait"};
 struct ProfPending { int kind; cudaEvent_t e0, e1; };
 struct Prof {
   int timing = 0;
@@ -1162,6 +1163,89 @@ int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, fl
   const int grid = int(g64 > 1184 ? 1184 : g64);
   ProfScope prof(K_MSE, st);
   mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- data-parallel exchange over NVLink peer memory (peer_kernels.cuh) ----------------------------------------------
+size_t wire_peer_header_bytes(void) { return size_t(kPeerHeaderBytes); }
+
+int wire_peer_alloc(size_t grad_floats, void** base, void* ipc_handle) {
+  if (!base || !ipc_handle) return fail("null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == WIRE_B200_IPC_HANDLE_BYTES, "ipc handle size");
+  void* ptr = nullptr;
+  const size_t bytes = kPeerHeaderBytes + ((grad_floats + 3) / 4) * 16;
+  CU_OK(cudaMalloc(&ptr, bytes));  // plain cudaMalloc: memory from the stream-ordered / VMM pools cannot be exported through cudaIpc
+  CU_OK(cudaMemset(ptr, 0, bytes));
+  CU_OK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { cudaFree(ptr); return fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+  memcpy(ipc_handle, &h, sizeof(h));
+  *base = ptr;
+  return 0;
+}
+
+int wire_peer_open(const void* ipc_handle, void** base) {
+  if (!base || !ipc_handle) return fail("null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  void* ptr = nullptr;
+  CU_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  *base = ptr;
+  return 0;
+}
+
+int wire_peer_close(void* base) {
+  if (base) CU_OK(cudaIpcCloseMemHandle(base));
+  return 0;
+}
+
+int wire_peer_free(void* base) {
+  if (base) CU_OK(cudaFree(base));
+  return 0;
+}
+
+static int make_peer_table(PeerTable& T, void* const* peer_bases, int32_t world, int32_t rank) {
+  if (!peer_bases) return fail("null argument");
+  if (world < 1 || world > kMaxPeers) return fail("world %d outside 1..%d", world, kMaxPeers);
+  if (rank < 0 || rank >= world) return fail("rank %d outside 0..%d", rank, world - 1);
+  memset(&T, 0, sizeof(T));
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bases[r]) return fail("peer buffer %d is null", r);
+    T.base[r] = peer_bases[r];
+  }
+  T.world = world;
+  T.rank = rank;
+  return 0;
+}
+
+int wire_adam_step_peer(float* param, void* const* peer_bases, int32_t world, int32_t rank, float* exp_avg, float* exp_avg_sq,
+                        int64_t count, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev,
+                        float grad_scale, uint32_t* scratch_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (count <= 0) return 0;
+  if (!param || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !scratch_dev) return fail("null argument");
+  if (count & 3) return fail("count must be a multiple of 4 floats");
+  PeerTable T;
+  TRY(make_peer_table(T, peer_bases, world, rank));
+  int64_t g64 = (count / 4 + 255) / 256;
+  const int grid = int(g64 > 296 ? 296 : g64);  // every block spins in the in-barrier: keep the grid co-resident
+  ProfScope prof(K_ADAM, st);
+  adam_peer_kernel<<<grid, 256, 0, st>>>(param, T, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
+                                         reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_peer_wait_done(void* const* peer_bases, int32_t world, int32_t rank, const int64_t* step_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!step_dev) return fail("null argument");
+  PeerTable T;
+  TRY(make_peer_table(T, peer_bases, world, rank));
+  ProfScope prof(K_PEER_WAIT, st);
+  peer_wait_kernel<<<1, 32, 0, st>>>(T, reinterpret_cast<const long long*>(step_dev));
   CU_OK(cudaGetLastError());
   return 0;
 }

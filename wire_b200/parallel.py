@@ -6,7 +6,8 @@ counterpart of its chunked loops (wire_occupancy.py:137-154).
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Sequence, Tuple
+import ctypes
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -67,3 +68,69 @@ def weighted_allreduce_gradients(params: Iterable[torch.Tensor], n_local: int, g
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     flat.div_(cnt)
     unflatten_into_grads(flat, params)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# gradient exchange fused with Adam over NVLink peer memory (csrc/peer_kernels.cuh, include/wire_b200.h)
+# ------------------------------------------------------------------------------------------------------------------
+class _RawCudaBuffer:
+    """Exposes a raw device allocation to torch (``torch.as_tensor``) through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerGradExchange:
+    """One peer-mapped gradient buffer per rank; every rank's Adam kernel sums all of them with P2P loads.
+
+    All ranks of `group` must live on ONE node with NVLink/PCIe peer access between their GPUs (the 8 B200s of a box).
+    ``grad`` is this rank's flat fp32 gradient buffer (a torch view of the peer allocation: point the backward pass at
+    it); ``bases`` is the ctypes array of every rank's buffer as mapped here, which the C ABI's ``wire_adam_step_peer`` /
+    ``wire_peer_wait_done`` take.  The exchange itself involves no torch.distributed call; the group is only used once,
+    here, to swap the 64-byte cudaIpc handles."""
+
+    def __init__(self, n_floats: int, device: torch.device, group=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 16:
+            raise _lib.WireB200Error("PeerGradExchange supports up to 16 ranks (one NVSwitch box)")
+        self.device = device
+        self.n_floats = (n_floats + 3) // 4 * 4
+        handle = ctypes.create_string_buffer(64)
+        base = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.wire_peer_alloc(self.n_floats, ctypes.byref(base), handle), "wire_peer_alloc")
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._own = base.value
+            self._opened: List[int] = []
+            self.bases = (ctypes.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    self.bases[r] = self._own
+                else:
+                    ptr = ctypes.c_void_p()
+                    _lib.check(self.lib.wire_peer_open(handles[r], ctypes.byref(ptr)), f"wire_peer_open(rank {r})")
+                    self.bases[r] = ptr.value
+                    self._opened.append(ptr.value)
+        header = int(self.lib.wire_peer_header_bytes())
+        self._raw = _RawCudaBuffer(self._own + header, self.n_floats)
+        self.grad = torch.as_tensor(self._raw, device=device)
+        dist.barrier(group=group)  # every rank has mapped every buffer before the first step touches them
+
+    def close(self) -> None:
+        if getattr(self, "_own", None) is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            try:
+                dist.barrier(group=self.group)  # nobody may still be reading a buffer that is about to be unmapped
+            except Exception:
+                pass
+            for ptr in self._opened:
+                self.lib.wire_peer_close(ptr)
+            self.lib.wire_peer_free(self._own)
+        self._own, self._opened, self.grad = None, [], None

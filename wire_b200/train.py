@@ -17,6 +17,7 @@ the learning rate live on the device (``set_lr`` implements the drivers' ``Lambd
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional
 
 import torch
@@ -29,7 +30,7 @@ from ._lib import NetGrads, WireB200Error, check
 
 class Trainer:
     def __init__(self, model, lr: float = 5e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 graph: bool = True, process_group=None):
+                 graph: bool = True, process_group=None, peer_exchange: Optional[bool] = None):
         self.model = model
         self.lib = _lib.load()
         layers = list(model.net)
@@ -64,7 +65,19 @@ class Trainer:
             self._starts.append(off)
             off += (s + 3) // 4 * 4
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros_like(self.flat)
+        # data-parallel exchange: by default (NCCL backend = GPUs of one box) the flat gradient lives in a peer-mapped
+        # buffer and the Adam kernel sums every rank's gradients itself over NVLink (parallel.PeerGradExchange); with
+        # peer_exchange=False the step does one torch.distributed all-reduce of the flat buffer instead.
+        if peer_exchange is None:
+            peer_exchange = self.world > 1 and dist.get_backend(process_group) == "nccl" and \
+                os.environ.get("WIRE_B200_PEER", "1") != "0"
+        self.peer = None
+        if peer_exchange and self.world > 1:
+            from .parallel import PeerGradExchange
+            self.peer = PeerGradExchange(off, dev, process_group)
+            self.flat_grad = self.peer.grad
+        else:
+            self.flat_grad = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self._grad_views = []
@@ -126,11 +139,20 @@ class Trainer:
                                    self.ws.data_ptr(), self.ws.numel(), 1, st), "wire_net_forward")
         check(lib.wire_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
                                      self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_mse_loss_grad")
+        if self.peer is not None:  # peers must have finished reading last step's gradients before they are overwritten
+            check(lib.wire_peer_wait_done(self.peer.bases, self.peer.world, self.peer.rank, self.step_dev.data_ptr(), st),
+                  "wire_peer_wait_done")
         check(lib.wire_net_backward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.gout_buf.data_ptr(),
                                     self.ws.data_ptr(), self.ws.numel(), ctypes.byref(self._G), None, st), "wire_net_backward")
 
     def _adam(self) -> None:
         b1, b2 = self.betas
+        if self.peer is not None:
+            check(self.lib.wire_adam_step_peer(self.flat.data_ptr(), self.peer.bases, self.peer.world, self.peer.rank,
+                                               self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.flat.numel(),
+                                               self.lr_dev.data_ptr(), b1, b2, self.eps, self.weight_decay, self.step_dev.data_ptr(),
+                                               1.0 / self.world, self.scratch.data_ptr(), F._stream()), "wire_adam_step_peer")
+            return
         check(self.lib.wire_adam_step_dev(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr_dev.data_ptr(), b1, b2, self.eps,
                                           self.weight_decay, self.step_dev.data_ptr(), 1.0 / self.world, self.scratch.data_ptr(),
@@ -138,7 +160,7 @@ class Trainer:
 
     def _whole_step(self) -> None:
         self._fwd_bwd()
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         self._adam()
 
@@ -156,7 +178,7 @@ class Trainer:
                 self._prepare(n)
             self.coords_buf.copy_(coords.reshape(n, d.in_features), non_blocking=True)
             self.target_buf.copy_(target.reshape(n, d.out_features), non_blocking=True)
-            if not self.use_graph or self.world > 1:
+            if not self.use_graph or (self.world > 1 and self.peer is None):
                 self._whole_step()
             else:
                 if self._graph is None:
@@ -175,6 +197,13 @@ class Trainer:
                 else:
                     self._graph.replay()
         return self.loss_dev[0]
+
+    def close(self) -> None:
+        """Release the peer-mapped gradient buffer (collective: every rank must call it)."""
+        if self.peer is not None:
+            self._graph = None
+            self.peer.close()
+            self.peer = None
 
     @torch.no_grad()
     def predict(self, coords: torch.Tensor) -> torch.Tensor:
