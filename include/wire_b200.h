@@ -153,6 +153,11 @@ int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
 /* grad_out[i] = 2*(pred[i]-target[i])/count ; *loss (device scalar, accumulated) += mean sq err */
 int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out,
                        float* loss, void* stream);
+/* Same for a rank that holds `count` elements of a global batch of `count_global`: grad_out = 2*(pred-target)/count_global,
+ * *loss += sum sq err / count_global, so gradients and losses of the ranks ADD UP to those of the global mean
+ * (criterion = MSELoss over the whole chunk, wire_occupancy.py:149) whatever the shard sizes. */
+int wire_mse_loss_grad_n(const float* pred, const float* target, int64_t count, int64_t count_global, float* grad_out,
+                         float* loss, void* stream);
 
 /* ---- data-parallel gradient exchange fused with Adam, over NVLink peer memory ----------------
  * The reference is single-GPU; its chunked loops (wire_occupancy.py:137-154) shard by coordinate batch, and the only
@@ -175,6 +180,28 @@ int wire_adam_step_peer(float* param, void* const* peer_bases, int32_t world, in
                         int64_t count, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
                         int64_t* step_dev, float grad_scale, uint32_t* scratch_dev, void* stream);
 int wire_peer_wait_done(void* const* peer_bases, int32_t world, int32_t rank, const int64_t* step_dev, void* stream);
+
+/* ---- on-device coordinate pipeline and metrics ----------------------------------
+ * Replace the host-side batch assembly of the reference's loops: CPU randperm + CPU gather + .cuda() per chunk
+ * (wire_image_denoise.py:142-147, wire_occupancy.py:137-144), rec[b_indices] = pixelvalues (wire_image_denoise.py:150-151,
+ * wire_occupancy.py:146-147) and the per-epoch metrics (modules/volutils.py:74-91, modules/utils.py:67-82).
+ *
+ * wire_grid_batch: for r < n, li = idx ? idx[r] : idx_base + r is a linear index into the (H, W[, T]) grid in the
+ *   reference's order (np.meshgrid 'xy': li = (i*W + j)*T + k -> coordinate (x_j, y_i, z_k)); coords[r] (n x ndim f32, may
+ *   be NULL) is that grid point with linspace_kind 0 = np.linspace float64 cast to f32 (utils.get_coords,
+ *   modules/utils.py:163-176) or 1 = torch.linspace float32 (wire_image_denoise.py:63-66), bit-exact; target[r]
+ *   (n x out_features, may be NULL) = signal[li].  An out-of-range index sets *err_flag (device int, may be NULL) to 1.
+ * wire_scatter_rows: dst[li] = src[r] for rows of `width` floats.
+ * wire_iou_counts: counts[0] += |pred AND gt|, counts[1] += |pred OR gt| after thresholding pred at `thres` when use_thres
+ *   (binarize_in_place also writes the 0/1 values back, which is what the reference does to its argument).
+ * wire_sq_err_stats: stats[0] += sum (x - xhat)^2, stats[1] = max(stats[1], max x)  (float64 on the device). */
+int wire_grid_batch(const int32_t* dims, int32_t ndim, int32_t linspace_kind, const int64_t* idx, int64_t idx_base, int64_t n,
+                    const float* signal, int32_t out_features, float* coords, float* target, int32_t* err_flag, void* stream);
+int wire_scatter_rows(const int64_t* idx, int64_t idx_base, int64_t n, const float* src, int32_t width, float* dst,
+                      int64_t dst_rows, int32_t* err_flag, void* stream);
+int wire_iou_counts(float* preds, const float* gt, int64_t count, float thres, int32_t use_thres, int32_t binarize_in_place,
+                    uint64_t* counts, void* stream);
+int wire_sq_err_stats(const float* x, const float* xhat, int64_t count, double* stats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -215,3 +215,42 @@ def volume_coords(H: int, W: int, T: int) -> torch.Tensor:
     X, Y, Z = np.meshgrid(np.linspace(-1, 1, W), np.linspace(-1, 1, H), np.linspace(-1, 1, T))
     c = np.hstack((X.reshape(-1, 1), Y.reshape(-1, 1), Z.reshape(-1, 1)))
     return torch.tensor(c.astype(np.float32))
+
+
+# ======================================================================================================================
+# Data pipeline either side of the hot path — restated for the parity tests of
+# wire_b200/csrc/data_kernels.cuh.  Pinned by tests/golden/data_pipeline.npz (oracle/make_golden_data.py runs the
+# reference's own modules/utils.py and modules/volutils.py).
+# ======================================================================================================================
+def get_coords_np(H: int, W: int, T: Optional[int] = None) -> np.ndarray:
+    """modules/utils.py:163-176 ``get_coords``: np.meshgrid (default 'xy') of float64 linspaces, hstack, cast to f32."""
+    if T is None:
+        X, Y = np.meshgrid(np.linspace(-1, 1, W), np.linspace(-1, 1, H))
+        coords = np.hstack((X.reshape(-1, 1), Y.reshape(-1, 1)))
+    else:
+        X, Y, Z = np.meshgrid(np.linspace(-1, 1, W), np.linspace(-1, 1, H), np.linspace(-1, 1, T))
+        coords = np.hstack((X.reshape(-1, 1), Y.reshape(-1, 1), Z.reshape(-1, 1)))
+    return coords.astype(np.float32)
+
+
+def image_coords_torch(H: int, W: int) -> np.ndarray:
+    """wire_image_denoise.py:63-66 (also wire_SISR.py, wire_ct.py): torch float32 CPU linspace, meshgrid 'xy', hstack."""
+    x = torch.linspace(-1, 1, W)
+    y = torch.linspace(-1, 1, H)
+    X, Y = torch.meshgrid(x, y, indexing="xy")
+    return torch.hstack((X.reshape(-1, 1), Y.reshape(-1, 1))).numpy()
+
+
+def iou_counts_np(preds: np.ndarray, gt: np.ndarray, thres: Optional[float] = None):
+    """modules/volutils.py:79-91 ``get_I_and_U``: thresholds ``preds`` IN PLACE (two masked assignments, in this order),
+    then counts logical_and / logical_or.  Returns (intersection, union) as Python ints."""
+    if thres is not None:
+        preds[preds < thres] = 0.0
+        preds[preds >= thres] = 1.0
+    return int(np.logical_and(preds, gt).sum()), int(np.logical_or(preds, gt).sum())
+
+
+def psnr_np(x: np.ndarray, xhat: np.ndarray) -> float:
+    """modules/utils.py:67-82 ``psnr``: 10 log10(max(x) / mean((x - xhat)^2))."""
+    err = x - xhat
+    return float(10 * np.log10(np.max(x) / np.mean(pow(err, 2))))

@@ -1,0 +1,159 @@
+"""GPU parity of the on-device coordinate pipeline and metrics (wire_b200/csrc/data_kernels.cuh, through the C ABI)
+against the reference's own outputs (tests/golden/data_pipeline.npz) and the oracle restatements — bit-exact: this is
+index / integer / rounding-exact work — plus the epoch loop built on it."""
+import numpy as np
+import pytest
+import torch
+
+import util
+import wire_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_grid_coordinates_bit_exact_vs_reference_fixtures():
+    import wire_b200
+    g = util.load_data_golden()
+    dev = torch.device("cuda", 0)
+    for key in g.files:
+        if key.startswith("coords_np_"):
+            H, W, T = (int(v) for v in key.split("_")[2:])
+            b = wire_b200.GridBatcher((H, W, T) if T else (H, W), linspace="numpy", device=dev)
+        elif key.startswith("coords_torch_"):
+            H, W = (int(v) for v in key.split("_")[2:])
+            b = wire_b200.GridBatcher((H, W), linspace="torch", device=dev)
+        else:
+            continue
+        got = b.coords().cpu().numpy()
+        assert np.array_equal(got, g[key]), key
+
+
+@pytest.mark.parametrize("shape,kind", [((512, 512), "torch"), ((96, 128, 80), "numpy"), ((1024, 1024), "torch"), ((37, 1, 5), "numpy")])
+def test_grid_batch_gather_scatter_vs_oracle_full_size(shape, kind):
+    """Random index batches at the BASELINE sizes (512^2, 1024^2, a 3-D volume): coordinates == the oracle's table rows,
+    targets == signal rows, scatter == index assignment; ranges (idx=None) and duplicates included."""
+    import wire_b200
+    dev = torch.device("cuda", 0)
+    table = O.get_coords_np(*shape) if kind == "numpy" else O.image_coords_torch(*shape)
+    total = table.shape[0]
+    out_f = 3 if len(shape) == 2 else 1
+    gen = torch.Generator().manual_seed(1)
+    signal = torch.rand(total, out_f, generator=gen)
+    b = wire_b200.GridBatcher(shape, signal.to(dev), linspace=kind)
+    idx = torch.randint(0, total, (min(total, 50000),), generator=gen)
+    idx[:3] = torch.tensor([0, total - 1, total // 2])
+    coords, target = b.assemble(idx.to(dev))
+    assert np.array_equal(coords.cpu().numpy(), table[idx.numpy()])
+    assert torch.equal(target.cpu(), signal[idx])
+    c2, t2 = b.assemble(start=total // 3, count=min(1000, total - total // 3))
+    assert np.array_equal(c2.cpu().numpy(), table[total // 3: total // 3 + c2.shape[0]])
+    assert torch.equal(t2.cpu(), signal[total // 3: total // 3 + c2.shape[0]])
+    perm = torch.randperm(total, generator=gen)[: min(total, 40000)]
+    src = torch.rand(perm.numel(), out_f, generator=gen)
+    rec = torch.zeros(total, out_f, device=dev)
+    b.scatter(rec, src.to(dev), perm.to(dev))
+    want = torch.zeros(total, out_f)
+    want[perm] = src
+    assert torch.equal(rec.cpu(), want)
+    b.check_indices()
+    # out-of-range indices are reported, not dereferenced
+    bad = torch.tensor([0, total], dtype=torch.int64, device=dev)
+    b.assemble(bad)
+    with pytest.raises(wire_b200.WireB200Error):
+        b.check_indices()
+    # empty batch
+    c0, t0 = b.assemble(torch.empty(0, dtype=torch.int64, device=dev))
+    assert c0.shape == (0, len(shape)) and t0.shape == (0, out_f)
+
+
+def test_iou_and_psnr_vs_reference_fixtures_and_large():
+    import wire_b200
+    from wire_b200 import data
+    g = util.load_data_golden()
+    dev = torch.device("cuda", 0)
+    gt = torch.from_numpy(g["iou_gt"]).to(dev)
+    for thres, inter, union in g["iou_results"]:
+        p = torch.from_numpy(g["iou_preds"].copy()).to(dev)
+        th = None if np.isnan(thres) else float(thres)
+        c = data.iou_counts(p, gt, th)
+        assert (int(c[0]), int(c[1])) == (int(inter), int(union)), thres
+        if th is not None:
+            assert np.array_equal(p.cpu().numpy(), g[f"iou_binarized_{thres}"])       # in place, like the reference
+            p2 = torch.from_numpy(g["iou_preds"].copy()).to(dev)
+            data.iou_counts(p2, gt, th, in_place=False)
+            assert np.array_equal(p2.cpu().numpy(), g["iou_preds"])
+    iou = data.get_IoU(torch.from_numpy(g["iou_preds"].copy()).to(dev), gt, 0.5)
+    assert abs(float(iou) - float(g["iou_value_0.5"])) < 1e-7
+    x, xhat = torch.from_numpy(g["psnr_x"]).to(dev), torch.from_numpy(g["psnr_xhat"]).to(dev)
+    assert abs(float(data.psnr(x, xhat)) - float(g["psnr_value"])) < 1e-6
+    # a 256^3 volume (16.7 M voxels): counts exact against numpy
+    rs = np.random.RandomState(0)
+    pv = rs.uniform(-0.2, 1.2, size=256 ** 3).astype(np.float32)
+    gv = (rs.uniform(size=256 ** 3) < 0.15).astype(np.float32)
+    want = O.iou_counts_np(pv.copy(), gv, 0.5)
+    c = data.iou_counts(torch.from_numpy(pv).to(dev), torch.from_numpy(gv).to(dev), 0.5)
+    assert (int(c[0]), int(c[1])) == want
+    xv = rs.uniform(size=1 << 22).astype(np.float32)
+    yv = (xv + rs.normal(scale=0.1, size=xv.shape)).astype(np.float32)
+    assert abs(float(data.psnr(torch.from_numpy(xv).to(dev), torch.from_numpy(yv).to(dev))) - O.psnr_np(xv.astype(np.float64), yv.astype(np.float64))) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "mixed16"])
+def test_epoch_loop_on_device_matches_reference_style_loop(precision):
+    """wire_occupancy.py:136-158 on a 24x20x16 volume, 3 epochs of 4 chunks (the last one ragged): the on-device pipeline
+    (run_epoch: indices -> generated coords + gathered targets -> fused step -> scatter) against the reference-style loop
+    (host permutation, coords table gather, module forward, MSELoss, torch.optim.Adam) on the same permutations."""
+    import wire_b200
+    dev = torch.device("cuda", 0)
+    H, W, T = 24, 20, 16
+    N = H * W * T
+    maxpoints = 2000
+    rs = np.random.RandomState(3)
+    vol = (rs.uniform(size=(H, W, T)) < 0.3).astype(np.float32)
+    imten = torch.from_numpy(vol).reshape(N, 1).to(dev)
+    coords_tab = torch.from_numpy(O.get_coords_np(H, W, T))
+    kw = dict(nonlin="wire", in_features=3, hidden_features=64, hidden_layers=2, out_features=1, first_omega_0=10.0,
+              hidden_omega_0=10.0, scale=5.0, precision=precision)
+    torch.manual_seed(0)
+    m_a = wire_b200.get_INR(**kw).to(dev)
+    m_b = wire_b200.get_INR(**kw).to(dev)
+    m_b.load_state_dict(m_a.state_dict())
+    perms = [torch.randperm(N, generator=torch.Generator().manual_seed(10 + e)) for e in range(3)]
+
+    # reference-style loop on the module API
+    opt = torch.optim.Adam(m_a.parameters(), lr=5e-3)
+    est_a = torch.zeros(N, 1, device=dev)
+    losses_a = []
+    for e in range(3):
+        indices = perms[e]
+        tot, nch = 0.0, 0
+        for b_idx in range(0, N, maxpoints):
+            b_indices = indices[b_idx:min(N, b_idx + maxpoints)]
+            b_coords = coords_tab[b_indices, ...].to(dev)
+            b_indices = b_indices.to(dev)
+            pix = m_a(b_coords[None, ...]).squeeze()[:, None]
+            with torch.no_grad():
+                est_a[b_indices, :] = pix
+            loss = torch.nn.functional.mse_loss(pix, imten[b_indices, :])
+            opt.zero_grad(); loss.backward(); opt.step()
+            tot += float(loss); nch += 1
+        losses_a.append(tot / nch)
+
+    # on-device pipeline
+    tr = wire_b200.Trainer(m_b, lr=5e-3)
+    batcher = wire_b200.GridBatcher((H, W, T), imten, linspace="numpy")
+    est_b = torch.zeros(N, 1, device=dev)
+    losses_b = [float(wire_b200.run_epoch(tr, batcher, maxpoints, indices=perms[e], rec=est_b)) for e in range(3)]
+    batcher.check_indices()
+    assert tr.steps_done == 3 * 4
+    tol = 1e-3 if precision == "fp32" else 2e-2
+    for a, b in zip(losses_a, losses_b):
+        assert abs(a - b) <= tol * max(abs(a), 1e-3), (losses_a, losses_b)
+    if precision == "fp32":
+        assert float((est_a - est_b).abs().max()) <= 5e-3
+    else:  # 12 Adam steps amplify the 16-bit rounding differences between two runs on a few voxels: bound the RMS
+        assert float((est_a - est_b).pow(2).mean().sqrt()) <= 0.08
+    from wire_b200 import data
+    iou_a = float(data.get_IoU(est_a.clone(), imten, 0.5))
+    iou_b = float(data.get_IoU(est_b.clone(), imten, 0.5))
+    assert abs(iou_a - iou_b) <= 0.005     # north_star's IoU bar

@@ -96,3 +96,28 @@ def test_c_oracle_matches_reference_c128(name):
     for k in (k for k in g.files if k.startswith("grad_c128.")):
         key = k[len("grad_c128."):]
         assert util.rel_err(grads[key], g[k]) < 1e-11, key
+
+
+# ---- data pipeline restatements (oracle/wire_oracle.py) vs the reference's own outputs (tests/golden/data_pipeline.npz) ----
+def test_data_pipeline_oracle_matches_reference_fixtures():
+    g = util.load_data_golden()
+    n_coords = 0
+    for key in g.files:
+        if key.startswith("coords_np_"):
+            H, W, T = (int(v) for v in key.split("_")[2:])
+            got = O.get_coords_np(H, W, T or None)
+        elif key.startswith("coords_torch_"):
+            H, W = (int(v) for v in key.split("_")[2:])
+            got = O.image_coords_torch(H, W)
+        else:
+            continue
+        assert got.dtype == np.float32 and np.array_equal(got, g[key]), key   # bit-exact
+        n_coords += 1
+    assert n_coords >= 9
+    for thres, inter, union in g["iou_results"]:
+        p = g["iou_preds"].copy()
+        i, u = O.iou_counts_np(p, g["iou_gt"], None if np.isnan(thres) else float(thres))
+        assert (i, u) == (int(inter), int(union))
+        if not np.isnan(thres):
+            assert np.array_equal(p, g[f"iou_binarized_{thres}"])             # in-place thresholding, as the reference
+    assert abs(O.psnr_np(g["psnr_x"], g["psnr_xhat"]) - float(g["psnr_value"])) < 1e-12

@@ -11,7 +11,12 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Network fixtures (tests/golden/wire*.npz); data_pipeline.npz is the fixture of the coordinate pipeline."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "wire*.npz")))
+
+
+def load_data_golden():
+    return np.load(os.path.join(GOLDEN_DIR, "data_pipeline.npz"), allow_pickle=False)
 
 
 def load_golden(name):

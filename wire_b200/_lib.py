@@ -73,6 +73,7 @@ SIGNATURES = {
     "wire_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
                                      c_float, c_void_p, c_float, c_void_p, c_void_p]),
     "wire_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "wire_mse_loss_grad_n": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "wire_peer_header_bytes": (c_size_t, []),
     "wire_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), c_void_p]),
     "wire_peer_open": (c_int32, [c_void_p, POINTER(c_void_p)]),
@@ -81,6 +82,11 @@ SIGNATURES = {
     "wire_adam_step_peer": (c_int32, [c_void_p, POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
                                       c_float, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_void_p]),
     "wire_peer_wait_done": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p]),
+    "wire_grid_batch": (c_int32, [POINTER(c_int32), c_int32, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "wire_scatter_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "wire_iou_counts": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int32, c_void_p, c_void_p]),
+    "wire_sq_err_stats": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

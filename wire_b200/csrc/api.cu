@@ -13,6 +13,7 @@
 #include "tc_launch.cuh"
 #include "simt16_kernels.cuh"
 #include "peer_kernels.cuh"
+#include "data_kernels.cuh"
 
 namespace {
 
@@ -60,10 +61,10 @@ int require_device() {
 // on the launching stream (bench.py's per-kernel roofline numbers come from here).
 // ------------------------------------------------------------------------------------------
 enum ProfKind { K_FIRST_FWD = 0, K_PACK, K_ROWS_FWD, K_FINAL_FWD, K_TOP_BWD, K_WGRAD, K_ROWS_BWD, K_ROWS_FIRST_BWD,
-                K_FIRST_WGRAD, K_GRAD_COORDS, K_LAYER_MISC, K_ADAM, K_MSE, K_PEER_WAIT, K_COUNT };
+                K_FIRST_WGRAD, K_GRAD_COORDS, K_LAYER_MISC, K_ADAM, K_MSE, K_PEER_WAIT, K_DATA, K_COUNT };
 const char* kProfNames[K_COUNT] = {"first_fwd", "pack_weights", "tc_rows_gabor_fwd", "final_fwd", "top_bwd", "tc_wgrad",
                                    "tc_rows_dgrad_gabor_bwd", "tc_rows_dgrad_first_bwd", "first_wgrad", "grad_coords",
-                                   "layer_misc", "adam", "mse_grad", "peer_wait"};
+                                   "layer_misc", "adam", "mse_grad", "peer_wait", "data_pipeline"};
 struct ProfPending { int kind; cudaEvent_t e0, e1; };
 struct Prof {
   int timing = 0;
@@ -1162,7 +1163,21 @@ int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, fl
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
   ProfScope prof(K_MSE, st);
-  mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss);
+  mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss, count);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_mse_loss_grad_n(const float* pred, const float* target, int64_t count, int64_t count_global, float* grad_out, float* loss,
+                         void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count <= 0) return 0;
+  if (!pred || !target || !grad_out) return fail("null argument");
+  if (count_global < count) return fail("count_global %lld < count %lld", (long long)count_global, (long long)count);
+  int64_t g64 = (count + 255) / 256;
+  const int grid = int(g64 > 1184 ? 1184 : g64);
+  ProfScope prof(K_MSE, st);
+  mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss, count_global);
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -1246,6 +1261,72 @@ int wire_peer_wait_done(void* const* peer_bases, int32_t world, int32_t rank, co
   TRY(make_peer_table(T, peer_bases, world, rank));
   ProfScope prof(K_PEER_WAIT, st);
   peer_wait_kernel<<<1, 32, 0, st>>>(T, reinterpret_cast<const long long*>(step_dev));
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- on-device coordinate pipeline and metrics (data_kernels.cuh) ----------------------------------------------------
+static int make_grid(GridSpec& g, const int32_t* dims, int32_t ndim, int32_t linspace_kind) {
+  if (!dims) return fail("null argument");
+  if (ndim != 2 && ndim != 3) return fail("grid must be 2-D (H, W) or 3-D (H, W, T), got %d dims", ndim);
+  if (linspace_kind != 0 && linspace_kind != 1) return fail("linspace_kind must be 0 (numpy float64) or 1 (torch float32)");
+  g.ndim = ndim;
+  g.linspace = linspace_kind;
+  g.dims[2] = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (dims[i] < 1) return fail("grid dimension %d is %d", i, dims[i]);
+    g.dims[i] = dims[i];
+  }
+  return 0;
+}
+static int grid_for(int64_t work) {
+  int64_t g64 = (work + 255) / 256;
+  return int(g64 > 2368 ? 2368 : (g64 < 1 ? 1 : g64));
+}
+
+int wire_grid_batch(const int32_t* dims, int32_t ndim, int32_t linspace_kind, const int64_t* idx, int64_t idx_base, int64_t n,
+                    const float* signal, int32_t out_features, float* coords, float* target, int32_t* err_flag, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GridSpec g;
+  TRY(make_grid(g, dims, ndim, linspace_kind));
+  if (n <= 0) return 0;
+  if (!coords && !target) return fail("nothing to produce: coords and target are both null");
+  if (target && (!signal || out_features < 1)) return fail("target requested without a signal");
+  ProfScope prof(K_DATA, st);
+  grid_batch_kernel<<<grid_for(n), 256, 0, st>>>(g, idx, idx_base, n, signal, out_features, coords, target, err_flag);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_scatter_rows(const int64_t* idx, int64_t idx_base, int64_t n, const float* src, int32_t width, float* dst, int64_t dst_rows,
+                      int32_t* err_flag, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) return 0;
+  if (!src || !dst || width < 1) return fail("null argument");
+  ProfScope prof(K_DATA, st);
+  scatter_rows_kernel<<<grid_for(n * width), 256, 0, st>>>(idx, idx_base, n, src, width, dst, dst_rows, err_flag);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_iou_counts(float* preds, const float* gt, int64_t count, float thres, int32_t use_thres, int32_t binarize_in_place,
+                    uint64_t* counts, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count <= 0) return 0;
+  if (!preds || !gt || !counts) return fail("null argument");
+  ProfScope prof(K_DATA, st);
+  iou_counts_kernel<<<grid_for(count), 256, 0, st>>>(preds, gt, count, thres, use_thres, binarize_in_place,
+                                                     reinterpret_cast<unsigned long long*>(counts));
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_sq_err_stats(const float* x, const float* xhat, int64_t count, double* stats, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count <= 0) return 0;
+  if (!x || !xhat || !stats) return fail("null argument");
+  ProfScope prof(K_DATA, st);
+  sq_err_stats_kernel<<<grid_for(count), 256, 0, st>>>(x, xhat, count, stats);
   CU_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,147 @@
+// data_kernels.cuh — the on-device coordinate pipeline either side of the WIRE hot path.
+//
+// The reference's training loops build every batch on the HOST: a CPU randperm, a CPU gather of the coordinate rows, a
+// host->device copy per chunk (wire_image_denoise.py:142-147, wire_occupancy.py:137-144), then scatter the prediction back
+// (rec[:, b_indices] = pixelvalues, wire_image_denoise.py:150-151) and compute PSNR / IoU with more torch ops and host
+// syncs (modules/utils.py:67-82, modules/volutils.py:74-91).  Here a batch is assembled from LINEAR INDICES on the device:
+// the coordinate of index i is generated, not gathered (the grid is a linspace product), the target row is gathered from the
+// resident signal, and the metrics are single-pass reductions.  All integer / index work is bit-exact with the reference;
+// the coordinates reproduce numpy's float64 linspace (modules/utils.py:163-176) or torch's float32 CPU linspace
+// (wire_image_denoise.py:63-66) bit for bit.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace wire {
+
+struct GridSpec {
+  int ndim;      // 2 or 3
+  int dims[3];   // H, W, T  (np.meshgrid 'xy' order: flat index = (i*W + j)*T + k  ->  coordinate (x_j, y_i, z_k))
+  int linspace;  // 0 = numpy float64 linspace cast to f32 (utils.get_coords), 1 = torch float32 CPU linspace (the image drivers)
+};
+
+// np.linspace(-1, 1, n)[j] cast to float32: y = j*step + start in float64 (two roundings, no FMA), last sample == stop
+__device__ __forceinline__ float linspace_np(int j, int n) {
+  if (n == 1) return -1.0f;
+  if (j == n - 1) return 1.0f;
+  const double step = 2.0 / double(n - 1);
+  return float(__dadd_rn(__dmul_rn(double(j), step), -1.0));
+}
+// torch.linspace(-1, 1, n)[j] (float32, CPU kernel): step = 2/(n-1) in f32; first half start + step*j, second half
+// end - step*(n-1-j), each with a single rounding (verified against torch for n = 2..1024)
+__device__ __forceinline__ float linspace_torch(int j, int n) {
+  if (n == 1) return -1.0f;
+  const float step = __fdiv_rn(2.0f, float(n - 1));
+  if (j < n / 2) return __fmaf_rn(step, float(j), -1.0f);
+  return __fmaf_rn(-step, float(n - 1 - j), 1.0f);
+}
+__device__ __forceinline__ float grid_value(int kind, int j, int n) { return kind ? linspace_torch(j, n) : linspace_np(j, n); }
+
+// coords[r] = grid coordinate of linear index idx[r] (idx == nullptr: r + idx_base), target[r] = signal[idx[r]] (optional)
+__global__ void grid_batch_kernel(GridSpec g, const int64_t* __restrict__ idx, int64_t idx_base, int64_t n,
+                                  const float* __restrict__ signal, int out_features, float* __restrict__ coords,
+                                  float* __restrict__ target, int* __restrict__ err) {
+  const int64_t total = g.ndim == 3 ? int64_t(g.dims[0]) * g.dims[1] * g.dims[2] : int64_t(g.dims[0]) * g.dims[1];
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x) {
+    int64_t li = idx ? idx[r] : idx_base + r;
+    if (li < 0 || li >= total) { if (err) atomicExch(err, 1); li = 0; }
+    if (coords) {
+      if (g.ndim == 3) {
+        const int k = int(li % g.dims[2]);
+        const int64_t ij = li / g.dims[2];
+        const int j = int(ij % g.dims[1]), i = int(ij / g.dims[1]);
+        coords[3 * r] = grid_value(g.linspace, j, g.dims[1]);
+        coords[3 * r + 1] = grid_value(g.linspace, i, g.dims[0]);
+        coords[3 * r + 2] = grid_value(g.linspace, k, g.dims[2]);
+      } else {
+        const int j = int(li % g.dims[1]), i = int(li / g.dims[1]);
+        coords[2 * r] = grid_value(g.linspace, j, g.dims[1]);
+        coords[2 * r + 1] = grid_value(g.linspace, i, g.dims[0]);
+      }
+    }
+    if (target) {
+      for (int o = 0; o < out_features; ++o) target[r * out_features + o] = __ldg(signal + li * out_features + o);
+    }
+  }
+}
+
+// dst[idx[r]] = src[r] (rows of `width` floats); idx == nullptr: dst[idx_base + r]
+__global__ void scatter_rows_kernel(const int64_t* __restrict__ idx, int64_t idx_base, int64_t n, const float* __restrict__ src,
+                                    int width, float* __restrict__ dst, int64_t dst_rows, int* __restrict__ err) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n * width; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = t / width;
+    const int o = int(t - r * width);
+    const int64_t li = idx ? idx[r] : idx_base + r;
+    if (li < 0 || li >= dst_rows) { if (err) atomicExch(err, 1); continue; }
+    dst[li * width + o] = src[t];
+  }
+}
+
+// volutils.get_I_and_U (modules/volutils.py:79-91): predictions are thresholded (IN PLACE in the reference; here only when
+// `binarize` is set) and intersection / union are counts of logical_and / logical_or with the ground truth.
+// counts[0] += intersection, counts[1] += union   (exact integer counts)
+__global__ void iou_counts_kernel(float* __restrict__ preds, const float* __restrict__ gt, int64_t count, float thres, int use_thres,
+                                  int binarize, unsigned long long* __restrict__ counts) {
+  unsigned int inter = 0, uni = 0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    float p = preds[i];
+    if (use_thres) {
+      if (p < thres) p = 0.0f;   // the reference's two masked assignments, in order (so thres <= 0 maps everything to 1,
+      if (p >= thres) p = 1.0f;  // and a NaN stays NaN)
+      if (binarize) preds[i] = p;
+    }
+    const bool pb = p != 0.0f, gb = gt[i] != 0.0f;  // logical_and / logical_or: non-zero (NaN included) is true
+    inter += (pb && gb);
+    uni += (pb || gb);
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    inter += __shfl_xor_sync(0xffffffffu, inter, s);
+    uni += __shfl_xor_sync(0xffffffffu, uni, s);
+  }
+  __shared__ unsigned int si[32], su[32];
+  if ((threadIdx.x & 31) == 0) { si[threadIdx.x >> 5] = inter; su[threadIdx.x >> 5] = uni; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) { a += si[w]; b += su[w]; }
+    if (a) atomicAdd(counts, a);
+    if (b) atomicAdd(counts + 1, b);
+  }
+}
+
+// stats[0] += sum (x - xhat)^2 (float64), stats[1] = max(stats[1], max x): utils.psnr = 10 log10(max(x) / mean err^2)
+// (modules/utils.py:67-82); the drivers' own -10 log10(mse) (wire_image_denoise.py:161-167) needs stats[0] only.
+__global__ void sq_err_stats_kernel(const float* __restrict__ x, const float* __restrict__ xhat, int64_t count, double* __restrict__ stats) {
+  double acc = 0.0;
+  float mx = -INFINITY;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float a = x[i];
+    const float d = a - xhat[i];
+    acc += double(d) * double(d);
+    mx = fmaxf(mx, a);
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  }
+  __shared__ double sa[32];
+  __shared__ float sm[32];
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = acc; sm[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    float m = -INFINITY;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) { a += sa[w]; m = fmaxf(m, sm[w]); }
+    atomicAdd(stats, a);
+    // double max through atomicCAS on the bit pattern
+    unsigned long long* addr = reinterpret_cast<unsigned long long*>(stats + 1);
+    unsigned long long old = *addr, assumed;
+    do {
+      assumed = old;
+      if (__longlong_as_double((long long)assumed) >= double(m)) break;
+      old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(double(m)));
+    } while (assumed != old);
+  }
+}
+
+}  // namespace wire

@@ -407,10 +407,12 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 }
 
 // grad = 2 (pred - target) / count ; loss += sum (pred-target)^2 / count
+// count_norm: the element count the mean is taken over (== count on one GPU; the GLOBAL batch's count when this rank holds
+// a shard of it, so that the ranks' gradients and losses simply add up to those of the global mean)
 __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
-                                float* __restrict__ grad, float* __restrict__ loss) {
+                                float* __restrict__ grad, float* __restrict__ loss, int64_t count_norm) {
   float local = 0.f;
-  const float inv = 1.0f / float(count);
+  const float inv = 1.0f / float(count_norm);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
     const float d = pred[i] - target[i];
     grad[i] = 2.0f * d * inv;

@@ -93,6 +93,9 @@ class Trainer:
         self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self._n = None
+        self._key = None
+        self._n_global = None
+        self._states = {}
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     # ------------------------------------------------------------------------------------------
@@ -103,33 +106,53 @@ class Trainer:
     def steps_done(self) -> int:
         return int(self.step_dev.item())
 
-    def _prepare(self, n: int) -> None:
+    # per-batch-size state: buffers, workspace, C-ABI pointer tables, captured graph.  Epoch loops alternate between the
+    # chunk size and one ragged last chunk (wire_occupancy.py:141), so a few sizes are kept instead of re-allocating.
+    _MAX_STATES = 4
+
+    def _prepare(self, n: int, n_global: Optional[int] = None) -> None:
+        key = (n, n_global)
+        self._n, self._key = n, key
+        st = self._states.get(key)
+        if st is not None:
+            self._states[key] = self._states.pop(key)  # most recently used last
+            self.__dict__.update(st)
+            return
+        while len(self._states) >= self._MAX_STATES:
+            self._states.pop(next(iter(self._states)))
         dev, d = self.device, self.desc
-        self._n = n
-        self._graph = None
-        self.coords_buf = torch.empty((n, d.in_features), dtype=torch.float32, device=dev)
-        self.target_buf = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
-        self.out_buf = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
-        self.gout_buf = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        st = {"_graph": None, "_n_global": n_global}
+        st["coords_buf"] = torch.empty((n, d.in_features), dtype=torch.float32, device=dev)
+        st["target_buf"] = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        st["out_buf"] = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        st["gout_buf"] = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
         nbytes = self.lib.wire_net_workspace_bytes(ctypes.byref(d), n, 1)
         if nbytes == 0:
             check(1, "wire_net_workspace_bytes")
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        check(self.lib.wire_net_workspace_init(ctypes.byref(d), n, 1, self.ws.data_ptr(), nbytes, F._stream()),
+        st["ws"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(self.lib.wire_net_workspace_init(ctypes.byref(d), n, 1, st["ws"].data_ptr(), nbytes, F._stream()),
               "wire_net_workspace_init")
         tensors = self.model.flat_params()
-        self._P = F._fill_net_params(d, F._check_net_tensors(d, tensors))
-        self._G = NetGrads()
+        st["_P"] = F._fill_net_params(d, F._check_net_tensors(d, tensors))
+        G = NetGrads()
         two_d = bool(d.two_d)
         vi = 0
         for l in range(d.hidden_layers + 1):
-            lg = self._G.layer[l]
+            lg = G.layer[l]
             lg.weight, lg.bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
             vi += 2
             if two_d:
                 lg.weight2, lg.bias2 = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
                 vi += 2
-        self._G.final_weight, self._G.final_bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+        G.final_weight, G.final_bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+        st["_G"] = G
+        self._states[key] = st
+        self.__dict__.update(st)
+
+    def _peer_wait(self) -> None:
+        # peers must have finished reading last step's gradients before they are overwritten
+        check(self.lib.wire_peer_wait_done(self.peer.bases, self.peer.world, self.peer.rank, self.step_dev.data_ptr(), F._stream()),
+              "wire_peer_wait_done")
 
     def _fwd_bwd(self) -> None:
         d, n, st = self.desc, self._n, F._stream()
@@ -137,36 +160,79 @@ class Trainer:
         self.loss_dev.zero_()
         check(lib.wire_net_forward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.out_buf.data_ptr(),
                                    self.ws.data_ptr(), self.ws.numel(), 1, st), "wire_net_forward")
-        check(lib.wire_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
-                                     self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_mse_loss_grad")
-        if self.peer is not None:  # peers must have finished reading last step's gradients before they are overwritten
-            check(lib.wire_peer_wait_done(self.peer.bases, self.peer.world, self.peer.rank, self.step_dev.data_ptr(), st),
-                  "wire_peer_wait_done")
+        if self._n_global is None:
+            check(lib.wire_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
+                                         self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_mse_loss_grad")
+        else:
+            check(lib.wire_mse_loss_grad_n(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
+                                           self._n_global * d.out_features, self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st),
+                  "wire_mse_loss_grad_n")
+        if self.peer is not None:
+            self._peer_wait()
         check(lib.wire_net_backward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.gout_buf.data_ptr(),
                                     self.ws.data_ptr(), self.ws.numel(), ctypes.byref(self._G), None, st), "wire_net_backward")
 
     def _adam(self) -> None:
         b1, b2 = self.betas
+        # equal shards with a local mean: average the ranks' gradients; shards of a global mean (n_global): they add up
+        scale = 1.0 if getattr(self, "_n_global", None) is not None else 1.0 / self.world
         if self.peer is not None:
             check(self.lib.wire_adam_step_peer(self.flat.data_ptr(), self.peer.bases, self.peer.world, self.peer.rank,
                                                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.flat.numel(),
                                                self.lr_dev.data_ptr(), b1, b2, self.eps, self.weight_decay, self.step_dev.data_ptr(),
-                                               1.0 / self.world, self.scratch.data_ptr(), F._stream()), "wire_adam_step_peer")
+                                               scale, self.scratch.data_ptr(), F._stream()), "wire_adam_step_peer")
             return
         check(self.lib.wire_adam_step_dev(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr_dev.data_ptr(), b1, b2, self.eps,
-                                          self.weight_decay, self.step_dev.data_ptr(), 1.0 / self.world, self.scratch.data_ptr(),
+                                          self.weight_decay, self.step_dev.data_ptr(), scale, self.scratch.data_ptr(),
                                           F._stream()), "wire_adam_step_dev")
 
-    def _whole_step(self) -> None:
-        self._fwd_bwd()
+    def _exchange_and_adam(self) -> None:
         if self.world > 1 and self.peer is None:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         self._adam()
 
-    def step(self, coords: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    def _whole_step(self) -> None:
+        self._fwd_bwd()
+        self._exchange_and_adam()
+
+    def _run(self) -> None:
+        """The training step on the current state's device buffers (eager the first time, then a CUDA-graph replay)."""
+        if not self.use_graph or (self.world > 1 and self.peer is None):
+            self._whole_step()
+        elif self._graph is None:
+            # one eager step first (lazy one-time setup inside the C ABI must not happen during capture),
+            # then capture; both count as training steps
+            self._whole_step()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self._whole_step()
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = g
+            self._states[self._key]["_graph"] = g
+        else:
+            self._graph.replay()
+
+    def _empty_step(self) -> None:
+        """This rank's shard of the batch is empty: contribute zero gradients, but take part in the exchange and in Adam."""
+        if self.peer is not None:
+            self._peer_wait()
+        self.flat_grad.zero_()
+        self.loss_dev.zero_()
+        self._n_global = 1  # gradients add up (scale 1)
+        self._exchange_and_adam()
+
+    def step(self, coords: torch.Tensor, target: torch.Tensor, n_global: Optional[int] = None) -> torch.Tensor:
         """One training iteration on (coords [..., in], target [..., out]); host or device tensors.
-        Returns the mean-squared error of this rank's batch as a device scalar (no host sync)."""
+        Returns the mean-squared error of this rank's batch as a device scalar (no host sync).
+
+        Data parallel: by default every rank passes an equally sized shard and the ranks' gradients are averaged.
+        With ``n_global`` (the coordinate count of the whole batch over all ranks) the loss is normalised by the global
+        count instead — shards may then be unequal, and the returned value is this rank's PART of the global mean."""
         d = self.desc
         n = coords.numel() // d.in_features
         if coords.dtype != torch.float32 or target.dtype != torch.float32:
@@ -174,34 +240,44 @@ class Trainer:
         if target.numel() != n * d.out_features:
             raise WireB200Error("target does not match coords")
         with torch.cuda.device(self.device):
-            if n != self._n:
-                self._prepare(n)
+            if n == 0:
+                self._empty_step()
+                return self.loss_dev[0]
+            if (n, n_global) != self._key:
+                self._prepare(n, n_global)
             self.coords_buf.copy_(coords.reshape(n, d.in_features), non_blocking=True)
             self.target_buf.copy_(target.reshape(n, d.out_features), non_blocking=True)
-            if not self.use_graph or (self.world > 1 and self.peer is None):
-                self._whole_step()
-            else:
-                if self._graph is None:
-                    # one eager step first (lazy one-time setup inside the C ABI must not happen during capture),
-                    # then capture; both count as training steps
-                    self._whole_step()
-                    torch.cuda.synchronize(self.device)
-                    g = torch.cuda.CUDAGraph()
-                    side = torch.cuda.Stream(self.device)
-                    side.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(side):
-                        with torch.cuda.graph(g, stream=side):
-                            self._whole_step()
-                    torch.cuda.current_stream().wait_stream(side)
-                    self._graph = g
-                else:
-                    self._graph.replay()
+            self._run()
+        return self.loss_dev[0]
+
+    def step_indexed(self, batcher, idx: Optional[torch.Tensor] = None, start: Optional[int] = None, count: Optional[int] = None,
+                     n_global: Optional[int] = None, rec: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One training iteration on the grid points ``idx`` (int64 device tensor of linear indices; or the range
+        ``start .. start+count``) of a ``wire_b200.data.GridBatcher``: coordinates are generated and targets gathered on the
+        device by one kernel, straight into the step's input buffers — the reference's
+        ``b_coords = coords[b_indices].cuda(); ... gt[b_indices]`` (wire_occupancy.py:142-149) without host work.
+        ``rec`` ([total, out], optional) receives the step's predictions: ``rec[b_indices] = pixelvalues``."""
+        d = self.desc
+        if batcher.ndim != d.in_features or batcher.out_features != d.out_features:
+            raise WireB200Error("GridBatcher does not match the model's in/out features")
+        n = idx.numel() if idx is not None else int(count)
+        with torch.cuda.device(self.device):
+            if n == 0:
+                self._empty_step()
+                return self.loss_dev[0]
+            if (n, n_global) != self._key:
+                self._prepare(n, n_global)
+            batcher.assemble_into(self.coords_buf, self.target_buf, idx, start, count)
+            self._run()
+            if rec is not None:
+                batcher.scatter(rec, self.out_buf, idx, start, count)
         return self.loss_dev[0]
 
     def close(self) -> None:
         """Release the peer-mapped gradient buffer (collective: every rank must call it)."""
+        self._states.clear()
+        self._graph = None
         if self.peer is not None:
-            self._graph = None
             self.peer.close()
             self.peer = None
 
