@@ -37,7 +37,7 @@ def trainer_case(name, kind, in_f, hidden, H, out_f, w0, s0, n, steps=10):
     ms = timeit(lambda: tr.step(coords, target), steps)
     M = model.width
     f = flops(kind, M, H, in_f, out_f) * n
-    print(json.dumps({"case": name, "kind": kind, "M": M, "H": H, "n": n, "ms_per_step": ms, "coords_per_s": n / ms * 1e3,
+    print(json.dumps({"case": name, "kind": kind, "precision": model.precision, "M": M, "H": H, "n": n, "ms_per_step": ms, "coords_per_s": n / ms * 1e3,
                       "algorithmic_tflops": f / ms * 1e-9, "frac_nominal_tf32": f / ms * 1e-9 / 1100.0}), flush=True)
     del tr, model
     torch.cuda.empty_cache()
