@@ -202,6 +202,11 @@ int wire_scatter_rows(const int64_t* idx, int64_t idx_base, int64_t n, const flo
 int wire_iou_counts(float* preds, const float* gt, int64_t count, float thres, int32_t use_thres, int32_t binarize_in_place,
                     uint64_t* counts, void* stream);
 int wire_sq_err_stats(const float* x, const float* xhat, int64_t count, double* stats, void* stream);
+/* wire_avgpool_mse_loss_grad: the super-resolution loss of wire_SISR.py:154-161 — pred is the HR prediction [H*W][channels],
+ *   target_lr the LR image [(H/scale)*(W/scale)][channels]; loss = mean((target_lr - AvgPool2d(scale)(pred))^2) is ADDED to
+ *   *loss (device scalar, may be NULL) and grad_out [H*W][channels] receives d loss / d pred. */
+int wire_avgpool_mse_loss_grad(const float* pred, const float* target_lr, int32_t H, int32_t W, int32_t channels, int32_t scale,
+                               float* grad_out, float* loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -157,3 +157,80 @@ def test_epoch_loop_on_device_matches_reference_style_loop(precision):
     iou_a = float(data.get_IoU(est_a.clone(), imten, 0.5))
     iou_b = float(data.get_IoU(est_b.clone(), imten, 0.5))
     assert abs(iou_a - iou_b) <= 0.005     # north_star's IoU bar
+
+
+@pytest.mark.parametrize("H,W,scale", [(64, 48, 4), (50, 37, 4), (1024, 1024, 4), (33, 33, 16)])
+def test_avgpool_mse_loss_grad_vs_torch_autograd(H, W, scale):
+    """wire_avgpool_mse_loss_grad == autograd of the reference's SISR loss (wire_SISR.py:151-161), including image sizes
+    that AvgPool2d truncates."""
+    import ctypes
+    from wire_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(H * W)
+    rec_hr = torch.rand(1, H * W, 3, device=dev, requires_grad=True)
+    H2, W2 = H // scale, W // scale
+    gt_lr = torch.rand(1, H2 * W2, 3, device=dev)
+    rec = torch.nn.AvgPool2d(scale)(rec_hr.reshape(H, W, 3).permute(2, 0, 1)[None, ...])
+    loss = ((gt_lr - rec.reshape(1, 3, -1).permute(0, 2, 1)) ** 2).mean()
+    loss.backward()
+    grad = torch.full((H * W, 3), 7.0, device=dev)
+    loss_dev = torch.zeros(1, device=dev)
+    _lib.check(lib.wire_avgpool_mse_loss_grad(rec_hr.data_ptr(), gt_lr.data_ptr(), H, W, 3, scale, grad.data_ptr(), loss_dev.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "wire_avgpool_mse_loss_grad")
+    assert abs(float(loss_dev) - float(loss)) <= 2e-6 * max(1.0, float(loss))
+    assert torch.allclose(grad, rec_hr.grad[0], rtol=1e-5, atol=1e-10)
+
+
+def test_trainer_sisr_loss_matches_reference_style_loop():
+    """wire2d 4x super-resolution (BASELINE config [2], scaled down to 96x96): Trainer with the fused pooled loss against
+    model(coords_hr) -> AvgPool2d -> MSE -> backward -> torch.optim.Adam (wire_SISR.py:154-177), FP32 kernels."""
+    import wire_b200
+    dev = torch.device("cuda", 0)
+    H = W = 96
+    scale = 4
+    x = torch.linspace(-1, 1, W); y = torch.linspace(-1, 1, H)
+    X, Y = torch.meshgrid(x, y, indexing="xy")
+    coords_hr = torch.hstack((X.reshape(-1, 1), Y.reshape(-1, 1)))[None, ...].to(dev)
+    torch.manual_seed(2)
+    gt_lr = torch.rand(1, (H // scale) * (W // scale), 3, device=dev)
+    kw = dict(nonlin="wire2d", in_features=2, hidden_features=64, hidden_layers=2, out_features=3, first_omega_0=8.0,
+              hidden_omega_0=8.0, scale=9.0, precision="fp32")
+    a = wire_b200.get_INR(**kw).to(dev)
+    b = wire_b200.get_INR(**kw).to(dev)
+    b.load_state_dict(a.state_dict())
+    opt = torch.optim.Adam(a.parameters(), lr=5e-3)
+    pool = torch.nn.AvgPool2d(scale)
+    ref = []
+    for _ in range(10):
+        rec_hr = a(coords_hr)
+        rec = pool(rec_hr.reshape(H, W, 3).permute(2, 0, 1)[None, ...])
+        loss = ((gt_lr - rec.reshape(1, 3, -1).permute(0, 2, 1)) ** 2).mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+        ref.append(float(loss))
+    tr = wire_b200.Trainer(b, lr=5e-3)
+    tr.set_loss_avgpool(H, W, scale)
+    got = [float(tr.step(coords_hr, gt_lr)) for _ in range(10)]
+    assert util.rel_err(np.array(got), np.array(ref)) < 2e-3, (got, ref)
+    with torch.no_grad():
+        assert util.rel_err(b(coords_hr).cpu().numpy(), a(coords_hr).cpu().numpy()) < 2e-2
+
+
+def test_trainer_step_from_pinned_host_buffers_is_pipelined_and_correct():
+    """Trainer.step with PINNED HOST inputs (copy stream + two staging buffers) follows the same trajectory as with device
+    inputs, also when the host buffers change every step."""
+    import wire_b200
+    dev = torch.device("cuda", 0)
+    kw = dict(nonlin="wire", in_features=2, hidden_features=100, hidden_layers=2, out_features=3, first_omega_0=7.0,
+              hidden_omega_0=7.0, scale=6.0, precision="fp32")
+    a = wire_b200.get_INR(**kw).to(dev)
+    b = wire_b200.get_INR(**kw).to(dev)
+    b.load_state_dict(a.state_dict())
+    gen = torch.Generator().manual_seed(0)
+    batches = [((torch.rand(1, 4096, 2, generator=gen) * 2 - 1), torch.rand(1, 4096, 3, generator=gen)) for _ in range(6)]
+    ta, tb = wire_b200.Trainer(a, lr=5e-3), wire_b200.Trainer(b, lr=5e-3)
+    la = [float(ta.step(c.to(dev), t.to(dev))) for c, t in batches]
+    pinned = [(c.pin_memory(), t.pin_memory()) for c, t in batches]
+    lb = [tb.step(c, t).clone() for c, t in pinned]       # no host sync between steps
+    lb = [float(v) for v in lb]
+    assert util.rel_err(np.array(lb), np.array(la)) < 1e-3, (la, lb)

@@ -1331,4 +1331,18 @@ int wire_sq_err_stats(const float* x, const float* xhat, int64_t count, double* 
   return 0;
 }
 
+int wire_avgpool_mse_loss_grad(const float* pred, const float* target_lr, int32_t H, int32_t W, int32_t channels, int32_t scale,
+                               float* grad_out, float* loss, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!pred || !target_lr || !grad_out) return fail("null argument");
+  if (H < 1 || W < 1 || channels < 1 || scale < 1) return fail("bad shape H=%d W=%d C=%d scale=%d", H, W, channels, scale);
+  if (H / scale < 1 || W / scale < 1) return fail("scale %d larger than the image %dx%d", scale, H, W);
+  if (H % scale || W % scale) CU_OK(cudaMemsetAsync(grad_out, 0, size_t(H) * W * channels * sizeof(float), st));
+  ProfScope prof(K_MSE, st);
+  avgpool_mse_grad_kernel<<<grid_for(int64_t(H / scale) * (W / scale) * channels), 256, 0, st>>>(pred, target_lr, H, W, channels, scale,
+                                                                                                grad_out, loss);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

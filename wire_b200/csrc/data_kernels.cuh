@@ -144,4 +144,40 @@ __global__ void sq_err_stats_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// The super-resolution loss of wire_SISR.py:154-161: the HR prediction [H*W, C] is average-pooled by `scale`
+// (torch.nn.AvgPool2d(scale): stride = scale, floor mode, so H2 = H / scale, W2 = W / scale and remainder rows / columns are
+// ignored) and compared with the LR target [H2*W2, C]:  loss = mean((gt_lr - pool(rec_hr))^2).  One thread per LR element
+// computes the pooled value, its squared error and writes the gradient of its scale x scale HR pixels:
+// grad[hr, c] = 2 (pool - gt_lr) / (H2*W2*C) / scale^2.   (grad of ignored remainder pixels is zeroed by the caller.)
+__global__ void avgpool_mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int C, int scale,
+                                        float* __restrict__ grad, float* __restrict__ loss) {
+  const int H2 = H / scale, W2 = W / scale;
+  const int64_t count = int64_t(H2) * W2 * C;
+  const float inv = 1.0f / float(count);
+  const float inv_pool = 1.0f / float(scale * scale);
+  float local = 0.f;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < count; t += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(t % C);
+    const int64_t px = t / C;
+    const int j = int(px % W2), i = int(px / W2);
+    float sum = 0.f;
+    for (int a = 0; a < scale; ++a)
+      for (int b = 0; b < scale; ++b) sum += pred[(int64_t(i * scale + a) * W + (j * scale + b)) * C + c];
+    const float d = sum * inv_pool - target[t];
+    local = fmaf(d, d, local);
+    const float gv = 2.0f * d * inv * inv_pool;
+    for (int a = 0; a < scale; ++a)
+      for (int b = 0; b < scale; ++b) grad[(int64_t(i * scale + a) * W + (j * scale + b)) * C + c] = gv;
+  }
+  for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
+  __shared__ float ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, v * inv);
+  }
+}
+
 }  // namespace wire

@@ -96,11 +96,23 @@ class Trainer:
         self._key = None
         self._n_global = None
         self._states = {}
+        self._copy_stream = None
+        self._pool = None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     # ------------------------------------------------------------------------------------------
     def set_lr(self, lr: float) -> None:
         self.lr_dev.fill_(float(lr))
+
+    def set_loss_avgpool(self, H: int, W: int, scale: int) -> None:
+        """Super-resolution loss (wire_SISR.py:151-161): ``step(coords_hr, gt_lr)`` then takes the H*W high-resolution
+        coordinates and the LOW-resolution target [(H//scale)*(W//scale), out]; the prediction is average-pooled by
+        ``scale`` (``torch.nn.AvgPool2d(scale)``) inside the fused loss kernel before the squared error."""
+        if H // scale < 1 or W // scale < 1:
+            raise WireB200Error("scale larger than the image")
+        self._pool = (int(H), int(W), int(scale))
+        self._states.clear()
+        self._key = None
 
     @property
     def steps_done(self) -> int:
@@ -123,7 +135,8 @@ class Trainer:
         dev, d = self.device, self.desc
         st = {"_graph": None, "_n_global": n_global}
         st["coords_buf"] = torch.empty((n, d.in_features), dtype=torch.float32, device=dev)
-        st["target_buf"] = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
+        n_target = n if self._pool is None else (self._pool[0] // self._pool[2]) * (self._pool[1] // self._pool[2])
+        st["target_buf"] = torch.empty((n_target, d.out_features), dtype=torch.float32, device=dev)
         st["out_buf"] = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
         st["gout_buf"] = torch.empty((n, d.out_features), dtype=torch.float32, device=dev)
         nbytes = self.lib.wire_net_workspace_bytes(ctypes.byref(d), n, 1)
@@ -160,7 +173,11 @@ class Trainer:
         self.loss_dev.zero_()
         check(lib.wire_net_forward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.out_buf.data_ptr(),
                                    self.ws.data_ptr(), self.ws.numel(), 1, st), "wire_net_forward")
-        if self._n_global is None:
+        if self._pool is not None:
+            Hh, Ww, sc = self._pool
+            check(lib.wire_avgpool_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), Hh, Ww, d.out_features, sc,
+                                                 self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_avgpool_mse_loss_grad")
+        elif self._n_global is None:
             check(lib.wire_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
                                          self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_mse_loss_grad")
         else:
@@ -237,7 +254,13 @@ class Trainer:
         n = coords.numel() // d.in_features
         if coords.dtype != torch.float32 or target.dtype != torch.float32:
             raise WireB200Error("coords and target must be float32")
-        if target.numel() != n * d.out_features:
+        n_target = n
+        if self._pool is not None:
+            Hh, Ww, sc = self._pool
+            if n != Hh * Ww or n_global is not None:
+                raise WireB200Error("the pooled loss needs the full H*W coordinate grid on one rank")
+            n_target = (Hh // sc) * (Ww // sc)
+        if target.numel() != n_target * d.out_features:
             raise WireB200Error("target does not match coords")
         with torch.cuda.device(self.device):
             if n == 0:
@@ -245,10 +268,43 @@ class Trainer:
                 return self.loss_dev[0]
             if (n, n_global) != self._key:
                 self._prepare(n, n_global)
-            self.coords_buf.copy_(coords.reshape(n, d.in_features), non_blocking=True)
-            self.target_buf.copy_(target.reshape(n, d.out_features), non_blocking=True)
+            self._load_inputs(coords.reshape(n, d.in_features), target.reshape(n_target, d.out_features))
             self._run()
         return self.loss_dev[0]
+
+    def _load_inputs(self, coords: torch.Tensor, target: torch.Tensor) -> None:
+        """Bring this step's inputs into the step's fixed input buffers.  Device tensors: one D2D copy each.  Pinned host
+        tensors (the reference's ``b_coords = coords[...].cuda()`` per chunk, wire_image_denoise.py:145-147): the
+        host->device copy runs on a COPY STREAM into one of two staging buffers, so it overlaps the previous step's
+        kernels; the compute stream then only does a device-to-device copy (microseconds) before the step's graph."""
+        if coords.device.type == "cuda" or not (coords.is_pinned() and target.is_pinned()):
+            self.coords_buf.copy_(coords, non_blocking=True)
+            self.target_buf.copy_(target, non_blocking=True)
+            return
+        st = self._states[self._key]
+        if "stage" not in st:
+            st["stage"] = [(torch.empty_like(self.coords_buf), torch.empty_like(self.target_buf)) for _ in range(2)]
+            st["stage_free"] = [None, None]   # event: the compute stream has consumed this staging pair
+            st["stage_i"] = 0
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        i = st["stage_i"]
+        st["stage_i"] = i ^ 1
+        sc, stg = st["stage"][i]
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            if st["stage_free"][i] is not None:
+                self._copy_stream.wait_event(st["stage_free"][i])
+            sc.copy_(coords, non_blocking=True)
+            stg.copy_(target, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        cur.wait_event(ready)
+        self.coords_buf.copy_(sc, non_blocking=True)
+        self.target_buf.copy_(stg, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        st["stage_free"][i] = done
 
     def step_indexed(self, batcher, idx: Optional[torch.Tensor] = None, start: Optional[int] = None, count: Optional[int] = None,
                      n_global: Optional[int] = None, rec: Optional[torch.Tensor] = None) -> torch.Tensor:
