@@ -477,7 +477,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
     for (int nb = (g_pitch + 255) / 256; nb <= 16 && zw_pitch == g_pitch; ++nb)
       if (g_pitch % nb == 0 && (g_pitch / nb) % 8 == 0 && g_pitch / nb <= 256) { n_box = nb; break; }
     const size_t tile_bytes = size_t(g_pitch) * kTopRows * 2;
-    const size_t smem16 = 4 * (w ? 2 : 1) * tile_bytes + 256;
+    const size_t smem16 = (kTopIn + kTopOut) * (w ? 2 : 1) * tile_bytes + 256;
     if (n_box > 0 && smem16 <= 200 * 1024 && d->width <= 992 && !getenv("WIRE_B200_TOP_SIMT")) {
       TopBwd16Params T;
       memset(&T, 0, sizeof(T));
@@ -491,14 +491,17 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       if (!ok) return fail("cuTensorMapEncodeTiled failed for top_bwd16");
       const int threads = round_up(d->width, 32) + 32;  // compute warps + the I/O warp
       const int n_tiles = int((n + kTopRows - 1) / kTopRows);
-      int per_sm = int((220 * 1024) / smem16);
-      if (per_sm * threads > 2048) per_sm = 2048 / threads;
-      if (per_sm < 1) per_sm = 1;
-      int grid16 = g_sm_count * per_sm;
-      if (grid16 > n_tiles) grid16 = n_tiles;
       auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 256);
         if (e != cudaSuccess) return e;
+        // persistent CTAs: exactly one wave of what is really resident (registers limit it to 4 CTAs of 256 threads per SM;
+        // a grid sized from shared memory alone ran 1.75 waves with a 75 %-occupied tail)
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem16);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        int grid16 = g_sm_count * per_sm;
+        if (grid16 > n_tiles) grid16 = n_tiles;
         kern<<<grid16, threads, smem16, st>>>(T);
         return cudaGetLastError();
       };

@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restric
 // registers), results are written to a BF16 smem tile that leaves by TMA (clipped to the 2M valid columns).
 // ---------------------------------------------------------------------------------------------
 constexpr int kTopRows = 8;
+constexpr int kTopOut = 3; // depth of the output ring
+constexpr int kTopIn = 4;  // depth of the input ring (ncu: with 2 the compute warps waited on TMA latency, long_scoreboard 3.0)
 struct TopBwd16Params {
   CUtensorMap z_map[2];   // z, w: [n][pitch] FP16, box {bw cols, kTopRows}, no swizzle
   CUtensorMap g_map[2];   // g_z, g_w: [n][2M] BF16 (row pitch = pitch), same box
@@ -127,15 +129,15 @@ template <bool TWO_D, int OUTF, int MAXT>
 __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__ TopBwd16Params P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t tsm[];
-  __shared__ __align__(8) uint64_t in_full[2], in_empty[2], out_full[2], out_empty[2];
-  __shared__ __align__(16) float s_go[2][kTopRows][4];
+  __shared__ __align__(8) uint64_t in_full[kTopIn], in_empty[kTopIn], out_full[kTopOut], out_empty[kTopOut];
+  __shared__ __align__(16) float s_go[kTopIn][kTopRows / 2][4][2];  // [stage][row pair][output][row of the pair]
   const uint32_t pad = ((smem_u32(tsm) + 127u) & ~127u) - smem_u32(tsm);
   uint8_t* sm = tsm + pad;
   const uint32_t base = smem_u32(sm);
   const uint32_t tile_bytes = uint32_t(P.pitch) * kTopRows * 2;   // one tensor, one stage
   constexpr int n_t = TWO_D ? 2 : 1;
-  // layout: in[2 stages][n_t tensors] | out[2 buffers][n_t tensors]
-  const uint32_t out_off = 2 * n_t * tile_bytes;
+  // layout: in[kTopIn stages][n_t tensors] | out[kTopOut buffers][n_t tensors]
+  const uint32_t out_off = kTopIn * n_t * tile_bytes;
   const uint32_t box_bytes = uint32_t(P.bw) * kTopRows * 2;
 
   const int n_tiles = (P.n + kTopRows - 1) / kTopRows;
@@ -147,9 +149,11 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
   const int n_cw = (blockDim.x >> 5) - 1;  // compute warps
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kTopIn; ++s) {
       mbar_init(smem_u32(&in_full[s]), 2);
       mbar_init(smem_u32(&in_empty[s]), n_cw);
+    }
+    for (int s = 0; s < kTopOut; ++s) {
       mbar_init(smem_u32(&out_full[s]), n_cw);
       mbar_init(smem_u32(&out_empty[s]), 1);
     }
@@ -159,7 +163,15 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
 
   if (warp == n_cw) {
     // ===================== I/O warp =====================
-    auto issue_load = [&](int tile, int stage) {
+    // One latency chain per tile would make this warp the bottleneck (measured: 4 CTAs/SM x one tile per ~2 us), so nothing
+    // here waits for a round trip: the g_out rows of the tile loaded NEXT iteration are prefetched into a register now,
+    // and a TMA store is only waited for (wait_read<1>) one iteration after it was issued.
+    const int rr = lane >> 2, o = lane & 3;
+    auto load_go = [&](int tile) -> float {
+      const int row = tile * kTopRows + rr;
+      return (tile < t_end && row < P.n && o < OUTF) ? __ldg(P.g_out + size_t(row) * OUTF + o) : 0.f;
+    };
+    auto issue_load = [&](int tile, int stage, float go) {
       if (lane == 0) {
         const uint32_t bar = smem_u32(&in_full[stage]);
         mbar_expect_tx(bar, n_t * tile_bytes);
@@ -168,51 +180,51 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
           for (int b = 0; b < P.n_box; ++b) tma_load_2d_hint(dst + b * box_bytes, &P.z_map[t], bar, b * P.bw, tile * kTopRows, kEvictFirst);
         }
       }
-      {  // this tile's g_out rows (zero beyond n)
-        const int rr = lane >> 2, o = lane & 3;
-        const int row = tile * kTopRows + rr;
-        s_go[stage][rr][o] = (rr < kTopRows && row < P.n && o < OUTF) ? __ldg(P.g_out + size_t(row) * OUTF + o) : 0.f;
-      }
+      s_go[stage][rr >> 1][o][rr & 1] = go;  // this tile's g_out rows (zero beyond n)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&in_full[stage]));
     };
-    if (t_begin < t_end) issue_load(t_begin, 0);
-    if (t_begin + 1 < t_end) issue_load(t_begin + 1, 1);
-    uint32_t ph[2] = {0, 0};
+    for (int s = 0; s < kTopIn; ++s)
+      if (t_begin + s < t_end) issue_load(t_begin + s, s, load_go(t_begin + s));
+    float go_next = load_go(t_begin + kTopIn);
     for (int tile = t_begin; tile < t_end; ++tile) {
-      const int stage = (tile - t_begin) & 1;
-      if (tile + 2 < t_end) {  // refill the in-stage as soon as every compute warp has read it
-        if (lane == 0) mbar_wait(smem_u32(&in_empty[stage]), ph[stage]);
+      const int it = tile - t_begin;
+      const int istage = it % kTopIn, ostage = it % kTopOut;
+      const uint32_t iph = (it / kTopIn) & 1, oph = (it / kTopOut) & 1;
+      if (tile + kTopIn < t_end) {  // refill the in-stage as soon as every compute warp has read it
+        if (lane == 0) mbar_wait(smem_u32(&in_empty[istage]), iph);
         __syncwarp();
-        issue_load(tile + 2, stage);
+        issue_load(tile + kTopIn, istage, go_next);
+        go_next = load_go(tile + 1 + kTopIn);
       }
       if (lane == 0) {
-        mbar_wait(smem_u32(&out_full[stage]), ph[stage]);
+        mbar_wait(smem_u32(&out_full[ostage]), oph);
         for (int t = 0; t < n_t; ++t) {
-          const uint32_t src = base + out_off + (stage * n_t + t) * tile_bytes;
+          const uint32_t src = base + out_off + (ostage * n_t + t) * tile_bytes;
           for (int b = 0; b < P.n_box; ++b)
             if (b * P.bw < 2 * P.M) tma_store_2d(&P.g_map[t], src + b * box_bytes, b * P.bw, tile * kTopRows);
         }
         tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(smem_u32(&out_empty[stage]));
+        tma_store_wait_read<1>();  // the PREVIOUS tile's store has read its buffer
+        if (it >= 1) mbar_arrive(smem_u32(&out_empty[(it - 1) % kTopOut]));
       }
-      ph[stage] ^= 1;
     }
     if (lane == 0) tma_store_wait_all<0>();
     return;
   }
 
   // ===================== compute warps =====================
+  // Thread k owns complex feature k and processes TWO ROWS at a time with the packed FP32 instructions (f32x2.cuh):
+  // every quantity below is a {row 2j, row 2j+1} pair, the feature's weights are broadcast pairs.
   const int k = threadIdx.x;  // complex feature owned by this thread
   const bool active = k < P.M;
-  const GaborConst G = make_gabor_const(__ldg(P.omega), __ldg(P.scale));
-  float wr[OUTF], wi[OUTF], ar[OUTF], ai[OUTF];
+  const GaborConst2 G2 = make_gabor_const2(make_gabor_const(__ldg(P.omega), __ldg(P.scale)));
+  f2 wr2[OUTF], nwi2[OUTF], ar2[OUTF], ai2[OUTF];
 #pragma unroll
   for (int o = 0; o < OUTF; ++o) {
-    wr[o] = active ? __ldg(P.Wf + (size_t(o) * P.M + k) * 2) : 0.f;
-    wi[o] = active ? __ldg(P.Wf + (size_t(o) * P.M + k) * 2 + 1) : 0.f;
-    ar[o] = ai[o] = 0.f;
+    wr2[o] = f2_bcast(active ? __ldg(P.Wf + (size_t(o) * P.M + k) * 2) : 0.f);
+    nwi2[o] = f2_bcast(active ? -__ldg(P.Wf + (size_t(o) * P.M + k) * 2 + 1) : 0.f);
+    ar2[o] = ai2[o] = 0ull;
   }
   float bsum = 0.f;
   // byte offset of this thread's (re, im) pair inside a tile: box b holds columns [b*bw, (b+1)*bw) as a dense [rows][bw] block
@@ -221,56 +233,72 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
   const uint32_t row_bytes = uint32_t(P.bw) * 2;
   const uint32_t off0 = uint32_t(bi) * box_bytes + uint32_t(col - bi * P.bw) * 2;
 
-  uint32_t ph[2] = {0, 0};
   for (int tile = t_begin; tile < t_end; ++tile) {
-    const int stage = (tile - t_begin) & 1;
-    mbar_wait(smem_u32(&in_full[stage]), ph[stage]);
-    mbar_wait(smem_u32(&out_empty[stage]), ph[stage] ^ 1);  // passes at once the first time a buffer is used
-    ph[stage] ^= 1;
+    const int it = tile - t_begin;
+    const int istage = it % kTopIn, stage = it % kTopOut;
+    mbar_wait(smem_u32(&in_full[istage]), (it / kTopIn) & 1);
+    mbar_wait(smem_u32(&out_empty[stage]), ((it / kTopOut) & 1) ^ 1);  // passes at once the first time a buffer is used
     if (threadIdx.x < OUTF) {
 #pragma unroll
-      for (int rr = 0; rr < kTopRows; ++rr) bsum += s_go[stage][rr][threadIdx.x];
+      for (int rp = 0; rp < kTopRows / 2; ++rp) bsum += s_go[istage][rp][threadIdx.x][0] + s_go[istage][rp][threadIdx.x][1];
     }
-    const uint8_t* zin = sm + (stage * n_t) * tile_bytes + off0;
+    const uint8_t* zin = sm + (istage * n_t) * tile_bytes + off0;
     uint8_t* zout = sm + out_off + (stage * n_t) * tile_bytes + off0;
-#pragma unroll 4
-    for (int rr = 0; rr < kTopRows; ++rr) {
-      const uint32_t zp = *reinterpret_cast<const uint32_t*>(zin + rr * row_bytes);
-      uint32_t wp = 0;
-      if constexpr (TWO_D) wp = *reinterpret_cast<const uint32_t*>(zin + tile_bytes + rr * row_bytes);
-      const float4 go = *reinterpret_cast<const float4*>(&s_go[stage][rr][0]);
-      const float g4[4] = {go.x, go.y, go.z, go.w};
-      float gyr = 0.f, gyi = 0.f;
 #pragma unroll
-      for (int o = 0; o < OUTF; ++o) { gyr = fmaf(g4[o], wr[o], gyr); gyi = fmaf(-g4[o], wi[o], gyi); }
-      const float2 z = unpack_f16(zp);
-      float2 w = make_float2(0.f, 0.f);
-      if constexpr (TWO_D) w = unpack_f16(wp);
-      const float wnorm = TWO_D ? fmaf(w.x, w.x, w.y * w.y) : 0.f;
-      float yr, yi, gzr, gzi;
-      gabor16(G, z.x, z.y, wnorm, yr, yi);
-      const float pr = gabor_bwd(yr, yi, z.x, z.y, gyr, gyi, G.omega, G.s2, gzr, gzi);
-      // (lanes past the last feature alias feature 0's slot: they compute on it but must not store)
-      if (active) *reinterpret_cast<uint32_t*>(zout + rr * row_bytes) = pack_bf16(gzr, gzi);
+    for (int rp = 0; rp < kTopRows / 2; ++rp) {
+      const uint32_t za = *reinterpret_cast<const uint32_t*>(zin + (2 * rp) * row_bytes);
+      const uint32_t zb = *reinterpret_cast<const uint32_t*>(zin + (2 * rp + 1) * row_bytes);
+      // {re row a, re row b} and {im row a, im row b} as half2, then one conversion each to an aligned float pair
+      const float2 zre = unpack_f16(__byte_perm(za, zb, 0x5410)), zim = unpack_f16(__byte_perm(za, zb, 0x7632));
+      const f2 zr = f2_make(zre.x, zre.y), zi = f2_make(zim.x, zim.y);
+      f2 wre = 0ull, wim = 0ull, wnorm = 0ull;
       if constexpr (TWO_D) {
-        const float t = -2.0f * G.s2 * pr;
-        if (active) *reinterpret_cast<uint32_t*>(zout + tile_bytes + rr * row_bytes) = pack_bf16(t * w.x, t * w.y);
+        const uint32_t wa = *reinterpret_cast<const uint32_t*>(zin + tile_bytes + (2 * rp) * row_bytes);
+        const uint32_t wb = *reinterpret_cast<const uint32_t*>(zin + tile_bytes + (2 * rp + 1) * row_bytes);
+        const float2 w_re = unpack_f16(__byte_perm(wa, wb, 0x5410)), w_im = unpack_f16(__byte_perm(wa, wb, 0x7632));
+        wre = f2_make(w_re.x, w_re.y); wim = f2_make(w_im.x, w_im.y);
+        wnorm = f2_fma(wre, wre, f2_mul(wim, wim));
+      }
+      const f2* go2 = reinterpret_cast<const f2*>(&s_go[istage][rp][0][0]);  // [o] -> {g_o row a, g_o row b}
+      f2 g2[OUTF];
+      f2 gyr = 0ull, gyi = 0ull;
+#pragma unroll
+      for (int o = 0; o < OUTF; ++o) {
+        g2[o] = go2[o];
+        gyr = f2_fma(g2[o], wr2[o], gyr);
+        gyi = f2_fma(g2[o], nwi2[o], gyi);
+      }
+      f2 yr, yi, gzr, gzi;
+      gabor_x2(G2, zr, zi, wnorm, yr, yi);
+      const f2 pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gyr, gyi, gzr, gzi);
+      // (lanes past the last feature alias feature 0's slot: they compute on it but must not store)
+      if (active) {
+        *reinterpret_cast<uint32_t*>(zout + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gzr), f2_lo(gzi));
+        *reinterpret_cast<uint32_t*>(zout + (2 * rp + 1) * row_bytes) = pack_bf16(f2_hi(gzr), f2_hi(gzi));
+      }
+      if constexpr (TWO_D) {
+        const f2 t = f2_mul(G2.m2s2, pr);
+        const f2 gwr = f2_mul(t, wre), gwi = f2_mul(t, wim);
+        if (active) {
+          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gwr), f2_lo(gwi));
+          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp + 1) * row_bytes) = pack_bf16(f2_hi(gwr), f2_hi(gwi));
+        }
       }
 #pragma unroll
-      for (int o = 0; o < OUTF; ++o) { ar[o] = fmaf(g4[o], yr, ar[o]); ai[o] = fmaf(-g4[o], yi, ai[o]); }
+      for (int o = 0; o < OUTF; ++o) { ar2[o] = f2_fma(g2[o], yr, ar2[o]); ai2[o] = f2_fma(g2[o], yi, ai2[o]); }
     }
     fence_proxy_async_smem();  // out tile written through the generic proxy -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(smem_u32(&in_empty[stage]));
+      mbar_arrive(smem_u32(&in_empty[istage]));
       mbar_arrive(smem_u32(&out_full[stage]));
     }
   }
   if (active) {
 #pragma unroll
-    for (int o = 0; o < OUTF; ++o) {
-      atomicAdd(P.g_Wf + (size_t(o) * P.M + k) * 2, ar[o]);
-      atomicAdd(P.g_Wf + (size_t(o) * P.M + k) * 2 + 1, ai[o]);
+    for (int o = 0; o < OUTF; ++o) {  // g_Wf = g_o^T conj(h): even-row + odd-row partial sums; the imaginary part is negated
+      atomicAdd(P.g_Wf + (size_t(o) * P.M + k) * 2, f2_lo(ar2[o]) + f2_hi(ar2[o]));
+      atomicAdd(P.g_Wf + (size_t(o) * P.M + k) * 2 + 1, -(f2_lo(ai2[o]) + f2_hi(ai2[o])));
     }
   }
   if (threadIdx.x < OUTF) atomicAdd(P.g_bf + 2 * threadIdx.x, bsum);
