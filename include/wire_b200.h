@@ -208,6 +208,13 @@ int wire_sq_err_stats(const float* x, const float* xhat, int64_t count, double* 
 int wire_avgpool_mse_loss_grad(const float* pred, const float* target_lr, int32_t H, int32_t W, int32_t channels, int32_t scale,
                                float* grad_out, float* loss, void* stream);
 
+/* Gradients of a layer's own omega_0 / scale_0 (trainable=True of ComplexGaborLayer(2D), modules/wire.py:66,80-81,
+ * modules/wire2d.py:27,42-43; autograd of wire.py:88-93 w.r.t. the two scalars): out2[0] += sum Im(conj(z) p),
+ * out2[1] += -2 s0 sum (|z|^2 + |w|^2) Re p, p = conj(y) grad_y, from the tensors wire_gabor_layer_forward saved.
+ * out2: two float64 on the device, accumulated. */
+int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, const float* z_save, const float* w_save,
+                            const float* grad_y, int64_t n, const float* omega0, const float* scale0, double* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

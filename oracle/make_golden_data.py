@@ -88,3 +88,56 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---- trainable omega_0 / scale_0 (modules/wire.py:66,80-81; modules/wire2d.py:27,42-43): the reference's own layers ----
+def trainable_fixture():
+    """ComplexGaborLayer / ComplexGaborLayer2D with trainable=True, first and hidden, forward + backward in complex64 and
+    complex128: gradients of omega_0, scale_0 (and of the Linear's parameters and the input, for completeness)."""
+    sys.path.insert(0, REF)
+    from modules import wire as ref_wire, wire2d as ref_wire2d
+    blob = {}
+    rs = np.random.RandomState(11)
+    for tag, cls, is_first, K, M, n, w0, s0 in [("wire_first", ref_wire.ComplexGaborLayer, True, 2, 24, 40, 7.0, 6.0),
+                                                 ("wire_hidden", ref_wire.ComplexGaborLayer, False, 24, 24, 40, 7.0, 6.0),
+                                                 ("wire2d_first", ref_wire2d.ComplexGaborLayer2D, True, 3, 16, 36, 8.0, 9.0),
+                                                 ("wire2d_hidden", ref_wire2d.ComplexGaborLayer2D, False, 16, 16, 36, 8.0, 9.0)]:
+        if is_first:
+            x = rs.uniform(-1, 1, size=(1, n, K))
+        else:
+            x = (rs.normal(size=(1, n, K)) + 1j * rs.normal(size=(1, n, K))) * 0.3
+        gy = rs.normal(size=(1, n, M)) + 1j * rs.normal(size=(1, n, M))
+        torch.manual_seed(5)
+        layer = cls(K, M, is_first=is_first, omega0=w0, sigma0=s0, trainable=True)
+        state = {k: v.clone() for k, v in layer.state_dict().items()}
+        for k, v in state.items():
+            a = v.numpy()
+            blob[f"{tag}.param.{k}"] = a
+        for prec, double in (("c64", False), ("c128", True)):
+            layer = cls(K, M, is_first=is_first, omega0=w0, sigma0=s0, trainable=True)
+            layer.load_state_dict(state)
+            if double:
+                for p in layer.parameters():
+                    p.data = p.data.to(torch.complex128 if p.is_complex() else torch.float64)
+            xt = torch.from_numpy(x.astype((np.float64 if double else np.float32) if is_first else (np.complex128 if double else np.complex64)))
+            xt.requires_grad_(True)
+            gt = torch.from_numpy(gy.astype(np.complex128 if double else np.complex64))
+            y = layer(xt)
+            torch.view_as_real(y).mul(torch.view_as_real(gt)).sum().backward()     # sum Re(conj(g) y): upstream gradient g
+            blob[f"{tag}.y_{prec}"] = y.detach().numpy()
+            blob[f"{tag}.g_omega_{prec}"] = layer.omega_0.grad.numpy()
+            blob[f"{tag}.g_scale_{prec}"] = layer.scale_0.grad.numpy()
+            blob[f"{tag}.g_x_{prec}"] = xt.grad.numpy()
+            blob[f"{tag}.g_weight_{prec}"] = layer.linear.weight.grad.numpy()
+        blob[f"{tag}.x"] = x
+        blob[f"{tag}.gy"] = gy
+        blob[f"{tag}.meta"] = np.array([int(is_first), K, M, n], dtype=np.int64)
+        blob[f"{tag}.hyper"] = np.array([w0, s0], dtype=np.float64)
+    out = os.path.join(HERE, "..", "tests", "golden", "trainable_scalars.npz")
+    np.savez_compressed(out, **blob)
+    print(f"wrote {out}: {os.path.getsize(out) / 1024:.1f} KiB; g_omega(wire_hidden) = {blob['wire_hidden.g_omega_c128']}, "
+          f"g_scale = {blob['wire_hidden.g_scale_c128']}")
+
+
+if __name__ == "__main__":
+    trainable_fixture()

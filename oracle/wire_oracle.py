@@ -254,3 +254,19 @@ def psnr_np(x: np.ndarray, xhat: np.ndarray) -> float:
     """modules/utils.py:67-82 ``psnr``: 10 log10(max(x) / mean((x - xhat)^2))."""
     err = x - xhat
     return float(10 * np.log10(np.max(x) / np.mean(pow(err, 2))))
+
+
+def gabor_scalar_grads_np(x, weight, bias, weight2, bias2, omega0, s0, gy):
+    """Closed-form gradients of a layer's own ``omega_0`` / ``scale_0`` (``trainable=True``, modules/wire.py:66,80-81 and
+    modules/wire2d.py:27,42-43) in float64: with z = x W^T + b, w = x W2^T + b2 (wire2d), y = exp(j w0 z - s0^2 (|z|^2 + |w|^2))
+    and p = conj(y) g_y:   g_omega0 = sum Im(conj(z) p),   g_scale0 = -2 s0 sum (|z|^2 + |w|^2) Re(p).
+    Pinned by tests/golden/trainable_scalars.npz (the reference's layers under autograd).  Returns (y, g_omega0, g_scale0)."""
+    x = np.asarray(x).astype(np.complex128)
+    z = x @ np.asarray(weight).astype(np.complex128).T + np.asarray(bias).astype(np.complex128)
+    t = np.abs(z) ** 2
+    if weight2 is not None:
+        w = x @ np.asarray(weight2).astype(np.complex128).T + np.asarray(bias2).astype(np.complex128)
+        t = t + np.abs(w) ** 2
+    y = np.exp(1j * omega0 * z - s0 * s0 * t)
+    p = np.conj(y) * np.asarray(gy).astype(np.complex128)
+    return y, float(np.sum((np.conj(z) * p).imag)), float(-2.0 * s0 * np.sum(t * p.real))

@@ -76,8 +76,14 @@ def test_no_cpu_fallback():
         m.net[0](torch.zeros(1, 8, 2))
     with pytest.raises(wire_b200.WireB200Error):
         wire_b200._lib.load(os.path.join(ROOT, "wire_b200", "lib", "does_not_exist.so"))
-    with pytest.raises(NotImplementedError):
+    # trainable omega_0 / scale_0 run through the layer-by-layer CUDA route: still no CPU path ...
+    with pytest.raises(wire_b200.WireB200Error, match="CUDA"):
         wire_b200.wire.ComplexGaborLayer(2, 8, is_first=True, trainable=True)(torch.zeros(4, 2))
+    # ... and the fused Trainer refuses them instead of silently freezing the scalars
+    m2 = wire_b200.get_INR("wire", 2, 64, None, 1, 3)
+    m2.net[1].omega_0.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        wire_b200.Trainer(m2)
 
 
 def test_product_never_imports_the_oracle():

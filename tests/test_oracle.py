@@ -1,5 +1,6 @@
 """The oracle is only trusted after it reproduces the reference's own outputs (tests/golden/*.npz were
 produced by oracle/make_golden.py running /root/reference/modules/{wire,wire2d}.py in c64 and c128)."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -121,3 +122,16 @@ def test_data_pipeline_oracle_matches_reference_fixtures():
         if not np.isnan(thres):
             assert np.array_equal(p, g[f"iou_binarized_{thres}"])             # in-place thresholding, as the reference
     assert abs(O.psnr_np(g["psnr_x"], g["psnr_xhat"]) - float(g["psnr_value"])) < 1e-12
+
+
+def test_trainable_scalar_grads_closed_form_matches_reference_autograd():
+    g = np.load(os.path.join(util.GOLDEN_DIR, "trainable_scalars.npz"))
+    for tag in ("wire_first", "wire_hidden", "wire2d_first", "wire2d_hidden"):
+        w0, s0 = (float(v) for v in g[f"{tag}.hyper"])
+        two_d = tag.startswith("wire2d")
+        y, g_om, g_s0 = O.gabor_scalar_grads_np(g[f"{tag}.x"], g[f"{tag}.param.linear.weight"], g[f"{tag}.param.linear.bias"],
+                                                 g[f"{tag}.param.scale_orth.weight"] if two_d else None,
+                                                 g[f"{tag}.param.scale_orth.bias"] if two_d else None, w0, s0, g[f"{tag}.gy"])
+        assert util.rel_err(y, g[f"{tag}.y_c128"]) < 1e-12
+        assert abs(g_om - float(g[f"{tag}.g_omega_c128"][0])) <= 1e-10 * max(1.0, abs(g_om)), tag
+        assert abs(g_s0 - float(g[f"{tag}.g_scale_c128"][0])) <= 1e-10 * max(1.0, abs(g_s0)), tag

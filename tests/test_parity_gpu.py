@@ -471,3 +471,66 @@ def test_peer_exchange_two_gpus():
     env = dict(os.environ, PEER_CHECK_N="20000", PEER_CHECK_STEPS="20")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "PEER_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("tag", ["wire_first", "wire_hidden", "wire2d_first", "wire2d_hidden"])
+def test_trainable_omega_scale_vs_reference_autograd(tag, precision):
+    """trainable=True (modules/wire.py:66,80-81): gradients of omega_0 / scale_0 from the CUDA layer route against the
+    reference's own layers under autograd (tests/golden/trainable_scalars.npz, complex128)."""
+    import os
+    import wire_b200
+    g = np.load(os.path.join(util.GOLDEN_DIR, "trainable_scalars.npz"))
+    is_first, K, M, n = (int(v) for v in g[f"{tag}.meta"])
+    w0, s0 = (float(v) for v in g[f"{tag}.hyper"])
+    two_d = tag.startswith("wire2d")
+    cls = wire_b200.wire2d.ComplexGaborLayer2D if two_d else wire_b200.wire.ComplexGaborLayer
+    layer = cls(K, M, is_first=bool(is_first), omega0=w0, sigma0=s0, trainable=True, precision=precision)
+    sd = {k[len(tag) + 7:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + ".param.")}
+    layer.load_state_dict(sd, strict=True)
+    layer = layer.cuda()
+    x = torch.from_numpy(g[f"{tag}.x"].astype(np.float32 if is_first else np.complex64)).cuda().requires_grad_(True)
+    gy = torch.from_numpy(g[f"{tag}.gy"].astype(np.complex64)).cuda()
+    y = layer(x)
+    torch.view_as_real(y).mul(torch.view_as_real(gy)).sum().backward()
+    tol = TOL[precision]
+    assert util.rel_err(y.detach().cpu().numpy(), g[f"{tag}.y_c128"]) < tol["layer"]
+    # the scalar gradients are sums of n*M terms of both signs: compare against the size of the summands
+    ref_om, ref_s0 = float(g[f"{tag}.g_omega_c128"][0]), float(g[f"{tag}.g_scale_c128"][0])
+    scale_om = max(abs(ref_om), 1.0)
+    scale_s0 = max(abs(ref_s0), 1.0)
+    bar = 2e-4 if precision == "fp32" else 2e-2
+    assert abs(float(layer.omega_0.grad) - ref_om) <= bar * scale_om * 5, (float(layer.omega_0.grad), ref_om)
+    assert abs(float(layer.scale_0.grad) - ref_s0) <= bar * scale_s0 * 5, (float(layer.scale_0.grad), ref_s0)
+    assert util.rel_err(x.grad.cpu().numpy(), g[f"{tag}.g_x_c128"]) < tol["grad"]
+    assert util.rel_err(layer.linear.weight.grad.cpu().numpy(), g[f"{tag}.g_weight_c128"]) < tol["grad"]
+
+
+def test_inr_with_trainable_scalars_trains_through_layer_route():
+    """An INR whose hidden layers have trainable omega_0 / scale_0 goes through the layer-by-layer route with autograd
+    end to end: gradients match the oracle (same op sequence as the reference) with the same flags set."""
+    import wire_b200
+    c = util.load_golden("wire_small")
+    ours, ref = build_ours(c, "fp32")
+    for m in (ours, ref):
+        for layer in list(m.net)[1:-1]:
+            layer.omega_0.requires_grad_(True)
+            layer.scale_0.requires_grad_(True)
+    coords = torch.from_numpy(c["g"]["coords"])
+    grad_out = torch.from_numpy(c["g"]["grad_out"])
+    out_ref = ref(coords)
+    (out_ref * grad_out).sum().backward()
+    out = ours(coords.cuda())
+    (out * grad_out.cuda()).sum().backward()
+    assert util.rel_err(out.detach().cpu().numpy(), out_ref.detach().numpy()) < TOL["fp32"]["out"]
+    for (k, pa), (_, pb) in zip(ours.named_parameters(), ref.named_parameters()):
+        if not pb.requires_grad:      # the first layer's omega_0 / scale_0 stay constants
+            assert pa.grad is None, k
+            continue
+        assert pa.grad is not None and pb.grad is not None, k
+        ga = torch.view_as_real(pa.grad).cpu().numpy() if pa.grad.is_complex() else pa.grad.cpu().numpy()
+        gb = torch.view_as_real(pb.grad).numpy() if pb.grad.is_complex() else pb.grad.numpy()
+        if k.endswith("omega_0") or k.endswith("scale_0"):
+            assert abs(float(ga) - float(gb)) <= 2e-3 * max(1.0, abs(float(gb))), (k, float(ga), float(gb))
+        else:
+            assert util.rel_err(ga, gb) < TOL["fp32"]["grad"], k

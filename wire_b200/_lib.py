@@ -87,6 +87,8 @@ SIGNATURES = {
     "wire_scatter_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "wire_iou_counts": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int32, c_void_p, c_void_p]),
     "wire_sq_err_stats": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "wire_gabor_scalar_grads": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
     "wire_avgpool_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -1348,4 +1348,17 @@ int wire_avgpool_mse_loss_grad(const float* pred, const float* target_lr, int32_
   return 0;
 }
 
+int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, const float* z_save, const float* w_save, const float* grad_y,
+                            int64_t n, const float* omega0, const float* scale0, double* out2, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!z_save || !grad_y || !omega0 || !scale0 || !out2) return fail("null argument");
+  if (two_d && !w_save) return fail("wire2d layer without its saved scale_orth pre-activation");
+  if (n <= 0 || width <= 0) return 0;
+  ProfScope prof(K_LAYER_MISC, st);
+  gabor_scalar_grads_kernel<<<grid_for(n * width), 256, 0, st>>>(z_save, two_d ? w_save : nullptr, grad_y, n * int64_t(width), is_first,
+                                                                 omega0, scale0, out2);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

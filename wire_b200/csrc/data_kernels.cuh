@@ -180,4 +180,43 @@ __global__ void avgpool_mse_grad_kernel(const float* __restrict__ pred, const fl
   }
 }
 
+// Gradients of the layer's own scalars omega_0 / scale_0 when they are trainable (``trainable=True`` of
+// ComplexGaborLayer / ComplexGaborLayer2D, modules/wire.py:66,80-81, modules/wire2d.py:27,42-43): with p = conj(y) g_y,
+//   g_omega0 = sum Im(conj(z) p)          g_scale0 = -2 s0 sum (|z|^2 + |w|^2) Re(p)          
+// y is recomputed from the saved pre-activation with the accurate libdevice functions; z (w) are complex [n][M] (real
+// [n][M] for the first layer), g_y complex [n][M].  out[0] += g_omega0, out[1] += g_scale0 (float64 accumulators).
+__global__ void gabor_scalar_grads_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ gy,
+                                          int64_t count, int is_first, const float* __restrict__ omega_p,
+                                          const float* __restrict__ scale_p, double* __restrict__ out) {
+  const float omega = *omega_p, s0 = *scale_p;
+  double a_om = 0.0, a_s = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    float zr, zi, wn = 0.f;
+    if (is_first) { zr = z[i]; zi = 0.f; if (w) wn = w[i] * w[i]; }
+    else { zr = z[2 * i]; zi = z[2 * i + 1]; if (w) wn = w[2 * i] * w[2 * i] + w[2 * i + 1] * w[2 * i + 1]; }
+    const float t = zr * zr + zi * zi + wn;
+    const float m = expf(-omega * zi - s0 * s0 * t);
+    float sn, cs;
+    sincosf(omega * zr, &sn, &cs);
+    const float yr = m * cs, yi = m * sn;
+    const float gr = gy[2 * i], gi = gy[2 * i + 1];
+    const float pr = yr * gr + yi * gi, pi = yr * gi - yi * gr;   // p = conj(y) g
+    a_om += double(zr * pi - zi * pr);                              // Im(conj(z) p)
+    a_s += double(t * pr);
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    a_om += __shfl_xor_sync(0xffffffffu, a_om, s);
+    a_s += __shfl_xor_sync(0xffffffffu, a_s, s);
+  }
+  __shared__ double so[32], ss[32];
+  if ((threadIdx.x & 31) == 0) { so[threadIdx.x >> 5] = a_om; ss[threadIdx.x >> 5] = a_s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0.0, y = 0.0;
+    for (int k = 0; k < int(blockDim.x >> 5); ++k) { x += so[k]; y += ss[k]; }
+    atomicAdd(out, x);
+    atomicAdd(out + 1, -2.0 * double(s0) * y);
+  }
+}
+
 }  // namespace wire

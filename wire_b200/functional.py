@@ -329,15 +329,63 @@ class GaborLayerFn(torch.autograd.Function):
                   "wire_gabor_layer_backward")
         if gx is not None:
             gx = gx.reshape(ctx.x_shape)
-        return (None, None, gx, gW, gb, gW2, gb2, None, None)
+        g_om = g_s0 = None
+        if ctx.needs_input_grad[7] or ctx.needs_input_grad[8]:   # trainable omega_0 / scale_0 (modules/wire.py:80-81)
+            acc = torch.zeros(2, dtype=torch.float64, device=flat.device)
+            zr = torch.view_as_real(z) if z.is_complex() else z
+            wr = (torch.view_as_real(w) if w.is_complex() else w) if two_d else None
+            with torch.cuda.device(flat.device):
+                check(lib.wire_gabor_scalar_grads(int(is_first), int(two_d), desc.width, zr.data_ptr(), _ptr(wr),
+                                                  torch.view_as_real(gy).data_ptr(), n, omega0.data_ptr(), scale0.data_ptr(),
+                                                  acc.data_ptr(), _stream()), "wire_gabor_scalar_grads")
+            acc = acc.float()
+            g_om = acc[0:1] if ctx.needs_input_grad[7] else None
+            g_s0 = acc[1:2] if ctx.needs_input_grad[8] else None
+        return (None, None, gx, gW, gb, gW2, gb2, g_om, g_s0)
 
 
 def gabor_layer(desc, is_first, x, weight, bias, weight2, bias2, omega0, scale0):
     return GaborLayerFn.apply(desc, is_first, x, weight, bias, weight2, bias2, omega0, scale0)
 
 
+class FinalLinearRealFn(torch.autograd.Function):
+    """Re(h W_f^T + b_f) with autograd (C ABI ``wire_final_linear_forward`` / ``_backward``): the output layer of the
+    layer-by-layer route (``modules/wire.py:156-165``), used when the fused whole-network kernels do not apply
+    (trainable omega_0 / scale_0, user-edited stacks)."""
+
+    @staticmethod
+    def forward(ctx, desc: NetDesc, h, weight, bias):
+        out = final_linear_real(desc, h, weight, bias)
+        ctx.desc, ctx.h_shape = desc, h.shape
+        ctx.save_for_backward(h, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        desc = ctx.desc
+        h, weight = ctx.saved_tensors
+        hc = h.contiguous().reshape(-1, h.shape[-1])
+        n = hc.shape[0]
+        go = _require_cuda(grad_out, "grad_out", torch.float32).reshape(n, desc.out_features)
+        weight = weight.contiguous()
+        gh = torch.empty_like(hc) if ctx.needs_input_grad[1] else None
+        gW = torch.empty_like(weight)
+        gb = torch.empty(desc.out_features, dtype=torch.complex64, device=hc.device)
+        with torch.cuda.device(hc.device):
+            check(lib.wire_final_linear_backward(ctypes.byref(desc), weight.data_ptr(), hc.data_ptr(), go.data_ptr(), n, _ptr(gh),
+                                                 gW.data_ptr(), gb.data_ptr(), _stream()), "wire_final_linear_backward")
+        if gh is not None:
+            gh = gh.reshape(ctx.h_shape)
+        return (None, gh, gW, gb)
+
+
+def final_linear_real_autograd(desc: NetDesc, h, weight, bias):
+    return FinalLinearRealFn.apply(desc, h, weight, bias)
+
+
 def final_linear_real(desc: NetDesc, h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """Re(h W^T + b) with the CUDA kernel (no autograd; the fused ``wire_net`` is the training path)."""
+    """Re(h W^T + b) with the CUDA kernel (no autograd: see ``final_linear_real_autograd``)."""
     lib = _lib.load()
     hc = _require_cuda(h, "h", torch.complex64)
     flat = hc.reshape(-1, hc.shape[-1])

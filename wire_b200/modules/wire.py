@@ -45,11 +45,17 @@ class _GaborBase(nn.Module):
             return lin.bias
         return torch.zeros(self.out_features, dtype=lin.weight.dtype, device=lin.weight.device)
 
+    @property
+    def scalars_trainable(self) -> bool:
+        return bool(self.omega_0.requires_grad or self.scale_0.requires_grad)
+
     def _check_trainable(self):
-        if self.omega_0.requires_grad or self.scale_0.requires_grad:
+        """The fused whole-network kernels and ``wire_b200.Trainer`` treat omega_0 / scale_0 as constants (every reference
+        driver uses trainable=False); trainable scalars are served by the layer-by-layer route instead."""
+        if self.scalars_trainable:
             raise NotImplementedError(
-                "trainable omega_0/scale_0 (trainable=True) is not implemented by the CUDA path yet; "
-                "every reference driver uses trainable=False (SURVEY.md §8f item 3)")
+                "trainable omega_0/scale_0 is supported by the layer-by-layer route (model(coords), model.net[i](x)) but "
+                "not by the fused Trainer (SURVEY.md §8f item 3)")
 
     def flat_params(self):
         """Parameter tensors in the order ``functional.wire_net`` expects."""
@@ -59,7 +65,6 @@ class _GaborBase(nn.Module):
         return ps + [self.omega_0, self.scale_0]
 
     def forward(self, input):
-        self._check_trainable()
         desc = F.make_desc(self.two_d, self.in_features, self.out_features, 1, 1, self.precision)
         so = self.scale_orth if self.two_d else None
         return F.gabor_layer(desc, self.is_first, input, self.linear.weight, self._bias(self.linear),
@@ -114,15 +119,17 @@ class _INRBase(nn.Module):
 
     def forward(self, coords):
         layers = list(self.net)
-        if self.hidden_layers < 1 or len(layers) != self.hidden_layers + 2:
-            # no hidden layer (or a user-edited Sequential): compose the per-layer kernels
+        if (self.hidden_layers < 1 or len(layers) != self.hidden_layers + 2
+                or any(getattr(layer, "scalars_trainable", False) for layer in layers[:-1])):
+            # no hidden layer, a user-edited Sequential, or trainable omega_0 / scale_0 (modules/wire.py:80-81): compose the
+            # per-layer kernels, each an autograd node of its own
             x = coords
             for layer in layers[:-1]:
                 x = layer(x)
             desc = F.make_desc(self.two_d, self.in_features, self.width, 1, self.out_features, self.precision)
+            if torch.is_grad_enabled() and (x.requires_grad or layers[-1].weight.requires_grad):
+                return F.final_linear_real_autograd(desc, x, layers[-1].weight, layers[-1].bias)
             return F.final_linear_real(desc, x, layers[-1].weight, layers[-1].bias)
-        for layer in layers[:-1]:
-            layer._check_trainable()
         desc = F.make_desc(self.two_d, self.in_features, self.width, self.hidden_layers, self.out_features,
                            self.precision)
         return F.wire_net(desc, coords, self.flat_params())
