@@ -307,6 +307,9 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.a_fmt = J.a_elem == kElemBF16 ? int(sm100::kFmtBF16) : int(sm100::kFmtF16);
   P.l2_prefetch = getenv("WIRE_B200_L2PF") ? 1 : 0;  // measured: no gain (0.165 vs 0.154 ms), the fill path is L2->SM bound
   P.b_fmt = P.a_fmt;
+  // sweep direction: reversing the last forward layer so that it starts on the rows the previous layer wrote last (still in
+  // L2) took 7 us off that launch under per-kernel timing but nothing off the captured step (1.0657 vs 1.0658 ms): off.
+  P.reverse = (op16 && getenv("WIRE_B200_REV") && J.e.fuse_final) ? 1 : 0;
   const int kbox = op16 ? 64 : 32;  // one 128-byte swizzle row of K columns
   for (int i = 0; i < 2; ++i) {
     const int src = (J.k_cols[i] > 0) ? i : 0;

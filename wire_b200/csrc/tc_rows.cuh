@@ -55,6 +55,7 @@ struct RowsParams {
   int o_fmt[3];    // element type of each STORED output slot (sm100_host::ElemType): f32 tiles are 32x32x4 B with the
                    // 128 B swizzle, 16-bit tiles (FP16 saved z / y, BF16 gradients) are dense 32x32x2 B
   int l2_prefetch;   // tc_rows16: the producer prefetches the next work unit's A rows into L2
+  int reverse;       // tc_rows16: walk the work units from the last row tile to the first (see api.cu: sweep directions)
   int a_fmt, b_fmt;  // OP16 kernels: operand formats of the kind::f16 MMA (sm100::kFmtF16 / kFmtBF16)
   int n_in;        // TMA-prefetched epilogue inputs (0, 1 = z, 2 = z and w)
   uint32_t staging_off;  // byte offsets inside dynamic smem (from the 1 KB aligned base)

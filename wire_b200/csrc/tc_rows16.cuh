@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   constexpr bool pair = PAIR;
   const bool leader = crank == 0;
   unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
+  // work unit of iteration `it`; reversed sweeps mirror the valid units (phantom units past the end stay phantom)
+  auto unit_of = [&](int it) { const int u = it * n_clusters + my_cluster; return (P.reverse && u < n_units) ? n_units - 1 - u : u; };
 
   // ---- shared parameter tables (zero padded: the epilogue needs no column checks) ----
   //  fwd  : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8] (wr[4], wi[4]) | fin exchange (FUSE)
@@ -187,14 +189,14 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       const long long t_begin = WIRE_CLK();
       for (int jb = 0; jb < n_jobs; ++jb) {
         const int it = jb / P.slices, sl = jb % P.slices;
-        const int unit = it * n_clusters + my_cluster;
+        const int unit = unit_of(it);
         const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
         const int brow = (unit % P.n_blocks) * P.nb + sl * P.ns + crank * P.b_box_rows;
         const uint64_t a_policy = (sl == P.slices - 1 && (unit % P.n_blocks) == P.n_blocks - 1) ? kEvictFirst : kEvictLast;
         if (sl == 0 && P.l2_prefetch && it + 1 < n_iters) {
           // pull the NEXT work unit's A rows into L2 now: their demand loads then see L2 latency instead of HBM latency
           // (the pipeline holds only ~5 stages; HBM latency under load starved the MMA thread, mma_wait_full 52 %)
-          const int unit_n = (it + 1) * n_clusters + my_cluster;
+          const int unit_n = unit_of(it + 1);
           if ((unit_n % P.n_blocks) == 0) {
             const int row_n = ((unit_n / P.n_blocks) * C + crank) * kTileRows;
             for (int kc = 0; kc < kc0; ++kc) tma_prefetch_l2_2d(&P.a_map[0], kc * kKC, row_n);
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
     for (int jb = 0; jb < n_jobs; ++jb) {
       const int it = jb / P.slices, sl = jb % P.slices;
       const int buf = jb & 1;
-      const int unit = it * n_clusters + my_cluster;
+      const int unit = unit_of(it);
       const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
       const int blk = unit % P.n_blocks;
       const int row = row0 + q * 32 + lane;
