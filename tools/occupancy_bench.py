@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precision", default="mixed16")
     ap.add_argument("--no-iou", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -64,13 +65,13 @@ def main():
     occupied = float(vol.mean())
     imten = vol.reshape(N, 1)
     batcher = wire_b200.GridBatcher((S, S, S), imten, linspace="numpy")
-    torch.manual_seed(0)
+    torch.manual_seed(args.seed)
     model = wire_b200.get_INR(nonlin="wire", in_features=3, hidden_features=300, hidden_layers=3, out_features=1,
                               first_omega_0=20.0, hidden_omega_0=20.0, scale=10.0, precision=args.precision).to(dev)   # wire_occupancy.py:43-45,107-116
     if world > 1:
         parallel.broadcast_parameters(model)
     tr = wire_b200.Trainer(model, lr=5e-3)
-    gen = torch.Generator(device=dev).manual_seed(1234)      # same seed, same device type: same permutation on every rank
+    gen = torch.Generator(device=dev).manual_seed(1234 + args.seed)      # same seed, same device type: same permutation on every rank
     perm = torch.randperm(N, device=dev, generator=gen)
     per_step = args.chunk * (world if args.scaling == "weak" else 1)
     est = torch.zeros(N, 1, device=dev)
@@ -126,7 +127,7 @@ def main():
                           "algorithmic_tflops": per_step * flop / ms * 1e-9, "frac_nominal_tf32_per_gpu": per_step * flop / ms * 1e-9 / 1100.0 / world,
                           "precision": args.precision, "exchange": "peer" if tr.peer is not None else ("nccl" if world > 1 else None),
                           "occupied_fraction": occupied, "final_chunk_loss_this_rank": float(loss),
-                          "iou_after_steps": iou, "steps_done": tr.steps_done}), flush=True)
+                          "iou_after_steps": iou, "steps_done": tr.steps_done, "seed": args.seed}), flush=True)
     tr.close()
     if world > 1:
         dist.destroy_process_group()
