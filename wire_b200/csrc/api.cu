@@ -141,6 +141,11 @@ bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, 
   return false;
 }
 
+// wire2d forward on the 16-bit path: two column blocks of [z half | w half] = 128 + 128 accumulator columns (M = 128, the
+// SISR width) are run as the two N-SLICES of one work unit (same packed-weight layout, TMEM 2 x 256 columns), so the whole
+// output row stays in one CTA and the final Linear can be fused into the last layer's epilogue like for wire.
+bool merge_2d_blocks(const Blocking& b, bool two_d, bool op16) { return two_d && op16 && b.n_blocks == 2 && b.nb == 256 && b.nbh == 128; }
+
 // ------------------------------------------------------------------------------------------
 // workspace layout
 // ------------------------------------------------------------------------------------------
@@ -203,7 +208,7 @@ int make_layout(const wire_net_desc* d, int64_t n, int training, Layout& L) {
   Blocking bf;
   if (!choose_blocking(L.two_m, d->two_d != 0, d->two_d ? 6 : 2, bf, 0, d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, true, false, mixed))
     return fail("no tile configuration for width %d", d->width);
-  L.fuse_final = bf.n_blocks == 1 && d->out_features <= kMaxOut;
+  L.fuse_final = (bf.n_blocks == 1 || merge_2d_blocks(bf, d->two_d != 0, mixed)) && d->out_features <= kMaxOut;
   size_t off = 0;
   auto act = [&](int elem) { return align_up(size_t(L.rows) * L.P * sm100_host::elem_bytes(elem), 1024); };
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
@@ -296,7 +301,9 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   P.n_blocks = J.blk.n_blocks;
   P.e = J.e;
   const bool op16 = J.a_elem != kElemF32;
-  const size_t smem = op16 ? rows16_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
+  int nb = J.blk.nb;
+  if (J.mode == MODE_GABOR2D_FWD && J.e.fuse_final && merge_2d_blocks(J.blk, true, op16)) { P.n_blocks = 1; nb = 2 * J.blk.nb; }
+  const size_t smem = op16 ? rows16_configure(P, nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
                                               cluster_size())
                            : rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
                                             cluster_size(), J.gen != 0);

@@ -29,7 +29,9 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
   if (nb <= 256) { P.slices = 1; P.ns = nb; P.buf_cols = 256; }
   else {
     // two N-slices, each with its own K loop and TMEM buffer (the MMAs of one overlap the epilogue of the other)
-    if (mode == MODE_GABOR2D_FWD || nb % 64 || nb > 512) return 0;
+    if (nb % 64 || nb > 512) return 0;
+    // wire2d forward: a slice is one column block [z half | w half] of nbh + nbh columns, so two slices need nb == 4 * nbh
+    if (mode == MODE_GABOR2D_FWD && nb != 4 * nbh) return 0;
     P.slices = 2; P.ns = nb / 2; P.buf_cols = nb / 2;
   }
   if (P.ns % 16 || (P.ns / cluster) % 8) return 0;
@@ -138,7 +140,9 @@ inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, i
   if (cluster != 1 && cluster != 2) return 0;
   if (nb <= 256) { P.slices = 1; P.ns = nb; P.buf_cols = 256; }
   else {
-    if (mode == MODE_GABOR2D_FWD || nb % 64 || nb > 512) return 0;
+    if (nb % 64 || nb > 512) return 0;
+    // wire2d forward: a slice is one column block [z half | w half] of nbh + nbh columns, so two slices need nb == 4 * nbh
+    if (mode == MODE_GABOR2D_FWD && nb != 4 * nbh) return 0;
     P.slices = 2; P.ns = nb / 2; P.buf_cols = nb / 2;
   }
   if (P.ns % 16 || (P.ns / cluster) % 8) return 0;
