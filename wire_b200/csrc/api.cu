@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "../../include/wire_b200.h"
 #include "simt_kernels.cuh"
@@ -37,6 +38,18 @@ int fail(const char* fmt, ...) {
     int r_ = (expr);       \
     if (r_) return r_;     \
   } while (0)
+
+
+// <<<>>> with the programmatic-dependent-launch attribute (tc_launch.cuh: add_pdl_attr) for kernels that call sm100::pdl_wait()
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr; cfg.numAttrs = 0;
+  add_pdl_attr(attr, cfg.numAttrs);
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 int g_sm_count = 0;
 int g_cc_major = -1;
@@ -441,13 +454,13 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
     const int rpb = int((n + nblk - 1) / nblk);
     const int grid = int((n + rpb - 1) / rpb);
     ProfScope prof(K_FIRST_FWD, st);
+    const float* nul = nullptr;
     if (d->two_d)
-      first_fwd16_kernel<true><<<grid, 256, smem, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, p.weight2, p.bias2, p.omega0, p.scale0,
-                                                         reinterpret_cast<__half*>(y), y_pitch, rpb);
+      CU_OK(launch_pdl(first_fwd16_kernel<true>, dim3(grid), dim3(256), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, p.weight2,
+                       p.bias2, p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb));
     else
-      first_fwd16_kernel<false><<<grid, 256, smem, st>>>(coords, int(n), in_f, d->width, p.weight, p.bias, nullptr, nullptr, p.omega0, p.scale0,
-                                                          reinterpret_cast<__half*>(y), y_pitch, rpb);
-    CU_OK(cudaGetLastError());
+      CU_OK(launch_pdl(first_fwd16_kernel<false>, dim3(grid), dim3(256), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, nul, nul,
+                       p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb));
     return 0;
   }
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
@@ -512,8 +525,12 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
         if (per_sm < 1) per_sm = 1;
         int grid16 = g_sm_count * per_sm;
         if (grid16 > n_tiles) grid16 = n_tiles;
-        kern<<<grid16, threads, smem16, st>>>(T);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid16); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem16; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        cfg.attrs = attr; cfg.numAttrs = 0;
+        add_pdl_attr(attr, cfg.numAttrs);
+        return cudaLaunchKernelEx(&cfg, kern, T);
       };
       cudaError_t e = cudaErrorInvalidValue;
       const bool small = threads <= 512;
@@ -576,8 +593,8 @@ int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t 
     if (in_f <= 3 && M <= 256 && (g_pitch % 8) == 0) {
       const int nblk = int(n < int64_t(2 * g_sm_count) * 256 ? (n + 255) / 256 : 2 * g_sm_count);
       const int rpb = int((n + nblk - 1) / nblk);
-      first_wgrad16_kernel<<<int((n + rpb - 1) / rpb), kFirstWgrad16Threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gz0), g_pitch, coords,
-                                                                                       int(n), in_f, M, gW, gb, rpb);
+      CU_OK(launch_pdl(first_wgrad16_kernel, dim3(int((n + rpb - 1) / rpb)), dim3(kFirstWgrad16Threads), 0, st,
+                       reinterpret_cast<const __nv_bfloat16*>(gz0), g_pitch, coords, int(n), in_f, M, gW, gb, rpb));
     } else {
       first_wgrad_kernel<true><<<grid, 256, 0, st>>>(gz0, g_pitch, coords, int(n), in_f, M, gW, gb, kRowsPerBlock);
     }
@@ -651,8 +668,7 @@ int pack_all16(const wire_net_desc* d, const wire_net_params* p, const Layout& L
   ProfScope prof(K_PACK, st);
   int gx = (max_total + 255) / 256;
   if (gx > 8 * g_sm_count) gx = 8 * g_sm_count;
-  pack_all16_kernel<<<dim3(gx, J.n), 256, 0, st>>>(J);
-  CU_OK(cudaGetLastError());
+  CU_OK(launch_pdl(pack_all16_kernel, dim3(gx, J.n), dim3(256), 0, st, J));
   return 0;
 }
 
@@ -1163,9 +1179,8 @@ int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 592 ? 592 : g64);
   ProfScope prof(K_ADAM, st);
-  adam_dev_kernel<<<grid, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
-                                        reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev);
-  CU_OK(cudaGetLastError());
+  CU_OK(launch_pdl(adam_dev_kernel, dim3(grid), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
+                   reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev));
   return 0;
 }
 
@@ -1176,8 +1191,7 @@ int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, fl
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
   ProfScope prof(K_MSE, st);
-  mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss, count);
-  CU_OK(cudaGetLastError());
+  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, loss, count));
   return 0;
 }
 
@@ -1190,8 +1204,7 @@ int wire_mse_loss_grad_n(const float* pred, const float* target, int64_t count, 
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
   ProfScope prof(K_MSE, st);
-  mse_grad_kernel<<<grid, 256, 0, st>>>(pred, target, count, grad_out, loss, count_global);
-  CU_OK(cudaGetLastError());
+  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, loss, count_global));
   return 0;
 }
 

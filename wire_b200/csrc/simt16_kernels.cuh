@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restric
   const int row0 = blockIdx.x * rows_per_block;
   int rows = n - row0;
   rows = rows > rows_per_block ? rows_per_block : rows;
+  sm100::pdl_trigger();
   if (rows <= 0) return;
   for (int k = threadIdx.x; k < 4 * nq; k += blockDim.x) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restric
     if constexpr (TWO_D) tab2[(k & 3) * nq + (k >> 2)] = t2;
   }
   __syncthreads();
+  sm100::pdl_wait();  // parameters only above; coords and the y buffer (still read by last step's kernels) below
   const GaborConst2 G2 = make_gabor_const2(make_gabor_const(__ldg(omega_p), __ldg(scale_p)));
   const int items = rows * nq;
   // (r, q) of this thread's first item and the per-step increment, without a division in the loop
@@ -160,6 +162,8 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == n_cw) {
     // ===================== I/O warp =====================
@@ -321,6 +325,8 @@ __global__ void __launch_bounds__(kFirstWgrad16Threads) first_wgrad16_kernel(con
   const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int range0 = blockIdx.x * rows_per_block;
   int range1 = range0 + rows_per_block;
   range1 = range1 > n ? n : range1;

@@ -108,6 +108,8 @@ struct PackJobs {
   int n, M_out, K_in;
 };
 __global__ void pack_all16_kernel(const __grid_constant__ PackJobs J) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();  // the packed matrices are still read by the previous step's backward kernels
   const PackJob& j = J.job[blockIdx.y];
   const int total = j.n_blocks * j.nb * j.k_pad_total;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -382,6 +384,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                 int64_t count, const float* __restrict__ lr_ptr, float b1, float b2, float eps, float wd,
                                 long long* __restrict__ step_ptr, float grad_scale, unsigned int* __restrict__ done_counter) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const long long step = *step_ptr + 1;
   const float lr = *lr_ptr;
   const float bc1 = 1.0f - powf(b1, float(step));
@@ -411,6 +415,8 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 // a shard of it, so that the ranks' gradients and losses simply add up to those of the global mean)
 __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
                                 float* __restrict__ grad, float* __restrict__ loss, int64_t count_norm) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   float local = 0.f;
   const float inv = 1.0f / float(count_norm);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {

@@ -360,6 +360,15 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running.  pdl_trigger(): this CTA no longer blocks the dependent grid from being scheduled (it still cannot
+// become resident before resources free up).  pdl_wait(): returns once the predecessor grid has COMPLETED and its memory
+// is visible — everything that reads tensors written by earlier kernels comes after it; only parameter tables (written
+// before the step started), barrier / TMEM set-up and descriptor prefetches come before.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace sm100
 
 // ------------------------------------------------------------------------------------------

@@ -129,6 +129,19 @@ inline cudaError_t launch_rows(int mode, const RowsParams& P, size_t smem, int s
   return cudaErrorInvalidValue;
 }
 
+// programmatic dependent launch for the kernels that call sm100::pdl_wait() (WIRE_B200_PDL=0 turns it off)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("WIRE_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+inline void add_pdl_attr(cudaLaunchAttribute* attr, unsigned& n) {
+  if (!pdl_enabled()) return;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  ++n;
+}
+
 // ---- 16-bit row-tile kernels (tc_rows16.cuh): 16 epilogue warps, 2 KB staging tiles, final-Linear exchange in dynamic smem ----
 inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, int n_in = 0, int out_cols = 0,
                                int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1) {
@@ -184,7 +197,7 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
   cfg.blockDim = dim3(kRows16Threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
@@ -204,6 +217,7 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
   if (clusters > units) clusters = units;
   if (clusters <= 0) return cudaSuccess;
   cfg.gridDim = dim3(clusters * C);
+  add_pdl_attr(attr, cfg.numAttrs);
   return cudaLaunchKernelEx(&cfg, tc_rows16_kernel<MODE, PAIR, FUSE>, P);
 }
 template <int MODE, bool FUSE = false>
@@ -276,13 +290,14 @@ inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_
   cfg.blockDim = dim3(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = PAIR ? 1 : 0;
+  add_pdl_attr(attr, cfg.numAttrs);
   return cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PAIR, GEN, OP16>, P);
 }
 inline cudaError_t launch_wgrad(const WgradParams& P, size_t smem, cudaStream_t st, bool gen = false, bool op16 = false) {

@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   if (pair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();  // the next kernel of the step may be scheduled (it becomes resident only as these CTAs exit)
+  pdl_wait();     // everything above read parameters only; the tensors of earlier kernels are read below
 
   if (warp == 0) {
     // ===================== TMA producer =====================

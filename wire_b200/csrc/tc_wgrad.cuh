@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // x / g_z tiles (and the gradient buffers this kernel accumulates into) belong to earlier kernels
 
   if (n_chunks > 0) {
     if (warp == 0) {
