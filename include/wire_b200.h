@@ -158,6 +158,13 @@ int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, fl
  * (criterion = MSELoss over the whole chunk, wire_occupancy.py:149) whatever the shard sizes. */
 int wire_mse_loss_grad_n(const float* pred, const float* target, int64_t count, int64_t count_global, float* grad_out,
                          float* loss, void* stream);
+/* Same, with the loss kept in a ring on the device: the loss of training step s = *step_dev (the optimiser-step counter of
+ * wire_adam_step_dev / _peer) is accumulated into loss_ring[s % ring_n] and slot (s+1) % ring_n is cleared for the next
+ * step; the host may read a step's loss at any time during the following ring_n - 1 steps (the reference reads
+ * loss.item() every chunk, wire_occupancy.py:156 — here without a reset kernel and without stalling the stream).
+ * loss_ring must start zeroed. */
+int wire_mse_loss_grad_ring(const float* pred, const float* target, int64_t count, int64_t count_global, float* grad_out,
+                            float* loss_ring, int32_t ring_n, const int64_t* step_dev, void* stream);
 
 /* ---- data-parallel gradient exchange fused with Adam, over NVLink peer memory ----------------
  * The reference is single-GPU; its chunked loops (wire_occupancy.py:137-154) shard by coordinate batch, and the only

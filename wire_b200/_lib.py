@@ -74,6 +74,7 @@ SIGNATURES = {
                                      c_float, c_void_p, c_float, c_void_p, c_void_p]),
     "wire_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "wire_mse_loss_grad_n": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "wire_mse_loss_grad_ring": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "wire_peer_header_bytes": (c_size_t, []),
     "wire_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), c_void_p]),
     "wire_peer_open": (c_int32, [c_void_p, POINTER(c_void_p)]),

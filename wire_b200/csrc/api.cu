@@ -1191,7 +1191,8 @@ int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, fl
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
   ProfScope prof(K_MSE, st);
-  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, loss, count));
+  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, loss, count, (float*)nullptr, 0,
+                   (const long long*)nullptr));
   return 0;
 }
 
@@ -1204,7 +1205,23 @@ int wire_mse_loss_grad_n(const float* pred, const float* target, int64_t count, 
   int64_t g64 = (count + 255) / 256;
   const int grid = int(g64 > 1184 ? 1184 : g64);
   ProfScope prof(K_MSE, st);
-  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, loss, count_global));
+  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, loss, count_global, (float*)nullptr, 0,
+                   (const long long*)nullptr));
+  return 0;
+}
+
+int wire_mse_loss_grad_ring(const float* pred, const float* target, int64_t count, int64_t count_global, float* grad_out, float* loss_ring,
+                            int32_t ring_n, const int64_t* step_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!pred || !target || !grad_out || !loss_ring || !step_dev) return fail("null argument");
+  if (ring_n < 2) return fail("loss ring needs at least 2 slots");
+  if (count <= 0) return fail("empty batch: clear the next ring slot on the host side instead");
+  if (count_global < count) return fail("count_global %lld < count %lld", (long long)count_global, (long long)count);
+  int64_t g64 = (count + 255) / 256;
+  const int grid = int(g64 > 1184 ? 1184 : g64);
+  ProfScope prof(K_MSE, st);
+  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, pred, target, count, grad_out, (float*)nullptr, count_global, loss_ring,
+                   int(ring_n), reinterpret_cast<const long long*>(step_dev)));
   return 0;
 }
 

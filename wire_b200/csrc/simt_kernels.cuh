@@ -413,10 +413,19 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 // grad = 2 (pred - target) / count ; loss += sum (pred-target)^2 / count
 // count_norm: the element count the mean is taken over (== count on one GPU; the GLOBAL batch's count when this rank holds
 // a shard of it, so that the ranks' gradients and losses simply add up to those of the global mean)
+// Loss ring (ring != nullptr): the loss of training step s (= *step_ptr, the count of completed optimiser steps) is
+// accumulated into ring[s % ring_n] and the NEXT slot is cleared for step s + 1, so the host can read a step's loss any time
+// within the following ring_n - 1 steps without a device-side reset kernel and without stalling the compute stream.
 __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
-                                float* __restrict__ grad, float* __restrict__ loss, int64_t count_norm) {
+                                float* __restrict__ grad, float* __restrict__ loss, int64_t count_norm,
+                                float* __restrict__ ring = nullptr, int ring_n = 0, const long long* __restrict__ step_ptr = nullptr) {
   sm100::pdl_trigger();
   sm100::pdl_wait();
+  if (ring) {
+    const long long s = *step_ptr;
+    loss = ring + (s % ring_n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ring[(s + 1) % ring_n] = 0.f;
+  }
   float local = 0.f;
   const float inv = 1.0f / float(count_norm);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {

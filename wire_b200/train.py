@@ -92,6 +92,8 @@ class Trainer:
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_ring = torch.zeros(256, dtype=torch.float32, device=dev)   # loss of optimiser step s at [s % 256]
+        self._issued = 0                                                        # optimiser steps issued (host mirror of step_dev)
         self._n = None
         self._key = None
         self._n_global = None
@@ -170,20 +172,21 @@ class Trainer:
     def _fwd_bwd(self) -> None:
         d, n, st = self.desc, self._n, F._stream()
         lib = self.lib
-        self.loss_dev.zero_()
+        if self._pool is not None:
+            self.loss_dev.zero_()
         check(lib.wire_net_forward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.out_buf.data_ptr(),
                                    self.ws.data_ptr(), self.ws.numel(), 1, st), "wire_net_forward")
         if self._pool is not None:
             Hh, Ww, sc = self._pool
             check(lib.wire_avgpool_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), Hh, Ww, d.out_features, sc,
                                                  self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_avgpool_mse_loss_grad")
-        elif self._n_global is None:
-            check(lib.wire_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
-                                         self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_mse_loss_grad")
         else:
-            check(lib.wire_mse_loss_grad_n(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
-                                           self._n_global * d.out_features, self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st),
-                  "wire_mse_loss_grad_n")
+            # the loss of optimiser step s lands in loss_ring[s % R] (and the next slot is cleared) — no reset kernel, and the
+            # host can read it for the next R - 1 steps without putting a copy on the compute stream's critical path
+            n_norm = n if self._n_global is None else self._n_global
+            check(lib.wire_mse_loss_grad_ring(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
+                                              n_norm * d.out_features, self.gout_buf.data_ptr(), self.loss_ring.data_ptr(),
+                                              self.loss_ring.numel(), self.step_dev.data_ptr(), st), "wire_mse_loss_grad_ring")
         if self.peer is not None:
             self._peer_wait()
         check(lib.wire_net_backward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.gout_buf.data_ptr(),
@@ -240,8 +243,11 @@ class Trainer:
             self._peer_wait()
         self.flat_grad.zero_()
         self.loss_dev.zero_()
+        R = self.loss_ring.numel()
+        self.loss_ring[(self._issued + 1) % R].zero_()   # what the loss kernel of a non-empty step does for the next slot
         self._n_global = 1  # gradients add up (scale 1)
         self._exchange_and_adam()
+        self._issued += 1
 
     def step(self, coords: torch.Tensor, target: torch.Tensor, n_global: Optional[int] = None) -> torch.Tensor:
         """One training iteration on (coords [..., in], target [..., out]); host or device tensors.
@@ -265,12 +271,20 @@ class Trainer:
         with torch.cuda.device(self.device):
             if n == 0:
                 self._empty_step()
-                return self.loss_dev[0]
+                return self._loss_of_last_step()
             if (n, n_global) != self._key:
                 self._prepare(n, n_global)
             self._load_inputs(coords.reshape(n, d.in_features), target.reshape(n_target, d.out_features))
             self._run()
-        return self.loss_dev[0]
+            self._issued += 1
+        return self._loss_of_last_step()
+
+    def _loss_of_last_step(self) -> torch.Tensor:
+        """Device scalar holding the loss of the step just issued: a slot of the loss ring, valid until ``len(loss_ring) - 1``
+        further steps have been issued (copy it, e.g. to pinned memory on a side stream, if it is needed for longer)."""
+        if self._pool is not None:
+            return self.loss_dev[0]
+        return self.loss_ring[(self._issued - 1) % self.loss_ring.numel()]
 
     def _load_inputs(self, coords: torch.Tensor, target: torch.Tensor) -> None:
         """Bring this step's inputs into the step's fixed input buffers.  Device tensors: one D2D copy each.  Pinned host
@@ -320,14 +334,15 @@ class Trainer:
         with torch.cuda.device(self.device):
             if n == 0:
                 self._empty_step()
-                return self.loss_dev[0]
+                return self._loss_of_last_step()
             if (n, n_global) != self._key:
                 self._prepare(n, n_global)
             batcher.assemble_into(self.coords_buf, self.target_buf, idx, start, count)
             self._run()
+            self._issued += 1
             if rec is not None:
                 batcher.scatter(rec, self.out_buf, idx, start, count)
-        return self.loss_dev[0]
+        return self._loss_of_last_step()
 
     def close(self) -> None:
         """Release the peer-mapped gradient buffer (collective: every rank must call it)."""
