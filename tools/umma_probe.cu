@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, int n_cols)
 }
 
 static int g_sms = 148;
+static bool g_skip_check = false;
 static int g_cluster = 1;
 
 static bool test_rows(int n_rows, int two_m, bool time_it) {
@@ -238,7 +239,7 @@ static bool test_wgrad(int n_rows, int k_in, int m_out, bool time_it) {
   CK(cudaMemcpy(Bv.data(), dBias, Bv.size() * 4, cudaMemcpyDeviceToHost));
   double max_err = 0, max_ref = 0; long bad = 0;
   const int jstep = m_out > 64 ? 7 : 1, kstep = k_in > 64 ? 5 : 1;
-  for (int j = 0; j < m_out; j += jstep) {
+  for (int j = 0; j < (g_skip_check ? 0 : m_out); j += jstep) {
     for (int k = 0; k < k_in; k += kstep) {
       double re = 0, im = 0;
       for (int n = 0; n < n_rows; ++n) {
@@ -394,7 +395,7 @@ static bool test_wgrad16(int n_rows, int k_in, int m_out, int x_elem, int g_elem
   CK(cudaMemcpy(Bv.data(), dBias, Bv.size() * 4, cudaMemcpyDeviceToHost));
   double max_err = 0, max_ref = 0; long bad = 0;
   const int jstep = m_out > 64 ? 7 : 1, kstep = k_in > 64 ? 5 : 1;
-  for (int j = 0; j < m_out; j += jstep) {
+  for (int j = 0; j < (g_skip_check ? 0 : m_out); j += jstep) {
     for (int k = 0; k < k_in; k += kstep) {
       double re = 0, im = 0;
       for (int n = 0; n < n_rows; ++n) {
@@ -425,6 +426,23 @@ static bool test_wgrad16(int n_rows, int k_in, int m_out, int x_elem, int g_elem
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
     printf("[wgrad16] %.3f ms  %.1f TFLOP/s (algorithmic 8MK)  read traffic %.1f GB/s\n", ms, 8.0 * n_rows * double(m_out) * k_in / ms * 1e-9,
            (double(n_rows) * (xc + gc) * 2) / ms * 1e-6);
+    if (g_skip_check) {  // per-CTA phase times (cycles): prologue, K loop, epilogue, teardown
+      unsigned long long* dd; CK(cudaMalloc(&dd, 8 * 8 * 1024)); CK(cudaMemset(dd, 0, 8 * 8 * 1024));
+      P.dbg = dd;
+      CK(wire::launch_wgrad(P, smem, 0, false, true));
+      CK(cudaDeviceSynchronize());
+      std::vector<unsigned long long> hd(8 * 1024);
+      CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
+      double ph[4] = {0, 0, 0, 0}; int cnt = 0;
+      unsigned long long first = ~0ull, last = 0;
+      for (int b = 0; b < 1024; ++b) if (hd[b * 8]) {
+        for (int k = 0; k < 4; ++k) ph[k] += double(hd[b * 8 + k + 1] - hd[b * 8 + k]);
+        ++cnt; if (hd[b * 8] < first) first = hd[b * 8]; if (hd[b * 8 + 4] > last) last = hd[b * 8 + 4];
+      }
+      printf("   [dbg] CTAs %d: prologue %.0f  K loop %.0f  epilogue %.0f  teardown %.0f cycles (avg); first entry -> last exit %.0f\n", cnt,
+             ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, ph[3] / cnt, double(last - first));
+      P.dbg = nullptr; cudaFree(dd);
+    }
   }
   cudaFree(dX); cudaFree(dG); cudaFree(dW); cudaFree(dBias);
   return bad == 0;
@@ -518,6 +536,11 @@ int main(int argc, char** argv) {
   printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, g_sms);
   srand(1234);
   if (argc > 1 && !strcmp(argv[1], "16")) return main16();
+  if (argc > 1 && !strcmp(argv[1], "wn")) {  // wgrad time against the row count: fixed cost (prologue, split-K atomics epilogue) vs per-row cost
+    g_cluster = 2; g_skip_check = true;
+    for (int k : {1, 2, 4, 8, 16, 32, 64, 111}) test_wgrad16(37 * 64 * k, 212, 212, 1, 2, true);
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "g16")) {
     g_cluster = 2;
     time_rows_gabor16(262144, 424, false);

@@ -59,6 +59,7 @@ struct WgradParams {
   int gen_two_d;
   uint32_t gen_tab_off;  // byte offset of the {w0[0..2], b0} tables inside dynamic smem
   int gen_tab_feats;     // padded feature count of the tables
+  unsigned long long* dbg;  // optional per-CTA time stamps [8] (tools/umma_probe): entry, prologue done, K loop done, epilogue done
 };
 
 // OP16: x is FP16 and g is BF16 (formats in P.x_fmt / P.g_fmt), both still MN-major; tiles are 64-column blocks of
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
 
   constexpr int C = PAIR ? 2 : 1;
   const bool conv = OP16 && P.x_conv;
+  unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 64) dbg[0] = clock64();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int crank = PAIR ? int(cluster_ctarank()) : 0;
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();
   pdl_wait();  // x / g_z tiles (and the gradient buffers this kernel accumulates into) belong to earlier kernels
+  if (dbg && threadIdx.x == 64) dbg[1] = clock64();
 
   if (n_chunks > 0) {
     if (warp == 0) {
@@ -343,24 +347,35 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
       const int nchunks = (nvalid + 31) / 32;
       mbar_wait(smem_u32(&bar_tmem_full), 0);
       tc_fence_after();
+      if (dbg && threadIdx.x == 64) dbg[2] = clock64();
+      // (Starting every K split at a different chunk, so that the ~37 CTAs adding into the same gradient entries do not walk
+      // the same L2 lines in step, changed nothing: the epilogue was bound by its own instruction stream, see below.)
       for (int ch = 0; ch < nchunks; ++ch) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + ch * 32, raw);
         tmem_wait_ld();
         const int r0 = nblk * P.nb + ch * 32;
+        // all 16 lane-pair exchanges first (independent shuffles in flight together), then straight-line reductions:
+        // the per-element branches of the first version serialised shuffle -> branch -> address -> red (80 cycles each)
+        float other[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a0 = __uint_as_float(raw[2 * i]);
-          const float a1 = __uint_as_float(raw[2 * i + 1]);
-          const float other = __shfl_xor_sync(0xffffffffu, a1, 1);
-          const int r = r0 + 2 * i;
-          if (r < P.g_cols) {
-            if (c < two_k) {
-              const float val = (lane & 1) ? (other - a0) : (a0 + other);
-              atomicAdd(gW + size_t(r >> 1) * two_k + c, val);
-            } else if (c == two_k) {
-              atomicAdd(gB + r, a0);
-              atomicAdd(gB + r + 1, a1);
+        for (int i = 0; i < 16; ++i) other[i] = __shfl_xor_sync(0xffffffffu, __uint_as_float(raw[2 * i + 1]), 1);
+        if (c < two_k) {
+          float* dst = gW + size_t(r0 >> 1) * two_k + c;
+          const int n_ok = (P.g_cols - r0 + 1) >> 1;  // complex outputs of this chunk inside the matrix (warp-uniform)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = __uint_as_float(raw[2 * i]);
+            const float val = (lane & 1) ? (other[i] - a0) : (a0 + other[i]);
+            if (i < n_ok) atomicAdd(dst + size_t(i) * two_k, val);
+          }
+        } else if (c == two_k) {  // the "ones" column: one lane of one CTA per tile
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = r0 + 2 * i;
+            if (r < P.g_cols) {
+              atomicAdd(gB + r, __uint_as_float(raw[2 * i]));
+              atomicAdd(gB + r + 1, __uint_as_float(raw[2 * i + 1]));
             }
           }
         }
@@ -368,6 +383,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
     }
   }
 
+  if (dbg && threadIdx.x == 64) dbg[3] = clock64();
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();
@@ -375,6 +391,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
     tc_fence_after();
     if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
+  if (dbg && threadIdx.x == 64) dbg[4] = clock64();
 }
 
 }  // namespace wire
