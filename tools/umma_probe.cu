@@ -188,10 +188,11 @@ static void time_rows_gabor(int n_rows, int two_m) {
   std::vector<unsigned long long> hd(8 * 1024);
   CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
   printf("[gabor_fwd] cluster=%d n_rows=%d 2M=%d nb=%d slices=%d stages=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.slices, P.stages, smem);
-  const char* names[8] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in"};
-  for (int k = 0; k < 8; ++k) {
+  const char* names[12] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in",
+                           "t_prologue", "t_producer_done", "t_cta_done", "t_exit"};
+  for (int k = 0; k < 12; ++k) {
     double sum = 0; int cnt = 0;
-    for (int b = 0; b < 1024; ++b) if (hd[b * 8 + k]) { sum += double(hd[b * 8 + k]); ++cnt; }
+    for (int b = 0; b < 1024; ++b) if (hd[b * 16 + k]) { sum += double(hd[b * 16 + k]); ++cnt; }
     printf("   [dbg] %-16s avg %.0f cycles over %d CTAs\n", names[k], cnt ? sum / cnt : 0.0, cnt);
   }
   P.dbg = nullptr;
@@ -479,18 +480,25 @@ static void time_rows_gabor16(int n_rows, int two_m, bool fuse_final, int mask_o
   ok &= sm100_host::make_tmap_2d_t(&P.o_map[1], dZ, n_rows, two_m, pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1);
   P.o_map[2] = P.o_map[0]; P.z_map[0] = P.a_map[0]; P.z_map[1] = P.a_map[0];
   if (!ok || !smem) { printf("gabor16 setup failed\n"); return; }
-  unsigned long long* dd; CK(cudaMalloc(&dd, 8 * 8 * 1024)); CK(cudaMemset(dd, 0, 8 * 8 * 1024));
+  unsigned long long* dd; CK(cudaMalloc(&dd, 16 * 8 * 1024)); CK(cudaMemset(dd, 0, 16 * 8 * 1024));
   P.dbg = dd;
   for (int i = 0; i < 3; ++i) CK(wire::launch_rows16(wire::MODE_GABOR_FWD, P, smem, g_sms, 0));
   CK(cudaDeviceSynchronize());
-  std::vector<unsigned long long> hd(8 * 1024);
+  std::vector<unsigned long long> hd(16 * 1024);
   CK(cudaMemcpy(hd.data(), dd, hd.size() * 8, cudaMemcpyDeviceToHost));
   printf("[gabor_fwd16] cluster=%d n_rows=%d 2M=%d nb=%d slices=%d stages=%d fuse_final=%d mask=%d smem=%zu\n", g_cluster, n_rows, two_m, nb, P.slices, P.stages, int(fuse_final), mask, smem);
-  const char* names[8] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in"};
-  for (int k = 0; k < 8; ++k) {
+  const char* names[12] = {"mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc", "epi_total", "prod_wait_empty", "prod_total", "epi_wait_in",
+                           "t_prologue", "t_producer_done", "t_cta_done", "t_exit"};
+  for (int k = 0; k < 12; ++k) {
     double sum = 0; int cnt = 0;
-    for (int b = 0; b < 1024; ++b) if (hd[b * 8 + k]) { sum += double(hd[b * 8 + k]); ++cnt; }
+    for (int b = 0; b < 1024; ++b) if (hd[b * 16 + k]) { sum += double(hd[b * 16 + k]); ++cnt; }
     printf("   [dbg] %-16s avg %.0f cycles over %d CTAs\n", names[k], cnt ? sum / cnt : 0.0, cnt);
+  }
+  {
+    double d[2] = {0, 0}, c10[2] = {0, 0}; int cn[2] = {0, 0};
+    for (int b = 0; b < 1024; ++b) if (hd[b * 16 + 11]) { d[b & 1] += double(hd[b * 16 + 11] - hd[b * 16 + 10]); c10[b & 1] += double(hd[b * 16 + 10]); ++cn[b & 1]; }
+    printf("   [dbg] exit - cta_done: leader CTAs %.0f, peer CTAs %.0f cycles; cta_done leader %.0f peer %.0f\n", d[0] / (cn[0] ? cn[0] : 1), d[1] / (cn[1] ? cn[1] : 1),
+           c10[0] / (cn[0] ? cn[0] : 1), c10[1] / (cn[1] ? cn[1] : 1));
   }
   P.dbg = nullptr;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -539,6 +547,13 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "wn")) {  // wgrad time against the row count: fixed cost (prologue, split-K atomics epilogue) vs per-row cost
     g_cluster = 2; g_skip_check = true;
     for (int k : {1, 2, 4, 8, 16, 32, 64, 111}) test_wgrad16(37 * 64 * k, 212, 212, 1, 2, true);
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "gp")) {  // phase stamps of the forward kernels (build with -DWIRE_B200_STALL_COUNTERS)
+    g_cluster = 2;
+    time_rows_gabor16(262144, 424, false);
+    time_rows_gabor16(262144, 424, true);
+    time_rows_gabor16(25000, 424, true);
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "g16")) {

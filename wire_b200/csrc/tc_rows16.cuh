@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   const int n_jobs = n_iters * P.slices;
   constexpr bool pair = PAIR;
   const bool leader = crank == 0;
-  unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
+  unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 16 : nullptr;  // [0..7] stall counters, [8..11] phase stamps
+  const long long t_entry = WIRE_CLK();
   // work unit of iteration `it`; reversed sweeps mirror the valid units (phantom units past the end stay phantom)
   auto unit_of = [&](int it) { const int u = it * n_clusters + my_cluster; return (P.reverse && u < n_units) ? n_units - 1 - u : u; };
 
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();  // the next kernel of the step may be scheduled (it becomes resident only as these CTAs exit)
   pdl_wait();     // everything above read parameters only; the tensors of earlier kernels are read below
+  if (dbg && threadIdx.x == 0) dbg[8] = (unsigned long long)(WIRE_CLK() - t_entry);  // prologue
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -569,13 +571,16 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   }
 
   // ===================== teardown =====================
+  if (dbg && threadIdx.x == 0) dbg[9] = (unsigned long long)(WIRE_CLK() - t_entry);   // producer done
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[10] = (unsigned long long)(WIRE_CLK() - t_entry);  // every warp of this CTA done
   if (pair) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     if (pair) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
+  if (dbg && threadIdx.x == 0) dbg[11] = (unsigned long long)(WIRE_CLK() - t_entry);  // exit
 }
 
 }  // namespace wire
