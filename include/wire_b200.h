@@ -115,6 +115,18 @@ int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const fl
                       int64_t n, const float* grad_out, void* workspace, size_t workspace_bytes,
                       const wire_net_grads* grads, float* grad_coords, void* stream);
 
+/* wire_net_backward with the MSE loss of the training loops fused into the top of the backward pass
+ * (loss = ((pixelvalues - gt)**2).mean(); loss.backward(): wire_image_denoise.py:153-156, wire_occupancy.py:149-153):
+ * grad_out is not an input — it is computed on the fly as 2 (pred - target) / count_global, where pred is the output
+ * wire_net_forward(training=1) wrote for the same coords and count_global is the element count the mean is taken over
+ * (n * out_features on one GPU; the whole batch's count when this rank holds a shard).  The loss is added to the device
+ * ring exactly as by wire_mse_loss_grad_ring.  grad_out_scratch ([n][out_features]) is used only by the precisions whose
+ * kernels cannot compute the gradient themselves. */
+int wire_net_backward_mse(const wire_net_desc* d, const wire_net_params* p, const float* coords, int64_t n, const float* pred,
+                          const float* target, int64_t count_global, float* loss_ring, int32_t ring_n, const int64_t* step_dev,
+                          float* grad_out_scratch, void* workspace, size_t workspace_bytes, const wire_net_grads* grads,
+                          float* grad_coords, void* stream);
+
 /* ---- single layers (model.net[i](x) and per-layer parity) ---------------------------- */
 
 size_t wire_gabor_layer_workspace_bytes(const wire_net_desc* d, int32_t is_first, int32_t in_features,

@@ -534,3 +534,24 @@ def test_inr_with_trainable_scalars_trains_through_layer_route():
             assert abs(float(ga) - float(gb)) <= 2e-3 * max(1.0, abs(float(gb))), (k, float(ga), float(gb))
         else:
             assert util.rel_err(ga, gb) < TOL["fp32"]["grad"], k
+
+
+@pytest.mark.parametrize("kind,hidden,out_f", [("wire", 300, 3), ("wire2d", 256, 3), ("wire", 200, 1)])
+def test_fused_mse_backward_matches_separate_loss_kernel(kind, hidden, out_f):
+    """wire_net_backward_mse (loss gradient computed by the top backward kernel, loss into the device ring) against
+    wire_mse_loss_grad_ring + wire_net_backward: same losses and parameters after a few steps."""
+    import wire_b200
+    torch.manual_seed(1)
+    init = wire_b200.get_INR(kind, 2, hidden, None, 2, out_f, True, 7.0, 7.0, 6.0)
+    sd = {k: v.clone() for k, v in init.state_dict().items()}
+    coords = (torch.rand(1, 5000, 2) * 2 - 1).cuda()
+    target = torch.rand(1, 5000, out_f).cuda()
+    res = []
+    for fused in (False, True):
+        m = wire_b200.get_INR(kind, 2, hidden, None, 2, out_f, True, 7.0, 7.0, 6.0); m.load_state_dict(sd); m.cuda()
+        tr = wire_b200.Trainer(m, lr=5e-3)
+        tr._fused_mse = fused
+        losses = [float(tr.step(coords, target)) for _ in range(6)]
+        res.append((losses, tr.flat.clone()))
+    assert util.rel_err(np.array(res[1][0]), np.array(res[0][0])) < 2e-3, (res[0][0], res[1][0])
+    assert util.rel_err(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) < 5e-2

@@ -58,6 +58,8 @@ SIGNATURES = {
                                    c_size_t, c_int32, c_void_p]),
     "wire_net_backward": (c_int32, [POINTER(NetDesc), POINTER(NetParams), c_void_p, c_int64, c_void_p, c_void_p,
                                     c_size_t, POINTER(NetGrads), c_void_p, c_void_p]),
+    "wire_net_backward_mse": (c_int32, [POINTER(NetDesc), POINTER(NetParams), c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                        c_int32, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(NetGrads), c_void_p, c_void_p]),
     "wire_gabor_layer_workspace_bytes": (c_size_t, [POINTER(NetDesc), c_int32, c_int32, c_int64]),
     "wire_gabor_layer_forward": (c_int32, [POINTER(NetDesc), c_int32, c_int32, POINTER(LayerParams), c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -486,11 +486,29 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
   return 0;
 }
 
+// the loss fused into the top of the backward pass (wire_net_backward_mse)
+struct MseFuse {
+  const float* pred; const float* target; int64_t count_norm; float* ring; int ring_n; const long long* step_ptr; float* scratch;
+};
+int run_mse_ring(const MseFuse& m, int64_t count, cudaStream_t st) {
+  int64_t g64 = (count + 255) / 256;
+  const int grid = int(g64 > 1184 ? 1184 : g64);
+  ProfScope prof(K_MSE, st);
+  CU_OK(launch_pdl(mse_grad_kernel, dim3(grid), dim3(256), 0, st, m.pred, m.target, count, m.scratch, (float*)nullptr, m.count_norm, m.ring,
+                   m.ring_n, m.step_ptr));
+  return 0;
+}
+
 int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const float* Wf, const float* z, const float* w, int zw_pitch,
                 int z_half,
                 const float* h, int h_pitch, const float* omega, const float* scale, float* gz, float* gw, int g_pitch, float* g_Wf,
-                float* g_bf, cudaStream_t st, int g_elem = kElemF32) {
+                float* g_bf, cudaStream_t st, int g_elem = kElemF32, const MseFuse* mse = nullptr) {
   if (n <= 0) return 0;
+  if (mse && g_elem != kElemBF16) {  // only the 16-bit TMA kernel computes the loss gradient itself
+    TRY(run_mse_ring(*mse, n * d->out_features, st));
+    g_out = mse->scratch;
+    mse = nullptr;
+  }
   if (g_elem == kElemBF16) {  // mixed16 whole-network path: FP16 z in, BF16 g_z out
     if (!(z && z_half && d->out_features <= 4 && d->width <= 1024 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0))
       return fail("BF16 top backward: unsupported shape");
@@ -507,6 +525,10 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       T.g_out = g_out; T.Wf = Wf; T.omega = omega; T.scale = scale; T.g_Wf = g_Wf; T.g_bf = g_bf;
       T.n = int(n); T.M = d->width; T.out_f = d->out_features; T.pitch = g_pitch; T.two_d = w ? 1 : 0;
       T.bw = g_pitch / n_box; T.n_box = n_box;
+      if (mse) {
+        T.pred = mse->pred; T.target = mse->target; T.g_scale = 2.0f / float(mse->count_norm); T.loss_scale = 1.0f / float(mse->count_norm);
+        T.ring = mse->ring; T.ring_n = mse->ring_n; T.step_ptr = mse->step_ptr;
+      }
       bool ok = sm100_host::make_tmap_2d_t(&T.z_map[0], z, n, g_pitch, zw_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemF16);
       ok &= sm100_host::make_tmap_2d_t(&T.z_map[1], w ? w : z, n, g_pitch, zw_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemF16);
       ok &= sm100_host::make_tmap_2d_t(&T.g_map[0], gz, n, 2 * d->width, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
@@ -547,6 +569,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       CU_OK(e);
       return 0;
     }
+    if (mse) { TRY(run_mse_ring(*mse, n * d->out_features, st)); g_out = mse->scratch; mse = nullptr; }
     const int thr = round_up((d->width + 1) / 2, 32) < 128 ? 128 : round_up((d->width + 1) / 2, 32);
     const int nblk = int(n < int64_t(10 * g_sm_count) * 64 ? (n + 63) / 64 : 10 * g_sm_count);
     const int rpb = int(((n + nblk - 1) / nblk + 63) / 64 * 64);
@@ -561,6 +584,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
   ProfScope prof(K_TOP_BWD, st);
   const bool tf = d->precision == WIRE_PRECISION_TF32;
   if (z && d->out_features <= 4 && d->width <= 1024 && (zw_pitch % 4) == 0 && (g_pitch % 4) == 0) {  // training path: streaming kernel
+    if (mse) { TRY(run_mse_ring(*mse, n * d->out_features, st)); g_out = mse->scratch; mse = nullptr; }
     const int thr = round_up((d->width + 1) / 2, 32) < 128 ? 128 : round_up((d->width + 1) / 2, 32);  // one feature pair per thread
     const int M = d->width, of = d->out_features;
     // few, long-lived blocks: every g_Wf address then sees only `nblk` atomics
@@ -820,8 +844,35 @@ int wire_net_forward(const wire_net_desc* d_in, const wire_net_params* p, const 
   return 0;
 }
 
+}  // extern "C"
+namespace {
+int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
+                      const MseFuse* mse, void* workspace, size_t workspace_bytes, const wire_net_grads* g, float* grad_coords, void* stream);
+}
+extern "C" {
 int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
                       void* workspace, size_t workspace_bytes, const wire_net_grads* g, float* grad_coords, void* stream) {
+  if (!grad_out) return fail("null argument");
+  return net_backward_impl(d_in, p, coords, n, grad_out, nullptr, workspace, workspace_bytes, g, grad_coords, stream);
+}
+
+int wire_net_backward_mse(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, const float* pred,
+                          const float* target, int64_t count_global, float* loss_ring, int32_t ring_n, const int64_t* step_dev,
+                          float* grad_out_scratch, void* workspace, size_t workspace_bytes, const wire_net_grads* g, float* grad_coords,
+                          void* stream) {
+  if (!pred || !target || !loss_ring || !step_dev || !grad_out_scratch) return fail("null argument");
+  if (ring_n < 2) return fail("loss ring needs at least 2 slots");
+  if (!d_in) return fail("null descriptor");
+  if (n <= 0) return fail("empty batch: clear the next ring slot on the host side instead");
+  if (count_global < n * int64_t(d_in->out_features)) return fail("count_global smaller than this rank's element count");
+  MseFuse m{pred, target, count_global, loss_ring, int(ring_n), reinterpret_cast<const long long*>(step_dev), grad_out_scratch};
+  return net_backward_impl(d_in, p, coords, n, grad_out_scratch, &m, workspace, workspace_bytes, g, grad_coords, stream);
+}
+}  // extern "C"
+
+namespace {
+int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
+                      const MseFuse* mse, void* workspace, size_t workspace_bytes, const wire_net_grads* g, float* grad_coords, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TRY(require_device());
   if (!d_in || !p || !coords || !grad_out || !g) return fail("null argument");
@@ -852,7 +903,7 @@ int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const
   TRY(run_top_bwd(d, grad_out, n, p->final_weight, at(workspace, L.off_z[H]), d->two_d ? at(workspace, L.off_w[H]) : nullptr, L.P,
                   L.z_elem != kElemF32, nullptr,
                   0, p->layer[H].omega0, p->layer[H].scale0, at(workspace, L.off_gz[cur]), d->two_d ? at(workspace, L.off_gw[cur]) : nullptr,
-                  L.P, g->final_weight, g->final_bias, st, L.g_elem));
+                  L.P, g->final_weight, g->final_bias, st, L.g_elem, mse));
   for (int l = H; l >= 1; --l) {
     const float* gz = at(workspace, L.off_gz[cur]);
     const float* gw = d->two_d ? at(workspace, L.off_gw[cur]) : nullptr;
@@ -923,7 +974,7 @@ int wire_net_backward(const wire_net_desc* d_in, const wire_net_params* p, const
   return 0;
 }
 
-}  // extern "C"
+}  // namespace (net_backward_impl)
 
 // ---------------------------------------------------------------------------------------------
 // single layers

@@ -121,6 +121,14 @@ struct TopBwd16Params {
   float* g_bf;
   int n, M, out_f, pitch, two_d;
   int bw, n_box;          // a row of `pitch` columns is moved as n_box boxes of bw columns (bw <= 256, bw % 8 == 0)
+  // Fused MSE (wire_net_backward_mse): g_out is not read but computed by the I/O warp as 2 (pred - target) / count_norm
+  // (wire_image_denoise.py:153 / criterion of wire_occupancy.py:149), and the loss goes to the device ring (see mse_grad_kernel).
+  const float* pred;      // [n][out_f] or nullptr
+  const float* target;
+  float g_scale, loss_scale;   // 2 / count_norm, 1 / count_norm
+  float* ring;
+  int ring_n;
+  const long long* step_ptr;
 };
 
 // Block = W compute warps (thread k owns complex feature k) + one I/O warp.  No block-wide barrier in the loop: tiles
@@ -171,9 +179,21 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
     // here waits for a round trip: the g_out rows of the tile loaded NEXT iteration are prefetched into a register now,
     // and a TMA store is only waited for (wait_read<1>) one iteration after it was issued.
     const int rr = lane >> 2, o = lane & 3;
+    float loss_acc = 0.f;
+    long long ring_step = 0;
+    if (P.pred) {
+      ring_step = *P.step_ptr;
+      if (blockIdx.x == 0 && lane == 0) P.ring[(ring_step + 1) % P.ring_n] = 0.f;   // slot of the next step
+    }
     auto load_go = [&](int tile) -> float {
       const int row = tile * kTopRows + rr;
-      return (tile < t_end && row < P.n && o < OUTF) ? __ldg(P.g_out + size_t(row) * OUTF + o) : 0.f;
+      if (!(tile < t_end && row < P.n && o < OUTF)) return 0.f;
+      if (P.pred) {
+        const float dlt = __ldg(P.pred + size_t(row) * OUTF + o) - __ldg(P.target + size_t(row) * OUTF + o);
+        loss_acc = fmaf(dlt, dlt, loss_acc);
+        return dlt * P.g_scale;
+      }
+      return __ldg(P.g_out + size_t(row) * OUTF + o);
     };
     auto issue_load = [&](int tile, int stage, float go) {
       if (lane == 0) {
@@ -212,6 +232,10 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
         tma_store_wait_read<1>();  // the PREVIOUS tile's store has read its buffer
         if (it >= 1) mbar_arrive(smem_u32(&out_empty[(it - 1) % kTopOut]));
       }
+    }
+    if (P.pred) {
+      for (int sft = 16; sft > 0; sft >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, sft);
+      if (lane == 0 && t_begin < t_end) atomicAdd(P.ring + (ring_step % P.ring_n), loss_acc * P.loss_scale);
     }
     if (lane == 0) tma_store_wait_all<0>();
     return;

@@ -93,6 +93,9 @@ class Trainer:
         self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss_ring = torch.zeros(256, dtype=torch.float32, device=dev)   # loss of optimiser step s at [s % 256]
+        # wire_net_backward_mse (loss gradient computed inside the top backward kernel) is parity-tested but measured equal to
+        # the separate 6-us loss kernel (the top kernel's I/O warp gets longer: 1.042 vs 1.042 ms/step), so it is opt-in
+        self._fused_mse = os.environ.get("WIRE_B200_FUSED_MSE", "0") == "1"
         self._issued = 0                                                        # optimiser steps issued (host mirror of step_dev)
         self._n = None
         self._key = None
@@ -180,15 +183,24 @@ class Trainer:
             Hh, Ww, sc = self._pool
             check(lib.wire_avgpool_mse_loss_grad(self.out_buf.data_ptr(), self.target_buf.data_ptr(), Hh, Ww, d.out_features, sc,
                                                  self.gout_buf.data_ptr(), self.loss_dev.data_ptr(), st), "wire_avgpool_mse_loss_grad")
-        else:
-            # the loss of optimiser step s lands in loss_ring[s % R] (and the next slot is cleared) — no reset kernel, and the
-            # host can read it for the next R - 1 steps without putting a copy on the compute stream's critical path
+        if self.peer is not None:
+            self._peer_wait()
+        if self._pool is None and not self._fused_mse:
             n_norm = n if self._n_global is None else self._n_global
             check(lib.wire_mse_loss_grad_ring(self.out_buf.data_ptr(), self.target_buf.data_ptr(), n * d.out_features,
                                               n_norm * d.out_features, self.gout_buf.data_ptr(), self.loss_ring.data_ptr(),
                                               self.loss_ring.numel(), self.step_dev.data_ptr(), st), "wire_mse_loss_grad_ring")
-        if self.peer is not None:
-            self._peer_wait()
+        elif self._pool is None:
+            # MSE fused into the top of the backward pass: grad_out is never materialised on the mixed16 path, and the loss
+            # of optimiser step s lands in loss_ring[s % R] (the next slot is cleared) — no loss / reset kernels, and the host
+            # can read it for the next R - 1 steps without putting a copy on the compute stream's critical path
+            n_norm = n if self._n_global is None else self._n_global
+            check(lib.wire_net_backward_mse(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n,
+                                            self.out_buf.data_ptr(), self.target_buf.data_ptr(), n_norm * d.out_features,
+                                            self.loss_ring.data_ptr(), self.loss_ring.numel(), self.step_dev.data_ptr(),
+                                            self.gout_buf.data_ptr(), self.ws.data_ptr(), self.ws.numel(), ctypes.byref(self._G), None, st),
+                  "wire_net_backward_mse")
+            return
         check(lib.wire_net_backward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.gout_buf.data_ptr(),
                                     self.ws.data_ptr(), self.ws.numel(), ctypes.byref(self._G), None, st), "wire_net_backward")
 
