@@ -249,7 +249,9 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   // a pair splits every MMA piece in block-aligned halves (blocks: 32 columns, or 64 for 16-bit operands); the
   // accumulator of one work item may use all 512 TMEM columns
   const int blk_cols = op16 ? 64 : 32;
-  const int gran = cluster == 2 ? 2 * blk_cols : blk_cols;
+  // 16-bit pair: a piece's per-CTA half may end in half a block (32 columns): 2M = 424 then runs as 256 + 192 = 448 accumulator
+  // columns instead of 512 (ncu: the tensor pipe is 70 % busy in this kernel, so padded columns are real time)
+  const int gran = cluster == 2 ? (op16 ? blk_cols : 2 * blk_cols) : blk_cols;
   const int nb_max = op16 ? 512 : 448;
   const int gpad = round_up(P.g_cols, gran);
   P.n_blocks = (gpad + nb_max - 1) / nb_max;
@@ -263,7 +265,8 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   if (splits > total_chunks) splits = total_chunks > 0 ? total_chunks : 1;
   P.splits = splits;
   // x: 128 columns per CTA; g: nb / cluster columns per CTA; one block = blk_cols columns x (32 | 64) rows x (4 | 2) bytes
-  const size_t stage = size_t(128 / blk_cols + P.nb / blk_cols / cluster) * (op16 ? 8192 : 4096);
+  const int n1c = (P.nb > 256 ? 256 : P.nb) / cluster, n2c = (P.nb > 256 ? P.nb - 256 : 0) / cluster;   // per-CTA halves of the MMA pieces
+  const size_t stage = size_t(128 / blk_cols + (n1c + blk_cols - 1) / blk_cols + (n2c + blk_cols - 1) / blk_cols) * (op16 ? 8192 : 4096);
   P.gen_tab_feats = round_up(P.k_in + 1, 16) + 64 * 4;  // covers every feature index a generator warp may touch
   const size_t tab_bytes = gen ? size_t(2) * P.gen_tab_feats * 16 : 0;
   int stages = int((kMaxDynSmem - 1024 - tab_bytes) / stage);

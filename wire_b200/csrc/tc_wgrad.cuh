@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   const uint32_t a_bytes = kXBlocks * blk_bytes;
   // MMA pieces along N (g columns): n1 + n2 = nb ; a pair splits each piece in halves (multiples of 32 columns)
   int nvalid = P.g_cols;  // per column block below
-  const int nbb_cta = P.nb / kBlkCols / C;    // g blocks this CTA stages per chunk
+  // g blocks this CTA stages per chunk: its half of each MMA piece (n1 <= 256, n2), each rounded up to whole blocks
+  const int n1_all = P.nb > 256 ? 256 : P.nb, n2_all = P.nb - n1_all;
+  const int pb1 = (n1_all / C + kBlkCols - 1) / kBlkCols, pb2 = (n2_all / C + kBlkCols - 1) / kBlkCols;
+  const int nbb_cta = PAIR ? pb1 + pb2 : P.nb / kBlkCols;
   const uint32_t b_bytes = uint32_t(nbb_cta) * blk_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
 
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
               for (int b = 0; b < kXBlocks; ++b)
                 tma_load_2d_2cta(a_dst + b * blk_bytes, &P.x_map, full_leader, x_col0 + b * kBlkCols, r0, kEvictNormal);
             // piece 1: columns [crank*n1/2, +n1/2) ; piece 2: columns [n1 + crank*n2/2, +n2/2)
-            const int p1 = n1 / (2 * kBlkCols), p2 = n2 / (2 * kBlkCols);
+            const int p1 = pb1, p2 = pb2;  // (a half that ends inside a block still loads the whole block; the MMA ignores the rest)
             for (int b = 0; b < p1; ++b)
               tma_load_2d_2cta(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], full_leader,
                                nblk * P.nb + crank * (n1 / 2) + b * kBlkCols, r0, kEvictNormal);
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
         const uint32_t desc_hi = uint32_t(make_sdesc(0, blk_bytes, kSBO, kLayout) >> 32);
         const uint32_t a_lo0 = uint32_t(make_sdesc(smem_base, blk_bytes, kSBO, kLayout));
         const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
-        const uint32_t b2_units = (uint32_t(PAIR ? n1 / (2 * kBlkCols) : n1 / kBlkCols) * blk_bytes) >> 4;
+        const uint32_t b2_units = (uint32_t(PAIR ? pb1 : n1 / kBlkCols) * blk_bytes) >> 4;
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_chunks; ++i) {
