@@ -200,3 +200,67 @@ def test_bench_reference_arm_emits_contract_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "cpu_baseline", "e2e"):
         assert k in line
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+# ---- the epoch loop's sharding logic (wire_b200.data.run_epoch) on gloo, world size 2, with stand-ins for the CUDA pieces ----
+class _StubBatcher:
+    def __init__(self, total):
+        self.total, self.device = total, torch.device("cpu")
+
+
+class _StubTrainer:
+    """Records what run_epoch asks each rank to do; 'loss' = this rank's part of the chunk mean of the index values."""
+
+    def __init__(self, world, rank):
+        self.world, self.group, self.rank, self.calls = world, None, rank, []
+
+    def step_indexed(self, batcher, idx, n_global=None, rec=None):
+        self.calls.append((idx.clone(), n_global))
+        if rec is not None:
+            rec[idx] = idx.float().reshape(-1, 1)          # "prediction" of an index = its value
+        return idx.float().sum() / float(n_global if n_global is not None else max(idx.numel(), 1))
+
+
+def _epoch_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wire_b200 import data
+    N, maxpoints = 1003, 250                                 # 5 chunks, the last one ragged (3 indices: unequal shards)
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(9))
+    tr = _StubTrainer(world, rank)
+    rec = torch.full((N, 1), -1.0)
+    loss = data.run_epoch(tr, _StubBatcher(N), maxpoints, indices=perm, rec=rec)
+    ret[rank] = ([(c.tolist(), g) for c, g in tr.calls], rec.reshape(-1).tolist(), float(loss))
+    dist.destroy_process_group()
+
+
+def test_run_epoch_shards_every_chunk_exactly_gloo():
+    world, port = 2, 30100 + (os.getpid() % 500)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_epoch_worker, args=(world, port, ret), nprocs=world, join=True)
+    N, maxpoints = 1003, 250
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(9))
+    chunks = [perm[b:min(N, b + maxpoints)] for b in range(0, N, maxpoints)]
+    for ci, chunk in enumerate(chunks):
+        parts = [ret[r][0][ci] for r in range(world)]
+        assert all(g == chunk.numel() for _, g in parts)                       # loss normalised by the GLOBAL chunk size
+        assert sum((p for p, _ in parts), []) == chunk.tolist()                  # contiguous shards, nothing lost or repeated
+        assert abs(len(parts[0][0]) - len(parts[1][0])) <= 1                     # balanced
+    # rec: every index predicted by exactly one rank, then summed over ranks (identical on both)
+    assert ret[0][1] == ret[1][1] == [float(i) for i in range(N)]
+    # this rank's loss parts add up to the epoch's mean chunk loss
+    want = float(np.mean([c.float().mean().item() for c in chunks]))
+    assert abs(ret[0][2] + ret[1][2] - want) < 1e-3 * want
+
+
+def test_data_module_has_no_cpu_path():
+    import wire_b200
+    with pytest.raises(wire_b200.WireB200Error):
+        wire_b200.GridBatcher((4, 4), torch.zeros(16, 3))                        # CPU signal
+    with pytest.raises(wire_b200.WireB200Error):
+        wire_b200.GridBatcher((4, 4), device=torch.device("cpu"))
+    with pytest.raises(wire_b200.WireB200Error):
+        wire_b200.data.iou_counts(torch.zeros(8), torch.zeros(8), 0.5)
+    with pytest.raises(wire_b200.WireB200Error):
+        wire_b200.data.psnr(torch.zeros(8), torch.zeros(8))
