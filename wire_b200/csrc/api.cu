@@ -418,7 +418,15 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
     P.x_conv = x_elem != g_elem;
     if (P.x_conv && !(x_elem == kElemF16 && g_elem == kElemBF16)) return fail("unsupported wgrad operand formats");
   }
-  const size_t smem = wgrad_configure(P, g_sm_count, cluster_size(), use_gen, op16);
+  // CTA pair (256 x-columns per tile) or single CTAs (128)?  Measured equal at M = 212 (0.108 vs 0.110 ms), so on the 16-bit
+  // path take whichever pads the 2K+1 x-columns less: at the SISR width (2K+1 = 257) pairs would spend half of their tiles
+  // on the single "ones" column (2 x 256 column slots against 3 x 128).
+  int cl = cluster_size();
+  if (op16 && cl == 2) {
+    const int xc = 2 * k_in + 1;
+    if ((xc + 127) / 128 * 128 < (xc + 255) / 256 * 256) cl = 1;
+  }
+  const size_t smem = wgrad_configure(P, g_sm_count, cl, use_gen, op16);
   if (!smem) return fail("wgrad configuration does not fit shared memory");
   if (use_gen) {
     P.coords = gen->coords; P.in_features = gen->in_features; P.w0 = gen->w0; P.b0 = gen->b0; P.w0b = gen->w0b; P.b0b = gen->b0b;
