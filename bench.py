@@ -37,7 +37,10 @@ LR = 5e-3
 # tf32: profiles/r01_ncu_full_v6_summary.txt (530.7 MB read + 835.0 MB written, hidden layer 1);
 # mixed16: profiles/r01_ncu_full_v11_mixed16_summary.txt, mean of the two forward launches of a step
 #          (layer 1: 251.4 + 398.4 MB, layer 2 with the fused final Linear: 242.4 + 182.1 MB)
-NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6, ("mixed16", "tc_rows_gabor_fwd"): 537.1e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the top kernel, from `ncu --set full` captures of this command
+# (mean of the H forward launches): profiles/r01_ncu_full_v6_summary.txt (tf32), profiles/r01_ncu_full_v14_mixed16_summary.txt
+# (mixed16: 252.0 + 402.2 MB for hidden layer 1, 242.3 + 184.8 MB for hidden layer 2)
+NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6, ("mixed16", "tc_rows_gabor_fwd"): 540.6e6}
 
 
 def flop_per_coord(M, H, in_f, out_f):
