@@ -1235,8 +1235,8 @@ int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (count <= 0) return 0;
   if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !scratch_dev) return fail("null argument");
-  int64_t g64 = (count + 255) / 256;
-  const int grid = int(g64 > 592 ? 592 : g64);
+  int64_t g64 = (count / 4 + 255) / 256;
+  const int grid = int(g64 > 592 ? 592 : (g64 < 1 ? 1 : g64));
   ProfScope prof(K_ADAM, st);
   CU_OK(launch_pdl(adam_dev_kernel, dim3(grid), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
                    reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev));

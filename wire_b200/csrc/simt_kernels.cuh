@@ -390,16 +390,28 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   const float lr = *lr_ptr;
   const float bc1 = 1.0f - powf(b1, float(step));
   const float bc2_sqrt = sqrtf(1.0f - powf(b2, float(step)));
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
-    float gi = g[i] * grad_scale;
-    const float pi = p[i];
-    if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
+  auto upd = [&](float gi, float& pp, float& mm, float& vv) {
+    gi *= grad_scale;
+    if (wd != 0.f) gi = fmaf(wd, pp, gi);
+    mm = fmaf(b1, mm, (1.f - b1) * gi);
+    vv = fmaf(b2, vv, (1.f - b2) * gi * gi);
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - (lr / bc1) * (mm / denom);
+  };
+  // 16-byte accesses when the four buffers allow it (the Trainer's flat buffers do), scalar tail / fallback otherwise
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = vec ? count >> 2 : 0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+  }
+  for (int64_t i = 4 * n4 + blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(g[i], pi, mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
   // the last block to finish bumps the step counter (every block has read it by then)
   __syncthreads();
