@@ -234,6 +234,12 @@ int wire_avgpool_mse_loss_grad(const float* pred, const float* target_lr, int32_
 int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, const float* z_save, const float* w_save,
                             const float* grad_y, int64_t n, const float* omega0, const float* scale0, double* out2, void* stream);
 
+/* RealGaborLayer (modules/wire.py:6-42; not used by INR): the fused activation y = cos(omega_0 f) exp(-(scale_0 s)^2) of the
+ * two real Linears' outputs f = freqs(x), s = scale(x) (modules/wire.py:38-42), and its derivative w.r.t. f and s. */
+int wire_real_gabor_forward(const float* f, const float* s, int64_t count, float omega0, float scale0, float* y, void* stream);
+int wire_real_gabor_backward(const float* f, const float* s, const float* grad_y, int64_t count, float omega0, float scale0,
+                             float* grad_f, float* grad_s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,41 @@ def trainable_fixture():
 
 if __name__ == "__main__":
     trainable_fixture()
+
+
+def real_gabor_fixture():
+    """RealGaborLayer (modules/wire.py:6-42), the reference's own class: forward + autograd in float32 and float64."""
+    sys.path.insert(0, REF)
+    from modules import wire as ref_wire
+    blob = {}
+    rs = np.random.RandomState(21)
+    K, M, n, w0, s0 = 3, 20, 50, 10.0, 10.0
+    x = rs.uniform(-1, 1, size=(1, n, K))
+    gy = rs.normal(size=(1, n, M))
+    torch.manual_seed(3)
+    layer = ref_wire.RealGaborLayer(K, M, omega0=w0, sigma0=s0)
+    state = {k: v.clone() for k, v in layer.state_dict().items()}
+    for k, v in state.items():
+        blob[f"param.{k}"] = v.numpy()
+    for prec, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        layer = ref_wire.RealGaborLayer(K, M, omega0=w0, sigma0=s0)
+        layer.load_state_dict(state)
+        layer = layer.to(dt)
+        xt = torch.from_numpy(x).to(dt).requires_grad_(True)
+        y = layer(xt)
+        (y * torch.from_numpy(gy).to(dt)).sum().backward()
+        blob[f"y_{prec}"] = y.detach().numpy()
+        blob[f"g_x_{prec}"] = xt.grad.numpy()
+        blob[f"g_freqs_w_{prec}"] = layer.freqs.weight.grad.numpy()
+        blob[f"g_scale_w_{prec}"] = layer.scale.weight.grad.numpy()
+        blob[f"g_scale_b_{prec}"] = layer.scale.bias.grad.numpy()
+    blob["x"], blob["gy"] = x, gy
+    blob["meta"] = np.array([K, M, n], dtype=np.int64)
+    blob["hyper"] = np.array([w0, s0])
+    out = os.path.join(HERE, "..", "tests", "golden", "real_gabor.npz")
+    np.savez_compressed(out, **blob)
+    print(f"wrote {out}: {os.path.getsize(out) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    real_gabor_fixture()

@@ -270,3 +270,11 @@ def gabor_scalar_grads_np(x, weight, bias, weight2, bias2, omega0, s0, gy):
     y = np.exp(1j * omega0 * z - s0 * s0 * t)
     p = np.conj(y) * np.asarray(gy).astype(np.complex128)
     return y, float(np.sum((np.conj(z) * p).imag)), float(-2.0 * s0 * np.sum(t * p.real))
+
+
+def real_gabor_np(x, w_freqs, b_freqs, w_scale, b_scale, omega0, s0):
+    """modules/wire.py:38-42 ``RealGaborLayer.forward`` in float64: cos(omega_0 freqs(x)) * exp(-(scale_0 scale(x))^2)."""
+    x = np.asarray(x, dtype=np.float64)
+    f = x @ np.asarray(w_freqs, dtype=np.float64).T + np.asarray(b_freqs, dtype=np.float64)
+    s = x @ np.asarray(w_scale, dtype=np.float64).T + np.asarray(b_scale, dtype=np.float64)
+    return np.cos(omega0 * f) * np.exp(-((s0 * s) ** 2))

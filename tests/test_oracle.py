@@ -135,3 +135,10 @@ def test_trainable_scalar_grads_closed_form_matches_reference_autograd():
         assert util.rel_err(y, g[f"{tag}.y_c128"]) < 1e-12
         assert abs(g_om - float(g[f"{tag}.g_omega_c128"][0])) <= 1e-10 * max(1.0, abs(g_om)), tag
         assert abs(g_s0 - float(g[f"{tag}.g_scale_c128"][0])) <= 1e-10 * max(1.0, abs(g_s0)), tag
+
+
+def test_real_gabor_restatement_matches_reference_fixture():
+    g = np.load(os.path.join(util.GOLDEN_DIR, "real_gabor.npz"))
+    w0, s0 = (float(v) for v in g["hyper"])
+    y = O.real_gabor_np(g["x"], g["param.freqs.weight"], g["param.freqs.bias"], g["param.scale.weight"], g["param.scale.bias"], w0, s0)
+    assert util.rel_err(y, g["y_f64"]) < 1e-6      # (the fixture's parameters are float32 values)

@@ -555,3 +555,28 @@ def test_fused_mse_backward_matches_separate_loss_kernel(kind, hidden, out_f):
         res.append((losses, tr.flat.clone()))
     assert util.rel_err(np.array(res[1][0]), np.array(res[0][0])) < 2e-3, (res[0][0], res[1][0])
     assert util.rel_err(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) < 5e-2
+
+
+def test_real_gabor_layer_vs_reference_fixture():
+    """wire.RealGaborLayer (modules/wire.py:6-42) against the reference's own class under autograd (tests/golden/real_gabor.npz)."""
+    import os
+    import wire_b200
+    g = np.load(os.path.join(util.GOLDEN_DIR, "real_gabor.npz"))
+    K, M, n = (int(v) for v in g["meta"])
+    w0, s0 = (float(v) for v in g["hyper"])
+    layer = wire_b200.wire.RealGaborLayer(K, M, omega0=w0, sigma0=s0)
+    layer.load_state_dict({k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")}, strict=True)
+    layer = layer.cuda()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x = torch.from_numpy(g["x"].astype(np.float32)).cuda().requires_grad_(True)
+        y = layer(x)
+        (y * torch.from_numpy(g["gy"].astype(np.float32)).cuda()).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert util.rel_err(y.detach().cpu().numpy(), g["y_f64"]) < 1e-4
+    assert util.rel_err(x.grad.cpu().numpy(), g["g_x_f64"]) < 1e-3
+    assert util.rel_err(layer.freqs.weight.grad.cpu().numpy(), g["g_freqs_w_f64"]) < 1e-3
+    assert util.rel_err(layer.scale.weight.grad.cpu().numpy(), g["g_scale_w_f64"]) < 1e-3
+    assert util.rel_err(layer.scale.bias.grad.cpu().numpy(), g["g_scale_b_f64"]) < 1e-3

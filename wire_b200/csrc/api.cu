@@ -1460,4 +1460,27 @@ int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, cons
   return 0;
 }
 
+int wire_real_gabor_forward(const float* f, const float* s, int64_t count, float omega0, float scale0, float* y, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (count <= 0) return 0;
+  if (!f || !s || !y) return fail("null argument");
+  ProfScope prof(K_LAYER_MISC, st);
+  real_gabor_fwd_kernel<<<grid_for(count), 256, 0, st>>>(f, s, count, omega0, scale0, y);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_real_gabor_backward(const float* f, const float* s, const float* grad_y, int64_t count, float omega0, float scale0, float* grad_f,
+                             float* grad_s, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (count <= 0) return 0;
+  if (!f || !s || !grad_y || !grad_f || !grad_s) return fail("null argument");
+  ProfScope prof(K_LAYER_MISC, st);
+  real_gabor_bwd_kernel<<<grid_for(count), 256, 0, st>>>(f, s, grad_y, count, omega0, scale0, grad_f, grad_s);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

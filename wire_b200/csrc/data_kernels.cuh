@@ -219,4 +219,27 @@ __global__ void gabor_scalar_grads_kernel(const float* __restrict__ z, const flo
   }
 }
 
+// RealGaborLayer (modules/wire.py:6-42, not used by INR): y = cos(omega_0 f) exp(-(scale_0 s)^2) with f = freqs(x), s = scale(x)
+// two real Linears (library GEMMs on the host side); this is the fused activation and its derivative:
+//   g_f = -omega_0 sin(omega_0 f) exp(-(scale_0 s)^2) g_y        g_s = -2 scale_0^2 s y g_y
+__global__ void real_gabor_fwd_kernel(const float* __restrict__ f, const float* __restrict__ sc, int64_t count, float omega, float s0,
+                                      float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float t = s0 * sc[i];
+    y[i] = cosf(omega * f[i]) * expf(-(t * t));
+  }
+}
+__global__ void real_gabor_bwd_kernel(const float* __restrict__ f, const float* __restrict__ sc, const float* __restrict__ gy, int64_t count,
+                                      float omega, float s0, float* __restrict__ gf, float* __restrict__ gs) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float t = s0 * sc[i];
+    const float e = expf(-(t * t));
+    float sn, cs;
+    sincosf(omega * f[i], &sn, &cs);
+    const float g = gy[i];
+    gf[i] = -omega * sn * e * g;
+    gs[i] = -2.0f * s0 * s0 * sc[i] * cs * e * g;
+  }
+}
+
 }  // namespace wire

@@ -396,3 +396,40 @@ def final_linear_real(desc: NetDesc, h: torch.Tensor, weight: torch.Tensor, bias
         check(lib.wire_final_linear_forward(ctypes.byref(desc), weight.data_ptr(), bias.data_ptr(), flat.data_ptr(),
                                             flat.shape[0], out.data_ptr(), _stream()), "wire_final_linear_forward")
     return out.reshape(*h.shape[:-1], desc.out_features)
+
+
+# --------------------------------------------------------------------------------------------
+# RealGaborLayer activation (modules/wire.py:38-42)
+# --------------------------------------------------------------------------------------------
+class RealGaborFn(torch.autograd.Function):
+    """y = cos(omega_0 f) * exp(-(scale_0 s)^2) — one fused kernel each way (C ABI ``wire_real_gabor_forward`` / ``_backward``)."""
+
+    @staticmethod
+    def forward(ctx, f, s, omega0: float, scale0: float):
+        lib = _lib.load()
+        fc = _require_cuda(f, "freqs output", torch.float32)
+        sc = _require_cuda(s, "scale output", torch.float32)
+        if fc.shape != sc.shape:
+            raise WireB200Error("freqs and scale outputs must have the same shape")
+        y = torch.empty_like(fc)
+        with torch.cuda.device(fc.device):
+            check(lib.wire_real_gabor_forward(fc.data_ptr(), sc.data_ptr(), fc.numel(), float(omega0), float(scale0), y.data_ptr(),
+                                              _stream()), "wire_real_gabor_forward")
+        ctx.save_for_backward(fc, sc)
+        ctx.consts = (float(omega0), float(scale0))
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        lib = _lib.load()
+        fc, sc = ctx.saved_tensors
+        gy = _require_cuda(grad_y, "grad_y", torch.float32)
+        gf, gs = torch.empty_like(fc), torch.empty_like(sc)
+        with torch.cuda.device(fc.device):
+            check(lib.wire_real_gabor_backward(fc.data_ptr(), sc.data_ptr(), gy.data_ptr(), fc.numel(), ctx.consts[0], ctx.consts[1],
+                                               gf.data_ptr(), gs.data_ptr(), _stream()), "wire_real_gabor_backward")
+        return gf, gs, None, None
+
+
+def real_gabor(f, s, omega0, scale0):
+    return RealGaborFn.apply(f, s, omega0, scale0)

@@ -78,6 +78,26 @@ class ComplexGaborLayer(_GaborBase):
     two_d = False
 
 
+class RealGaborLayer(nn.Module):
+    """modules/wire.py:6-42 — real Gabor layer ``cos(omega_0 freqs(x)) * exp(-(scale_0 scale(x))^2)`` (not used by ``INR``).
+    Same constructor and parameter names (``freqs``, ``scale``; ``omega_0`` / ``scale_0`` are plain floats, as in the
+    reference); the two real Linears are library GEMMs, the activation and its derivative one fused CUDA kernel each."""
+
+    def __init__(self, in_features, out_features, bias=True, is_first=False, omega0=10.0, sigma0=10.0, trainable=False):
+        super().__init__()
+        self.omega_0 = omega0
+        self.scale_0 = sigma0
+        self.is_first = is_first
+        self.in_features = in_features
+        self.freqs = nn.Linear(in_features, out_features, bias=bias)
+        self.scale = nn.Linear(in_features, out_features, bias=bias)
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise F.WireB200Error("RealGaborLayer input must be a CUDA tensor: wire_b200 has no CPU path")
+        return F.real_gabor(self.freqs(input), self.scale(input), self.omega_0, self.scale_0)
+
+
 class FinalLinear(nn.Linear):
     """The complex output Linear (modules/wire.py:156).  Inside ``INR.forward`` it is fused into the last
     Gabor kernel; called on its own (layer-by-layer evaluation) it returns the complex output like
