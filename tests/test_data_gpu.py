@@ -234,3 +234,26 @@ def test_trainer_step_from_pinned_host_buffers_is_pipelined_and_correct():
     lb = [tb.step(c, t).clone() for c, t in pinned]       # no host sync between steps
     lb = [float(v) for v in lb]
     assert util.rel_err(np.array(lb), np.array(la)) < 1e-3, (la, lb)
+
+
+def test_empty_shard_step_keeps_the_trainer_consistent():
+    """A rank whose shard of a chunk is empty (chunk smaller than the world) still takes an optimiser step with zero
+    gradients; the loss ring and the per-size states stay consistent for the steps that follow."""
+    import wire_b200
+    dev = torch.device("cuda", 0)
+    H, W = 32, 24
+    gen = torch.Generator().manual_seed(4)
+    signal = torch.rand(H * W, 3, generator=gen).to(dev)
+    batcher = wire_b200.GridBatcher((H, W), signal, linspace="torch")
+    model = wire_b200.get_INR(nonlin="wire", in_features=2, hidden_features=64, hidden_layers=2, out_features=3, first_omega_0=7.0,
+                              hidden_omega_0=7.0, scale=6.0, precision="fp32").to(dev)
+    tr = wire_b200.Trainer(model, lr=5e-3, graph=False)
+    idx = torch.randperm(H * W, generator=gen).to(dev)
+    l0 = float(tr.step_indexed(batcher, idx[:300], n_global=600))          # this rank holds half of a 600-coordinate chunk
+    before = tr.flat.clone()
+    le = float(tr.step_indexed(batcher, idx[:0], n_global=5))              # empty shard
+    assert le == 0.0 and tr.steps_done == 2
+    assert not torch.equal(tr.flat, before)                                 # Adam still moved the parameters (momentum)
+    l1 = float(tr.step_indexed(batcher, idx[:300], n_global=600))          # same key as the first step: state must be intact
+    assert np.isfinite(l1) and 0.2 * l0 < l1 < 1.5 * l0
+    assert tr._n_global == 600 and tr.steps_done == 3

@@ -204,10 +204,11 @@ class Trainer:
         check(lib.wire_net_backward(ctypes.byref(d), ctypes.byref(self._P), self.coords_buf.data_ptr(), n, self.gout_buf.data_ptr(),
                                     self.ws.data_ptr(), self.ws.numel(), ctypes.byref(self._G), None, st), "wire_net_backward")
 
-    def _adam(self) -> None:
+    def _adam(self, scale: Optional[float] = None) -> None:
         b1, b2 = self.betas
         # equal shards with a local mean: average the ranks' gradients; shards of a global mean (n_global): they add up
-        scale = 1.0 if getattr(self, "_n_global", None) is not None else 1.0 / self.world
+        if scale is None:
+            scale = 1.0 if getattr(self, "_n_global", None) is not None else 1.0 / self.world
         if self.peer is not None:
             check(self.lib.wire_adam_step_peer(self.flat.data_ptr(), self.peer.bases, self.peer.world, self.peer.rank,
                                                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.flat.numel(),
@@ -219,10 +220,10 @@ class Trainer:
                                           self.weight_decay, self.step_dev.data_ptr(), scale, self.scratch.data_ptr(),
                                           F._stream()), "wire_adam_step_dev")
 
-    def _exchange_and_adam(self) -> None:
+    def _exchange_and_adam(self, scale: Optional[float] = None) -> None:
         if self.world > 1 and self.peer is None:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-        self._adam()
+        self._adam(scale)
 
     def _whole_step(self) -> None:
         self._fwd_bwd()
@@ -233,8 +234,8 @@ class Trainer:
         if not self.use_graph or (self.world > 1 and self.peer is None):
             self._whole_step()
         elif self._graph is None:
-            # one eager step first (lazy one-time setup inside the C ABI must not happen during capture),
-            # then capture; both count as training steps
+            # one eager step first (lazy one-time setup inside the C ABI must not happen during capture), then the capture
+            # (which records the step without executing it): this call performs exactly one training step
             self._whole_step()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
@@ -257,8 +258,7 @@ class Trainer:
         self.loss_dev.zero_()
         R = self.loss_ring.numel()
         self.loss_ring[(self._issued + 1) % R].zero_()   # what the loss kernel of a non-empty step does for the next slot
-        self._n_global = 1  # gradients add up (scale 1)
-        self._exchange_and_adam()
+        self._exchange_and_adam(scale=1.0)   # an empty shard only occurs with n_global batches: the ranks' gradients add up
         self._issued += 1
 
     def step(self, coords: torch.Tensor, target: torch.Tensor, n_global: Optional[int] = None) -> torch.Tensor:
