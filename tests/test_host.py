@@ -264,3 +264,26 @@ def test_data_module_has_no_cpu_path():
         wire_b200.data.iou_counts(torch.zeros(8), torch.zeros(8), 0.5)
     with pytest.raises(wire_b200.WireB200Error):
         wire_b200.data.psnr(torch.zeros(8), torch.zeros(8))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path: the oracle port on the host cores) prints ONE JSON line with the
+    contract's keys; non-zero ranks of a torchrun launch print nothing and exit 0."""
+    import json
+    import subprocess
+    bench = os.path.join(ROOT, "bench.py")
+    res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "coords/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert res.returncode == 0 and res.stdout.strip() == ""
