@@ -108,8 +108,11 @@ struct PackJobs {
   int n, M_out, K_in;
 };
 __global__ void pack_all16_kernel(const __grid_constant__ PackJobs J) {
+  // First kernel of a step: wait BEFORE letting the dependents go.  The kernels behind it read parameters in their
+  // pre-wait prologues, which is only safe once whatever wrote the parameters (the optimiser kernel in front of this one,
+  // if it sits directly in front) has completed.
+  sm100::pdl_wait();  // (also: the packed matrices are still read by the previous step's backward kernels)
   sm100::pdl_trigger();
-  sm100::pdl_wait();  // the packed matrices are still read by the previous step's backward kernels
   const PackJob& j = J.job[blockIdx.y];
   const int total = j.n_blocks * j.nb * j.k_pad_total;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
