@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define WIRE_B200_ABI_VERSION 1
+#define WIRE_B200_ABI_VERSION 2
 #define WIRE_B200_MAX_LAYERS 16 /* first layer + hidden layers */
 
 /* TF32    : GEMM operands TF32 (10-bit mantissa, fp32 storage), FP32 accumulate, saved pre-activations FP16.
@@ -76,10 +76,21 @@ typedef struct wire_layer_grads {
   float* bias2;
 } wire_layer_grads;
 
+/* How wire_net_backward clears the accumulation targets before its kernels add into them (split-K partial sums are
+ * accumulated with fp32 atomics, so every slot must start at zero):
+ *   WIRE_GRADS_CLEAR_SLOTS  one memset per slot (default; the slots may live anywhere)
+ *   WIRE_GRADS_CLEAR_FLAT   every slot lies inside [flat_base, flat_base + flat_floats): ONE memset of that range
+ *   WIRE_GRADS_PREZEROED    the caller guarantees the slots are zero on entry (e.g. wire_adam_step_dev(..., zero_grad=1) cleared
+ *                           them while consuming the previous step's gradients): no memset at all */
+enum { WIRE_GRADS_CLEAR_SLOTS = 0, WIRE_GRADS_CLEAR_FLAT = 1, WIRE_GRADS_PREZEROED = 2 };
+
 typedef struct wire_net_grads {
   wire_layer_grads layer[WIRE_B200_MAX_LAYERS];
   float* final_weight;
   float* final_bias;
+  int32_t clear_mode;  /* WIRE_GRADS_* */
+  float* flat_base;    /* WIRE_GRADS_CLEAR_FLAT: the flat gradient buffer that contains every slot */
+  size_t flat_floats;
 } wire_net_grads;
 
 int wire_b200_abi_version(void);
@@ -87,6 +98,8 @@ const char* wire_b200_last_error(void);
 /* 0 if the current device can run the kernels (compute capability 10.x) */
 int wire_b200_device_ok(void);
 int wire_b200_sm_count(void);
+/* rows per pass of an inference (training == 0) forward: workspaces are sized for min(n, this) rows */
+int64_t wire_b200_infer_chunk_rows(void);
 
 /* ---- launch accounting / per-kernel device timing (bench.py) --------------------------- */
 /* Every kernel launch is counted per kind. With timing != 0 each launch is also bracketed by CUDA
@@ -114,6 +127,20 @@ int wire_net_forward(const wire_net_desc* d, const wire_net_params* p, const flo
 int wire_net_backward(const wire_net_desc* d, const wire_net_params* p, const float* coords,
                       int64_t n, const float* grad_out, void* workspace, size_t workspace_bytes,
                       const wire_net_grads* grads, float* grad_coords, void* stream);
+
+/* Inspection of a TRAINING workspace (per-layer parity tests of the fused path; saved activations for diagnostics): copies one
+ * tensor out as dense fp32, converting from the storage type of the precision mode (FP16 activations / pre-activations, BF16
+ * gradients under MIXED16).  which / index:
+ *   WIRE_WS_Y   y_index, the output of layer `index` = the input of layer index+1 (0..H-1; H too when the final Linear is not fused)
+ *   WIRE_WS_Z   z_index = x W^T + b of hidden layer `index` (1..H)        WIRE_WS_W  the scale_orth pre-activation (wire2d)
+ *   WIRE_WS_GZ  gradient buffer `index` (0..1): after wire_net_backward, g_z of hidden layer l (dL/dRe z + j dL/dIm z) is in
+ *               buffer (H - l) & 1 -- the two buffers alternate, so only the last two layers written (l = 1, 2) survive
+ *   WIRE_WS_GW  same for the scale_orth branch (wire2d)
+ *   WIRE_WS_GZ0 real g_z of the first layer [n][M]                         WIRE_WS_GW0 same for its scale_orth branch
+ * out: [n][2M] floats (interleaved re, im), or [n][M] for GZ0 / GW0. */
+enum { WIRE_WS_Y = 0, WIRE_WS_Z = 1, WIRE_WS_W = 2, WIRE_WS_GZ = 3, WIRE_WS_GW = 4, WIRE_WS_GZ0 = 5, WIRE_WS_GW0 = 6 };
+int wire_net_workspace_read(const wire_net_desc* d, int64_t n, const void* workspace, size_t workspace_bytes, int32_t which,
+                            int32_t index, float* out, void* stream);
 
 /* wire_net_backward with the MSE loss of the training loops fused into the top of the backward pass
  * (loss = ((pixelvalues - gt)**2).mean(); loss.backward(): wire_image_denoise.py:153-156, wire_occupancy.py:149-153):
@@ -158,10 +185,12 @@ int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float grad_scale, void* stream);
 /* Same update with the step counter (*step_dev, 0-based count of completed steps, incremented by the kernel) and the
  * learning rate (*lr_dev) on the device, so a captured CUDA graph of a whole training step can be replayed.
- * scratch_dev: one zero-initialised uint32 used by the kernel to detect its last block. */
-int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
+ * scratch_dev: one zero-initialised uint32 used by the kernel to detect its last block.
+ * zero_grad != 0: every gradient element is set to zero after it has been read (optim.zero_grad() folded into the step), so the
+ * next wire_net_backward can run with WIRE_GRADS_PREZEROED and the training step contains no memset. */
+int wire_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
                        const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
-                       int64_t* step_dev, float grad_scale, uint32_t* scratch_dev, void* stream);
+                       int64_t* step_dev, float grad_scale, uint32_t* scratch_dev, int32_t zero_grad, void* stream);
 /* grad_out[i] = 2*(pred[i]-target[i])/count ; *loss (device scalar, accumulated) += mean sq err */
 int wire_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad_out,
                        float* loss, void* stream);

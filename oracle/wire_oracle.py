@@ -187,6 +187,43 @@ def backward_np(state: Dict[str, np.ndarray], coords: np.ndarray, grad_out: np.n
 
 
 # --------------------------------------------------------------------------------------------
+# single stages of the closed form (the per-kernel parity tests feed each CUDA kernel's own inputs through these)
+# --------------------------------------------------------------------------------------------
+def gabor_np(z, w, omega, scale):
+    """modules/wire.py:91-93 / modules/wire2d.py:62-67 on given pre-activations: exp(j w0 z - s0^2 (|z|^2 [+ |w|^2]))."""
+    mag = np.abs(z) ** 2 + (0.0 if w is None else np.abs(w) ** 2)
+    return np.exp(1j * omega * np.asarray(z, dtype=np.complex128) - scale ** 2 * mag)
+
+
+def layer_forward_np(L, x):
+    """One layer of ``forward_np`` from a given input x (L: an entry of ``_layers_from_state``): returns z, w (None for wire), y."""
+    cplx = np.iscomplexobj(L["W"])
+    x = np.asarray(x, dtype=np.complex128 if cplx else np.float64)
+    z = x @ L["W"].astype(np.complex128 if cplx else np.float64).T + L["b"]
+    w = None if L["W2"] is None else x @ L["W2"].astype(np.complex128 if cplx else np.float64).T + L["b2"]
+    return z, w, gabor_np(z, w, L["omega"], L["scale"])
+
+
+def gabor_backward_np(L, z, w, g_y):
+    """A.2 on given pre-activations: p = conj(y) g_y; hidden: g_z = -j w0 p - 2 s0^2 z Re p; first layer (real z):
+    g_z = w0 Im p - 2 s0^2 z Re p; wire2d: g_w = -2 s0^2 w Re p.  Returns g_z, g_w (None for wire)."""
+    y = gabor_np(z, w, L["omega"], L["scale"])
+    p = np.conj(y) * g_y
+    s2 = L["scale"] ** 2
+    if np.iscomplexobj(L["W"]):
+        g_z = -1j * L["omega"] * p - 2.0 * s2 * z * p.real
+    else:
+        g_z = L["omega"] * p.imag - 2.0 * s2 * np.real(z) * p.real
+    g_w = None if w is None else -2.0 * s2 * w * p.real
+    return g_z, g_w
+
+
+def linear_backward_np(W, x, g_z):
+    """Complex (or real) Linear backward, PyTorch convention: g_x = g_z conj(W), g_W = g_z^T conj(x), g_b = sum_n g_z."""
+    return g_z @ np.conj(W), g_z.T @ np.conj(x), g_z.sum(0)
+
+
+# --------------------------------------------------------------------------------------------
 # metrics the parity harness needs (restated, not imported)
 # --------------------------------------------------------------------------------------------
 def psnr(x: np.ndarray, xhat: np.ndarray) -> float:

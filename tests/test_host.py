@@ -27,7 +27,7 @@ def test_library_exports_every_symbol_the_header_declares():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/wire_b200.h but not exported"
     assert declared == set(wire_b200._lib.SIGNATURES), "ctypes SIGNATURES and the header disagree"
-    assert lib.wire_b200_abi_version() == 1
+    assert lib.wire_b200_abi_version() == 2
     assert lib.wire_b200_prof_kinds() >= 8
 
 

@@ -55,6 +55,44 @@ def test_closed_form_matches_reference_c128(name):
     assert np.all(grads[f"net.{last}.bias"].imag == 0)
 
 
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_single_stage_closed_forms_compose_to_the_reference(name):
+    """layer_forward_np / gabor_backward_np / linear_backward_np (what the per-kernel GPU parity tests check each CUDA kernel
+    against) chained over the stack reproduce the reference's complex128 outputs and gradients."""
+    c = util.load_golden(name)
+    g = c["g"]
+    m = util.oracle_model(c)
+    state = {k: v.numpy().astype(np.complex128 if v.is_complex() else np.float64) for k, v in m.state_dict().items()}
+    layers, final = O._layers_from_state(state)
+    x = g["coords"].reshape(-1, c["in_f"]).astype(np.float64)
+    saved = []
+    for i, L in enumerate(layers):
+        z, w, y = O.layer_forward_np(L, x)
+        if f"layer{i}_c128" in g.files:   # the big fixtures keep only outputs and (sub-sampled) gradients
+            assert util.rel_err(y, g[f"layer{i}_c128"].reshape(y.shape)) < 1e-12, i
+        saved.append((x, z, w))
+        x = y
+    out = (x @ final["W"].T + final["b"]).real
+    assert util.rel_err(out, g["out_c128"].reshape(out.shape)) < 1e-12
+    g_o = g["grad_out"].reshape(out.shape).astype(np.complex128)
+    g_y, g_Wf, g_bf = O.linear_backward_np(final["W"], x, g_o)
+    idx = len(layers)
+    got = {f"net.{idx}.weight": g_Wf, f"net.{idx}.bias": g_bf}
+    for i in range(len(layers) - 1, -1, -1):
+        L = layers[i]
+        xin, z, w = saved[i]
+        g_z, g_w = O.gabor_backward_np(L, z, w, g_y)
+        g_y, got[f"net.{i}.linear.weight"], got[f"net.{i}.linear.bias"] = O.linear_backward_np(L["W"], xin, g_z)
+        if g_w is not None:
+            gx2, got[f"net.{i}.scale_orth.weight"], got[f"net.{i}.scale_orth.bias"] = O.linear_backward_np(L["W2"], xin, g_w)
+            g_y = g_y + gx2
+    assert util.rel_err(np.real(g_y), g["gcoords_c128"].reshape(g_y.shape)) < 1e-11
+    for k in (k for k in g.files if k.startswith("grad_c128.")):
+        key = k[len("grad_c128."):]
+        a, b = util.golden_grad(c, "c128", key, got[key])
+        assert util.rel_err(a, b) < 1e-11, key
+
+
 def test_layer_outputs_match_reference():
     c = util.load_golden("wire_small")
     g = c["g"]

@@ -442,7 +442,7 @@ def test_peer_adam_kernel_single_rank_matches_adam_dev():
                                                        0.9, 0.999, 1e-8, 0.0, step.data_ptr(), 0.5, scratch.data_ptr(), st), "peer")
                 else:
                     _lib.check(lib.wire_adam_step_dev(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), count, lr.data_ptr(),
-                                                      0.9, 0.999, 1e-8, 0.0, step.data_ptr(), 0.5, scratch.data_ptr(), st), "dev")
+                                                      0.9, 0.999, 1e-8, 0.0, step.data_ptr(), 0.5, scratch.data_ptr(), 0, st), "dev")
             torch.cuda.synchronize()
             assert int(step) == 5
             state[which] = (p, m, v)

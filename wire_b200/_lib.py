@@ -37,8 +37,12 @@ class LayerGrads(Structure):
     _fields_ = [("weight", c_void_p), ("bias", c_void_p), ("weight2", c_void_p), ("bias2", c_void_p)]
 
 
+GRADS_CLEAR_SLOTS, GRADS_CLEAR_FLAT, GRADS_PREZEROED = 0, 1, 2
+
+
 class NetGrads(Structure):
-    _fields_ = [("layer", LayerGrads * MAX_LAYERS), ("final_weight", c_void_p), ("final_bias", c_void_p)]
+    _fields_ = [("layer", LayerGrads * MAX_LAYERS), ("final_weight", c_void_p), ("final_bias", c_void_p),
+                ("clear_mode", c_int32), ("flat_base", c_void_p), ("flat_floats", c_size_t)]
 
 
 # name -> (restype, argtypes); mirrors include/wire_b200.h one to one
@@ -47,6 +51,7 @@ SIGNATURES = {
     "wire_b200_last_error": (c_char_p, []),
     "wire_b200_device_ok": (c_int32, []),
     "wire_b200_sm_count": (c_int32, []),
+    "wire_b200_infer_chunk_rows": (c_int64, []),
     "wire_b200_prof_enable": (c_int32, [c_int32]),
     "wire_b200_prof_reset": (c_int32, []),
     "wire_b200_prof_kinds": (c_int32, []),
@@ -58,6 +63,7 @@ SIGNATURES = {
                                    c_size_t, c_int32, c_void_p]),
     "wire_net_backward": (c_int32, [POINTER(NetDesc), POINTER(NetParams), c_void_p, c_int64, c_void_p, c_void_p,
                                     c_size_t, POINTER(NetGrads), c_void_p, c_void_p]),
+    "wire_net_workspace_read": (c_int32, [POINTER(NetDesc), c_int64, c_void_p, c_size_t, c_int32, c_int32, c_void_p, c_void_p]),
     "wire_net_backward_mse": (c_int32, [POINTER(NetDesc), POINTER(NetParams), c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                         c_int32, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(NetGrads), c_void_p, c_void_p]),
     "wire_gabor_layer_workspace_bytes": (c_size_t, [POINTER(NetDesc), c_int32, c_int32, c_int64]),
@@ -73,7 +79,7 @@ SIGNATURES = {
     "wire_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                  c_float, c_float, c_int64, c_float, c_void_p]),
     "wire_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
-                                     c_float, c_void_p, c_float, c_void_p, c_void_p]),
+                                     c_float, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "wire_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "wire_mse_loss_grad_n": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "wire_mse_loss_grad_ring": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),

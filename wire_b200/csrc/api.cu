@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <utility>
 
 #include "../../include/wire_b200.h"
@@ -51,17 +52,37 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-int g_sm_count = 0;
-int g_cc_major = -1;
+// Per-device facts, cached per device (a process may drive several GPUs: `with torch.cuda.device(...)`); g_sm_count / g_cc_major
+// are the CURRENT device's values for the calling thread, refreshed by every entry point through require_device().
+struct DevInfo { int sm_count = 0; int cc_major = -1; };
+DevInfo g_dev[kMaxDevices];
+thread_local int g_sm_count = 0;
+thread_local int g_cc_major = -1;
 int device_info() {
-  if (g_cc_major >= 0) return 0;
   int dev = 0;
   CU_OK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CU_OK(cudaGetDeviceProperties(&prop, dev));
-  g_sm_count = prop.multiProcessorCount;
-  g_cc_major = prop.major;
+  if (dev < 0 || dev >= kMaxDevices) return fail("device index %d outside 0..%d", dev, kMaxDevices - 1);
+  if (g_dev[dev].cc_major < 0) {
+    int sm = 0, cc = 0;
+    CU_OK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    CU_OK(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
+    g_dev[dev].sm_count = sm;
+    g_dev[dev].cc_major = cc;
+  }
+  g_sm_count = g_dev[dev].sm_count;
+  g_cc_major = g_dev[dev].cc_major;
   return 0;
+}
+// bound of the in-kernel peer spins in SM cycles (peer_kernels.cuh): WIRE_B200_PEER_TIMEOUT_S seconds at ~2 GHz, default 600 s
+long long peer_spin_limit() {
+  static long long v = 0;
+  if (v == 0) {
+    const char* e = getenv("WIRE_B200_PEER_TIMEOUT_S");
+    double s = e ? atof(e) : 600.0;
+    if (!(s > 0.0)) s = 600.0;
+    v = (long long)(s * 2.0e9);
+  }
+  return v;
 }
 int require_device() {
   TRY(device_info());
@@ -78,7 +99,9 @@ enum ProfKind { K_FIRST_FWD = 0, K_PACK, K_ROWS_FWD, K_FINAL_FWD, K_TOP_BWD, K_W
 const char* kProfNames[K_COUNT] = {"first_fwd", "pack_weights", "tc_rows_gabor_fwd", "final_fwd", "top_bwd", "tc_wgrad",
                                    "tc_rows_dgrad_gabor_bwd", "tc_rows_dgrad_first_bwd", "first_wgrad", "grad_coords",
                                    "layer_misc", "adam", "mse_grad", "peer_wait", "data_pipeline"};
+// (one process-wide table guarded by a mutex: the entry points may be called from several host threads)
 struct ProfPending { int kind; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
 struct Prof {
   int timing = 0;
   unsigned long long launches[K_COUNT] = {};
@@ -87,20 +110,23 @@ struct Prof {
   int n_pending = 0;
 } g_prof;
 struct ProfScope {
-  int kind; cudaStream_t st; cudaEvent_t e1 = nullptr; bool on = false;
+  int kind; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on = false;
   ProfScope(int k, cudaStream_t s, int n_launches = 1) : kind(k), st(s) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.launches[k] += n_launches;
-    if (g_prof.timing && g_prof.n_pending < 4096) {
-      cudaEvent_t e0;
+    if (g_prof.timing) {
       if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
         cudaEventRecord(e0, st);
-        g_prof.pending[g_prof.n_pending] = {k, e0, e1};
         on = true;
       }
     }
   }
-  ~ProfScope() {
-    if (on) { cudaEventRecord(e1, st); ++g_prof.n_pending; }
+  ~ProfScope() {  // the pair is published only once both events are recorded (scopes of several threads may interleave)
+    if (!on) return;
+    cudaEventRecord(e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof.n_pending < 4096) g_prof.pending[g_prof.n_pending++] = {kind, e0, e1};
+    else { cudaEventDestroy(e0); cudaEventDestroy(e1); }
   }
 };
 int rows_kind(int mode) {
@@ -780,9 +806,11 @@ int wire_b200_abi_version(void) { return WIRE_B200_ABI_VERSION; }
 const char* wire_b200_last_error(void) { return g_err; }
 int wire_b200_device_ok(void) { return require_device(); }
 int wire_b200_sm_count(void) { return device_info() ? 0 : g_sm_count; }
+int64_t wire_b200_infer_chunk_rows(void) { return kInferChunk; }
 
-int wire_b200_prof_enable(int32_t timing) { g_prof.timing = timing; return 0; }
+int wire_b200_prof_enable(int32_t timing) { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.timing = timing; return 0; }
 int wire_b200_prof_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (int i = 0; i < g_prof.n_pending; ++i) { cudaEventDestroy(g_prof.pending[i].e0); cudaEventDestroy(g_prof.pending[i].e1); }
   g_prof.n_pending = 0;
   for (int k = 0; k < K_COUNT; ++k) { g_prof.launches[k] = 0; g_prof.ms[k] = 0.0; }
@@ -793,6 +821,7 @@ const char* wire_b200_prof_name(int32_t kind) { return (kind >= 0 && kind < K_CO
 /* Resolves pending events (synchronises on them) and returns launches + accumulated device ms of one kind. */
 int wire_b200_prof_get(int32_t kind, uint64_t* launches, double* ms) {
   if (kind < 0 || kind >= K_COUNT) return fail("bad profile kind %d", kind);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (int i = 0; i < g_prof.n_pending; ++i) {
     float t = 0.f;
     if (cudaEventSynchronize(g_prof.pending[i].e1) == cudaSuccess &&
@@ -852,6 +881,49 @@ int wire_net_forward(const wire_net_desc* d_in, const wire_net_params* p, const 
   return 0;
 }
 
+
+/* Copies one tensor of a training workspace out as dense fp32 (converting FP16 / BF16): what the forward pass saved and the
+ * backward pass left behind -- activations y_l, pre-activations z_l / w_l, gradient buffers g_z / g_w / g_z0 / g_w0. */
+int wire_net_workspace_read(const wire_net_desc* d_in, int64_t n, const void* workspace, size_t workspace_bytes, int32_t which,
+                            int32_t index, float* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!d_in || !workspace || !out) return fail("null argument");
+  TRY(check_desc(d_in));
+  wire_net_desc de = *d_in;
+  de.precision = net_precision(d_in);
+  Layout L;
+  TRY(make_layout(&de, n, 1, L));
+  if (workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
+  if (n <= 0) return 0;
+  size_t off = 0;
+  int elem = kElemF32, pitch = L.P, cols = L.two_m;
+  switch (which) {
+    case WIRE_WS_Y:
+      if (index < 0 || index >= L.n_act) return fail("activation y_%d is not kept (layers 0..%d are)", index, L.n_act - 1);
+      off = L.off_y[index]; elem = L.y_elem; break;
+    case WIRE_WS_Z: case WIRE_WS_W:
+      if (index < 1 || index > L.H) return fail("pre-activation index %d outside 1..%d", index, L.H);
+      if (which == WIRE_WS_W && !de.two_d) return fail("w tensors exist for wire2d only");
+      off = which == WIRE_WS_Z ? L.off_z[index] : L.off_w[index]; elem = L.z_elem; break;
+    case WIRE_WS_GZ: case WIRE_WS_GW:
+      if (index < 0 || index > 1) return fail("gradient slot %d outside 0..1", index);
+      if (which == WIRE_WS_GW && !de.two_d) return fail("g_w tensors exist for wire2d only");
+      off = which == WIRE_WS_GZ ? L.off_gz[index] : L.off_gw[index]; elem = L.g_elem; break;
+    case WIRE_WS_GZ0: case WIRE_WS_GW0:
+      if (which == WIRE_WS_GW0 && !de.two_d) return fail("g_w0 exists for wire2d only");
+      off = which == WIRE_WS_GZ0 ? L.off_gz0 : L.off_gw0; elem = L.g_elem; pitch = L.PR; cols = L.M; break;
+    default: return fail("unknown workspace tensor %d", which);
+  }
+  const void* src = static_cast<const char*>(workspace) + off;
+  int64_t g64 = (n * cols + 255) / 256;
+  const int grid = int(g64 > 1184 * 8 ? 1184 * 8 : g64);
+  if (elem == kElemF16) read_rows_kernel<1><<<grid, 256, 0, st>>>(src, pitch, n, cols, out);
+  else if (elem == kElemBF16) read_rows_kernel<2><<<grid, 256, 0, st>>>(src, pitch, n, cols, out);
+  else read_rows_kernel<0><<<grid, 256, 0, st>>>(src, pitch, n, cols, out);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"
 namespace {
 int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const float* coords, int64_t n, const float* grad_out,
@@ -892,16 +964,24 @@ int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const
   TRY(make_layout(d, n, 1, L));
   if (!workspace || workspace_bytes < L.total) return fail("workspace too small: %zu < %zu", workspace_bytes, L.total);
   const int M = L.M, H = L.H, in_f = d->in_features;
-  // gradients are overwritten: clear the accumulation targets
-  TRY(zero(g->final_weight, size_t(d->out_features) * M * 2, st));
-  TRY(zero(g->final_bias, size_t(d->out_features) * 2, st));
-  TRY(zero(g->layer[0].weight, size_t(M) * in_f, st));
-  TRY(zero(g->layer[0].bias, size_t(M), st));
-  if (d->two_d) { TRY(zero(g->layer[0].weight2, size_t(M) * in_f, st)); TRY(zero(g->layer[0].bias2, size_t(M), st)); }
-  for (int l = 1; l <= H; ++l) {
-    TRY(zero(g->layer[l].weight, size_t(M) * M * 2, st));
-    TRY(zero(g->layer[l].bias, size_t(M) * 2, st));
-    if (d->two_d) { TRY(zero(g->layer[l].weight2, size_t(M) * M * 2, st)); TRY(zero(g->layer[l].bias2, size_t(M) * 2, st)); }
+  // gradients are overwritten: clear the accumulation targets (one memset per slot, one for a flat buffer, or none)
+  if (g->clear_mode == WIRE_GRADS_CLEAR_FLAT) {
+    if (!g->flat_base || g->flat_floats == 0) return fail("WIRE_GRADS_CLEAR_FLAT without a flat buffer");
+    TRY(zero(g->flat_base, g->flat_floats, st));
+  } else if (g->clear_mode != WIRE_GRADS_PREZEROED && g->clear_mode != WIRE_GRADS_CLEAR_SLOTS) {
+    return fail("unknown clear_mode %d", g->clear_mode);
+  }
+  if (g->clear_mode == WIRE_GRADS_CLEAR_SLOTS) {
+    TRY(zero(g->final_weight, size_t(d->out_features) * M * 2, st));
+    TRY(zero(g->final_bias, size_t(d->out_features) * 2, st));
+    TRY(zero(g->layer[0].weight, size_t(M) * in_f, st));
+    TRY(zero(g->layer[0].bias, size_t(M), st));
+    if (d->two_d) { TRY(zero(g->layer[0].weight2, size_t(M) * in_f, st)); TRY(zero(g->layer[0].bias2, size_t(M), st)); }
+    for (int l = 1; l <= H; ++l) {
+      TRY(zero(g->layer[l].weight, size_t(M) * M * 2, st));
+      TRY(zero(g->layer[l].bias, size_t(M) * 2, st));
+      if (d->two_d) { TRY(zero(g->layer[l].weight2, size_t(M) * M * 2, st)); TRY(zero(g->layer[l].bias2, size_t(M) * 2, st)); }
+    }
   }
   if (n <= 0) return 0;
   if (!g->final_weight || !g->final_bias) return fail("final layer gradient buffers are required");
@@ -1229,9 +1309,9 @@ int wire_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   return 0;
 }
 
-int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, const float* lr_dev,
+int wire_adam_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, const float* lr_dev,
                        float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev, float grad_scale,
-                       uint32_t* scratch_dev, void* stream) {
+                       uint32_t* scratch_dev, int32_t zero_grad, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (count <= 0) return 0;
   if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !scratch_dev) return fail("null argument");
@@ -1239,7 +1319,7 @@ int wire_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
   const int grid = int(g64 > 592 ? 592 : (g64 < 1 ? 1 : g64));
   ProfScope prof(K_ADAM, st);
   CU_OK(launch_pdl(adam_dev_kernel, dim3(grid), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
-                   reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev));
+                   reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev, int(zero_grad)));
   return 0;
 }
 
@@ -1351,7 +1431,7 @@ int wire_adam_step_peer(float* param, void* const* peer_bases, int32_t world, in
   const int grid = int(g64 > 296 ? 296 : g64);  // every block spins in the in-barrier: keep the grid co-resident
   ProfScope prof(K_ADAM, st);
   adam_peer_kernel<<<grid, 256, 0, st>>>(param, T, exp_avg, exp_avg_sq, count, lr_dev, beta1, beta2, eps, weight_decay,
-                                         reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev);
+                                         reinterpret_cast<long long*>(step_dev), grad_scale, scratch_dev, peer_spin_limit());
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -1362,7 +1442,7 @@ int wire_peer_wait_done(void* const* peer_bases, int32_t world, int32_t rank, co
   PeerTable T;
   TRY(make_peer_table(T, peer_bases, world, rank));
   ProfScope prof(K_PEER_WAIT, st);
-  peer_wait_kernel<<<1, 32, 0, st>>>(T, reinterpret_cast<const long long*>(step_dev));
+  peer_wait_kernel<<<1, 32, 0, st>>>(T, reinterpret_cast<const long long*>(step_dev), peer_spin_limit());
   CU_OK(cudaGetLastError());
   return 0;
 }

@@ -16,7 +16,10 @@
 //   out-signal : the last block to finish stores done[r] = e into every rank's header.
 //   peer_wait  : before the NEXT step's backward pass overwrites grad, a one-block kernel waits until the local done[p] >=
 //                (completed steps) for all p, i.e. every peer has finished reading this rank's gradients.
-// Waits are bounded (~20 s of SM clock) and trap instead of hanging the GPU if a peer died.
+// Waits are bounded (spin_limit SM cycles: WIRE_B200_PEER_TIMEOUT_S, default 600 s) and trap instead of hanging the GPU forever
+// if a peer died.  All ranks must issue their steps in lock-step: a rank that pauses between steps for longer than the bound
+// (rank-0-only evaluation, checkpointing) makes its peers trap -- use the all-reduce exchange (Trainer(peer_exchange=False))
+// for such loops, or raise the bound.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -45,12 +48,12 @@ __device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-// spin until *flag >= want (monotonic counters); traps after ~20 s so a dead peer cannot hang the box
-__device__ __forceinline__ void peer_spin(const uint32_t* flag, uint32_t want) {
+// spin until *flag >= want (monotonic counters); traps after spin_limit cycles so a dead peer cannot hang the box
+__device__ __forceinline__ void peer_spin(const uint32_t* flag, uint32_t want, long long spin_limit) {
   const long long t0 = clock64();
   while (int32_t(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(64);
-    if (clock64() - t0 > 40000000000ll) __trap();
+    if (clock64() - t0 > spin_limit) __trap();
   }
 }
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ void peer_spin(const uint32_t* flag, uint32_t want) {
 __global__ void __launch_bounds__(256) adam_peer_kernel(float* __restrict__ p, const PeerTable T, float* __restrict__ m, float* __restrict__ v,
                                                         int64_t count, const float* __restrict__ lr_ptr, float b1, float b2, float eps, float wd,
                                                         long long* __restrict__ step_ptr, float grad_scale,
-                                                        unsigned int* __restrict__ done_counter) {
+                                                        unsigned int* __restrict__ done_counter, long long spin_limit) {
   const long long step = *step_ptr + 1;
   const uint32_t e = uint32_t(step);
   uint32_t* local = static_cast<uint32_t*>(T.base[T.rank]);
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float* __restrict__ p, c
     __threadfence_system();
     st_release_sys(static_cast<uint32_t*>(T.base[threadIdx.x]) + T.rank, e);
   }
-  if (threadIdx.x < T.world) peer_spin(local + threadIdx.x, e);
+  if (threadIdx.x < T.world) peer_spin(local + threadIdx.x, e, spin_limit);
   __syncthreads();
 
   const float lr = *lr_ptr;
@@ -113,10 +116,10 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float* __restrict__ p, c
 }
 
 // waits until every peer has finished reading this rank's gradient buffer of the last completed step
-__global__ void peer_wait_kernel(const PeerTable T, const long long* __restrict__ step_ptr) {
+__global__ void peer_wait_kernel(const PeerTable T, const long long* __restrict__ step_ptr, long long spin_limit) {
   const uint32_t e = uint32_t(*step_ptr);
   const uint32_t* local = static_cast<const uint32_t*>(T.base[T.rank]) + kMaxPeers;
-  if (threadIdx.x < T.world) peer_spin(local + threadIdx.x, e);
+  if (threadIdx.x < T.world) peer_spin(local + threadIdx.x, e, spin_limit);
 }
 
 }  // namespace wire

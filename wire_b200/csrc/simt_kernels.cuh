@@ -362,6 +362,21 @@ __global__ void set_column16_kernel(uint16_t* __restrict__ dst, int pitch, int64
     dst[r * pitch + col] = bits;
 }
 
+// workspace tensor (fp32, FP16 or BF16, row pitch in elements) -> dense fp32 [n][cols] (wire_net_workspace_read)
+template <int ELEM>  // sm100_host::ElemType: 0 = f32, 1 = f16, 2 = bf16
+__global__ void read_rows_kernel(const void* __restrict__ src, int src_pitch, int64_t n, int cols, float* __restrict__ dst) {
+  const int64_t total = n * cols;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = int(i % cols);
+    float v;
+    if constexpr (ELEM == 1) v = __half2float(reinterpret_cast<const __half*>(src)[r * src_pitch + c]);
+    else if constexpr (ELEM == 2) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[r * src_pitch + c]);
+    else v = reinterpret_cast<const float*>(src)[r * src_pitch + c];
+    dst[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam, amsgrad=False, maximize=False) on a flat fp32 view; complex params are
 // their view_as_real, which is exactly how torch treats them.
@@ -384,9 +399,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 // Same update with the step counter and the learning rate living on the device, so a captured CUDA graph can be
 // replayed: *step_ptr is read (1-based step = *step_ptr + 1) by every thread and incremented by one thread at the end.
-__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+// zero_grad: the gradient is cleared as it is consumed, so the next backward pass can accumulate without a memset.
+__global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                 int64_t count, const float* __restrict__ lr_ptr, float b1, float b2, float eps, float wd,
-                                long long* __restrict__ step_ptr, float grad_scale, unsigned int* __restrict__ done_counter) {
+                                long long* __restrict__ step_ptr, float grad_scale, unsigned int* __restrict__ done_counter,
+                                int zero_grad) {
   sm100::pdl_trigger();
   sm100::pdl_wait();
   const long long step = *step_ptr + 1;
@@ -410,11 +427,13 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
     float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
     upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
     reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t i = 4 * n4 + blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
     upd(g[i], pi, mi, vi);
     p[i] = pi; m[i] = mi; v[i] = vi;
+    if (zero_grad) g[i] = 0.f;
   }
   // the last block to finish bumps the step counter (every block has read it by then)
   __syncthreads();

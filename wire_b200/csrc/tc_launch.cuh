@@ -12,6 +12,15 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 constexpr size_t kMaxDynSmem = 232448 - 6144;  // 227 KB minus the static barriers / exchange buffers
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize and cluster occupancy are per device: the launchers below cache them per
+// (kernel instantiation, device), so a process that drives several GPUs sets the attribute on each of them.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+
 // Fill in nb-dependent fields and pick the deepest pipeline that fits. Returns dynamic smem bytes
 // (0 if the configuration does not fit).
 // `n_in`   : TMA-prefetched epilogue inputs (z / w tiles of the backward modes)
@@ -60,8 +69,11 @@ inline size_t rows_configure(RowsParams& P, int nb, int nbh, int store_mask, int
 
 template <int MODE, bool PAIR, bool GEN = false, bool OP16 = false>
 inline cudaError_t launch_rows_mode_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
-  static bool attr_set = false;
-  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  static bool attr_set_dev[kMaxDevices] = {};
+  static int max_clusters_dev[kMaxDevices][5] = {};
+  const int dev = current_device_slot();
+  bool& attr_set = attr_set_dev[dev];
+  int* max_clusters = max_clusters_dev[dev];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_rows_kernel<MODE, PAIR, GEN, OP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
@@ -183,8 +195,11 @@ inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, i
 
 template <int MODE, bool PAIR, bool FUSE>
 inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
-  static bool attr_set = false;
-  static int max_clusters = 0;
+  static bool attr_set_dev[kMaxDevices] = {};
+  static int max_clusters_dev[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  bool& attr_set = attr_set_dev[dev];
+  int& max_clusters = max_clusters_dev[dev];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_rows16_kernel<MODE, PAIR, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
@@ -279,7 +294,8 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
 
 template <bool PAIR, bool GEN = false, bool OP16 = false>
 inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<PAIR, GEN, OP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;

@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
     const int ew = warp - 2;   // 0..15
     const int q = warp & 3;    // TMEM sub-partition (lanes 32q..32q+31)
     const int part = ew >> 2;  // 0..3: which of the sub-partition's four warps
-    const bool st0 = P.store_mask & 1, st1 = P.store_mask & 2, st2 = P.store_mask & 4;
+    // (a layer whose epilogue applies the final Linear never stores y: known at compile time, so its packed y is never kept)
+    const bool st0 = FUSE ? false : bool(P.store_mask & 1), st1 = P.store_mask & 2, st2 = P.store_mask & 4;
     const int n_out = int(st0) + int(st1) + int(st2);
     const int slots = n_out + P.n_in;
     const uint32_t wbuf = staging_base + ew * (slots * kTile16Bytes);
@@ -374,25 +375,23 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * P.buf_cols + ch * kChunk;
         const int c = col0 + ch * kChunk;  // first real output column of this chunk (also the smem table index)
         uint32_t raw[32];
-        f2 wn[8];  // 2D fwd: |w|^2 per feature pair
+        f2 wn[8];          // 2D fwd: |w|^2 per feature pair
+        uint32_t pkw[16];  // 2D fwd: the packed w half, staged together with y and z below
         if constexpr (MODE == MODE_GABOR2D_FWD) {
           // w half first: |w|^2 per feature is all the Gabor needs; w itself goes straight to its staging tile
           tmem_ld32(taddr + P.nbh, raw);
           tmem_wait_ld();
-          if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint32_t pk[4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float4 b = s_bias24[(c >> 2) + 2 * g + h];
               const f2 wr = f2_add(f2_bits(raw[8 * g + 4 * h], raw[8 * g + 4 * h + 1]), f2_make(b.x, b.y));
               const f2 wi = f2_add(f2_bits(raw[8 * g + 4 * h + 2], raw[8 * g + 4 * h + 3]), f2_make(b.z, b.w));
               wn[2 * g + h] = f2_fma(wr, wr, f2_mul(wi, wi));
-              pk[2 * h] = pack_f16(f2_lo(wr), f2_lo(wi));
-              pk[2 * h + 1] = pack_f16(f2_hi(wr), f2_hi(wi));
+              pkw[4 * g + 2 * h] = pack_f16(f2_lo(wr), f2_lo(wi));
+              pkw[4 * g + 2 * h + 1] = pack_f16(f2_hi(wr), f2_hi(wi));
             }
-            if (st2) sts128(sw64_addr(wbuf2, lane, g), pk[0], pk[1], pk[2], pk[3]);
           }
         }
         tmem_ld32(taddr, raw);
@@ -413,12 +412,12 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
             sts128(sw64_addr(wbuf, lane, g), pk[0], pk[1], pk[2], pk[3]);
           }
         } else if constexpr (kFwd) {
-          if constexpr (MODE != MODE_GABOR2D_FWD) {
-            if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
-          }
+          // all the math of the chunk first (results packed into the registers the accumulators leave behind), THEN the wait
+          // for the previous chunk's TMA stores to have read the staging tiles: the stores drain behind ~500 cycles of math
+          // instead of in front of it (ncu r01 v15: long_scoreboard 6.9 warps per issue cycle in the two-store forward layer)
+          uint32_t py[16], pz[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint32_t py[4], pz[4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {  // two feature pairs per group of 8 accumulator columns
               const float4 b = s_bias4[(c >> 2) + 2 * g + h];
@@ -434,13 +433,20 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
                 facc2[2] = f2_fma(yr, f2_make(w1.x, w1.y), f2_fma(yi, f2_make(w3.x, w3.y), facc2[2]));
                 facc2[3] = f2_fma(yr, f2_make(w1.z, w1.w), f2_fma(yi, f2_make(w3.z, w3.w), facc2[3]));
               }
-              py[2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
-              py[2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
-              pz[2 * h] = pack_f16(f2_lo(zr), f2_lo(zi));
-              pz[2 * h + 1] = pack_f16(f2_hi(zr), f2_hi(zi));
+              py[4 * g + 2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
+              py[4 * g + 2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
+              pz[4 * g + 2 * h] = pack_f16(f2_lo(zr), f2_lo(zi));
+              pz[4 * g + 2 * h + 1] = pack_f16(f2_hi(zr), f2_hi(zi));
             }
-            if (st0) sts128(sw64_addr(wbuf, lane, g), py[0], py[1], py[2], py[3]);
-            if (st1) sts128(sw64_addr(wbuf1, lane, g), pz[0], pz[1], pz[2], pz[3]);
+          }
+          if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (st0) sts128(sw64_addr(wbuf, lane, g), py[4 * g], py[4 * g + 1], py[4 * g + 2], py[4 * g + 3]);
+            if (st1) sts128(sw64_addr(wbuf1, lane, g), pz[4 * g], pz[4 * g + 1], pz[4 * g + 2], pz[4 * g + 3]);
+            if constexpr (MODE == MODE_GABOR2D_FWD) {
+              if (st2) sts128(sw64_addr(wbuf2, lane, g), pkw[4 * g], pkw[4 * g + 1], pkw[4 * g + 2], pkw[4 * g + 3]);
+            }
           }
         } else if constexpr (kBwd) {
           // this chunk's saved z (w) tile: copy the packed halves to registers, then prefetch the next tile into the same buffer
@@ -463,11 +469,9 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
             for (int s = 0; s < P.n_in; ++s)
               tma_load_2d(inbuf + s * kTile16Bytes, &P.z_map[s], bar, c + kEpi16Parts * kChunk, row0 + q * 32);
           }
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
+          uint32_t pz[16], pw[16];  // math first, store-read wait after it (see the forward branch)
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint32_t pz[4], pw[4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float2 za = unpack_f16(zp[4 * g + 2 * h]), zb = unpack_f16(zp[4 * g + 2 * h + 1]);
@@ -483,17 +487,22 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
               f2 yr, yi, gzr, gzi;
               gabor_x2(G2, zr, zi, wnorm, yr, yi);
               const f2 pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gr, gi, gzr, gzi);
-              pz[2 * h] = pack_bf16(f2_lo(gzr), f2_lo(gzi));
-              pz[2 * h + 1] = pack_bf16(f2_hi(gzr), f2_hi(gzi));
+              pz[4 * g + 2 * h] = pack_bf16(f2_lo(gzr), f2_lo(gzi));
+              pz[4 * g + 2 * h + 1] = pack_bf16(f2_hi(gzr), f2_hi(gzi));
               if constexpr (k2D) {
                 const f2 t = f2_mul(G2.m2s2, pr);
                 const f2 gwr = f2_mul(t, wr), gwi = f2_mul(t, wi);
-                pw[2 * h] = pack_bf16(f2_lo(gwr), f2_lo(gwi));
-                pw[2 * h + 1] = pack_bf16(f2_hi(gwr), f2_hi(gwi));
+                pw[4 * g + 2 * h] = pack_bf16(f2_lo(gwr), f2_lo(gwi));
+                pw[4 * g + 2 * h + 1] = pack_bf16(f2_hi(gwr), f2_hi(gwi));
               }
             }
-            if (st0) sts128(sw64_addr(wbuf, lane, g), pz[0], pz[1], pz[2], pz[3]);
-            if constexpr (k2D) { if (st1) sts128(sw64_addr(wbuf1, lane, g), pw[0], pw[1], pw[2], pw[3]); }
+          }
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (st0) sts128(sw64_addr(wbuf, lane, g), pz[4 * g], pz[4 * g + 1], pz[4 * g + 2], pz[4 * g + 3]);
+            if constexpr (k2D) { if (st1) sts128(sw64_addr(wbuf1, lane, g), pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]); }
           }
         } else {  // kFirst: real z0 recomputed from the coordinates and the smem weight table; BF16 direct stores
           uint32_t gzp[8], gwp[8];  // 16 real outputs as packed BF16 pairs (features A, B of each pair are adjacent)

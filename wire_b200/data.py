@@ -180,6 +180,9 @@ def run_epoch(trainer, batcher: GridBatcher, maxpoints: int, indices: Optional[t
     N = batcher.total
     world, rank = trainer.world, (dist.get_rank(trainer.group) if trainer.world > 1 else 0)
     if indices is None:
+        if world > 1 and generator is None:
+            raise WireB200Error("data-parallel run_epoch needs the epoch's permutation (indices=) or a generator that is in the "
+                                "same state on every rank: each rank would otherwise draw its own permutation")
         indices = torch.randperm(N, device=dev, generator=generator)
     indices = indices.to(dev, non_blocking=True)
     if rec is not None and world > 1:

@@ -78,7 +78,8 @@ class WorkspacePool:
     def lease_net(self, desc: NetDesc, n: int, training: bool, device) -> _Lease:
         lib = _lib.load()
         key = ("net", desc.two_d, desc.in_features, desc.width, desc.hidden_layers, desc.out_features,
-               desc.precision, int(n) if training else min(int(n), 1 << 19), bool(training), str(device))
+               desc.precision, int(n) if training else min(int(n), int(lib.wire_b200_infer_chunk_rows())), bool(training),
+               str(device))
         with self._lock:
             lst = self._free.get(key)
             buf = lst.pop() if lst else None
@@ -227,6 +228,7 @@ class WireNetFn(torch.autograd.Function):
                 lg.weight2, lg.bias2 = ptrs[2], ptrs[3]
             grads += [None, None]  # omega_0, scale_0 (non-trainable in every reference driver)
         G.final_weight, G.final_bias = views[vi].data_ptr(), views[vi + 1].data_ptr()
+        G.clear_mode, G.flat_base, G.flat_floats = _lib.GRADS_CLEAR_FLAT, flatg.data_ptr(), flatg.numel()   # one memset
         grads.append(torch.view_as_complex(views[vi].view(*tensors[-2].shape, 2)))
         grads.append(torch.view_as_complex(views[vi + 1].view(*tensors[-1].shape, 2)))
         g_coords = None
@@ -241,6 +243,23 @@ class WireNetFn(torch.autograd.Function):
         if g_coords is not None:
             g_coords = g_coords.reshape(ctx.coords_shape)
         return (None, g_coords, *grads)
+
+
+_WS_TENSORS = {"y": 0, "z": 1, "w": 2, "gz": 3, "gw": 4, "gz0": 5, "gw0": 6}
+
+
+def workspace_read(desc: NetDesc, n: int, workspace: torch.Tensor, which: str, index: int = 0) -> torch.Tensor:
+    """One tensor of a training workspace as dense float32 (C ABI ``wire_net_workspace_read``): ``which`` in
+    y / z / w / gz / gw / gz0 / gw0.  Complex tensors come back as complex64 ``[n, M]``, the first layer's real gradients
+    as float32 ``[n, M]``.  ``workspace`` is the buffer a ``wire_net_forward(training=1)`` (+ ``wire_net_backward``) ran on —
+    for the autograd route, ``out.grad_fn.lease.buf`` of the tensor ``model(coords)`` returned."""
+    lib = _lib.load()
+    real = which in ("gz0", "gw0")
+    out = torch.empty((n, desc.width if real else 2 * desc.width), dtype=torch.float32, device=workspace.device)
+    with torch.cuda.device(workspace.device):
+        check(lib.wire_net_workspace_read(ctypes.byref(desc), n, workspace.data_ptr(), workspace.numel(), _WS_TENSORS[which],
+                                          int(index), out.data_ptr(), _stream()), "wire_net_workspace_read")
+    return out if real else torch.view_as_complex(out.view(n, desc.width, 2))
 
 
 def wire_net(desc: NetDesc, coords: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -80,6 +80,34 @@ class _RawCudaBuffer:
         self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+def peer_exchange_possible(device: torch.device, group=None):
+    """(ok, reason): True when every rank of `group` runs on the same host and this rank's GPU has peer access to every other
+    rank's GPU — the precondition of ``PeerGradExchange`` (cudaIpc handles do not cross hosts).  Collective: every rank of
+    the group must call it; all ranks get the same answer."""
+    import socket
+    world = dist.get_world_size(group)
+    info = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), int(torch.device(device).index or 0)), group=group)
+    rank = dist.get_rank(group)
+    ok, why = True, ""
+    if len({h for h, _ in info}) != 1:
+        ok, why = False, "ranks span several hosts"
+    elif world > 16:
+        ok, why = False, "more than 16 ranks"
+    else:
+        me = info[rank][1]
+        for r, (_, d) in enumerate(info):
+            if r != rank and d != me and not torch.cuda.can_device_access_peer(me, d):
+                ok, why = False, f"no peer access between GPU {me} and GPU {d}"
+                break
+    flags = [None] * world
+    dist.all_gather_object(flags, (ok, why), group=group)
+    for o, w in flags:
+        if not o:
+            return False, w
+    return True, ""
+
+
 class PeerGradExchange:
     """One peer-mapped gradient buffer per rank; every rank's Adam kernel sums all of them with P2P loads.
 
@@ -108,14 +136,28 @@ class PeerGradExchange:
             self._own = base.value
             self._opened: List[int] = []
             self.bases = (ctypes.c_void_p * self.world)()
+            err = None
             for r in range(self.world):
                 if r == self.rank:
                     self.bases[r] = self._own
                 else:
                     ptr = ctypes.c_void_p()
-                    _lib.check(self.lib.wire_peer_open(handles[r], ctypes.byref(ptr)), f"wire_peer_open(rank {r})")
+                    try:
+                        _lib.check(self.lib.wire_peer_open(handles[r], ctypes.byref(ptr)), f"wire_peer_open(rank {r})")
+                    except _lib.WireB200Error as exc:
+                        err = str(exc)
+                        break
                     self.bases[r] = ptr.value
                     self._opened.append(ptr.value)
+            # every rank must reach the same verdict, or some would wait in the barrier kernels for peers that gave up
+            errs: List[Optional[str]] = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)
+            if any(e is not None for e in errs):
+                for ptr in self._opened:
+                    self.lib.wire_peer_close(ptr)
+                self.lib.wire_peer_free(self._own)
+                self._own, self._opened = None, []
+                raise _lib.WireB200Error("peer mapping failed: " + next(e for e in errs if e is not None))
         header = int(self.lib.wire_peer_header_bytes())
         self._raw = _RawCudaBuffer(self._own + header, self.n_floats)
         self.grad = torch.as_tensor(self._raw, device=device)

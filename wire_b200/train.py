@@ -65,16 +65,26 @@ class Trainer:
             self._starts.append(off)
             off += (s + 3) // 4 * 4
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        # data-parallel exchange: by default (NCCL backend = GPUs of one box) the flat gradient lives in a peer-mapped
-        # buffer and the Adam kernel sums every rank's gradients itself over NVLink (parallel.PeerGradExchange); with
-        # peer_exchange=False the step does one torch.distributed all-reduce of the flat buffer instead.
-        if peer_exchange is None:
-            peer_exchange = self.world > 1 and dist.get_backend(process_group) == "nccl" and \
-                os.environ.get("WIRE_B200_PEER", "1") != "0"
+        # data-parallel exchange.  peer_exchange=None (default): when every rank of the group sits on ONE host and every pair of
+        # their GPUs has peer access (the 8 B200s of an NVSwitch box), the flat gradient lives in a peer-mapped buffer and the
+        # Adam kernel sums every rank's gradients itself over NVLink (parallel.PeerGradExchange) — the ranks must then issue
+        # their steps in lock-step (a rank that pauses longer than WIRE_B200_PEER_TIMEOUT_S, default 600 s, makes the others
+        # trap).  Anything else (several hosts, no peer access, mapping failure, WIRE_B200_PEER=0, peer_exchange=False): one
+        # torch.distributed all-reduce of the flat buffer per step.  peer_exchange=True insists and raises if it cannot.
         self.peer = None
-        if peer_exchange and self.world > 1:
-            from .parallel import PeerGradExchange
-            self.peer = PeerGradExchange(off, dev, process_group)
+        if self.world > 1 and peer_exchange is not False:
+            from .parallel import PeerGradExchange, peer_exchange_possible
+            want = peer_exchange is True or os.environ.get("WIRE_B200_PEER", "1") != "0"
+            ok, why = peer_exchange_possible(dev, process_group) if want else (False, "disabled by WIRE_B200_PEER=0")
+            if ok:
+                try:
+                    self.peer = PeerGradExchange(off, dev, process_group)
+                except WireB200Error as exc:   # every rank fails or succeeds together (PeerGradExchange agrees on it)
+                    ok, why = False, str(exc)
+            if not ok and peer_exchange is True:
+                raise WireB200Error(f"peer gradient exchange requested but not possible: {why}")
+            self.peer_fallback_reason = None if ok else why
+        if self.peer is not None:
             self.flat_grad = self.peer.grad
         else:
             self.flat_grad = torch.zeros_like(self.flat)
@@ -88,6 +98,9 @@ class Trainer:
                 view.copy_(src)
                 p.data = torch.view_as_complex(view.view(*p.shape, 2)) if p.is_complex() else view.view(p.shape)
                 self._grad_views.append(self.flat_grad[o:o + s])
+        if self.world > 1:
+            # replicas must start from the same parameters (the peer path keeps them bit-identical from then on)
+            dist.broadcast(self.flat, 0, group=process_group)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -163,6 +176,12 @@ class Trainer:
                 lg.weight2, lg.bias2 = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
                 vi += 2
         G.final_weight, G.final_bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+        if self.peer is None:
+            # the Adam kernel clears every gradient element as it consumes it (zero_grad=1): no memset in the step
+            G.clear_mode = _lib.GRADS_PREZEROED
+        else:
+            # peers read this buffer during their Adam kernels: it is cleared after peer_wait, by ONE memset
+            G.clear_mode, G.flat_base, G.flat_floats = _lib.GRADS_CLEAR_FLAT, self.flat_grad.data_ptr(), self.flat_grad.numel()
         st["_G"] = G
         self._states[key] = st
         self.__dict__.update(st)
@@ -217,7 +236,7 @@ class Trainer:
             return
         check(self.lib.wire_adam_step_dev(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr_dev.data_ptr(), b1, b2, self.eps,
-                                          self.weight_decay, self.step_dev.data_ptr(), scale, self.scratch.data_ptr(),
+                                          self.weight_decay, self.step_dev.data_ptr(), scale, self.scratch.data_ptr(), 1,
                                           F._stream()), "wire_adam_step_dev")
 
     def _exchange_and_adam(self, scale: Optional[float] = None) -> None:
@@ -295,7 +314,7 @@ class Trainer:
         """Device scalar holding the loss of the step just issued: a slot of the loss ring, valid until ``len(loss_ring) - 1``
         further steps have been issued (copy it, e.g. to pinned memory on a side stream, if it is needed for longer)."""
         if self._pool is not None:
-            return self.loss_dev[0]
+            return self.loss_dev[0].clone()   # the pooled-loss kernel accumulates into one scalar that the next step clears
         return self.loss_ring[(self._issued - 1) % self.loss_ring.numel()]
 
     def _load_inputs(self, coords: torch.Tensor, target: torch.Tensor) -> None:
@@ -355,6 +374,31 @@ class Trainer:
             if rec is not None:
                 batcher.scatter(rec, self.out_buf, idx, start, count)
         return self._loss_of_last_step()
+
+    def step_sisr(self, coords_hr: torch.Tensor, gt_lr: torch.Tensor, gt_hr: Optional[torch.Tensor] = None):
+        """One iteration of the super-resolution loop (wire_SISR.py:154-177) after ``set_loss_avgpool(H, W, scale)``:
+
+            rec_hr = model(coords_hr); rec = AvgPool2d(scale)(rec_hr); loss = ((gt_lr - rec)**2).mean()     # :157-161
+            with torch.no_grad(): rec_hr = model(coords_hr); mse = ((gt - rec_hr)**2).mean()                 # :163-168
+            optim.zero_grad(); loss.backward(); optim.step()                                                 # :173-175
+
+        The reference's second, ``no_grad`` forward sees the same weights and coordinates as the first (the optimiser steps
+        after it), so it reproduces the first one bit for bit; here ONE forward serves both: the prediction the training
+        forward wrote is returned as ``rec_hr`` (a view of the step's output buffer, valid until the next step) and, when
+        ``gt_hr`` is given, its mean squared error against the high-resolution image is computed on the device.
+        Returns ``(loss, rec_hr, mse_hr or None)`` — device tensors, no host sync."""
+        if self._pool is None:
+            raise WireB200Error("call set_loss_avgpool(H, W, scale) first")
+        loss = self.step(coords_hr, gt_lr)
+        rec_hr = self.out_buf
+        mse_hr = None
+        if gt_hr is not None:
+            from . import data
+            g = gt_hr.reshape(rec_hr.shape)
+            if g.device != rec_hr.device:
+                g = g.to(rec_hr.device, non_blocking=True)
+            mse_hr = data.mse(g.contiguous(), rec_hr)
+        return loss, rec_hr, mse_hr
 
     def close(self) -> None:
         """Release the peer-mapped gradient buffer (collective: every rank must call it)."""
