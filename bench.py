@@ -176,17 +176,23 @@ def gpu_eager_reference_run(size, dev, steps=5, warmup=2):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (the oracle port: same op sequence as
+    modules/wire.py, `/root/reference` does not travel to the GPU box) on all host cores, on THIS arm's config — the full
+    512x512 batch per step (about 3 s per step on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = 256  # bounded sample of the 512x512 workload: a quarter of the coordinates per step
+    size = args.size
     r = cpu_reference_run(size, args.steps, max(args.warmup, 1))
     M = int(CFG["hidden_features"] / np.sqrt(2))
+    n = size * size
     line = {"impl": "reference", "metric": METRIC, "value": r["coords_per_s"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "WIRE image fit, 512x512 RGB, M=212 H=2 (sampled: 256x256 coords per step on CPU)",
-                       "width": M, "hidden_layers": CFG["hidden_layers"]},
+            "config": {"workload": f"WIRE image fit {size}x{size} RGB ({n} coords/GPU full-batch fwd+bwd+Adam), "
+                                   f"wire_image_denoise.py defaults: hidden 300 -> M={M}, H=2, omega0=7, sigma0=6",
+                       "width": M, "hidden_layers": CFG["hidden_layers"], "coords_per_gpu": n,
+                       "api": "oracle port of modules/wire.py INR + torch.optim.Adam on the host CPU (one process, all cores)"},
             "cpu_baseline": {"value": r["coords_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["coords_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -202,6 +208,52 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def pin_to_gpu_numa_node(local):
+    """Bind this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node of its GPU.
+    torchrun starts every rank unbound; with eight ranks on one socket the per-step staging copies and the Python thread of
+    each rank compete for the same memory controller (SCALE_r01: e2e efficiency 0.71-0.85 against 0.98 device-timed)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+    return None
+
+
+def timed_steps(trainer, coords, target, steps, barrier, world, dev, dist):
+    """`steps` training steps on device-resident inputs between CUDA events; max over ranks; ms per step."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        trainer.step(coords, target)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    return ms_total / steps
+
+
+E2E_LAG = 8   # the host consumes the loss of step i while step i + E2E_LAG is being enqueued
+
+
 def run_ours(args):
     import torch.distributed as dist
     import wire_b200
@@ -213,6 +265,7 @@ def run_ours(args):
     sys.stdout.flush()
     stdout_fd = os.dup(1)
     os.dup2(2, 1)
+    affinity = pin_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -223,18 +276,17 @@ def run_ours(args):
     size = args.size
     n = size * size
     M = int(CFG["hidden_features"] / np.sqrt(2))
+    H = CFG["hidden_layers"]
     torch.manual_seed(0)
     model = wire_b200.get_INR(**CFG, precision=args.precision).to(dev)
-    if world > 1:
-        from wire_b200 import parallel
-        parallel.broadcast_parameters(model)
     # weak scaling: every rank fits its own 512x512 tile of a (512*world) x 512 synthetic image
     _, noisy = synthetic_image(size, size, seed=rank)
     coords_h = image_coords(size, size).pin_memory()
     target_h = torch.from_numpy(noisy.reshape(1, n, 3)).pin_memory()
     coords = coords_h.to(dev)
     target = target_h.to(dev)
-    # the public training API: one call = forward + MSE + backward (+ gradient all-reduce) + Adam
+    # the public training API: one call = forward + MSE + backward (+ gradient exchange) + Adam; the constructor broadcasts
+    # rank 0's parameters
     trainer = wire_b200.Trainer(model, lr=LR, graph=not args.no_graph)
 
     def barrier():
@@ -268,22 +320,14 @@ def run_ours(args):
     launches_per_step = counters()
 
     # ---------------- timed region: device-resident inputs, CUDA events, max over ranks ----------------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        trainer.step(coords, target)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t)
-    ms_step = ms_total / args.steps
+    ms_step = timed_steps(trainer, coords, target, args.steps, barrier, world, dev, dist)
     value = world * n / (ms_step * 1e-3)
 
-    # ---------------- e2e: pinned host inputs, H2D every step, D2H loss read every step ----------------
+    # ---------------- e2e: pinned host inputs, H2D every step, D2H loss copy every step ----------------
+    # Every step copies its inputs host -> device and its loss device -> host (both inside the timed region).  The HOST reads
+    # the loss of step i only E2E_LAG steps later (the trainer keeps 256 steps of losses in its device ring, as the drivers'
+    # tqdm/loss.item() bookkeeping allows): a rank's Python thread may then run ahead of its GPU by a few steps, which
+    # absorbs host jitter instead of passing every hiccup of any rank on to all ranks through the in-kernel barrier.
     loss_pin = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
     evs = [torch.cuda.Event() for _ in range(args.steps)]
     losses = []
@@ -294,15 +338,16 @@ def run_ours(args):
         loss = trainer.step(coords_h, target_h)            # host -> device copies of this step's inputs inside
         done = torch.cuda.Event()
         done.record()
-        with torch.cuda.stream(side):                        # device -> host read of this step's loss, off the compute stream's
-            side.wait_event(done)                            # critical path (the loss lives in the trainer's ring for 255 more steps)
+        with torch.cuda.stream(side):                        # device -> host copy of this step's loss, off the compute stream's
+            side.wait_event(done)                            # critical path
             loss_pin[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
             evs[i].record(side)
-        if i > 0:                                            # consume the previous step's loss on the host
-            evs[i - 1].synchronize()
-            losses.append(float(loss_pin[i - 1]))
-    evs[-1].synchronize()
-    losses.append(float(loss_pin[-1]))
+        if i >= E2E_LAG:                                     # consume an earlier step's loss on the host
+            evs[i - E2E_LAG].synchronize()
+            losses.append(float(loss_pin[i - E2E_LAG]))
+    for i in range(max(0, args.steps - E2E_LAG), args.steps):
+        evs[i].synchronize()
+        losses.append(float(loss_pin[i]))
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if world > 1:
@@ -310,16 +355,29 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt)
     e2e = {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": coords_h.numel() * 4 + target_h.numel() * 4,
-           "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3, "final_loss": losses[-1],
-           "note": "trainer.step(host pinned coords, host pinned target): H2D staged on a copy stream; loss copied to pinned memory "
-                   "every step on a side stream and read on the host one step later"}
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3, "final_loss": losses[-1], "host_read_lag_steps": E2E_LAG,
+           "host_affinity": affinity,
+           "note": "trainer.step(host pinned coords, host pinned target): H2D staged on a copy stream; the loss of every step is "
+                   "copied to pinned memory on a side stream and read by the host E2E_LAG steps later; wall clock, max over ranks"}
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + e2e region"
 
+    # ---------------- sustained: >= 2000 consecutive steps (a real fit is 2000 iterations), its own clock samples ----------
+    sustained = None
+    if args.sustained_steps > 0:
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        ms_sus = timed_steps(trainer, coords, target, args.sustained_steps, barrier, world, dev, dist)
+        c2 = s2.stop() if rank == 0 else None
+        sustained = {"steps": args.sustained_steps, "ms_per_step": ms_sus, "value": world * n / (ms_sus * 1e-3), "unit": UNIT,
+                     "clocks": c2}
+
     # ---------------- the nn.Module + torch.optim.Adam route (what the reference drivers call) ----------------
-    module_ms = None
+    module_api = None
     if world == 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         opt = torch.optim.Adam(model.parameters(), lr=LR)
         for _ in range(3):
             loss = ((model(coords) - target) ** 2).mean(); opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
@@ -330,6 +388,10 @@ def run_ours(args):
         e1.record()
         barrier()
         module_ms = e0.elapsed_time(e1) / args.steps
+        module_api = {"ms_per_step": module_ms, "value": n / (module_ms * 1e-3), "unit": UNIT,
+                      "note": "the drop-in route the reference's drivers take unchanged: model(coords) (autograd.Function over the "
+                              "C ABI) -> torch MSE -> loss.backward() -> torch.optim.Adam.step(), eager, device-resident inputs"}
+        del opt
 
     # ---------------- per-kernel device time (CUDA events on the launching stream, eager replay of the step) ----
     roofline, kernels = None, {}
@@ -342,6 +404,12 @@ def run_ours(args):
         trainer.step(coords, target)
     barrier()
     trainer.use_graph = saved
+    step_flop = flop_per_coord(M, H, CFG["in_features"], CFG["out_features"]) * n
+    peaks, peaks_src = load_peaks()
+    mixed = args.precision == "mixed16"
+    # the peak of the PIPE USED: kind::f16 MMAs against the measured cuBLAS BF16 figure (burst: these regions last tens of
+    # milliseconds), kind::tf32 MMAs issue at half that rate; FP32 FMAs have no tensor roofline
+    tensor_peak = peaks["bf16_tflops"] / (1.0 if mixed else 2.0)
     if rank == 0:
         total_ms = 0.0
         for k in range(lib.wire_b200_prof_kinds()):
@@ -353,15 +421,12 @@ def run_ours(args):
                 total_ms += ms.value
         lib.wire_b200_prof_enable(0)
         lib.wire_b200_prof_reset()
-        peaks, peaks_src = load_peaks()
         top = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
-        gemm_flop = 8.0 * M * M * n  # one complex M x M GEMM over n coordinates (fwd, dgrad and wgrad alike)
-        unit_b = 8.0 * M * n         # one complex fp32 activation tensor [n, M] in HBM (DESIGN.md 3.4)
-        # algorithmic HBM bytes per launch, in units; a = activation y, g = gradient g_z, z = saved pre-activation (FP16 on
-        # both tensor-core paths), real fp32 g_z0 = 0.5.  The forward entry is the average over the H launches (the last
-        # layer's y is never written: the final Linear is fused into its epilogue).
-        H = CFG["hidden_layers"]
-        mixed = args.precision == "mixed16"
+        gemm_flop = 8.0 * M * M * n  # one complex M x M GEMM over n coordinates (fwd, dgrad and wgrad alike), SURVEY 8(d)
+        unit_b = 8.0 * M * n         # one complex fp32 activation tensor [n, M] in HBM (DESIGN.md 3)
+        # algorithmic HBM bytes per launch of THIS design, in units; a = activation y, g = gradient g_z, z = saved
+        # pre-activation (FP16 on both tensor-core paths), real g_z0 = half of that.  The forward entry is the average over the H
+        # launches (the last layer's y is never written: the final Linear is fused into its epilogue).
         a_u = 0.5 if mixed else 1.0
         g_u = 0.5 if mixed else 1.0
         z_u = 1.0 if args.precision == "fp32" else 0.5
@@ -372,54 +437,94 @@ def run_ours(args):
         alg_bytes = {k: v * unit_b for k, v in alg_units.items()}
         step_units = (alg_units["first_fwd"] + H * alg_units["tc_rows_gabor_fwd"] + alg_units["top_bwd"] + H * alg_units["tc_wgrad"]
                       + (H - 1) * alg_units["tc_rows_dgrad_gabor_bwd"] + alg_units["tc_rows_dgrad_first_bwd"] + alg_units["first_wgrad"])
-        tensor_peak = peaks["bf16_tflops_sustained"] / (1.0 if mixed else 2.0)
         for k, v in kernels.items():
             if k in alg_bytes:
                 v["hbm_gbs"] = alg_bytes[k] / (v["ms_avg"] * 1e-3) / 1e9
                 v["hbm_frac"] = v["hbm_gbs"] / peaks["hbm_gbs"]
             if k.startswith("tc_"):
                 v["tflops"] = gemm_flop / (v["ms_avg"] * 1e-3) / 1e12
-        if top is not None:
-            # Each hidden-layer kernel must move 3 activation-sized tensors through HBM for 8 M^2 flop/coord
-            # (M/3 flop/B = 71 at M=212, below the TF32 ridge of ~170): the binding roofline is HBM.
-            ach = kernels[top].get("hbm_gbs")
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": (ach / peaks["hbm_gbs"]) if ach else None,
-                        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this kernel
-                        # (profiles/r01_ncu_full_v6_summary.txt): 530.7 MB + 835.0 MB
+                v["tensor_frac"] = v["tflops"] / tensor_peak
+        if top is not None and "tflops" in kernels[top]:
+            # the binding roofline of the dense complex contraction is the TENSOR pipe; HBM is the co-constraint
+            ach = kernels[top]["tflops"]
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                        "frac": ach / tensor_peak,
                         "traffic": NCU_TRAFFIC.get((args.precision, top)) if size == 512 else None,
-                        "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs",
-                        "algorithmic_bytes_per_launch": alg_bytes.get(top),
-                        "tensor_achieved_tflops": kernels[top].get("tflops"),
-                        "tensor_peak_tflops": tensor_peak,
-                        "tensor_frac": (kernels[top]["tflops"] / tensor_peak) if "tflops" in kernels[top] else None,
-                        "tensor_peak_source": f"{peaks_src} bf16_tflops_sustained" + ("" if mixed else "/2 (TF32 issues at half the BF16 rate)"),
+                        "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops (burst)" + ("" if mixed else " / 2 (kind::tf32 issues at half the BF16 rate)"),
+                        "algorithmic_flop_per_launch": gemm_flop,
                         "share_of_step": kernels[top]["ms_total"] / total_ms if total_ms else None,
-                        "step_algorithmic_bytes": step_units * unit_b,
-                        "step_hbm_frac": step_units * unit_b / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-        step_flop = flop_per_coord(M, CFG["hidden_layers"], CFG["in_features"], CFG["out_features"]) * n
+                        "hbm": {"achieved": kernels[top].get("hbm_gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": kernels[top].get("hbm_frac"), "algorithmic_bytes_per_launch": alg_bytes.get(top),
+                                "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs"},
+                        "step": {"algorithmic_flop": step_flop, "tflops": step_flop / (ms_step * 1e-3) / 1e12,
+                                 "tensor_frac": step_flop / (ms_step * 1e-3) / 1e12 / tensor_peak,
+                                 "design_bytes": step_units * unit_b,
+                                 "hbm_frac": step_units * unit_b / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                 "fused_minimum_bytes": float(n * (4 * CFG["in_features"] + 8 * CFG["out_features"]))}}
+
+    # ---------------- secondary: the 32-bit-operand (TF32) mode on the same workload ----------------
+    trainer.close()
+    del trainer
+    tf32 = None
+    if args.precision == "mixed16" and not args.no_extras:
+        m32 = wire_b200.get_INR(**CFG, precision="tf32").to(dev)
+        t32 = wire_b200.Trainer(m32, lr=LR, graph=not args.no_graph)
+        for _ in range(3):
+            t32.step(coords, target)
+        ms32 = timed_steps(t32, coords, target, args.steps, barrier, world, dev, dist)
+        tf32 = {"ms_per_step": ms32, "value": world * n / (ms32 * 1e-3), "unit": UNIT,
+                "algorithmic_tflops_per_gpu": step_flop / (ms32 * 1e-3) / 1e12,
+                "frac_of_nominal_tf32_peak": step_flop / (ms32 * 1e-3) / 1e12 / 1100.0,
+                "frac_of_measured_bf16_burst_halved": step_flop / (ms32 * 1e-3) / 1e12 / (peaks["bf16_tflops"] / 2.0)}
+        t32.close()
+        del t32, m32
+        torch.cuda.empty_cache()
+
+    # ---------------- BASELINE configs [2] and [3] under the same clock: wire2d SISR 1024^2, occupancy 512^3 ----------------
+    extras = {}
+    if not args.no_extras:
+        if world == 1:
+            try:
+                extras["sisr_1024"] = sisr_extra(dev, args.steps)
+            except Exception as exc:
+                extras["sisr_1024"] = {"error": repr(exc)[:300]}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import occupancy_bench as OB
+            vol = OB.synthetic_volume(args.occupancy_size, dev)
+            occ = {}
+            for scaling in (("weak", "strong") if world > 1 else ("weak",)):
+                occ[scaling] = OB.run_occupancy(dev, world, rank, size=args.occupancy_size, chunk=200000, steps=args.occupancy_steps,
+                                                warmup=5, scaling=scaling, precision=args.precision, iou=True, vol=vol)
+            if world == 1:
+                occ["strong"] = occ["weak"]    # one GPU: the same run
+            del vol
+            extras["occupancy_512cube"] = occ
+        except Exception as exc:
+            extras["occupancy_512cube"] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        cpu = cpu_reference_run(256, 3, 1) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = cpu_reference_run(size, 3, 1) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"tf32": "tf32", "fp32": "f32", "mixed16": "f16 activations x bf16 gradients, f32 accumulate"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"WIRE image fit {size}x{size} RGB ({n} coords/GPU full-batch fwd+bwd+Adam), "
                                        f"wire_image_denoise.py defaults: hidden 300 -> M={M}, H=2, omega0=7, sigma0=6",
-                           "width": M, "hidden_layers": CFG["hidden_layers"], "coords_per_gpu": n,
-                           "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if trainer.use_graph and (world == 1 or trainer.peer is not None) else ""),
+                           "width": M, "hidden_layers": H, "coords_per_gpu": n,
+                           "api": "wire_b200.Trainer.step" + (" (CUDA graph)" if saved and (world == 1 or launches_per_step) else ""),
                            "parallelism": f"coord-sharded dp{world}" if world > 1 else "single GPU",
-                           "exchange": (None if world == 1 else
-                                        ("flat fp32 gradients summed by the Adam kernel with P2P loads over NVLink (no NCCL call per step)"
-                                         if trainer.peer is not None else "one NCCL all-reduce of the flat fp32 gradient per step")),
+                           "exchange": (None if world == 1 else "flat fp32 gradients summed by the Adam kernel with P2P loads over NVLink "
+                                        "(no NCCL call per step) when the ranks share a host with peer access, else one all-reduce"),
                            "precision": args.precision,
-                           "l2": "per-step activation traffic (>4 GB) far exceeds the 126 MB L2; no explicit flush"},
+                           "l2": "per-step activation traffic (>3.7 GB) far exceeds the 126 MB L2; no explicit flush"},
                 "algorithmic_tflops": world * step_flop / (ms_step * 1e-3) / 1e12,
-                "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,  # per GPU
-                "module_api_ms_per_step": module_ms,
+                "frac_of_measured_bf16_burst": step_flop / (ms_step * 1e-3) / 1e12 / tensor_peak,   # per GPU, peak of the pipe used
+                "frac_of_nominal_tf32_peak": step_flop / (ms_step * 1e-3) / 1e12 / 1100.0,  # per GPU (the north-star's denominator)
                 "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "clocks": clocks, "roofline": roofline, "kernels": kernels}
+                "clocks": clocks, "roofline": roofline, "sustained": sustained, "module_api": module_api, "tf32": tf32,
+                "extras": extras, "kernels": kernels}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["gpu_eager_baseline"] = gpu_eager_reference_run(size, dev)
@@ -432,9 +537,48 @@ def run_ours(args):
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    trainer.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sisr_extra(dev, steps):
+    """BASELINE config [2]: wire2d 4x super-resolution of a synthetic 1024x1024 image (wire_SISR.py:154-177: grad forward over
+    the 1 048 576 HR coordinates, AvgPool2d(4) + MSE against the 256x256 LR image, backward, Adam; the reference's second
+    no_grad forward is the same numbers as the first and is served by it — Trainer.step_sisr)."""
+    import wire_b200
+    Hh = Ww = 1024
+    scale = 4
+    img, _ = synthetic_image(Hh, Ww, seed=5)
+    gt_hr = torch.from_numpy(img.reshape(Hh * Ww, 3)).to(dev)
+    gt_lr = torch.nn.functional.avg_pool2d(gt_hr.reshape(Hh, Ww, 3).permute(2, 0, 1)[None], scale)[0].permute(1, 2, 0).reshape(-1, 3).contiguous()
+    coords = image_coords(Hh, Ww).to(dev)
+    torch.manual_seed(0)
+    model = wire_b200.get_INR(nonlin="wire2d", in_features=2, hidden_features=256, hidden_layers=2, out_features=3,
+                              first_omega_0=8.0, hidden_omega_0=8.0, scale=9.0).to(dev)     # wire_SISR.py:50-56,111-120
+    tr = wire_b200.Trainer(model, lr=5e-3)
+    tr.set_loss_avgpool(Hh, Ww, scale)
+    for _ in range(3):
+        tr.step_sisr(coords, gt_lr, gt_hr)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, rec_hr, mse_hr = tr.step_sisr(coords, gt_lr, gt_hr)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    M, H = model.width, 2
+    train_flop = (48 * H * M * M + 12 * M * 3 + 8 * 2 * M) * Hh * Ww
+    peaks, _ = load_peaks()
+    res = {"workload": "wire2d 4x SISR, 1024x1024 HR (1 048 576 coords) -> 256x256 LR, M=128, H=2, omega0=8, sigma0=9",
+           "ms_per_iteration": ms, "coords_per_s": Hh * Ww / (ms * 1e-3), "steps": steps,
+           "algorithmic_tflops": train_flop / (ms * 1e-3) / 1e12,
+           "frac_of_measured_bf16_burst": train_flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+           "loss": float(loss), "mse_hr": float(mse_hr),
+           "note": "one iteration = grad forward + pooled MSE + backward + Adam + HR metrics (MSE against the HR image on the "
+                   "device); the reference's second no_grad forward is shared with the first (bit-identical inputs and weights)"}
+    tr.close()
+    return res
 
 
 def main():
@@ -447,6 +591,10 @@ def main():
     ap.add_argument("--precision", default="mixed16", choices=["mixed16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tf32 / wire2d SISR / occupancy 512^3 secondary measurements")
+    ap.add_argument("--sustained-steps", type=int, default=2000)
+    ap.add_argument("--occupancy-size", type=int, default=512)
+    ap.add_argument("--occupancy-steps", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

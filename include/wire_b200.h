@@ -74,6 +74,11 @@ typedef struct wire_layer_grads {
   float* bias;
   float* weight2;
   float* bias2;
+  /* trainable=True of ComplexGaborLayer(2D) (modules/wire.py:66,80-81): gradients of the layer's own omega_0 / scale_0, one float
+   * each, accumulated inside the fused backward kernels of wire_net_backward (MIXED16 only); NULL = the scalars are constants.
+   * Ignored by the single-layer entry points (wire_gabor_scalar_grads serves those). */
+  float* omega0;
+  float* scale0;
 } wire_layer_grads;
 
 /* How wire_net_backward clears the accumulation targets before its kernels add into them (split-K partial sums are
@@ -255,6 +260,16 @@ int wire_sq_err_stats(const float* x, const float* xhat, int64_t count, double* 
  *   *loss (device scalar, may be NULL) and grad_out [H*W][channels] receives d loss / d pred. */
 int wire_avgpool_mse_loss_grad(const float* pred, const float* target_lr, int32_t H, int32_t W, int32_t channels, int32_t scale,
                                float* grad_out, float* loss, void* stream);
+
+/* Radon forward operator of the CT driver and its adjoint (modules/lin_inverse.py:19-40 `radon`, called every iteration by
+ * wire_ct.py:126-128): image [nimg][H][W] -> sinogram [nangles][nimg][W], each angle (degrees) rotating the image about its centre
+ * like kornia.geometry.rotate (bilinear, zeros outside, align_corners=True) and summing over the rows.  wire_radon_backward
+ * OVERWRITES grad_image [nimg][H][W] with the adjoint applied to grad_sinogram (autograd of the above).  kornia is not part of
+ * the build image: the rotation convention is restated from its published source, parity against kornia itself is unpinned. */
+int wire_radon_forward(const float* image, int32_t nimg, int32_t H, int32_t W, const float* angles_deg, int32_t nangles, float* sinogram,
+                       void* stream);
+int wire_radon_backward(const float* grad_sinogram, int32_t nimg, int32_t H, int32_t W, const float* angles_deg, int32_t nangles,
+                        float* grad_image, void* stream);
 
 /* Gradients of a layer's own omega_0 / scale_0 (trainable=True of ComplexGaborLayer(2D), modules/wire.py:66,80-81,
  * modules/wire2d.py:27,42-43; autograd of wire.py:88-93 w.r.t. the two scalars): out2[0] += sum Im(conj(z) p),

@@ -315,3 +315,58 @@ def real_gabor_np(x, w_freqs, b_freqs, w_scale, b_scale, omega0, s0):
     f = x @ np.asarray(w_freqs, dtype=np.float64).T + np.asarray(b_freqs, dtype=np.float64)
     s = x @ np.asarray(w_scale, dtype=np.float64).T + np.asarray(b_scale, dtype=np.float64)
     return np.cos(omega0 * f) * np.exp(-((s0 * s) ** 2))
+
+
+# ======================================================================================================================
+# Radon forward operator of the CT driver — PARITY UNPINNED: the reference computes it with
+# ``kornia.geometry.rotate`` (modules/lin_inverse.py:19-40), kornia (pinned 0.6.9 in the reference's requirements) is neither
+# under /root/reference nor installed in the build image, and the reference ships no sinogram fixture.  Restated from kornia's
+# published source: rotate(tensor, angle) = warp_affine with get_rotation_matrix2d(center=((W-1)/2, (H-1)/2), angle [deg],
+# scale 1) = [[a, b, (1-a) cx - b cy], [-b, a, b cx + (1-a) cy]], a = cos, b = sin; warp_affine inverts the matrix in
+# normalised coordinates and samples with F.affine_grid / F.grid_sample(mode='bilinear', padding_mode='zeros',
+# align_corners=True).  So out[i][j] = bilinear(im, c + R^T ((j, i) - c)), R^T = [[cos, -sin], [sin, cos]].
+# ======================================================================================================================
+def rotate_torch(imten: torch.Tensor, angles_deg: torch.Tensor) -> torch.Tensor:
+    """kornia.geometry.rotate(imten [B,C,H,W], angles [B]) restated with affine_grid / grid_sample (autograd-capable)."""
+    B, C, H, W = imten.shape
+    t = angles_deg.to(imten.dtype) * (math.pi / 180.0)
+    cs, sn = torch.cos(t), torch.sin(t)
+    ry = (H - 1) / max(W - 1, 1)
+    rx = (W - 1) / max(H - 1, 1)
+    zero = torch.zeros_like(cs)
+    theta = torch.stack([torch.stack([cs, -sn * ry, zero], -1), torch.stack([sn * rx, cs, zero], -1)], 1)   # [B, 2, 3]
+    grid = torch.nn.functional.affine_grid(theta, [B, C, H, W], align_corners=True)
+    return torch.nn.functional.grid_sample(imten, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+
+
+def radon_torch(imten: torch.Tensor, angles_deg: torch.Tensor, is_3d: bool = False) -> torch.Tensor:
+    """modules/lin_inverse.py:19-40 line for line, with ``rotate_torch`` in the place of ``kornia.geometry.rotate``."""
+    nangles = len(angles_deg)
+    imten_rep = torch.repeat_interleave(imten, nangles, 0)
+    imten_rot = rotate_torch(imten_rep, angles_deg)
+    if is_3d:
+        return imten_rot.sum(2).squeeze().permute(1, 0, 2)
+    return imten_rot.sum(2).squeeze()
+
+
+def radon_np(im: np.ndarray, angles_deg) -> np.ndarray:
+    """Direct float64 loops over the same formula (small cases): im [H][W] -> sinogram [nangles][W]."""
+    H, W = im.shape
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    out = np.zeros((len(angles_deg), W))
+    for a, deg in enumerate(angles_deg):
+        t = np.deg2rad(float(deg))
+        c, s = np.cos(t), np.sin(t)
+        for j in range(W):
+            acc = 0.0
+            for i in range(H):
+                xs = cx + c * (j - cx) - s * (i - cy)
+                ys = cy + s * (j - cx) + c * (i - cy)
+                x0, y0 = int(np.floor(xs)), int(np.floor(ys))
+                ax, ay = xs - x0, ys - y0
+                for yy, wy in ((y0, 1 - ay), (y0 + 1, ay)):
+                    for xx, wx in ((x0, 1 - ax), (x0 + 1, ax)):
+                        if 0 <= xx < W and 0 <= yy < H:
+                            acc += wx * wy * im[yy, xx]
+            out[a, j] = acc
+    return out

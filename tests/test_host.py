@@ -79,11 +79,16 @@ def test_no_cpu_fallback():
     # trainable omega_0 / scale_0 run through the layer-by-layer CUDA route: still no CPU path ...
     with pytest.raises(wire_b200.WireB200Error, match="CUDA"):
         wire_b200.wire.ComplexGaborLayer(2, 8, is_first=True, trainable=True)(torch.zeros(4, 2))
-    # ... and the fused Trainer refuses them instead of silently freezing the scalars
-    m2 = wire_b200.get_INR("wire", 2, 64, None, 1, 3)
+    # ... the fused Trainer takes them on the mixed16 path (CUDA only), and refuses them for the other precisions instead of
+    # silently freezing the scalars
+    m2 = wire_b200.get_INR("wire", 2, 64, None, 1, 3, precision="tf32")
     m2.net[1].omega_0.requires_grad_(True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(wire_b200.WireB200Error, match="mixed16"):
         wire_b200.Trainer(m2)
+    m3 = wire_b200.get_INR("wire", 2, 64, None, 1, 3)
+    m3.net[1].omega_0.requires_grad_(True)
+    with pytest.raises(wire_b200.WireB200Error, match="CUDA"):
+        wire_b200.Trainer(m3)
 
 
 def test_product_never_imports_the_oracle():

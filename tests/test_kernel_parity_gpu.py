@@ -27,21 +27,28 @@ record = util.record
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# (1) per kernel, from identical inputs.  Relative RMS error bars by (precision, kind of output):
-#   fwd : z / y / out of a forward kernel       bwd : g_z / g_w of a backward kernel (stored BF16 under mixed16: 2^-9 rounding
-#   wgrad : weight / bias gradients (sums over n coordinates)                          of every element = 2.3e-3 RMS by itself)
-# north_star: "about 1e-3 at TF32" per layer from identical inputs.
+# (1) per kernel, from identical inputs.  Bars on the relative RMS error by (precision, kind of output), each <= 3x the
+# largest value measured on a B200 over the four network shapes (profiles/r02_parity_measured.json):
+#   fwd   : z / y / out of a forward kernel.  Measured mixed16 = tf32 (FP16 carries TF32's significand): z 2.9e-4, y 2.7e-4 ..
+#           5.1e-4, out 6.3e-4 on the denoise / SISR networks; the occupancy network's omega_0 = 20 turns the same z error into
+#           a 3x larger phase error of y (9.1e-4 .. 1.9e-3), hence its own bar.  fp32: <= 1.9e-6.
+#   bwd   : g_z / g_w of a backward kernel, coordinate gradient.  tf32 2.1e-4 .. 3.0e-4; mixed16 1.7e-3 .. 2.4e-3, which is the
+#           BF16 STORAGE rounding of the result itself (2^-9 uniform = 2.3e-3 RMS), not accumulated GEMM error.  fp32 <= 4.7e-7.
+#   wgrad : weight / bias gradients.  fp32 and tf32 <= 1.3e-6 (sums over n coordinates average the rounding out); mixed16
+#           1.4e-3 .. 1.8e-3 (the FP16 -> BF16 conversion of the x operand).
+# north_star: "about 1e-3 at TF32" per layer from identical inputs — met by tf32 and by mixed16's forward on the image
+# networks; mixed16's backward sits at the BF16 storage floor.
 # ---------------------------------------------------------------------------------------------------------------------
 KERNEL_BARS = {
-    "fp32": dict(fwd=2e-5, bwd=2e-5, wgrad=5e-5),
-    "tf32": dict(fwd=1.5e-3, bwd=1.5e-3, wgrad=1.5e-3),
-    "mixed16": dict(fwd=1.5e-3, bwd=6e-3, wgrad=6e-3),
+    "fp32": dict(fwd=6e-6, fwd_w20=6e-6, bwd=1.5e-6, wgrad=4e-6),
+    "tf32": dict(fwd=1.9e-3, fwd_w20=5.7e-3, bwd=9e-4, wgrad=4e-6),
+    "mixed16": dict(fwd=1.9e-3, fwd_w20=5.7e-3, bwd=7e-3, wgrad=5.4e-3),
 }
 
 
-def _bar_kind(stage):
+def _bar_kind(stage, case):
     if stage.startswith("fwd"):
-        return "fwd"
+        return "fwd_w20" if case.startswith("occupancy") else "fwd"
     if stage.startswith("wgrad") or stage.startswith("top.g_Wf") or stage.startswith("top.g_bf"):
         return "wgrad"
     return "bwd"
@@ -58,7 +65,7 @@ def test_every_kernel_from_identical_inputs(case, precision):
     err = KP.kernel_errors(m, ref, coords, grad_out)
     record("per_kernel", f"{case}/{precision}", err)
     bars = KERNEL_BARS[precision]
-    bad = {k: v for k, v in err.items() if not (v < bars[_bar_kind(k)])}
+    bad = {k: v for k, v in err.items() if not (v < bars[_bar_kind(k, case)])}
     assert not bad, (case, precision, bad)
     # every stage of the step was reached (a silently skipped comparison would look like a pass)
     assert any(k.startswith("top.g_z") for k in err) or c["H"] > 2
@@ -75,12 +82,16 @@ SIZE_CASES = {
         np.random.RandomState(3).uniform(-1, 1, size=(1, 200000, 3)).astype(np.float32))),
     "wire2d_sisr_131072": ("sisr2d", lambda: O.image_coords(512, 256)),
 }
-# relative RMS of (output, worst parameter gradient) against the complex128 oracle; the oracle's own complex64 run sits at
-# ~1e-6 / ~1e-5 (recorded next to the measurements)
+# bars on the relative RMS of (output, worst of the parameter / coordinate gradients) against the complex128 oracle, <= 3x the
+# values measured on a B200 (profiles/r02_parity_measured.json): denoise fp32 2.0e-6 / 3.6e-6, tf32 2.1e-3 / 3.3e-3, mixed16
+# 2.1e-3 / 5.1e-3; occupancy chunk (random init, omega_0 20, s0 10, three hidden layers: SURVEY.md 7 predicted 5e-2 for
+# TF32-rounded operands) fp32 4.8e-5 / 7.2e-5, tf32 5.2e-2 / 7.8e-2, mixed16 5.2e-2 / 7.8e-2; wire2d fp32 8.1e-7 / 2.0e-6, tf32
+# 1.2e-3 / 2.5e-3, mixed16 1.2e-3 / 5.3e-3.  The oracle's own complex64 run sits at 1.7e-6 / 2.5e-6 (denoise) and 5.3e-5 / 8.1e-5
+# (occupancy) from the same truth: the FP32 kernels are as close to complex128 as the reference's own arithmetic.
 SIZE_BARS = {
-    "denoise_512x512": {"fp32": (1e-4, 1e-3), "tf32": (6e-3, 1.5e-2), "mixed16": (6e-3, 1.5e-2)},
-    "occupancy_chunk_200k": {"fp32": (1e-3, 5e-3), "tf32": (1.5e-1, 3e-1), "mixed16": (1.5e-1, 3e-1)},
-    "wire2d_sisr_131072": {"fp32": (1e-4, 1e-3), "tf32": (1e-2, 3e-2), "mixed16": (1e-2, 3e-2)},
+    "denoise_512x512": {"fp32": (6e-6, 1.1e-5), "tf32": (6.3e-3, 1e-2), "mixed16": (6.3e-3, 1.55e-2)},
+    "occupancy_chunk_200k": {"fp32": (1.5e-4, 2.2e-4), "tf32": (1.56e-1, 2.3e-1), "mixed16": (1.56e-1, 2.3e-1)},
+    "wire2d_sisr_131072": {"fp32": (2.5e-6, 6e-6), "tf32": (3.6e-3, 7.6e-3), "mixed16": (3.6e-3, 1.6e-2)},
 }
 _oracle_cache = {}
 

@@ -180,3 +180,24 @@ def test_real_gabor_restatement_matches_reference_fixture():
     w0, s0 = (float(v) for v in g["hyper"])
     y = O.real_gabor_np(g["x"], g["param.freqs.weight"], g["param.freqs.bias"], g["param.scale.weight"], g["param.scale.bias"], w0, s0)
     assert util.rel_err(y, g["y_f64"]) < 1e-6      # (the fixture's parameters are float32 values)
+
+
+def test_radon_restatement_is_self_consistent():
+    """The Radon oracle (parity unpinned: kornia absent, see oracle/wire_oracle.py): affine_grid / grid_sample form == direct
+    float64 loops; angle 0 is the plain column sum, 180 degrees the mirrored one, 90 degrees of a square image the row sums."""
+    rs = np.random.RandomState(0)
+    im = rs.uniform(size=(9, 12))
+    ang = [0.0, 17.0, 90.0, 133.5, 180.0, -45.0]
+    a = O.radon_torch(torch.from_numpy(im)[None, None], torch.tensor(ang, dtype=torch.float64)).numpy()
+    b = O.radon_np(im, ang)
+    assert a.shape == (len(ang), 12) and np.abs(a - b).max() < 1e-12
+    assert np.abs(a[0] - im.sum(0)).max() < 1e-12
+    assert np.abs(a[4] - im.sum(0)[::-1]).max() < 1e-9
+    sq = rs.uniform(size=(8, 8))
+    r = O.radon_np(sq, [90.0])[0]
+    assert np.abs(r - sq.sum(1)).max() < 1e-9 or np.abs(r - sq.sum(1)[::-1]).max() < 1e-9
+    # is_3d: (1, nimg, H, W) -> (nimg, nangles, W)
+    vol = torch.from_numpy(rs.uniform(size=(1, 3, 8, 8)))
+    s3 = O.radon_torch(vol, torch.tensor([0.0, 30.0], dtype=torch.float64), is_3d=True)
+    assert tuple(s3.shape) == (3, 2, 8)
+    assert np.abs(s3[1, 0].numpy() - vol[0, 1].numpy().sum(0)).max() < 1e-12

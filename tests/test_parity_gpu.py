@@ -27,6 +27,10 @@ TOL = {
 }
 
 
+# fixtures whose hyper-parameters amplify operand rounding (occupancy: omega_0 = 20, s0 = 10): multiplier on the bars above
+GOLDEN_GAIN = {}
+
+
 def build_ours(c, precision):
     import wire_b200
     kw = dict(nonlin=c["kind"], in_features=c["in_f"], hidden_features=c["hidden"], hidden_layers=c["H"],
@@ -50,15 +54,22 @@ def test_net_forward_backward_vs_golden(name, precision):
     assert out.dtype == torch.float32 and tuple(out.shape) == tuple(g["out_c64"].shape)
     (out * grad_out).sum().backward()
     torch.cuda.synchronize()
-    # truth = the reference in complex128; also report distance of the reference's own c64 run
-    assert util.rel_err(out.detach().cpu().numpy(), g["out_c128"]) < tol["out"]
-    assert util.rel_err(coords.grad.cpu().numpy(), g["gcoords_c128"]) < tol["grad"]
+    # truth = the reference in complex128
+    e_out = util.rel_err(out.detach().cpu().numpy(), g["out_c128"])
+    e_gc = util.rel_err(coords.grad.cpu().numpy(), g["gcoords_c128"])
+    e_g = {}
     for k, p in m.named_parameters():
         if not p.requires_grad:
             assert p.grad is None
             continue
         a, b = util.golden_grad(c, "c128", k, p.grad.detach().cpu().numpy())
-        assert util.rel_err(a, b) < tol["grad"], (k, util.rel_err(a, b))
+        e_g[k] = util.rel_err(a, b)
+    util.record("golden", f"{name}/{precision}", {"out": e_out, "gcoords": e_gc, "grad_max": max(e_g.values())})
+    hi = GOLDEN_GAIN.get(name, 1.0)
+    assert e_out < hi * tol["out"], e_out
+    assert e_gc < hi * tol["grad"], e_gc
+    for k, e in e_g.items():
+        assert e < hi * tol["grad"], (k, e)
     last = max(int(k.split(".")[1]) for k in m.state_dict())
     assert torch.all(m.net[last].bias.grad.imag == 0)  # exact zero, as in the reference
 
@@ -79,7 +90,9 @@ def test_per_layer_from_identical_inputs(name, precision):
         y = m.net[i](xg)
         want = g[f"layer{i}_c128"]
         assert y.dtype == torch.complex64
-        assert util.rel_err(y.detach().cpu().numpy(), want) < tol["layer"], (i, util.rel_err(y.detach().cpu().numpy(), want))
+        e_y = util.rel_err(y.detach().cpu().numpy(), want)
+        util.record("per_layer_api", f"{name}/{precision}/layer{i}", e_y)
+        assert e_y < tol["layer"], (i, e_y)
         # per-layer backward against complex128 autograd of the oracle layer on the same input
         rl = ref.net[i]
         for p in rl.parameters():
@@ -114,6 +127,28 @@ def test_final_layer_standalone_and_layer_walk():
             x = m.net[i](x)
             assert util.rel_err(x.cpu().numpy(), g[f"layer{i}_c64"]) < 5e-5, i
         assert x.is_complex()
+
+
+def test_final_linear_complex_output_with_autograd_has_no_eager_path():
+    """model.net[-1](h) under autograd (layer walks of modules/utils.py:251-252 with gradients enabled): complex output and the
+    gradients w.r.t. h, weight and bias from two FinalLinearRealFn passes, against torch's complex128 Linear on the CPU."""
+    import wire_b200
+    torch.manual_seed(4)
+    lin = wire_b200.wire.FinalLinear(212, 3, dtype=torch.cfloat).cuda()
+    h = torch.randn(777, 212, dtype=torch.cfloat, device="cuda", requires_grad=True)
+    gy = torch.randn(777, 3, dtype=torch.cfloat, device="cuda")
+    out = lin(h)
+    assert out.is_complex() and out.grad_fn is not None
+    torch.view_as_real(out).mul(torch.view_as_real(gy)).sum().backward()
+    W = lin.weight.detach().cpu().to(torch.complex128).requires_grad_(True)
+    b = lin.bias.detach().cpu().to(torch.complex128).requires_grad_(True)
+    hr = h.detach().cpu().to(torch.complex128).requires_grad_(True)
+    ref = torch.nn.functional.linear(hr, W, b)
+    torch.view_as_real(ref).mul(torch.view_as_real(gy.cpu().to(torch.complex128))).sum().backward()
+    assert util.rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert util.rel_err(h.grad.cpu().numpy(), hr.grad.numpy()) < 1e-5
+    assert util.rel_err(lin.weight.grad.cpu().numpy(), W.grad.numpy()) < 1e-5
+    assert util.rel_err(lin.bias.grad.cpu().numpy(), b.grad.numpy()) < 1e-5
 
 
 @pytest.mark.parametrize("kind,in_f,hidden,H,out_f,n", [
@@ -152,6 +187,9 @@ def test_shapes_edge_cases_tf32_vs_fp32_vs_oracle(kind, in_f, hidden, H, out_f, 
         assert util.rel_err(g32[k].numpy(), v.numpy()) < (5e-3 if deep else 1e-3), k
     for precision in ("tf32", "mixed16"):
         out_t, g_t, gc_t = res[precision]
+        util.record("edge_shapes", f"{kind}-{in_f}-{hidden}-{H}-{out_f}-{n}/{precision}",
+                    {"out": util.rel_err(out_t.numpy(), out32.numpy()), "gcoords": util.rel_err(gc_t.numpy(), gc32.numpy()),
+                     "grad_max": max(util.rel_err(g_t[k].numpy(), v.numpy()) for k, v in g32.items())})
         assert util.rel_err(out_t.numpy(), out32.numpy()) < (0.3 if deep else 3e-2), precision
         assert util.rel_err(gc_t.numpy(), gc32.numpy()) < (0.5 if deep else 6e-2), precision
         for k, v in g32.items():
@@ -534,6 +572,80 @@ def test_inr_with_trainable_scalars_trains_through_layer_route():
             assert abs(float(ga) - float(gb)) <= 2e-3 * max(1.0, abs(float(gb))), (k, float(ga), float(gb))
         else:
             assert util.rel_err(ga, gb) < TOL["fp32"]["grad"], k
+
+
+@pytest.mark.parametrize("case", ["denoise", "sisr2d", "occupancy"])
+def test_fused_path_trainable_omega_scale_vs_oracle_autograd(case):
+    """trainable=True on every Gabor layer (modules/wire.py:66,80-81) with the default mixed16 precision: the whole-network
+    kernels accumulate g_omega0 = sum Im(conj(z) p) and g_scale0 = -2 s0 sum (|z|^2 + |w|^2) Re p in their backward epilogues
+    (no per-layer route, no extra pass); against complex128 autograd of the oracle with the same flags set."""
+    import kernel_parity as KP
+    m, ref, c = KP.build_case(case, "mixed16")
+    for p in ref.parameters():
+        p.data = p.data.to(torch.complex128 if p.is_complex() else torch.float64)
+    for mod in (m, ref):
+        for layer in list(mod.net)[:-1]:
+            layer.omega_0.requires_grad_(True)
+            layer.scale_0.requires_grad_(True)
+    assert m.fused_scalar_grads_ok()
+    n = 4099
+    rs = np.random.RandomState(2)
+    coords = torch.from_numpy(rs.uniform(-1, 1, size=(1, n, c["in_f"])).astype(np.float32))
+    grad_out = torch.from_numpy((rs.normal(size=(1, n, c["out_f"])) / n).astype(np.float32))
+    out_r = ref(coords.double())
+    (out_r * grad_out.double()).sum().backward()
+    out = m(coords.cuda())
+    assert type(out.grad_fn).__name__.startswith("WireNetFn")          # the fused route, not the layer walk
+    (out * grad_out.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    rec = {}
+    for (k, pa), (_, pb) in zip(m.named_parameters(), ref.named_parameters()):
+        assert pa.grad is not None and pb.grad is not None, k
+        if k.endswith("omega_0") or k.endswith("scale_0"):
+            ga, gb = float(pa.grad), float(pb.grad)
+            rec[k] = {"cuda": ga, "oracle": gb}
+            # a sum of n*M terms of both signs: measured against the size of the reference value (or 1 when it cancels)
+            assert abs(ga - gb) <= 3e-2 * max(1.0, abs(gb)), (k, ga, gb)
+        else:
+            va = torch.view_as_real(pa.grad).cpu().numpy() if pa.grad.is_complex() else pa.grad.cpu().numpy()
+            vb = torch.view_as_real(pb.grad).numpy() if pb.grad.is_complex() else pb.grad.numpy()
+            assert util.rel_err(va, vb) < (0.3 if case == "occupancy" else 3e-2), (k, util.rel_err(va, vb))
+    util.record("fused_trainable_scalars", case, rec)
+
+
+def test_trainer_with_trainable_scalars_matches_module_plus_torch_adam():
+    """wire_b200.Trainer no longer refuses trainable omega_0 / scale_0: they join the flat parameter / gradient buffers and the
+    fused Adam step; against model(coords) -> mse -> backward -> torch.optim.Adam on the same CUDA modules."""
+    import wire_b200
+    torch.manual_seed(0)
+    kw = dict(nonlin="wire", in_features=2, hidden_features=300, hidden_layers=2, out_features=3, first_omega_0=7.0,
+              hidden_omega_0=7.0, scale=6.0)
+    init = wire_b200.get_INR(**kw)
+    sd = {k: v.clone() for k, v in init.state_dict().items()}
+    coords = (torch.rand(1, 3000, 2) * 2 - 1).cuda()
+    target = torch.rand(1, 3000, 3).cuda()
+    models = []
+    for _ in range(2):
+        m = wire_b200.get_INR(**kw)
+        m.load_state_dict(sd)
+        for layer in list(m.net)[1:-1]:
+            layer.omega_0.requires_grad_(True)
+            layer.scale_0.requires_grad_(True)
+        models.append(m.cuda())
+    a, b = models
+    opt = torch.optim.Adam([p for p in a.parameters() if p.requires_grad], lr=5e-3)
+    ref_losses = []
+    for _ in range(20):
+        loss = ((a(coords) - target) ** 2).mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+        ref_losses.append(float(loss))
+    tr = wire_b200.Trainer(b, lr=5e-3)
+    losses = [float(tr.step(coords, target)) for _ in range(20)]
+    assert util.rel_err(np.array(losses), np.array(ref_losses)) < 1e-2, (losses[-3:], ref_losses[-3:])
+    for la, lb in zip(list(a.net)[1:-1], list(b.net)[1:-1]):
+        assert abs(float(la.omega_0) - 7.0) > 1e-3                      # the scalars really moved ...
+        assert abs(float(la.omega_0) - float(lb.omega_0)) < 2e-2       # ... the same way on both routes
+        assert abs(float(la.scale_0) - float(lb.scale_0)) < 2e-2
 
 
 @pytest.mark.parametrize("kind,hidden,out_f", [("wire", 300, 3), ("wire2d", 256, 3), ("wire", 200, 1)])

@@ -43,6 +43,83 @@ def synthetic_volume(S, dev):
     return vol
 
 
+def run_occupancy(dev, world, rank, size=512, chunk=200000, steps=200, warmup=5, scaling="weak", precision="mixed16",
+                  iou=True, seed=0, vol=None):
+    """One timed occupancy run (the process group, if any, is already initialised); returns the result dict on every rank.
+    `vol`: a volume built earlier by synthetic_volume (re-used between the weak and the strong run)."""
+    S = size
+    N = S ** 3
+    if vol is None:
+        vol = synthetic_volume(S, dev)
+    occupied = float(vol.mean())
+    imten = vol.reshape(N, 1)
+    batcher = wire_b200.GridBatcher((S, S, S), imten, linspace="numpy")
+    torch.manual_seed(seed)
+    model = wire_b200.get_INR(nonlin="wire", in_features=3, hidden_features=300, hidden_layers=3, out_features=1,
+                              first_omega_0=20.0, hidden_omega_0=20.0, scale=10.0, precision=precision).to(dev)   # wire_occupancy.py:43-45,107-116
+    tr = wire_b200.Trainer(model, lr=5e-3)   # (broadcasts the parameters of rank 0)
+    gen = torch.Generator(device=dev).manual_seed(1234 + seed)      # same seed, same device type: same permutation on every rank
+    perm = torch.randperm(N, device=dev, generator=gen)
+    per_step = chunk * (world if scaling == "weak" else 1)
+    per_step = min(per_step, N)
+    est = torch.zeros(N, 1, device=dev)
+
+    def step(i):
+        b = (i * per_step) % (N - per_step + 1)
+        c = perm[b:b + per_step]
+        lo, hi = parallel.shard_range(per_step, rank, world)
+        return tr.step_indexed(batcher, c[lo:hi], n_global=per_step if world > 1 else None, rec=est)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    batcher.check_indices()
+
+    iou_val = None
+    if iou:
+        # IoU over the whole volume: each rank infers its contiguous shard of the grid, counts are summed over ranks
+        lo, hi = parallel.shard_range(N, rank, world)
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        blk = 1 << 22
+        with torch.no_grad():
+            for b in range(lo, hi, blk):
+                n = min(blk, hi - b)
+                c = batcher.coords(b, n)
+                pred = model(c[None, ...]).reshape(n, 1).contiguous()
+                counts += data.iou_counts(pred, imten[b:b + n], 0.5)
+        if world > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        iou_val = float(counts[0] / counts[1])
+    M, H = model.width, 3
+    flop = 24 * H * M * M + 12 * M * 1 + 4 * 3 * M
+    res = {"workload": f"WIRE occupancy {S}^3 ({N} coords), chunks of {chunk}", "n_gpus": world,
+           "scaling": scaling, "coords_per_step": per_step, "steps": steps, "ms_per_step": ms,
+           "coords_per_s": per_step / ms * 1e3, "epoch_s_at_this_rate": N / (per_step / ms * 1e3),
+           "algorithmic_tflops": per_step * flop / ms * 1e-9, "frac_nominal_tf32_per_gpu": per_step * flop / ms * 1e-9 / 1100.0 / world,
+           "precision": precision, "exchange": "peer" if tr.peer is not None else ("nccl" if world > 1 else None),
+           "occupied_fraction": occupied, "final_chunk_loss_this_rank": float(loss),
+           "iou_after_steps": iou_val, "steps_done": tr.steps_done, "seed": seed}
+    tr.close()
+    del tr, model, est, perm, batcher
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=512)
@@ -59,76 +136,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    S = args.size
-    N = S ** 3
-    vol = synthetic_volume(S, dev)
-    occupied = float(vol.mean())
-    imten = vol.reshape(N, 1)
-    batcher = wire_b200.GridBatcher((S, S, S), imten, linspace="numpy")
-    torch.manual_seed(args.seed)
-    model = wire_b200.get_INR(nonlin="wire", in_features=3, hidden_features=300, hidden_layers=3, out_features=1,
-                              first_omega_0=20.0, hidden_omega_0=20.0, scale=10.0, precision=args.precision).to(dev)   # wire_occupancy.py:43-45,107-116
-    if world > 1:
-        parallel.broadcast_parameters(model)
-    tr = wire_b200.Trainer(model, lr=5e-3)
-    gen = torch.Generator(device=dev).manual_seed(1234 + args.seed)      # same seed, same device type: same permutation on every rank
-    perm = torch.randperm(N, device=dev, generator=gen)
-    per_step = args.chunk * (world if args.scaling == "weak" else 1)
-    est = torch.zeros(N, 1, device=dev)
-
-    def step(i):
-        b = (i * per_step) % (N - per_step + 1)
-        chunk = perm[b:b + per_step]
-        lo, hi = parallel.shard_range(per_step, rank, world)
-        return tr.step_indexed(batcher, chunk[lo:hi], n_global=per_step if world > 1 else None, rec=est)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = step(args.warmup + i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
-    batcher.check_indices()
-
-    iou = None
-    if not args.no_iou:
-        # IoU over the whole volume: each rank infers its contiguous shard of the grid, counts are summed over ranks
-        lo, hi = parallel.shard_range(N, rank, world)
-        counts = torch.zeros(2, dtype=torch.int64, device=dev)
-        blk = 1 << 22
-        with torch.no_grad():
-            for b in range(lo, hi, blk):
-                n = min(blk, hi - b)
-                c = batcher.coords(b, n)
-                pred = model(c[None, ...]).reshape(n, 1).contiguous()
-                counts += data.iou_counts(pred, imten[b:b + n], 0.5)
-        if world > 1:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-        iou = float(counts[0] / counts[1])
-    M, H = model.width, 3
-    flop = 24 * H * M * M + 12 * M * 1 + 4 * 3 * M
+    res = run_occupancy(dev, world, rank, args.size, args.chunk, args.steps, args.warmup, args.scaling, args.precision,
+                        not args.no_iou, args.seed)
     if rank == 0:
-        print(json.dumps({"workload": f"WIRE occupancy {S}^3 ({N} coords), chunks of {args.chunk}", "n_gpus": world,
-                          "scaling": args.scaling, "coords_per_step": per_step, "steps": args.steps, "ms_per_step": ms,
-                          "coords_per_s": per_step / ms * 1e3, "epoch_s_at_this_rate": N / (per_step / ms * 1e3),
-                          "algorithmic_tflops": per_step * flop / ms * 1e-9, "frac_nominal_tf32_per_gpu": per_step * flop / ms * 1e-9 / 1100.0 / world,
-                          "precision": args.precision, "exchange": "peer" if tr.peer is not None else ("nccl" if world > 1 else None),
-                          "occupied_fraction": occupied, "final_chunk_loss_this_rank": float(loss),
-                          "iou_after_steps": iou, "steps_done": tr.steps_done, "seed": args.seed}), flush=True)
-    tr.close()
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,7 +12,8 @@ from .modules.models import get_INR
 from .patch import patch_reference
 from .train import Trainer
 from . import data
+from . import lin_inverse
 from .data import GridBatcher, run_epoch
 
-__all__ = ["models", "wire", "wire2d", "get_INR", "patch_reference", "Trainer", "GridBatcher", "run_epoch", "data", "WireB200Error", "_lib"]
+__all__ = ["models", "wire", "wire2d", "get_INR", "patch_reference", "Trainer", "GridBatcher", "run_epoch", "data", "lin_inverse", "WireB200Error", "_lib"]
 __version__ = "0.1.0"

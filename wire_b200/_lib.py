@@ -34,7 +34,8 @@ class NetParams(Structure):
 
 
 class LayerGrads(Structure):
-    _fields_ = [("weight", c_void_p), ("bias", c_void_p), ("weight2", c_void_p), ("bias2", c_void_p)]
+    _fields_ = [("weight", c_void_p), ("bias", c_void_p), ("weight2", c_void_p), ("bias2", c_void_p),
+                ("omega0", c_void_p), ("scale0", c_void_p)]
 
 
 GRADS_CLEAR_SLOTS, GRADS_CLEAR_FLAT, GRADS_PREZEROED = 0, 1, 2
@@ -96,6 +97,8 @@ SIGNATURES = {
     "wire_scatter_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "wire_iou_counts": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int32, c_void_p, c_void_p]),
     "wire_sq_err_stats": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "wire_radon_forward": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "wire_radon_backward": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "wire_gabor_scalar_grads": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
     "wire_real_gabor_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),

@@ -536,8 +536,10 @@ int run_mse_ring(const MseFuse& m, int64_t count, cudaStream_t st) {
 int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const float* Wf, const float* z, const float* w, int zw_pitch,
                 int z_half,
                 const float* h, int h_pitch, const float* omega, const float* scale, float* gz, float* gw, int g_pitch, float* g_Wf,
-                float* g_bf, cudaStream_t st, int g_elem = kElemF32, const MseFuse* mse = nullptr) {
+                float* g_bf, cudaStream_t st, int g_elem = kElemF32, const MseFuse* mse = nullptr, float* g_omega = nullptr,
+                float* g_scale = nullptr) {
   if (n <= 0) return 0;
+  if ((g_omega || g_scale) && g_elem != kElemBF16) return fail("omega_0 / scale_0 gradients in the fused path need the mixed16 kernels");
   if (mse && g_elem != kElemBF16) {  // only the 16-bit TMA kernel computes the loss gradient itself
     TRY(run_mse_ring(*mse, n * d->out_features, st));
     g_out = mse->scratch;
@@ -559,6 +561,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       T.g_out = g_out; T.Wf = Wf; T.omega = omega; T.scale = scale; T.g_Wf = g_Wf; T.g_bf = g_bf;
       T.n = int(n); T.M = d->width; T.out_f = d->out_features; T.pitch = g_pitch; T.two_d = w ? 1 : 0;
       T.bw = g_pitch / n_box; T.n_box = n_box;
+      T.gs_omega = g_omega; T.gs_scale = g_scale;
       if (mse) {
         T.pred = mse->pred; T.target = mse->target; T.g_scale = 2.0f / float(mse->count_norm); T.loss_scale = 1.0f / float(mse->count_norm);
         T.ring = mse->ring; T.ring_n = mse->ring_n; T.step_ptr = mse->step_ptr;
@@ -590,6 +593,20 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       };
       cudaError_t e = cudaErrorInvalidValue;
       const bool small = threads <= 512;
+      if (g_omega || g_scale) {
+        switch (d->out_features * 2 + (w ? 1 : 0)) {
+          case 2: e = small ? launch(top_bwd16_kernel<false, 1, 512, true>) : launch(top_bwd16_kernel<false, 1, 1024, true>); break;
+          case 3: e = small ? launch(top_bwd16_kernel<true, 1, 512, true>) : launch(top_bwd16_kernel<true, 1, 1024, true>); break;
+          case 4: e = small ? launch(top_bwd16_kernel<false, 2, 512, true>) : launch(top_bwd16_kernel<false, 2, 1024, true>); break;
+          case 5: e = small ? launch(top_bwd16_kernel<true, 2, 512, true>) : launch(top_bwd16_kernel<true, 2, 1024, true>); break;
+          case 6: e = small ? launch(top_bwd16_kernel<false, 3, 512, true>) : launch(top_bwd16_kernel<false, 3, 1024, true>); break;
+          case 7: e = small ? launch(top_bwd16_kernel<true, 3, 512, true>) : launch(top_bwd16_kernel<true, 3, 1024, true>); break;
+          case 8: e = small ? launch(top_bwd16_kernel<false, 4, 512, true>) : launch(top_bwd16_kernel<false, 4, 1024, true>); break;
+          case 9: e = small ? launch(top_bwd16_kernel<true, 4, 512, true>) : launch(top_bwd16_kernel<true, 4, 1024, true>); break;
+        }
+        CU_OK(e);
+        return 0;
+      }
       switch (d->out_features * 2 + (w ? 1 : 0)) {
         case 2: e = small ? launch(top_bwd16_kernel<false, 1, 512>) : launch(top_bwd16_kernel<false, 1, 1024>); break;
         case 3: e = small ? launch(top_bwd16_kernel<true, 1, 512>) : launch(top_bwd16_kernel<true, 1, 1024>); break;
@@ -603,6 +620,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       CU_OK(e);
       return 0;
     }
+    if (g_omega || g_scale) return fail("omega_0 / scale_0 gradients: this width is outside the TMA-streamed top backward kernel");
     if (mse) { TRY(run_mse_ring(*mse, n * d->out_features, st)); g_out = mse->scratch; mse = nullptr; }
     const int thr = round_up((d->width + 1) / 2, 32) < 128 ? 128 : round_up((d->width + 1) / 2, 32);
     const int nblk = int(n < int64_t(10 * g_sm_count) * 64 ? (n + 63) / 64 : 10 * g_sm_count);
@@ -972,6 +990,7 @@ int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const
     return fail("unknown clear_mode %d", g->clear_mode);
   }
   if (g->clear_mode == WIRE_GRADS_CLEAR_SLOTS) {
+    for (int l = 0; l <= H; ++l) { TRY(zero(g->layer[l].omega0, 1, st)); TRY(zero(g->layer[l].scale0, 1, st)); }
     TRY(zero(g->final_weight, size_t(d->out_features) * M * 2, st));
     TRY(zero(g->final_bias, size_t(d->out_features) * 2, st));
     TRY(zero(g->layer[0].weight, size_t(M) * in_f, st));
@@ -991,7 +1010,7 @@ int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const
   TRY(run_top_bwd(d, grad_out, n, p->final_weight, at(workspace, L.off_z[H]), d->two_d ? at(workspace, L.off_w[H]) : nullptr, L.P,
                   L.z_elem != kElemF32, nullptr,
                   0, p->layer[H].omega0, p->layer[H].scale0, at(workspace, L.off_gz[cur]), d->two_d ? at(workspace, L.off_gw[cur]) : nullptr,
-                  L.P, g->final_weight, g->final_bias, st, L.g_elem, mse));
+                  L.P, g->final_weight, g->final_bias, st, L.g_elem, mse, g->layer[H].omega0, g->layer[H].scale0));
   for (int l = H; l >= 1; --l) {
     const float* gz = at(workspace, L.off_gz[cur]);
     const float* gw = d->two_d ? at(workspace, L.off_gw[cur]) : nullptr;
@@ -1027,6 +1046,9 @@ int net_backward_impl(const wire_net_desc* d_in, const wire_net_params* p, const
     J.store_mask = mask;
     J.e = base_epi(n, L.two_m, d->precision);
     J.e.omega = p->layer[l - 1].omega0; J.e.scale = p->layer[l - 1].scale0;
+    J.e.g_omega = g->layer[l - 1].omega0; J.e.g_scale = g->layer[l - 1].scale0;   // trainable scalars of the layer below
+    if ((J.e.g_omega || J.e.g_scale) && d->precision != WIRE_PRECISION_MIXED16)
+      return fail("omega_0 / scale_0 gradients in the fused path need the mixed16 precision (use the per-layer entry points otherwise)");
     if (!to_first) {
       J.mode = d->two_d ? MODE_GABOR2D_BWD : MODE_GABOR_BWD;
       J.e.z_src = at(workspace, L.off_z[l - 1]); J.e.w_src = d->two_d ? at(workspace, L.off_w[l - 1]) : nullptr; J.e.zw_pitch = L.P;
@@ -1536,6 +1558,33 @@ int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, cons
   ProfScope prof(K_LAYER_MISC, st);
   gabor_scalar_grads_kernel<<<grid_for(n * width), 256, 0, st>>>(z_save, two_d ? w_save : nullptr, grad_y, n * int64_t(width), is_first,
                                                                  omega0, scale0, out2);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_radon_forward(const float* image, int32_t nimg, int32_t H, int32_t W, const float* angles_deg, int32_t nangles, float* sinogram,
+                       void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!image || !angles_deg || !sinogram) return fail("null argument");
+  if (nimg < 1 || H < 1 || W < 1 || nangles < 1) return fail("bad shape nimg=%d H=%d W=%d nangles=%d", nimg, H, W, nangles);
+  ProfScope prof(K_DATA, st);
+  radon_fwd_kernel<<<grid_for(int64_t(nangles) * nimg * W), 256, 0, st>>>(image, nimg, H, W, angles_deg, nangles, sinogram);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_radon_backward(const float* grad_sinogram, int32_t nimg, int32_t H, int32_t W, const float* angles_deg, int32_t nangles,
+                        float* grad_image, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!grad_sinogram || !angles_deg || !grad_image) return fail("null argument");
+  if (nimg < 1 || H < 1 || W < 1 || nangles < 1) return fail("bad shape nimg=%d H=%d W=%d nangles=%d", nimg, H, W, nangles);
+  CU_OK(cudaMemsetAsync(grad_image, 0, size_t(nimg) * H * W * sizeof(float), st));
+  const int rpt = 16;  // rows per thread: enough threads to fill the machine at 100 angles x 256 columns
+  ProfScope prof(K_DATA, st);
+  radon_bwd_kernel<<<grid_for(int64_t(nangles) * nimg * ((H + rpt - 1) / rpt) * W), 256, 0, st>>>(grad_sinogram, nimg, H, W, angles_deg, nangles,
+                                                                                                 rpt, grad_image);
   CU_OK(cudaGetLastError());
   return 0;
 }

@@ -242,4 +242,79 @@ __global__ void real_gabor_bwd_kernel(const float* __restrict__ f, const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Radon forward operator of the CT driver (modules/lin_inverse.py:19-40, wire_ct.py:126-128): every angle rotates the image
+// about its centre (kornia.geometry.rotate: bilinear, zeros outside, align_corners=True, centre ((W-1)/2, (H-1)/2), positive
+// angle = counter-clockwise with the origin at the top-left pixel) and sums over the rows:
+//     sino[a][m][j] = sum_i rot_a(im[m])[i][j],   rot_a(im)[i][j] = bilinear(im, xs, ys)
+//     xs = cx + cos(t) (j - cx) - sin(t) (i - cy),   ys = cy + sin(t) (j - cx) + cos(t) (i - cy),   t = angle_a in radians
+// One thread per (angle, image, column) walks the rows: neighbouring threads sample neighbouring source pixels (coalesced up
+// to the rotation), and the 4 bilinear taps hit L1/L2 (a 512^2 image is 1 MB).  The adjoint scatters w * g_sino[a][m][j] to the
+// same 4 taps with atomics (the gradient of the image the network produced).  HBM bytes are negligible next to the network.
+// ---------------------------------------------------------------------------------------------
+struct RadonTaps { int x0, y0; float w00, w01, w10, w11; };
+__device__ __forceinline__ RadonTaps radon_taps(float cs, float sn, float cx, float cy, int i, int j) {
+  const float dx = float(j) - cx, dy = float(i) - cy;
+  const float xs = fmaf(cs, dx, fmaf(-sn, dy, cx)), ys = fmaf(sn, dx, fmaf(cs, dy, cy));
+  const float xf = floorf(xs), yf = floorf(ys);
+  const float ax = xs - xf, ay = ys - yf;
+  RadonTaps t;
+  t.x0 = int(xf); t.y0 = int(yf);
+  t.w00 = (1.f - ax) * (1.f - ay); t.w01 = ax * (1.f - ay); t.w10 = (1.f - ax) * ay; t.w11 = ax * ay;
+  return t;
+}
+__global__ void radon_fwd_kernel(const float* __restrict__ im, int nimg, int H, int W, const float* __restrict__ angles, int nangles,
+                                 float* __restrict__ sino) {
+  const int64_t total = int64_t(nangles) * nimg * W;
+  const float cx = 0.5f * float(W - 1), cy = 0.5f * float(H - 1);
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int j = int(t % W);
+    const int m = int((t / W) % nimg);
+    const int a = int(t / (int64_t(W) * nimg));
+    float sn, cs;
+    sincosf(angles[a] * 0.017453292519943295f, &sn, &cs);
+    const float* src = im + size_t(m) * H * W;
+    float acc = 0.f;
+    for (int i = 0; i < H; ++i) {
+      const RadonTaps k = radon_taps(cs, sn, cx, cy, i, j);
+      const bool xa = k.x0 >= 0 && k.x0 < W, xb = k.x0 + 1 >= 0 && k.x0 + 1 < W;
+      const bool ya = k.y0 >= 0 && k.y0 < H, yb = k.y0 + 1 >= 0 && k.y0 + 1 < H;
+      float v = 0.f;
+      if (ya && xa) v = fmaf(k.w00, __ldg(src + size_t(k.y0) * W + k.x0), v);
+      if (ya && xb) v = fmaf(k.w01, __ldg(src + size_t(k.y0) * W + k.x0 + 1), v);
+      if (yb && xa) v = fmaf(k.w10, __ldg(src + size_t(k.y0 + 1) * W + k.x0), v);
+      if (yb && xb) v = fmaf(k.w11, __ldg(src + size_t(k.y0 + 1) * W + k.x0 + 1), v);
+      acc += v;
+    }
+    sino[t] = acc;
+  }
+}
+// g_im (pre-zeroed) += adjoint of the above applied to g_sino; one thread per (angle, image, row block, column)
+__global__ void radon_bwd_kernel(const float* __restrict__ g_sino, int nimg, int H, int W, const float* __restrict__ angles, int nangles,
+                                 int rows_per_thread, float* __restrict__ g_im) {
+  const int rblocks = (H + rows_per_thread - 1) / rows_per_thread;
+  const int64_t total = int64_t(nangles) * nimg * rblocks * W;
+  const float cx = 0.5f * float(W - 1), cy = 0.5f * float(H - 1);
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int j = int(t % W);
+    const int rb = int((t / W) % rblocks);
+    const int m = int((t / (int64_t(W) * rblocks)) % nimg);
+    const int a = int(t / (int64_t(W) * rblocks * nimg));
+    float sn, cs;
+    sincosf(angles[a] * 0.017453292519943295f, &sn, &cs);
+    const float g = g_sino[(size_t(a) * nimg + m) * W + j];
+    float* dst = g_im + size_t(m) * H * W;
+    const int i1 = min(H, (rb + 1) * rows_per_thread);
+    for (int i = rb * rows_per_thread; i < i1; ++i) {
+      const RadonTaps k = radon_taps(cs, sn, cx, cy, i, j);
+      const bool xa = k.x0 >= 0 && k.x0 < W, xb = k.x0 + 1 >= 0 && k.x0 + 1 < W;
+      const bool ya = k.y0 >= 0 && k.y0 < H, yb = k.y0 + 1 >= 0 && k.y0 + 1 < H;
+      if (ya && xa) atomicAdd(dst + size_t(k.y0) * W + k.x0, k.w00 * g);
+      if (ya && xb) atomicAdd(dst + size_t(k.y0) * W + k.x0 + 1, k.w01 * g);
+      if (yb && xa) atomicAdd(dst + size_t(k.y0 + 1) * W + k.x0, k.w10 * g);
+      if (yb && xb) atomicAdd(dst + size_t(k.y0 + 1) * W + k.x0 + 1, k.w11 * g);
+    }
+  }
+}
+
 }  // namespace wire

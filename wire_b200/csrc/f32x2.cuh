@@ -80,6 +80,21 @@ __device__ __forceinline__ f2 gabor_bwd_x2(const GaborConst2& c, f2 yr, f2 yi, f
   gzi = f2_fma(c.nomega, pr, f2_mul(t, zi));
   return pr;
 }
+// The same with Im p handed out as well (trainable omega_0 / scale_0: g_omega0 = sum Im(conj(z) p), g_scale0 = -2 s0 sum (|z|^2 + |w|^2) Re p)
+__device__ __forceinline__ f2 gabor_bwd_x2_p(const GaborConst2& c, f2 yr, f2 yi, f2 zr, f2 zi, f2 gr, f2 gi, f2& gzr, f2& gzi, f2& pi) {
+  const f2 pr = f2_fma(yi, gi, f2_mul(yr, gr));
+  pi = f2_fma(f2_mul(yi, c.none), gr, f2_mul(yr, gi));
+  const f2 t = f2_mul(c.m2s2, pr);
+  gzr = f2_fma(c.omega, pi, f2_mul(t, zr));
+  gzi = f2_fma(c.nomega, pr, f2_mul(t, zi));
+  return pr;
+}
+__device__ __forceinline__ f2 gabor_first_bwd_x2_p(const GaborConst2& c, f2 yr, f2 yi, f2 z, f2 gr, f2 gi, f2& gz, f2& pi) {
+  const f2 pr = f2_fma(yi, gi, f2_mul(yr, gr));
+  pi = f2_fma(f2_mul(yi, c.none), gr, f2_mul(yr, gi));
+  gz = f2_fma(c.omega, pi, f2_mul(f2_mul(c.m2s2, pr), z));
+  return pr;
+}
 // first layer (real z): g_z = w Im p - 2 s2 z Re p ; returns Re p
 __device__ __forceinline__ f2 gabor_first_bwd_x2(const GaborConst2& c, f2 yr, f2 yi, f2 z, f2 gr, f2 gi, f2& gz) {
   const f2 pr = f2_fma(yi, gi, f2_mul(yr, gr));

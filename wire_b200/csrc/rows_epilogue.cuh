@@ -55,6 +55,10 @@ struct RowsEpi {
   float* out;
   int out_features;
   int fuse_final;
+  // trainable omega_0 / scale_0 of the layer whose nonlinearity backward runs in this epilogue (modules/wire.py:66,80-81):
+  // device floats ACCUMULATED by the 16-bit kernels' SCAL instantiations (nullptr = the scalars are constants)
+  float* g_omega;
+  float* g_scale;
 };
 
 __device__ __forceinline__ void load_row32(const float* src, bool ok, float (&v)[32]) {

@@ -129,13 +129,16 @@ struct TopBwd16Params {
   float* ring;
   int ring_n;
   const long long* step_ptr;
+  // trainable omega_0 / scale_0 of the last hidden layer (SCAL instantiations): accumulated device floats, or nullptr
+  float* gs_omega;
+  float* gs_scale;
 };
 
 // Block = W compute warps (thread k owns complex feature k) + one I/O warp.  No block-wide barrier in the loop: tiles
 // flow through two-deep in / out rings guarded by mbarriers (in_full: TMA bytes + g_out rows staged by the I/O warp;
 // in_empty / out_full: one arrival per compute warp; out_empty: the I/O warp, once the TMA store has read the tile).
 // MAXT: launch bound (512 leaves 128 registers per thread for the usual widths; 1024 covers M up to 992)
-template <bool TWO_D, int OUTF, int MAXT>
+template <bool TWO_D, int OUTF, int MAXT, bool SCAL = false>
 __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__ TopBwd16Params P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t tsm[];
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
     ar2[o] = ai2[o] = 0ull;
   }
   float bsum = 0.f;
+  f2 s_om = 0ull, s_sc = 0ull;  // SCAL: sum Im(conj(z) p), sum (|z|^2 + |w|^2) Re p over this thread's feature
   // byte offset of this thread's (re, im) pair inside a tile: box b holds columns [b*bw, (b+1)*bw) as a dense [rows][bw] block
   const int col = active ? 2 * k : 0;
   const int bi = col / P.bw;
@@ -298,7 +302,15 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
       }
       f2 yr, yi, gzr, gzi;
       gabor_x2(G2, zr, zi, wnorm, yr, yi);
-      const f2 pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gyr, gyi, gzr, gzi);
+      f2 pr;
+      if constexpr (SCAL) {
+        f2 pi;
+        pr = gabor_bwd_x2_p(G2, yr, yi, zr, zi, gyr, gyi, gzr, gzi, pi);
+        s_om = f2_fma(zr, pi, f2_fma(f2_mul(zi, G2.none), pr, s_om));
+        s_sc = f2_fma(f2_fma(zi, zi, f2_fma(zr, zr, wnorm)), pr, s_sc);
+      } else {
+        pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gyr, gyi, gzr, gzi);
+      }
       // (lanes past the last feature alias feature 0's slot: they compute on it but must not store)
       if (active) {
         *reinterpret_cast<uint32_t*>(zout + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gzr), f2_lo(gzi));
@@ -330,6 +342,16 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
     }
   }
   if (threadIdx.x < OUTF) atomicAdd(P.g_bf + 2 * threadIdx.x, bsum);
+  if constexpr (SCAL) {
+    // (rows past n arrive as TMA zero fill with g_o = 0: p = 0; threads past the last feature are masked here)
+    float a = active ? f2_lo(s_om) + f2_hi(s_om) : 0.f, b = active ? f2_lo(s_sc) + f2_hi(s_sc) : 0.f;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, sft); b += __shfl_xor_sync(0xffffffffu, b, sft); }
+    if (lane == 0) {
+      if (P.gs_omega) atomicAdd(P.gs_omega, a);
+      if (P.gs_scale) atomicAdd(P.gs_scale, -2.0f * __ldg(P.scale) * b);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

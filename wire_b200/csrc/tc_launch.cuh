@@ -193,7 +193,7 @@ inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, i
   return stages * stage + staging + pbytes + 1024;
 }
 
-template <int MODE, bool PAIR, bool FUSE>
+template <int MODE, bool PAIR, bool FUSE, bool SCAL = false>
 inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   static bool attr_set_dev[kMaxDevices] = {};
   static int max_clusters_dev[kMaxDevices] = {};
@@ -201,7 +201,7 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
   bool& attr_set = attr_set_dev[dev];
   int& max_clusters = max_clusters_dev[dev];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_rows16_kernel<MODE, PAIR, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
+    cudaError_t e = cudaFuncSetAttribute(tc_rows16_kernel<MODE, PAIR, FUSE, SCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -223,7 +223,7 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
     cfg.gridDim = dim3(sm_count / C * C);
     cfg.dynamicSmemBytes = kMaxDynSmem;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows16_kernel<MODE, PAIR, FUSE>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc_rows16_kernel<MODE, PAIR, FUSE, SCAL>, &cfg) != cudaSuccess || nc <= 0) nc = sm_count / C / 2;
     (void)cudaGetLastError();
     max_clusters = nc;
     cfg.dynamicSmemBytes = smem;
@@ -233,11 +233,20 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
   if (clusters <= 0) return cudaSuccess;
   cfg.gridDim = dim3(clusters * C);
   add_pdl_attr(attr, cfg.numAttrs);
-  return cudaLaunchKernelEx(&cfg, tc_rows16_kernel<MODE, PAIR, FUSE>, P);
+  return cudaLaunchKernelEx(&cfg, tc_rows16_kernel<MODE, PAIR, FUSE, SCAL>, P);
 }
 template <int MODE, bool FUSE = false>
 inline cudaError_t launch_rows16_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   return P.cluster == 2 ? launch_rows16_p<MODE, true, FUSE>(P, smem, sm_count, st) : launch_rows16_p<MODE, false, FUSE>(P, smem, sm_count, st);
+}
+// backward modes: with gradient slots for the epilogue layer's own omega_0 / scale_0 the SCAL instantiation runs (CTA pairs only)
+template <int MODE>
+inline cudaError_t launch_rows16_bwd(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
+  if (P.e.g_omega || P.e.g_scale) {
+    if (P.cluster != 2) return cudaErrorNotSupported;
+    return launch_rows16_p<MODE, true, false, true>(P, smem, sm_count, st);
+  }
+  return launch_rows16_mode<MODE>(P, smem, sm_count, st);
 }
 // P configured by rows16_configure; 16-bit tensor maps: A/B boxes of 64 columns (SWIZZLE_128B), output / saved-z tiles
 // of 32x32 elements with SWIZZLE_64B
@@ -248,10 +257,10 @@ inline cudaError_t launch_rows16(int mode, const RowsParams& P, size_t smem, int
     case MODE_PLAIN: return launch_rows16_mode<MODE_PLAIN>(P, smem, sm_count, st);
     case MODE_GABOR_FWD: return fuse ? launch_rows16_mode<MODE_GABOR_FWD, true>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR_FWD>(P, smem, sm_count, st);
     case MODE_GABOR2D_FWD: return fuse ? launch_rows16_mode<MODE_GABOR2D_FWD, true>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st);
-    case MODE_GABOR_BWD: return launch_rows16_mode<MODE_GABOR_BWD>(P, smem, sm_count, st);
-    case MODE_GABOR2D_BWD: return launch_rows16_mode<MODE_GABOR2D_BWD>(P, smem, sm_count, st);
-    case MODE_FIRST_BWD: return launch_rows16_mode<MODE_FIRST_BWD>(P, smem, sm_count, st);
-    case MODE_FIRST2D_BWD: return launch_rows16_mode<MODE_FIRST2D_BWD>(P, smem, sm_count, st);
+    case MODE_GABOR_BWD: return launch_rows16_bwd<MODE_GABOR_BWD>(P, smem, sm_count, st);
+    case MODE_GABOR2D_BWD: return launch_rows16_bwd<MODE_GABOR2D_BWD>(P, smem, sm_count, st);
+    case MODE_FIRST_BWD: return launch_rows16_bwd<MODE_FIRST_BWD>(P, smem, sm_count, st);
+    case MODE_FIRST2D_BWD: return launch_rows16_bwd<MODE_FIRST2D_BWD>(P, smem, sm_count, st);
   }
   return cudaErrorInvalidValue;
 }

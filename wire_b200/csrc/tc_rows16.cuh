@@ -67,7 +67,9 @@ __device__ __forceinline__ void gabor16(const GaborConst& g, float zr, float zi,
 }
 
 // FUSE: the final Linear (.real) is accumulated in this epilogue (GABOR_FWD / GABOR2D_FWD only)
-template <int MODE, bool PAIR, bool FUSE = false>
+// SCAL: backward modes only -- the gradients of the epilogue layer's own omega_0 / scale_0 are accumulated on the way
+//       (per-thread partial sums over everything the thread touches, one warp reduction + two atomics per warp at the end)
+template <int MODE, bool PAIR, bool FUSE = false, bool SCAL = false>
 __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __grid_constant__ RowsParams P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   constexpr bool kFirst = (MODE == MODE_FIRST_BWD || MODE == MODE_FIRST2D_BWD);
   constexpr bool k2D = (MODE == MODE_GABOR2D_FWD || MODE == MODE_GABOR2D_BWD || MODE == MODE_FIRST2D_BWD);
   static_assert(!FUSE || kFwd, "only the forward modes fuse the final Linear");
+  static_assert(!SCAL || kBwd || kFirst, "omega_0 / scale_0 gradients belong to the backward modes");
   constexpr int kKC = 64;  // K columns per pipeline stage (one 128 B swizzle row of 16-bit elements)
 
   const int warp = threadIdx.x >> 5;
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
     const long long e_begin = WIRE_CLK();
     f2 cin2[3] = {0ull, 0ull, 0ull};          // first-layer modes: this row's coordinates, broadcast pairs
     f2 facc2[kMaxOut] = {0ull, 0ull, 0ull, 0ull};  // FUSE: partial sums of the final Linear over even / odd features
+    f2 s_om = 0ull, s_sc = 0ull;               // SCAL: sum Im(conj(z) p) and sum (|z|^2 + |w|^2) Re p over this thread's elements
     auto release = [&](int buf) {
       tc_fence_before();
       __syncwarp();
@@ -486,7 +490,15 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
               const f2 gi = f2_bits(raw[8 * g + 4 * h + 2], raw[8 * g + 4 * h + 3]);
               f2 yr, yi, gzr, gzi;
               gabor_x2(G2, zr, zi, wnorm, yr, yi);
-              const f2 pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gr, gi, gzr, gzi);
+              f2 pr;
+              if constexpr (SCAL) {
+                f2 pi;
+                pr = gabor_bwd_x2_p(G2, yr, yi, zr, zi, gr, gi, gzr, gzi, pi);
+                s_om = f2_fma(zr, pi, f2_fma(f2_mul(zi, G2.none), pr, s_om));
+                s_sc = f2_fma(f2_fma(zi, zi, f2_fma(zr, zr, wnorm)), pr, s_sc);
+              } else {
+                pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gr, gi, gzr, gzi);
+              }
               pz[4 * g + 2 * h] = pack_bf16(f2_lo(gzr), f2_lo(gzi));
               pz[4 * g + 2 * h + 1] = pack_bf16(f2_hi(gzr), f2_hi(gzi));
               if constexpr (k2D) {
@@ -518,7 +530,15 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
             }
             f2 yr, yi, gz;
             gabor_real_x2(G2, z0, wnorm, yr, yi);
-            const f2 pr = gabor_first_bwd_x2(G2, yr, yi, z0, f2_bits(raw[4 * j], raw[4 * j + 1]), f2_bits(raw[4 * j + 2], raw[4 * j + 3]), gz);
+            f2 pr;
+            if constexpr (SCAL) {
+              f2 pi;
+              pr = gabor_first_bwd_x2_p(G2, yr, yi, z0, f2_bits(raw[4 * j], raw[4 * j + 1]), f2_bits(raw[4 * j + 2], raw[4 * j + 3]), gz, pi);
+              s_om = f2_fma(z0, pi, s_om);
+              s_sc = f2_fma(f2_fma(z0, z0, wnorm), pr, s_sc);
+            } else {
+              pr = gabor_first_bwd_x2(G2, yr, yi, z0, f2_bits(raw[4 * j], raw[4 * j + 1]), f2_bits(raw[4 * j + 2], raw[4 * j + 3]), gz);
+            }
             gzp[j] = pack_bf16(f2_lo(gz), f2_hi(gz));
             if constexpr (k2D) {
               const f2 gw = f2_mul(f2_mul(G2.m2s2, pr), w0v);
@@ -573,6 +593,16 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
               if (oo < E.out_features) E.out[size_t(row) * E.out_features + oo] = r[oo] + __ldg(E.bf + 2 * oo);
           }
         }
+      }
+    }
+    if constexpr (SCAL) {
+      // rows past the end and padded feature columns contribute exact zeros (their accumulators / z tiles are TMA zero fill)
+      float a = f2_lo(s_om) + f2_hi(s_om), b = f2_lo(s_sc) + f2_hi(s_sc);
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, sft); b += __shfl_xor_sync(0xffffffffu, b, sft); }
+      if (lane == 0) {
+        if (E.g_omega) atomicAdd(E.g_omega, a);
+        if (E.g_scale) atomicAdd(E.g_scale, -2.0f * __ldg(E.scale) * b);
       }
     }
     if (lane == 0) tma_store_wait_all<0>();

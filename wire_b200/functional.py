@@ -204,6 +204,13 @@ class WireNetFn(torch.autograd.Function):
                 t = tensors[l * per + i]
                 sizes.append(t.numel() * (2 if t.is_complex() else 1))
         sizes += [tensors[-2].numel() * 2, tensors[-1].numel() * 2]
+        # trainable omega_0 / scale_0 (modules/wire.py:66,80-81): one float slot each, filled by the fused backward kernels
+        scal_slots = {}
+        for l in range(desc.hidden_layers + 1):
+            for j in range(2):
+                if ctx.needs_input_grad[2 + l * per + n_w + j]:
+                    scal_slots[(l, j)] = len(sizes)
+                    sizes.append(1)
         # every slot starts on a 16-byte boundary (view_as_complex needs an even offset; kernels like float4)
         starts, off = [], 0
         for s in sizes:
@@ -226,7 +233,13 @@ class WireNetFn(torch.autograd.Function):
             lg.weight, lg.bias = ptrs[0], ptrs[1]
             if two_d:
                 lg.weight2, lg.bias2 = ptrs[2], ptrs[3]
-            grads += [None, None]  # omega_0, scale_0 (non-trainable in every reference driver)
+            for j in range(2):   # omega_0, scale_0: None unless trainable (non-trainable in every reference driver)
+                k = scal_slots.get((l, j))
+                if k is None:
+                    grads.append(None)
+                else:
+                    setattr(lg, "omega0" if j == 0 else "scale0", views[k].data_ptr())
+                    grads.append(views[k].view(tensors[l * per + n_w + j].shape))
         G.final_weight, G.final_bias = views[vi].data_ptr(), views[vi + 1].data_ptr()
         G.clear_mode, G.flat_base, G.flat_floats = _lib.GRADS_CLEAR_FLAT, flatg.data_ptr(), flatg.numel()   # one memset
         grads.append(torch.view_as_complex(views[vi].view(*tensors[-2].shape, 2)))

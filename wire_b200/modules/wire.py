@@ -49,13 +49,6 @@ class _GaborBase(nn.Module):
     def scalars_trainable(self) -> bool:
         return bool(self.omega_0.requires_grad or self.scale_0.requires_grad)
 
-    def _check_trainable(self):
-        """The fused whole-network kernels and ``wire_b200.Trainer`` treat omega_0 / scale_0 as constants (every reference
-        driver uses trainable=False); trainable scalars are served by the layer-by-layer route instead."""
-        if self.scalars_trainable:
-            raise NotImplementedError(
-                "trainable omega_0/scale_0 is supported by the layer-by-layer route (model(coords), model.net[i](x)) but "
-                "not by the fused Trainer (SURVEY.md §8f item 3)")
 
     def flat_params(self):
         """Parameter tensors in the order ``functional.wire_net`` expects."""
@@ -104,11 +97,17 @@ class FinalLinear(nn.Linear):
     ``nn.Linear`` does, computed by the CUDA kernel when no gradient is required."""
 
     def forward(self, input):
-        if torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad):
-            return super().forward(input)  # stand-alone training of the bare Linear is not a WIRE code path
         desc = F.make_desc(False, 1, self.in_features, 1, self.out_features, DEFAULT_PRECISION)
-        re = F.final_linear_real(desc, input, self.weight, self.bias)
-        im = F.final_linear_real(desc, input, self.weight * (-1j), self.bias * (-1j))
+        bias = self.bias if self.bias is not None else torch.zeros(self.out_features, dtype=self.weight.dtype, device=self.weight.device)
+        # Re and Im of h W^T + b as two real-output passes of the CUDA kernel: Im(h W^T + b) = Re(h (-jW)^T + (-jb)).  Under
+        # autograd each pass is a FinalLinearRealFn node (the [n, M]-sized work stays in the hand-written kernels; only the
+        # multiplication of the [out, M] weight by -j is a torch op) — there is no eager nn.Linear path.
+        if torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad):
+            re = F.final_linear_real_autograd(desc, input, self.weight, bias)
+            im = F.final_linear_real_autograd(desc, input, self.weight * (-1j), bias * (-1j))
+        else:
+            re = F.final_linear_real(desc, input, self.weight, bias)
+            im = F.final_linear_real(desc, input, self.weight * (-1j), bias * (-1j))
         return torch.complex(re, im)
 
 
@@ -137,11 +136,17 @@ class _INRBase(nn.Module):
         final = self.net[-1]
         return ps + [final.weight, final.bias]
 
+    def fused_scalar_grads_ok(self) -> bool:
+        """Trainable omega_0 / scale_0 (modules/wire.py:66,80-81) are differentiated inside the fused backward kernels of the
+        mixed16 path (extra epilogue reductions); the other precisions and shapes outside that path use the per-layer route."""
+        return (self.precision == "mixed16" and self.in_features <= 3 and self.out_features <= 4 and self.width <= 992)
+
     def forward(self, coords):
         layers = list(self.net)
+        trainable_scalars = any(getattr(layer, "scalars_trainable", False) for layer in layers[:-1])
         if (self.hidden_layers < 1 or len(layers) != self.hidden_layers + 2
-                or any(getattr(layer, "scalars_trainable", False) for layer in layers[:-1])):
-            # no hidden layer, a user-edited Sequential, or trainable omega_0 / scale_0 (modules/wire.py:80-81): compose the
+                or (trainable_scalars and torch.is_grad_enabled() and not self.fused_scalar_grads_ok())):
+            # no hidden layer, a user-edited Sequential, or trainable omega_0 / scale_0 outside the mixed16 path: compose the
             # per-layer kernels, each an autograd node of its own
             x = coords
             for layer in layers[:-1]:

@@ -2,7 +2,8 @@
 
 ``patch_reference(modules_pkg)`` rebinds the reference's own entry points for the hot path —
 ``modules.wire.INR`` / ``ComplexGaborLayer`` (modules/wire.py:44-167), ``modules.wire2d.INR`` /
-``ComplexGaborLayer2D`` (modules/wire2d.py:6-127) and ``modules.models.get_INR`` (modules/models.py:27-77)
+``ComplexGaborLayer2D`` (modules/wire2d.py:6-127), ``modules.models.get_INR`` (modules/models.py:27-77) and
+``modules.lin_inverse.radon`` (modules/lin_inverse.py:19-40)
 — to the CUDA-backed implementations, so `wire_image_denoise.py`, `wire_SISR.py`, `wire_occupancy.py`,
 `wire_ct.py` and `wire_multi_sr.py` keep their source untouched.
 """
@@ -45,4 +46,13 @@ def patch_reference(modules_pkg=None):
             ref_models.model_dict["wire"] = m_wire
             ref_models.model_dict["wire2d"] = m_wire2d
         patched.append(f"{name}.models.get_INR")
+    # the CT driver's forward operator (modules/lin_inverse.py:19-40); the reference module itself needs kornia at import
+    try:
+        ref_lin = sys.modules.get(f"{name}.lin_inverse") or importlib.import_module(f"{name}.lin_inverse")
+    except Exception:
+        ref_lin = None
+    if ref_lin is not None:
+        from . import lin_inverse as m_lin
+        ref_lin.radon = m_lin.radon
+        patched.append(f"{name}.lin_inverse.radon")
     return patched

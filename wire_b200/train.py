@@ -36,8 +36,9 @@ class Trainer:
         layers = list(model.net)
         if model.hidden_layers < 1 or len(layers) != model.hidden_layers + 2:
             raise WireB200Error("Trainer needs the standard WIRE stack (first layer, >=1 hidden layers, final Linear)")
-        for layer in layers[:-1]:
-            layer._check_trainable()
+        if any(layer.scalars_trainable for layer in layers[:-1]) and not model.fused_scalar_grads_ok():
+            raise WireB200Error("trainable omega_0 / scale_0 in the fused Trainer need precision='mixed16' (in_features <= 3, "
+                                "out_features <= 4); other configurations train through model(coords) + torch.optim")
         self.desc = F.make_desc(model.two_d, model.in_features, model.width, model.hidden_layers, model.out_features,
                                 model.precision)
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
@@ -52,11 +53,22 @@ class Trainer:
         # ---- flat parameter / gradient / Adam buffers (16-byte aligned slots) ----
         two_d = bool(self.desc.two_d)
         self._train_params: List[torch.nn.Parameter] = []
-        for layer in layers[:-1]:
+        self._slots: List[tuple] = []          # (layer index or -1 for the final Linear, field of wire_layer_grads / wire_net_grads)
+        for l, layer in enumerate(layers[:-1]):
             self._train_params += [layer.linear.weight, layer.linear.bias]
+            self._slots += [(l, "weight"), (l, "bias")]
             if two_d:
                 self._train_params += [layer.scale_orth.weight, layer.scale_orth.bias]
+                self._slots += [(l, "weight2"), (l, "bias2")]
+            # trainable=True (modules/wire.py:66,80-81): the layer's own omega_0 / scale_0 join the flat buffers
+            if layer.omega_0.requires_grad:
+                self._train_params.append(layer.omega_0)
+                self._slots.append((l, "omega0"))
+            if layer.scale_0.requires_grad:
+                self._train_params.append(layer.scale_0)
+                self._slots.append((l, "scale0"))
         self._train_params += [layers[-1].weight, layers[-1].bias]
+        self._slots += [(-1, "final_weight"), (-1, "final_bias")]
         if any(p is None for p in self._train_params):
             raise WireB200Error("Trainer requires bias=True layers")
         sizes = [p.numel() * (2 if p.is_complex() else 1) for p in self._train_params]
@@ -166,16 +178,8 @@ class Trainer:
         tensors = self.model.flat_params()
         st["_P"] = F._fill_net_params(d, F._check_net_tensors(d, tensors))
         G = NetGrads()
-        two_d = bool(d.two_d)
-        vi = 0
-        for l in range(d.hidden_layers + 1):
-            lg = G.layer[l]
-            lg.weight, lg.bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
-            vi += 2
-            if two_d:
-                lg.weight2, lg.bias2 = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
-                vi += 2
-        G.final_weight, G.final_bias = self._grad_views[vi].data_ptr(), self._grad_views[vi + 1].data_ptr()
+        for (l, field), view in zip(self._slots, self._grad_views):
+            setattr(G if l < 0 else G.layer[l], field, view.data_ptr())
         if self.peer is None:
             # the Adam kernel clears every gradient element as it consumes it (zero_grad=1): no memset in the step
             G.clear_mode = _lib.GRADS_PREZEROED
