@@ -15,20 +15,21 @@ import wire_oracle as O
 pytestmark = pytest.mark.gpu
 
 TOL = {
-    # relative RMS (||a-b||/||b||) of: one layer from identical inputs / whole-net output / gradients.
-    # TF32 per layer ~1e-3 (north_star); end to end the omega_0, scale_0^2 gains amplify it 3-10x per layer:
-    # SURVEY.md §7 measured 1.6e-3 (denoise) ... 5e-2 (occupancy, omega_0=20, s0=10) for TF32-rounded operands.
-    "tf32": dict(layer=3e-3, out=6e-2, grad=1e-1),
-    "fp32": dict(layer=1e-4, out=5e-4, grad=1e-3),
-    # mixed16: FP16 activations / forward weights carry the same 11-bit significand as TF32, so the forward bars are the
-    # TF32 ones; gradients and dgrad/wgrad operands are BF16 (8-bit mantissa: ~1e-3 relative RMS per GEMM), measured
-    # 3-5e-3 on the denoise net next to TF32's 3e-3 (tools/precision_sim.py).  The single-layer API runs the TF32 kernels.
-    "mixed16": dict(layer=3e-3, out=6e-2, grad=1e-1),
+    # relative RMS (||a-b||/||b||) of: one layer from identical inputs (layer API) / whole-net output / gradients, each <= 3x the
+    # largest value measured on a B200 over the fixtures (profiles/r02_parity_measured.json, sections "golden" and
+    # "per_layer_api").  "_w20" = the occupancy fixture (omega_0 = 20, s0 = 10, three hidden layers), whose gains amplify
+    # operand rounding ~16x (SURVEY.md 7 predicted 5e-2 there for TF32-rounded operands; measured 3.0e-2 / 6.1e-2).
+    # Measured: fp32 out <= 1.7e-6, grads <= 3.7e-6 (occupancy 1.9e-5 / 4.4e-5); tf32 out <= 1.84e-3, grads <= 3.8e-3;
+    # mixed16 out <= 1.84e-3 (FP16 = TF32's significand), grads <= 6.8e-3 (BF16 gradient tensors).
+    "tf32": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=3e-2, out=5.5e-3, grad=1.15e-2, out_w20=8.9e-2, grad_w20=1.83e-1),
+    "fp32": dict(layer=2e-6, layer_w20=1e-4, layer_bwd=1e-3, out=5.2e-6, grad=1.1e-5, out_w20=5.8e-5, grad_w20=1.3e-4),
+    # the single-layer API runs the TF32 kernels under mixed16 (the 16-bit kernels are checked one by one from identical
+    # inputs in tests/test_kernel_parity_gpu.py)
+    "mixed16": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=3e-2, out=5.5e-3, grad=2e-2, out_w20=8.9e-2, grad_w20=1.77e-1),
 }
 
 
-# fixtures whose hyper-parameters amplify operand rounding (occupancy: omega_0 = 20, s0 = 10): multiplier on the bars above
-GOLDEN_GAIN = {}
+W20_FIXTURES = ("wire_occ_small",)   # fixtures with the occupancy hyper-parameters: the "_w20" bars apply
 
 
 def build_ours(c, precision):
@@ -65,11 +66,11 @@ def test_net_forward_backward_vs_golden(name, precision):
         a, b = util.golden_grad(c, "c128", k, p.grad.detach().cpu().numpy())
         e_g[k] = util.rel_err(a, b)
     util.record("golden", f"{name}/{precision}", {"out": e_out, "gcoords": e_gc, "grad_max": max(e_g.values())})
-    hi = GOLDEN_GAIN.get(name, 1.0)
-    assert e_out < hi * tol["out"], e_out
-    assert e_gc < hi * tol["grad"], e_gc
+    sfx = "_w20" if name in W20_FIXTURES else ""
+    assert e_out < tol["out" + sfx], e_out
+    assert e_gc < tol["grad" + sfx], e_gc
     for k, e in e_g.items():
-        assert e < hi * tol["grad"], (k, e)
+        assert e < tol["grad" + sfx], (k, e)
     last = max(int(k.split(".")[1]) for k in m.state_dict())
     assert torch.all(m.net[last].bias.grad.imag == 0)  # exact zero, as in the reference
 
@@ -92,7 +93,7 @@ def test_per_layer_from_identical_inputs(name, precision):
         assert y.dtype == torch.complex64
         e_y = util.rel_err(y.detach().cpu().numpy(), want)
         util.record("per_layer_api", f"{name}/{precision}/layer{i}", e_y)
-        assert e_y < tol["layer"], (i, e_y)
+        assert e_y < tol["layer_w20" if name in W20_FIXTURES else "layer"], (i, e_y)
         # per-layer backward against complex128 autograd of the oracle layer on the same input
         rl = ref.net[i]
         for p in rl.parameters():
@@ -105,13 +106,16 @@ def test_per_layer_from_identical_inputs(name, precision):
         torch.autograd.backward(yr, gy)
         torch.autograd.backward(y, gy.to(torch.complex64).cuda())
         torch.cuda.synchronize()
-        assert util.rel_err(xg.grad.cpu().numpy(), xr.grad.numpy()) < 10 * tol["layer"]
+        e_gx = util.rel_err(xg.grad.cpu().numpy(), xr.grad.numpy())
+        util.record("per_layer_api_bwd", f"{name}/{precision}/layer{i}/g_x", e_gx)
+        assert e_gx < tol["layer_bwd"]
         ours = dict(m.net[i].named_parameters())
         for k, p in rl.named_parameters():
             if p.grad is None:
                 continue
             e = util.rel_err(ours[k].grad.cpu().numpy(), p.grad.numpy())
-            assert e < 10 * tol["layer"], (i, k, e)
+            util.record("per_layer_api_bwd", f"{name}/{precision}/layer{i}/{k}", e)
+            assert e < tol["layer_bwd"], (i, k, e)
         for p in m.parameters():
             p.grad = None
 
@@ -190,10 +194,12 @@ def test_shapes_edge_cases_tf32_vs_fp32_vs_oracle(kind, in_f, hidden, H, out_f, 
         util.record("edge_shapes", f"{kind}-{in_f}-{hidden}-{H}-{out_f}-{n}/{precision}",
                     {"out": util.rel_err(out_t.numpy(), out32.numpy()), "gcoords": util.rel_err(gc_t.numpy(), gc32.numpy()),
                      "grad_max": max(util.rel_err(g_t[k].numpy(), v.numpy()) for k, v in g32.items())})
-        assert util.rel_err(out_t.numpy(), out32.numpy()) < (0.3 if deep else 3e-2), precision
-        assert util.rel_err(gc_t.numpy(), gc32.numpy()) < (0.5 if deep else 6e-2), precision
+        # <= 3x measured (profiles/r02_parity_measured.json "edge_shapes"): out <= 5.0e-3, gradients <= 1.06e-2 for H <= 3;
+        # five hidden layers compound to 4.6e-2 / 8.1e-2
+        assert util.rel_err(out_t.numpy(), out32.numpy()) < (1.4e-1 if deep else 1.5e-2), precision
+        assert util.rel_err(gc_t.numpy(), gc32.numpy()) < (2.5e-1 if deep else 3.2e-2), precision
         for k, v in g32.items():
-            assert util.rel_err(g_t[k].numpy(), v.numpy()) < (0.5 if deep else 6e-2), (precision, k)
+            assert util.rel_err(g_t[k].numpy(), v.numpy()) < (2.5e-1 if deep else 3.2e-2), (precision, k)
 
 
 def test_no_grad_inference_and_batched_coords():
@@ -531,7 +537,10 @@ def test_trainable_omega_scale_vs_reference_autograd(tag, precision):
     gy = torch.from_numpy(g[f"{tag}.gy"].astype(np.complex64)).cuda()
     y = layer(x)
     torch.view_as_real(y).mul(torch.view_as_real(gy)).sum().backward()
-    tol = TOL[precision]
+    tol = dict(layer=1e-4, grad=1e-3) if precision == "fp32" else dict(layer=3e-3, grad=3e-2)
+    util.record("trainable_layer_api", f"{tag}/{precision}", {
+        "y": util.rel_err(y.detach().cpu().numpy(), g[f"{tag}.y_c128"]), "g_x": util.rel_err(x.grad.cpu().numpy(), g[f"{tag}.g_x_c128"]),
+        "g_W": util.rel_err(layer.linear.weight.grad.cpu().numpy(), g[f"{tag}.g_weight_c128"])})
     assert util.rel_err(y.detach().cpu().numpy(), g[f"{tag}.y_c128"]) < tol["layer"]
     # the scalar gradients are sums of n*M terms of both signs: compare against the size of the summands
     ref_om, ref_s0 = float(g[f"{tag}.g_omega_c128"][0]), float(g[f"{tag}.g_scale_c128"][0])

@@ -176,38 +176,40 @@ def occupancy_loop(model, coords_tab, imten, perms, niters, maxpoints, lr=5e-3, 
 
 
 def test_occupancy_64cube_iou_within_0p005_of_the_reference_trajectory():
-    """BASELINE config [3]'s network (in 3, M 212, H 3, omega0 20, s0 10) on a 64^3 volume = 262 144 coordinates per epoch in
-    chunks of 200 000 (the reference's maxpoints): 25 epochs = 50 optimiser steps, on the module route (what the driver
-    calls) for all three precisions and on the fused on-device route (Trainer + GridBatcher + run_epoch) for mixed16."""
+    """BASELINE config [3]'s network (in 3, M 212, H 3, omega0 20, s0 10, lr 5e-3, LambdaLR 0.2**) on a 64^3 volume, 600 epochs of
+    one 262 144-coordinate batch (wire_occupancy.py:67 ``maxpoints = min(H*W*T, maxpoints)`` with maxpoints >= the volume), on
+    the module route (what the driver calls) for all three precisions and on the fused on-device route (Trainer + GridBatcher
+    + run_epoch) for mixed16.
+
+    This fit sits at IoU 0 for some 250 epochs (every Gaussian window nearly closed), takes off and saturates near 0.97; with
+    the reference's default 200 000-point chunks the ragged second chunk kills it for every seed tried, and a comparison
+    during the take-off measures only when it happened, so the IoU is compared after saturation.  Measured with the oracle
+    (tools/occ_explore.py, B200): complex64 0.9700, complex64 with another summation order 0.9740, complex128 0.9594 — the
+    reference does not reproduce its own IoU to the north-star's 0.005, which is why the bar is max(0.005, 1.5 x spread)."""
     import wire_b200
     H = W = T = 64
     N = H * W * T
-    niters, maxpoints = 25, 200000
+    niters, maxpoints = 600, N
     vol = synthetic_volume(H, W, T)
     imten = torch.from_numpy(vol).reshape(N, 1).to(DEV)
     coords_tab = torch.from_numpy(O.get_coords_np(H, W, T)).to(DEV)
     perms = [torch.randperm(N, generator=torch.Generator().manual_seed(300 + e)).to(DEV) for e in range(niters)]
-    # same chunks, another order inside every chunk: identical mini-batches and losses, different summation order
-    perms_b = []
-    for e, p in enumerate(perms):
-        q = p.clone()
-        for b in range(0, N, maxpoints):
-            seg = q[b:b + maxpoints]
-            q[b:b + maxpoints] = seg[torch.randperm(seg.numel(), generator=torch.Generator().manual_seed(700 + e)).to(DEV)]
-        perms_b.append(q)
+    # the same (full) batch visited in another order: identical losses, different summation order
+    perms_b = [torch.randperm(N, generator=torch.Generator().manual_seed(7300 + e)).to(DEV) for e in range(niters)]
     cfg = ("wire", 3, 300, 3, 1, 20.0, 10.0)
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        ref, init = _oracle(*cfg, seed=31)
+        ref, init = _oracle(*cfg, seed=32)
         iou_ref = occupancy_loop(ref, coords_tab, imten, perms, niters, maxpoints)
-        ref_b, _ = _oracle(*cfg, seed=31)
+        ref_b, _ = _oracle(*cfg, seed=32)
         iou_ref_order = occupancy_loop(ref_b, coords_tab, imten, perms_b, niters, maxpoints)
-        ref128, _ = _oracle(*cfg, seed=31, cdtype=torch.complex128)
+        ref128, _ = _oracle(*cfg, seed=32, cdtype=torch.complex128)
         iou_ref128 = occupancy_loop(ref128, coords_tab, imten, perms, niters, maxpoints, dtype=torch.float64)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     del ref, ref_b, ref128
+    torch.cuda.empty_cache()
     spread = max(abs(iou_ref_order[-1] - iou_ref[-1]), abs(iou_ref128[-1] - iou_ref[-1]))
     got = {}
     for precision in ("fp32", "tf32", "mixed16"):
@@ -224,12 +226,13 @@ def test_occupancy_64cube_iou_within_0p005_of_the_reference_trajectory():
         wire_b200.run_epoch(tr, batcher, maxpoints, indices=perms[e], rec=est)
     batcher.check_indices()
     got["mixed16 fused Trainer"] = iou(est, imten)
-    record("trajectory", "occupancy_64cube", {"iou_reference_c64": iou_ref, "iou_reference_c64_other_order": iou_ref_order[-1],
+    record("trajectory", "occupancy_64cube", {"iou_reference_c64_every_50": iou_ref[49::50], "iou_reference_c64": iou_ref[-1],
+                                              "iou_reference_c64_other_order": iou_ref_order[-1],
                                               "iou_reference_c128": iou_ref128[-1], "reference_spread": spread,
                                               "iou_cuda": got, "diff": {p: got[p] - iou_ref[-1] for p in got}})
     print(f"occupancy 64^3: reference IoU {iou_ref[-1]:.4f} (other order {iou_ref_order[-1]:.4f}, c128 {iou_ref128[-1]:.4f}; "
           f"spread {spread:.4f}); CUDA " + ", ".join(f"{p} {v:.4f}" for p, v in got.items()))
-    assert iou_ref[-1] > 0.5, iou_ref   # the reference fit itself must be alive for the comparison to mean anything
+    assert iou_ref[-1] > 0.9, iou_ref[49::50]   # the reference fit itself must have converged for the comparison to mean anything
     bar = max(0.005, 1.5 * spread)
     for p, v in got.items():
         assert abs(v - iou_ref[-1]) <= bar, (p, v, iou_ref[-1], spread)
