@@ -195,18 +195,6 @@ def test_coordinate_sharded_dp_matches_single_process_gloo():
     assert torch.equal(ret["w"], torch.view_as_real(ref.net[1].linear.weight.data))  # broadcast made ranks identical
 
 
-def test_bench_reference_arm_emits_contract_line():
-    import json
-    import subprocess
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr
-    line = json.loads(out.stdout.strip().splitlines()[-1])
-    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "cpu_baseline", "e2e"):
-        assert k in line
-    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
-
-
 # ---- the epoch loop's sharding logic (wire_b200.data.run_epoch) on gloo, world size 2, with stand-ins for the CUDA pieces ----
 class _StubBatcher:
     def __init__(self, total):
@@ -277,12 +265,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json
     import subprocess
     bench = os.path.join(ROOT, "bench.py")
-    res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
-                         timeout=600)
+    # (--size 128 keeps this test short; the arm's default is the full 512 x 512 batch of the GPU arm's config)
+    res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1", "--size", "128"],
+                         capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
+    assert "128x128" in d["config"]["workload"] and d["config"]["coords_per_gpu"] == 128 * 128
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
               "cpu_baseline", "e2e"):
         assert k in d, k
@@ -292,3 +282,41 @@ def test_bench_reference_arm_prints_the_contract_line():
     res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                          timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_mixed16_is_not_used_where_fp16_activations_could_overflow():
+    """|y| peaks at exp(omega_0^2 / (4 scale_0^2)): models whose hyper-parameters push that beyond FP16's range fall back to the
+    32-bit-operand kernels (with a warning); every driver's pair stays on the default mixed16 path."""
+    import warnings
+    import wire_b200
+    for w0, s0 in ((7.0, 6.0), (8.0, 9.0), (20.0, 10.0), (3.0, 4.0), (30.0, 10.0)):
+        assert wire_b200.get_INR("wire", 2, 64, None, 2, 3, True, w0, w0, s0).precision == "mixed16"
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        m = wire_b200.get_INR("wire", 2, 64, None, 2, 3, True, 30.0, 30.0, 4.0)
+    assert m.precision == "tf32" and all(layer.precision == "tf32" for layer in list(m.net)[:-1])
+    assert any("FP16" in str(w.message) for w in rec)
+
+
+def _peer_possible_worker(rank, world, port, ret, fake_hosts):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import socket
+    from wire_b200 import parallel
+    if fake_hosts:
+        socket.gethostname = lambda: f"node{rank}"
+    ok, why = parallel.peer_exchange_possible(torch.device("cuda", 0), None)
+    ret[rank] = (ok, why)
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_is_only_offered_on_one_host_gloo():
+    """The NVLink peer-memory exchange maps cudaIpc handles, which do not cross hosts: every rank must reach the same verdict
+    (ranks on two hosts -> fall back to the all-reduce), decided collectively before anything is mapped."""
+    mgr = mp.Manager()
+    for fake, want in ((True, False), (False, True)):
+        ret = mgr.dict()
+        mp.spawn(_peer_possible_worker, args=(2, 29600 + (os.getpid() % 300) + int(fake), ret, fake), nprocs=2, join=True)
+        assert ret[0] == ret[1] and ret[0][0] is want, dict(ret)
+        if fake:
+            assert "several hosts" in ret[0][1]

@@ -315,7 +315,7 @@ inline cudaError_t launch_wgrad_p(const WgradParams& P, size_t smem, cudaStream_
   if (grid <= 0 || P.n_rows <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0));
+  cfg.blockDim = dim3(wgrad_threads(GEN, OP16));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

@@ -22,7 +22,10 @@
 
 namespace wire {
 
-constexpr int kWgradThreads = 192;
+constexpr int kWgradThreads = 192;      // TF32 kernels: producer + MMA issuer + 4 epilogue warps
+constexpr int kWgradEpi16Warps = 8;     // 16-bit kernels: 8 epilogue / converter warps (two per TMEM sub-partition)
+constexpr int kWgradThreads16 = 64 + 32 * kWgradEpi16Warps;
+constexpr int wgrad_threads(bool gen, bool op16) { return op16 ? kWgradThreads16 : kWgradThreads + (gen ? 32 * 4 : 0); }
 constexpr int kWgradGenWarps = 4;  // GEN kernels: x = y0 = gabor(coords W0^T + b0) is computed in place (first hidden layer)
 constexpr int kWgradKC = 32;    // coordinates per pipeline stage (TF32 operands: 32 rows x 128 B per 32-column block)
 constexpr int kWgradKC16 = 64;  // 16-bit operands: 64 rows x 128 B per 64-column block (8 KB blocks, 128 B swizzle)
@@ -67,7 +70,7 @@ struct WgradParams {
 // 64 coordinates per stage, MMA kind::f16 (K = 16 = 2048 B per step).  (A first version used 32-column blocks of
 // 64-byte rows: every TMA row request then moved only two sectors and the loads, not the MMAs, set the pace.)
 template <bool PAIR, bool GEN = false, bool OP16 = false>
-__global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0), 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
+__global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(const __grid_constant__ WgradParams P) {
   using namespace sm100;
   static_assert(!(GEN && OP16), "the in-place generator writes TF32 tiles");
   constexpr int kKC = OP16 ? kWgradKC16 : kWgradKC;
@@ -84,6 +87,10 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   __shared__ uint32_t tmem_slot;
 
   constexpr int C = PAIR ? 2 : 1;
+  // epilogue warps (they also convert the x tiles during the K loop): the 16-bit kernels run eight — the FP16 -> BF16
+  // conversion sits on the critical path of every pipeline stage and the red.add stream of the epilogue is bound by how many
+  // warps issue it (18 us fixed per launch with four, profiles/r01: 12.9 k cycles)
+  constexpr int kEpiW = OP16 ? kWgradEpi16Warps : 4;
   const bool conv = OP16 && P.x_conv;
   unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 64) dbg[0] = clock64();
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : (conv ? 1 + 4 * C : 1));
+      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : (conv ? 1 + kEpiW * C : 1));
       mbar_init(smem_u32(&bar_empty[s]), 1);
       mbar_init(smem_u32(&bar_x[s]), 1);
     }
@@ -248,11 +255,11 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
         if (PAIR) umma_commit_2cta_mcast(smem_u32(&bar_tmem_full), 3);
         else umma_commit(smem_u32(&bar_tmem_full));
       }
-    } else if (GEN && warp >= 6) {
+    } else if (GEN && warp >= 2 + kEpiW) {
       // ===================== x-operand generator warps =====================
       // warp b writes column block b (16 complex features) of every stage; lane = coordinate row of the chunk.
       // MN-major tile, 128B swizzle with 32B atoms: 32-byte chunk index ^= (row & 3).
-      const int b = warp - 6;
+      const int b = warp - (2 + kEpiW);
       const GaborConst G0 = make_gabor_const(__ldg(P.gen_omega), __ldg(P.gen_scale));
       const float4* tab = gtab;
       const float4* tab2 = gtab + P.gen_tab_feats;
@@ -313,15 +320,16 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
     } else {
       if (conv) {
         // ===================== x converters (epilogue warps, during the K loop) =====================
-        // warp b converts quarter b (4 KB = 8 x 16 B per lane) of every landed 16 KB x tile FP16 -> BF16 in place
+        // warp b converts slice b (16 KB / kEpiW = 16-byte pieces per lane) of every landed x tile FP16 -> BF16 in place
         const int b = warp - 2;
+        constexpr int kPieces = 16384 / kEpiW / 512;
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_chunks; ++i) {
           mbar_wait(smem_u32(&bar_x[stage]), phase);
-          const uint32_t blk = smem_base + stage * stage_bytes + b * 4096;
+          const uint32_t blk = smem_base + stage * stage_bytes + b * (16384 / kEpiW);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kPieces; ++j) {
             const uint32_t addr = blk + (j * 32 + lane) * 16;
             uint32_t h[4];
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr) : "memory");
@@ -343,6 +351,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
         }
       }
       const int q = warp & 3;
+      const int part = (warp - 2) >> 2;                      // which of the sub-partition's kEpiW / 4 warps
       const int c = (mt * C + crank) * 128 + q * 32 + lane;  // row of G = real column of x
       const int two_k = 2 * P.k_in;
       float* gW = P.gW[gi];
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(kWgradThreads + (GEN ? 32 * kWgradGenWarps : 0
       if (dbg && threadIdx.x == 64) dbg[2] = clock64();
       // (Starting every K split at a different chunk, so that the ~37 CTAs adding into the same gradient entries do not walk
       // the same L2 lines in step, changed nothing: the epilogue was bound by its own instruction stream, see below.)
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = part; ch < nchunks; ch += kEpiW / 4) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + ch * 32, raw);
         tmem_wait_ld();

@@ -119,6 +119,16 @@ class _INRBase(nn.Module):
         self.complex = True
         self.wavelet = 'gabor'
         self.pos_encode = False  # legacy attribute read by modules/utils.py:246
+        # |y| = exp(-omega Im z - s^2 |z|^2) peaks at exp(omega^2 / (4 s^2)); mixed16 stores y in FP16 (max 65504 = e^11.09), so
+        # hyper-parameters with omega_0 / scale_0 > ~6 (none of the reference's drivers: 7/6, 8/9, 20/10, 3/4) would overflow
+        # where the complex64 reference stays finite: such models run the 32-bit-operand kernels instead.
+        if precision == "mixed16":
+            ratio = max(abs(float(first_omega_0)), abs(float(hidden_omega_0))) / max(abs(float(scale)), 1e-12)
+            if ratio * ratio / 4.0 > 9.0:
+                import warnings
+                warnings.warn(f"wire_b200: omega_0 / scale_0 = {ratio:.2f} lets |y| reach e^{ratio * ratio / 4:.1f}, beyond the FP16 "
+                              "activations of precision='mixed16'; using precision='tf32' for this model")
+                precision = "tf32"
         self.precision = precision
         self.in_features, self.width = in_features, width
         self.hidden_layers, self.out_features = hidden_layers, out_features
