@@ -172,7 +172,9 @@ bool choose_blocking(int out_cols, bool two_d_fwd, int store_mask, Blocking& b, 
       nbh = nb;
     }
     RowsParams tmp;
-    if (op16 ? rows16_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C) == 0
+    // (hidden layers are square: the GEMM's K is out_cols per A part; the wire2d dgrad has two parts)
+    const int k_stages = ((mode == MODE_GABOR2D_BWD || mode == MODE_FIRST2D_BWD) ? 2 : 1) * ((out_cols + 63) / 64);
+    if (op16 ? rows16_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C, k_stages, nblk) == 0
              : rows_configure(tmp, nb, nbh, store_mask, n_in, out_cols, mode, fuse_final, C, gen) == 0) continue;
     b.n_blocks = nblk; b.nb = nb; b.nbh = nbh;
     return true;
@@ -343,7 +345,7 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
   int nb = J.blk.nb;
   if (J.mode == MODE_GABOR2D_FWD && J.e.fuse_final && merge_2d_blocks(J.blk, true, op16)) { P.n_blocks = 1; nb = 2 * J.blk.nb; }
   const size_t smem = op16 ? rows16_configure(P, nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
-                                              cluster_size())
+                                              cluster_size(), (J.k_cols[0] + 63) / 64 + (J.k_cols[1] + 63) / 64, P.n_blocks)
                            : rows_configure(P, J.blk.nb, J.blk.nbh, J.store_mask, job_n_in(J.mode), J.e.n_cols, J.mode, J.e.fuse_final != 0,
                                             cluster_size(), J.gen != 0);
   P.gen_omega = J.gen_omega; P.gen_scale = J.gen_scale; P.gen_two_d = J.gen_two_d;

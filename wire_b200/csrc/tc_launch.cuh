@@ -155,8 +155,15 @@ inline void add_pdl_attr(cudaLaunchAttribute* attr, unsigned& n) {
 }
 
 // ---- 16-bit row-tile kernels (tc_rows16.cuh): 16 epilogue warps, 2 KB staging tiles, final-Linear exchange in dynamic smem ----
+// B-stationary schedule (RowsParams::bstat): WIRE_B200_BSTAT = 0 off, 1 (default) where it pays, 2 wherever it fits
+inline int bstat_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("WIRE_B200_BSTAT"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+  return v;
+}
+// k_stages: 64-column K stages of the GEMM (0 = unknown); n_blocks: column blocks of the job (0 = unknown)
 inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, int n_in = 0, int out_cols = 0,
-                               int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1) {
+                               int mode = MODE_PLAIN, bool fuse_final = false, int cluster = 1, int k_stages = 0, int n_blocks = 0) {
   P.nb = nb;
   P.nbh = nbh;
   P.store_mask = store_mask;
@@ -183,6 +190,28 @@ inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, i
   if (mode == MODE_FIRST_BWD || mode == MODE_FIRST2D_BWD) pfloats = size_t(two_d ? 2 : 1) * (pcols / 2) * 4;
   const size_t pbytes = (pfloats * sizeof(float) + 127) / 128 * 128;
   const size_t budget = kMaxDynSmem - 1024;
+  P.bstat = 0;
+  P.bres_off = 0;
+  // Measured (profiles/r02_probe_bstat.log): with staging tiles in the budget only 3 A stages fit and the schedule is a wash
+  // (forward 154.6 vs 156.4 us, dgrad + Gabor backward 146 vs 140 us); without staging (the first-layer dgrad: 7 A stages)
+  // it wins 7 us.  WIRE_B200_BSTAT=2 forces it for every eligible job.
+  const bool bstat_ok = bstat_mode() == 2 || (bstat_mode() == 1 && n_out + n_in == 0);
+  if (P.slices == 2 && !fuse_final && n_blocks == 1 && k_stages > 0 && bstat_ok) {
+    // B-stationary: the slice's packed weights stay resident (k_stages tiles of b_box_rows x 128 B), the stages hold A only
+    const size_t a_stage = size_t(kTileRows) * 128;
+    const size_t bres = size_t(k_stages) * P.b_box_rows * 128;
+    if (staging + pbytes + bres + 3 * a_stage <= budget) {
+      int stages = int((budget - staging - pbytes - bres) / a_stage);
+      if (stages > 8) stages = 8;
+      P.bstat = 1;
+      P.stages = stages;
+      P.bres_off = uint32_t(stages * a_stage);
+      P.staging_off = uint32_t(stages * a_stage + bres);
+      P.param_off = uint32_t(stages * a_stage + bres + staging);
+      P.param_cols = pcols;
+      return stages * a_stage + bres + staging + pbytes + 1024;
+    }
+  }
   if (staging + pbytes + 2 * stage > budget) return 0;
   int stages = int((budget - staging - pbytes) / stage);
   if (stages > 8) stages = 8;
@@ -229,7 +258,11 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
     cfg.dynamicSmemBytes = smem;
   }
   int clusters = C > 1 ? max_clusters : sm_count;
-  if (clusters > units) clusters = units;
+  if (P.bstat) {  // every cluster owns one slice: a multiple of the slice count, at most one cluster per (row group, slice)
+    if (clusters > units * P.slices) clusters = units * P.slices;
+    clusters -= clusters % P.slices;
+    if (clusters < P.slices) return cudaErrorInvalidConfiguration;
+  } else if (clusters > units) clusters = units;
   if (clusters <= 0) return cudaSuccess;
   cfg.gridDim = dim3(clusters * C);
   add_pdl_attr(attr, cfg.numAttrs);

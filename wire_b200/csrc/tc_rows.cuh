@@ -51,6 +51,11 @@ struct RowsParams {
   int cluster;              // 1 = one CTA per tile (cta_group::1); 2 = CTA pair (cta_group::2): a 256-row tile, each
                             // CTA stages its own 128 rows of A and HALF of the B tile, halving the smem fill per flop
   int stages;
+  int bstat;             // tc_rows16, two N-slices, one column block: B-STATIONARY schedule — every cluster owns ONE slice for the
+                         // whole launch, loads that slice's packed weights (all K stages) into shared memory once and then
+                         // streams only A tiles; the other slice of the same rows runs on the neighbouring cluster (its A reads
+                         // hit L2).  Per row tile the SM's TMA unit moves 112 KB of operands instead of 420 KB.
+  uint32_t bres_off;     // byte offset of the resident B region inside dynamic smem
   int store_mask;  // which epilogue results are TMA-stored: bit0 = o0, bit1 = o1, bit2 = o2
   int o_fmt[3];    // element type of each STORED output slot (sm100_host::ElemType): f32 tiles are 32x32x4 B with the
                    // 128 B swizzle, 16-bit tiles (FP16 saved z / y, BF16 gradients) are dense 32x32x2 B

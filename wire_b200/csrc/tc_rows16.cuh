@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ __align__(8) uint64_t bar_in[kEpi16Warps];
+  __shared__ __align__(8) uint64_t bar_b;  // B-stationary schedule: the resident weight slice has landed
   __shared__ uint32_t tmem_slot;
 
   constexpr bool kFwd = (MODE == MODE_GABOR_FWD || MODE == MODE_GABOR2D_FWD);
@@ -94,7 +95,9 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_bytes = kTileRows * 128;
   const uint32_t b_bytes = uint32_t(P.b_box_rows) * 128;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const bool bstat = P.bstat != 0;
+  const uint32_t stage_bytes = bstat ? a_bytes : a_bytes + b_bytes;   // B-stationary: the pipeline stages hold A tiles only
+  const uint32_t bres_base = smem_base + P.bres_off;
   const uint32_t staging_base = smem_base + P.staging_off;
   float* params = reinterpret_cast<float*>(smem_gen + P.param_off);
   const RowsEpi& E = P.e;
@@ -110,14 +113,25 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
   const int my_cluster = blockIdx.x / C;
   const int row_groups = (row_tiles + C - 1) / C;
   const int n_units = row_groups * P.n_blocks;
-  const int n_iters = (n_units + n_clusters - 1) / n_clusters;
-  const int n_jobs = n_iters * P.slices;
+  // B-stationary: cluster c owns slice c % slices and walks the row groups c / slices, c / slices + cps, ... (n_blocks == 1, so a
+  // unit is a row group); the launcher makes the cluster count a multiple of the slice count
+  const int cps = n_clusters / P.slices;
+  const int my_sl = bstat ? my_cluster % P.slices : 0;
+  const int my_seq = my_cluster / P.slices;
+  const int n_iters = bstat ? (cps > 0 && my_seq < cps ? (row_groups + cps - 1) / cps : 0) : (n_units + n_clusters - 1) / n_clusters;
+  const int n_jobs = bstat ? n_iters : n_iters * P.slices;
+  auto job_it = [&](int jb) { return bstat ? jb : jb / P.slices; };
+  auto job_sl = [&](int jb) { return bstat ? my_sl : jb % P.slices; };
   constexpr bool pair = PAIR;
   const bool leader = crank == 0;
   unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 16 : nullptr;  // [0..7] stall counters, [8..11] phase stamps
   const long long t_entry = WIRE_CLK();
   // work unit of iteration `it`; reversed sweeps mirror the valid units (phantom units past the end stay phantom)
-  auto unit_of = [&](int it) { const int u = it * n_clusters + my_cluster; return (P.reverse && u < n_units) ? n_units - 1 - u : u; };
+  auto unit_of = [&](int it) {
+    if (bstat) return it * cps + my_seq;
+    const int u = it * n_clusters + my_cluster;
+    return (P.reverse && u < n_units) ? n_units - 1 - u : u;
+  };
 
   // ---- shared parameter tables (zero padded: the epilogue needs no column checks) ----
   //  fwd  : bias[param_cols] | bias2[param_cols] (2D) | wf[(param_cols/2)][8] (wr[4], wi[4]) | fin exchange (FUSE)
@@ -168,6 +182,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       mbar_init(smem_u32(&bar_tmem_empty[b]), kEpi16Warps * C);
     }
     for (int w = 0; w < kEpi16Warps; ++w) mbar_init(smem_u32(&bar_in[w]), 1);
+    mbar_init(smem_u32(&bar_b), 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -194,13 +209,24 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       uint32_t phase = 0;
       long long t_wait = 0;
       const long long t_begin = WIRE_CLK();
+      if (bstat && n_jobs > 0) {  // the resident weight slice: every K stage, once
+        const uint32_t bb = smem_u32(&bar_b);
+        const int brow_res = my_sl * P.ns + crank * P.b_box_rows;
+        if (!pair) {
+          mbar_expect_tx(bb, kc_total * b_bytes);
+          for (int kc = 0; kc < kc_total; ++kc) tma_load_2d_hint(bres_base + kc * b_bytes, &P.b_map, bb, kc * kKC, brow_res, kEvictLast);
+        } else {
+          if (leader) mbar_expect_tx(bb, 2 * kc_total * b_bytes);
+          for (int kc = 0; kc < kc_total; ++kc) tma_load_2d_2cta(bres_base + kc * b_bytes, &P.b_map, bb & kPeerBitMask, kc * kKC, brow_res, kEvictLast);
+        }
+      }
       for (int jb = 0; jb < n_jobs; ++jb) {
-        const int it = jb / P.slices, sl = jb % P.slices;
+        const int it = job_it(jb), sl = job_sl(jb);
         const int unit = unit_of(it);
         const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
         const int brow = (unit % P.n_blocks) * P.nb + sl * P.ns + crank * P.b_box_rows;
-        const uint64_t a_policy = (sl == P.slices - 1 && (unit % P.n_blocks) == P.n_blocks - 1) ? kEvictFirst : kEvictLast;
-        if (sl == 0 && P.l2_prefetch && it + 1 < n_iters) {
+        const uint64_t a_policy = (!bstat && sl == P.slices - 1 && (unit % P.n_blocks) == P.n_blocks - 1) ? kEvictFirst : kEvictLast;
+        if (!bstat && sl == 0 && P.l2_prefetch && it + 1 < n_iters) {
           // pull the NEXT work unit's A rows into L2 now: their demand loads then see L2 latency instead of HBM latency
           // (the pipeline holds only ~5 stages; HBM latency under load starved the MMA thread, mma_wait_full 52 %)
           const int unit_n = unit_of(it + 1);
@@ -221,12 +247,12 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
           if (!pair) {
             mbar_expect_tx(full_own, stage_bytes);
             tma_load_2d_hint(a_dst, &P.a_map[part], full_own, kcol, row0, a_policy);
-            tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kKC, brow, kEvictLast);
+            if (!bstat) tma_load_2d_hint(a_dst + a_bytes, &P.b_map, full_own, kc * kKC, brow, kEvictLast);
           } else {
             const uint32_t full_leader = full_own & kPeerBitMask;
             if (leader) mbar_expect_tx(full_own, 2 * stage_bytes);
             tma_load_2d_2cta(a_dst, &P.a_map[part], full_leader, kcol, row0, a_policy);
-            tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kKC, brow, kEvictLast);
+            if (!bstat) tma_load_2d_2cta(a_dst + a_bytes, &P.b_map, full_leader, kc * kKC, brow, kEvictLast);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
@@ -240,6 +266,8 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       const uint32_t desc_hi = uint32_t(make_sdesc_sw128(0, 16, 1024) >> 32);
       const uint32_t a_lo0 = uint32_t(make_sdesc_sw128(smem_base, 16, 1024));
       const uint32_t stage_units = stage_bytes >> 4, b_units = a_bytes >> 4;
+      const uint32_t bres_lo0 = a_lo0 + (P.bres_off >> 4), bres_units = b_bytes >> 4;
+      if (bstat && n_jobs > 0) { mbar_wait(smem_u32(&bar_b), 0); tc_fence_after(); }
       auto tail_steps = [](int cols, int kc) {
         const int st = (cols - (kc - 1) * kKC + 15) / 16;
         return st > 4 ? 4 : st;
@@ -265,7 +293,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
           w_full += WIRE_CLK() - t1;
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * stage_units;
-          const uint32_t b_lo = a_lo + b_units;
+          const uint32_t b_lo = bstat ? bres_lo0 + kc * bres_units : a_lo + b_units;
           const int steps = (kc == kc0 - 1) ? last0 : ((kc == kc_total - 1) ? last1 : 4);
           auto mma = [&](int ks, uint32_t acc) {
             const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + 2 * ks);
@@ -328,7 +356,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       if (lane == 0) { if (pair) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0); else mbar_arrive(buf ? empty_addr1 : empty_addr0); }
     };
     for (int jb = 0; jb < n_jobs; ++jb) {
-      const int it = jb / P.slices, sl = jb % P.slices;
+      const int it = job_it(jb), sl = job_sl(jb);
       const int buf = jb & 1;
       const int unit = unit_of(it);
       const int row0 = ((unit / P.n_blocks) * C + crank) * kTileRows;
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       int my_last = -1;
       if (nchunks > ch0) my_last = ch0 + kEpi16Parts * ((nchunks - 1 - ch0) / kEpi16Parts);
 
-      if (sl == 0) {
+      if (bstat || sl == 0) {  // a new row tile
         if constexpr (kFirst) {
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
           if (row_ok) {
