@@ -32,15 +32,11 @@ UNIT = "coords/s"
 CFG = dict(nonlin="wire", in_features=2, hidden_features=300, hidden_layers=2, out_features=3,
            first_omega_0=7.0, hidden_omega_0=7.0, scale=6.0)
 LR = 5e-3
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures of this
-# command at the default size (profiles/*_ncu_full_*_summary.txt): (precision, kernel) -> bytes
-# tf32: profiles/r01_ncu_full_v6_summary.txt (530.7 MB read + 835.0 MB written, hidden layer 1);
-# mixed16: profiles/r01_ncu_full_v11_mixed16_summary.txt, mean of the two forward launches of a step
-#          (layer 1: 251.4 + 398.4 MB, layer 2 with the fused final Linear: 242.4 + 182.1 MB)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the top kernel, from `ncu --set full` captures of this command
-# (mean of the H forward launches): profiles/r01_ncu_full_v6_summary.txt (tf32), profiles/r01_ncu_full_v14_mixed16_summary.txt
-# (mixed16: 252.0 + 402.2 MB for hidden layer 1, 242.3 + 184.8 MB for hidden layer 2)
-NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6, ("mixed16", "tc_rows_gabor_fwd"): 540.6e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (mean of the H forward launches of a step), from
+# `ncu --set full` captures of this command at the default size: (precision, kernel) -> bytes
+#   tf32:    profiles/r01_ncu_full_v6_summary.txt (530.7 MB read + 835.0 MB written, hidden layer 1)
+#   mixed16: profiles/r02_ncu_full_step_kernels.txt (layer 1: 251.1 + 399.6 MB; layer 2 with the fused final Linear: 242.2 + 183.3 MB)
+NCU_TRAFFIC = {("tf32", "tc_rows_gabor_fwd"): 1365.6e6, ("mixed16", "tc_rows_gabor_fwd"): 538.1e6}
 
 
 def flop_per_coord(M, H, in_f, out_f):

@@ -216,6 +216,53 @@ def test_trainer_sisr_loss_matches_reference_style_loop():
         assert util.rel_err(b(coords_hr).cpu().numpy(), a(coords_hr).cpu().numpy()) < 2e-2
 
 
+@pytest.mark.parametrize("precision", ["mixed16", "tf32", "fp32"])
+def test_sisr_iteration_shares_one_forward(precision):
+    """wire_SISR.py:154-177 runs the model twice per iteration on the same coordinates with the same weights (a grad forward for
+    the loss, a ``no_grad`` forward for the metrics) — the second reproduces the first bit for bit, so ``Trainer.step_sisr``
+    serves both from one forward.  Checked here against REAL second forwards: (a) the training forward and the no_grad forward
+    of the CUDA module are bit-identical; (b) step_sisr's rec_hr / mse_hr equal what the reference-style iteration computes."""
+    import wire_b200
+    dev = torch.device("cuda", 0)
+    H = W = 128
+    scale = 4
+    x = torch.linspace(-1, 1, W); y = torch.linspace(-1, 1, H)
+    X, Y = torch.meshgrid(x, y, indexing="xy")
+    coords_hr = torch.hstack((X.reshape(-1, 1), Y.reshape(-1, 1)))[None, ...].to(dev)
+    torch.manual_seed(3)
+    gt = torch.rand(1, H * W, 3, device=dev)
+    gt_lr = torch.nn.AvgPool2d(scale)(gt.reshape(H, W, 3).permute(2, 0, 1)[None, ...]).reshape(1, 3, -1).permute(0, 2, 1).contiguous()
+    kw = dict(nonlin="wire2d", in_features=2, hidden_features=256, hidden_layers=2, out_features=3, first_omega_0=8.0,
+              hidden_omega_0=8.0, scale=9.0, precision=precision)
+    a = wire_b200.get_INR(**kw).to(dev)
+    b = wire_b200.get_INR(**kw).to(dev)
+    b.load_state_dict(a.state_dict())
+    # (a) grad forward == no_grad forward, bit for bit
+    rec_train = a(coords_hr)
+    with torch.no_grad():
+        rec_eval = a(coords_hr)
+    assert rec_train.requires_grad and not rec_eval.requires_grad
+    assert torch.equal(rec_train.detach(), rec_eval)
+    # (b) the reference-style iteration against step_sisr
+    opt = torch.optim.Adam(a.parameters(), lr=5e-3)
+    pool = torch.nn.AvgPool2d(scale)
+    tr = wire_b200.Trainer(b, lr=5e-3)
+    tr.set_loss_avgpool(H, W, scale)
+    for it in range(4):
+        rec_hr = a(coords_hr)
+        rec = pool(rec_hr.reshape(H, W, 3).permute(2, 0, 1)[None, ...])
+        loss = ((gt_lr - rec.reshape(1, 3, -1).permute(0, 2, 1)) ** 2).mean()
+        with torch.no_grad():
+            rec_hr2 = a(coords_hr)
+            mse_ref = float(((gt - rec_hr2) ** 2).mean())
+        opt.zero_grad(); loss.backward(); opt.step()
+        loss_b, rec_b, mse_b = tr.step_sisr(coords_hr, gt_lr, gt)
+        tol = 1e-4 if precision == "fp32" else 2e-2
+        assert abs(float(loss_b) - float(loss)) <= tol * max(float(loss), 1e-6), (it, float(loss_b), float(loss))
+        assert abs(float(mse_b) - mse_ref) <= tol * mse_ref, (it, float(mse_b), mse_ref)
+        assert util.rel_err(rec_b.cpu().numpy(), rec_hr2.reshape(-1, 3).cpu().numpy()) < (1e-4 if precision == "fp32" else 3e-2)
+
+
 def test_trainer_step_from_pinned_host_buffers_is_pipelined_and_correct():
     """Trainer.step with PINNED HOST inputs (copy stream + two staging buffers) follows the same trajectory as with device
     inputs, also when the host buffers change every step."""

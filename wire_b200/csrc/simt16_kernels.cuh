@@ -382,20 +382,24 @@ __global__ void __launch_bounds__(kFirstWgrad16Threads) first_wgrad16_kernel(con
   const int range0 = blockIdx.x * rows_per_block;
   int range1 = range0 + rows_per_block;
   range1 = range1 > n ? n : range1;
-  const bool col_ok = 8 * lane < g_pitch;
+  // narrow rows (wire2d at the SISR width: 128 features = 16 lanes) are packed two or four to a warp, so every lane loads
+  const int lpr = g_pitch <= 64 ? 8 : (g_pitch <= 128 ? 16 : 32);  // lanes per row
+  const int rpw = 32 / lpr;                                         // rows per warp and load
+  const int oct = lane % lpr, rsub = lane / lpr;
+  const bool col_ok = 8 * oct < g_pitch;
   float acc[8][4];
 #pragma unroll
   for (int f = 0; f < 8; ++f)
 #pragma unroll
     for (int d = 0; d < 4; ++d) acc[f][d] = 0.f;
-  for (int rb = range0 + wg; rb < range1; rb += 4 * kWarps) {
+  for (int rb = range0 + wg * rpw; rb < range1; rb += 4 * kWarps * rpw) {
     uint4 g[4];
     float c[4][3];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int row = rb + kWarps * u;
+      const int row = rb + kWarps * rpw * u + rsub;
       const bool ok = row < range1 && col_ok;
-      g[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(gz0 + size_t(row) * g_pitch + 8 * lane)) : make_uint4(0u, 0u, 0u, 0u);
+      g[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(gz0 + size_t(row) * g_pitch + 8 * oct)) : make_uint4(0u, 0u, 0u, 0u);
       const int rc = row < range1 ? row : range0;
       c[u][0] = __ldg(coords + size_t(rc) * in_f);
       c[u][1] = in_f > 1 ? __ldg(coords + size_t(rc) * in_f + 1) : 0.f;
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kFirstWgrad16Threads) first_wgrad16_kernel(con
 #pragma unroll
   for (int f = 0; f < 8; ++f)
 #pragma unroll
-    for (int d = 0; d < 4; ++d) atomicAdd(&red[lane][4 * f + d], acc[f][d]);
+    for (int d = 0; d < 4; ++d) atomicAdd(&red[oct][4 * f + d], acc[f][d]);
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
     const int l = i >> 5, v = i & 31, f = v >> 2, d = v & 3;
