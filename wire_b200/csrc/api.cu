@@ -556,7 +556,15 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
     for (int nb = (g_pitch + 255) / 256; nb <= 16 && zw_pitch == g_pitch; ++nb)
       if (g_pitch % nb == 0 && (g_pitch / nb) % 8 == 0 && g_pitch / nb <= 256) { n_box = nb; break; }
     const size_t tile_bytes = size_t(g_pitch) * kTopRows * 2;
-    const size_t smem16 = (kTopIn + kTopOut) * (w ? 2 : 1) * tile_bytes + 256;
+    // ring depths: the maxima for wire; wire2d (two tensors per stage) at narrow widths runs 3 + 2 so that a fourth CTA fits per SM
+    // (WIRE_B200_TOP_DEPTH="in,out" overrides)
+    int in_depth = 4, out_depth = 3;
+    if (w && d->width <= 160) { in_depth = 3; out_depth = 3; }   // measured at M = 128, 1 M rows: 0.48 ms against 0.53 (4 + 3), 0.66 (3 + 2)
+    if (const char* e = getenv("WIRE_B200_TOP_DEPTH")) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && a <= kTopIn && b >= 2 && b <= kTopOut) { in_depth = a; out_depth = b; }
+    }
+    const size_t smem16 = size_t(in_depth + out_depth) * (w ? 2 : 1) * tile_bytes + 256;
     if (n_box > 0 && smem16 <= 200 * 1024 && d->width <= 992 && !getenv("WIRE_B200_TOP_SIMT")) {
       TopBwd16Params T;
       memset(&T, 0, sizeof(T));
@@ -564,6 +572,7 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       T.n = int(n); T.M = d->width; T.out_f = d->out_features; T.pitch = g_pitch; T.two_d = w ? 1 : 0;
       T.bw = g_pitch / n_box; T.n_box = n_box;
       T.gs_omega = g_omega; T.gs_scale = g_scale;
+      T.in_depth = in_depth; T.out_depth = out_depth;
       if (mse) {
         T.pred = mse->pred; T.target = mse->target; T.g_scale = 2.0f / float(mse->count_norm); T.loss_scale = 1.0f / float(mse->count_norm);
         T.ring = mse->ring; T.ring_n = mse->ring_n; T.step_ptr = mse->step_ptr;

@@ -108,8 +108,11 @@ __global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restric
 // registers), results are written to a BF16 smem tile that leaves by TMA (clipped to the 2M valid columns).
 // ---------------------------------------------------------------------------------------------
 constexpr int kTopRows = 8;
-constexpr int kTopOut = 3; // depth of the output ring
-constexpr int kTopIn = 4;  // depth of the input ring (ncu: with 2 the compute warps waited on TMA latency, long_scoreboard 3.0)
+constexpr int kTopOut = 4; // maximum depth of the output ring
+constexpr int kTopIn = 4;  // maximum depth of the input ring (ncu: with 2 the compute warps waited on TMA latency, long_scoreboard 3.0)
+// The depths actually used are launch parameters (TopBwd16Params::in_depth / out_depth <= the maxima): wire2d doubles the bytes
+// per stage, and at the SISR width (M = 128) a CTA is only four compute warps, so shallower rings that let more CTAs share an
+// SM beat deep ones.
 struct TopBwd16Params {
   CUtensorMap z_map[2];   // z, w: [n][pitch] FP16, box {bw cols, kTopRows}, no swizzle
   CUtensorMap g_map[2];   // g_z, g_w: [n][2M] BF16 (row pitch = pitch), same box
@@ -132,6 +135,7 @@ struct TopBwd16Params {
   // trainable omega_0 / scale_0 of the last hidden layer (SCAL instantiations): accumulated device floats, or nullptr
   float* gs_omega;
   float* gs_scale;
+  int in_depth, out_depth;  // ring depths (<= kTopIn / kTopOut)
 };
 
 // Block = W compute warps (thread k owns complex feature k) + one I/O warp.  No block-wide barrier in the loop: tiles
@@ -150,7 +154,8 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
   const uint32_t tile_bytes = uint32_t(P.pitch) * kTopRows * 2;   // one tensor, one stage
   constexpr int n_t = TWO_D ? 2 : 1;
   // layout: in[kTopIn stages][n_t tensors] | out[kTopOut buffers][n_t tensors]
-  const uint32_t out_off = kTopIn * n_t * tile_bytes;
+  const int kIn = P.in_depth, kOut = P.out_depth;
+  const uint32_t out_off = kIn * n_t * tile_bytes;
   const uint32_t box_bytes = uint32_t(P.bw) * kTopRows * 2;
 
   const int n_tiles = (P.n + kTopRows - 1) / kTopRows;
@@ -162,11 +167,11 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
   const int n_cw = (blockDim.x >> 5) - 1;  // compute warps
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTopIn; ++s) {
+    for (int s = 0; s < kIn; ++s) {
       mbar_init(smem_u32(&in_full[s]), 2);
       mbar_init(smem_u32(&in_empty[s]), n_cw);
     }
-    for (int s = 0; s < kTopOut; ++s) {
+    for (int s = 0; s < kOut; ++s) {
       mbar_init(smem_u32(&out_full[s]), n_cw);
       mbar_init(smem_u32(&out_empty[s]), 1);
     }
@@ -211,18 +216,18 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&in_full[stage]));
     };
-    for (int s = 0; s < kTopIn; ++s)
+    for (int s = 0; s < kIn; ++s)
       if (t_begin + s < t_end) issue_load(t_begin + s, s, load_go(t_begin + s));
-    float go_next = load_go(t_begin + kTopIn);
+    float go_next = load_go(t_begin + kIn);
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int it = tile - t_begin;
-      const int istage = it % kTopIn, ostage = it % kTopOut;
-      const uint32_t iph = (it / kTopIn) & 1, oph = (it / kTopOut) & 1;
-      if (tile + kTopIn < t_end) {  // refill the in-stage as soon as every compute warp has read it
+      const int istage = it % kIn, ostage = it % kOut;
+      const uint32_t iph = (it / kIn) & 1, oph = (it / kOut) & 1;
+      if (tile + kIn < t_end) {  // refill the in-stage as soon as every compute warp has read it
         if (lane == 0) mbar_wait(smem_u32(&in_empty[istage]), iph);
         __syncwarp();
-        issue_load(tile + kTopIn, istage, go_next);
-        go_next = load_go(tile + 1 + kTopIn);
+        issue_load(tile + kIn, istage, go_next);
+        go_next = load_go(tile + 1 + kIn);
       }
       if (lane == 0) {
         mbar_wait(smem_u32(&out_full[ostage]), oph);
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
         }
         tma_store_commit();
         tma_store_wait_read<1>();  // the PREVIOUS tile's store has read its buffer
-        if (it >= 1) mbar_arrive(smem_u32(&out_empty[(it - 1) % kTopOut]));
+        if (it >= 1) mbar_arrive(smem_u32(&out_empty[(it - 1) % kOut]));
       }
     }
     if (P.pred) {
@@ -337,8 +342,8 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
       mbar_arrive(smem_u32(&out_full[stage]));
     }
     zin += in_stride; zout += in_stride;
-    if (++istage == kTopIn) { istage = 0; iphase ^= 1; zin = sm + off0; }
-    if (++stage == kTopOut) { stage = 0; ophase ^= 1; zout = sm + out_off + off0; }
+    if (++istage == kIn) { istage = 0; iphase ^= 1; zin = sm + off0; }
+    if (++stage == kOut) { stage = 0; ophase ^= 1; zout = sm + out_off + off0; }
   }
   if (active) {
 #pragma unroll

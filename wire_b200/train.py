@@ -122,6 +122,8 @@ class Trainer:
         # the separate 6-us loss kernel (the top kernel's I/O warp gets longer: 1.042 vs 1.042 ms/step), so it is opt-in
         self._fused_mse = os.environ.get("WIRE_B200_FUSED_MSE", "0") == "1"
         self._issued = 0                                                        # optimiser steps issued (host mirror of step_dev)
+        # staging pairs for pinned host inputs: the copy of step i + depth - 1 may run while step i computes
+        self._stage_depth = max(2, int(os.environ.get("WIRE_B200_STAGE_DEPTH", "2")))
         self._n = None
         self._key = None
         self._n_global = None
@@ -332,13 +334,14 @@ class Trainer:
             return
         st = self._states[self._key]
         if "stage" not in st:
-            st["stage"] = [(torch.empty_like(self.coords_buf), torch.empty_like(self.target_buf)) for _ in range(2)]
-            st["stage_free"] = [None, None]   # event: the compute stream has consumed this staging pair
+            depth = self._stage_depth
+            st["stage"] = [(torch.empty_like(self.coords_buf), torch.empty_like(self.target_buf)) for _ in range(depth)]
+            st["stage_free"] = [None] * depth   # event: the compute stream has consumed this staging pair
             st["stage_i"] = 0
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         i = st["stage_i"]
-        st["stage_i"] = i ^ 1
+        st["stage_i"] = (i + 1) % len(st["stage"])
         sc, stg = st["stage"][i]
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(self._copy_stream):
