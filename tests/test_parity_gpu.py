@@ -20,12 +20,13 @@ TOL = {
     # "per_layer_api").  "_w20" = the occupancy fixture (omega_0 = 20, s0 = 10, three hidden layers), whose gains amplify
     # operand rounding ~16x (SURVEY.md 7 predicted 5e-2 there for TF32-rounded operands; measured 3.0e-2 / 6.1e-2).
     # Measured: fp32 out <= 1.7e-6, grads <= 3.7e-6 (occupancy 1.9e-5 / 4.4e-5); tf32 out <= 1.84e-3, grads <= 3.8e-3;
-    # mixed16 out <= 1.84e-3 (FP16 = TF32's significand), grads <= 6.8e-3 (BF16 gradient tensors).
-    "tf32": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=3e-2, out=5.5e-3, grad=1.15e-2, out_w20=8.9e-2, grad_w20=1.83e-1),
-    "fp32": dict(layer=2e-6, layer_w20=1e-4, layer_bwd=1e-3, out=5.2e-6, grad=1.1e-5, out_w20=5.8e-5, grad_w20=1.3e-4),
+    # mixed16 out <= 1.84e-3 (FP16 = TF32's significand), grads <= 6.8e-3 (BF16 gradient tensors).  layer_bwd (per-layer API,
+    # gradients from identical inputs): tf32 <= 2.5e-3, fp32 <= 5.5e-7.
+    "tf32": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=7.5e-3, out=5.5e-3, grad=1.15e-2, out_w20=8.9e-2, grad_w20=1.83e-1),
+    "fp32": dict(layer=2e-6, layer_w20=1e-4, layer_bwd=1.7e-6, out=5.2e-6, grad=1.1e-5, out_w20=5.8e-5, grad_w20=1.3e-4),
     # the single-layer API runs the TF32 kernels under mixed16 (the 16-bit kernels are checked one by one from identical
     # inputs in tests/test_kernel_parity_gpu.py)
-    "mixed16": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=3e-2, out=5.5e-3, grad=2e-2, out_w20=8.9e-2, grad_w20=1.77e-1),
+    "mixed16": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=7.5e-3, out=5.5e-3, grad=2e-2, out_w20=8.9e-2, grad_w20=1.77e-1),
 }
 
 
@@ -537,7 +538,9 @@ def test_trainable_omega_scale_vs_reference_autograd(tag, precision):
     gy = torch.from_numpy(g[f"{tag}.gy"].astype(np.complex64)).cuda()
     y = layer(x)
     torch.view_as_real(y).mul(torch.view_as_real(gy)).sum().backward()
-    tol = dict(layer=1e-4, grad=1e-3) if precision == "fp32" else dict(layer=3e-3, grad=3e-2)
+    # <= 3x measured (profiles/r02_parity_measured.json "trainable_layer_api"): fp32 y <= 3.0e-7, gradients <= 4.4e-7; tf32 y <= 1.15e-3,
+    # gradients <= 1.09e-3
+    tol = dict(layer=9e-7, grad=1.3e-6) if precision == "fp32" else dict(layer=3.4e-3, grad=3.2e-3)
     util.record("trainable_layer_api", f"{tag}/{precision}", {
         "y": util.rel_err(y.detach().cpu().numpy(), g[f"{tag}.y_c128"]), "g_x": util.rel_err(x.grad.cpu().numpy(), g[f"{tag}.g_x_c128"]),
         "g_W": util.rel_err(layer.linear.weight.grad.cpu().numpy(), g[f"{tag}.g_weight_c128"])})
