@@ -126,7 +126,7 @@ def cpu_reference_run(size, steps, warmup, threads=None):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        float(loss)
+        float(loss.detach())
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     n = size * size
@@ -486,6 +486,12 @@ def run_ours(args):
                 extras["sisr_1024"] = sisr_extra(dev, args.steps)
             except Exception as exc:
                 extras["sisr_1024"] = {"error": repr(exc)[:300]}
+        if world == 1:
+            try:
+                extras["width_sweep"] = width_sweep_extra(dev, max(5, args.steps // 2))
+            except Exception as exc:
+                extras["width_sweep"] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import occupancy_bench as OB
@@ -537,6 +543,39 @@ def run_ours(args):
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+
+
+def width_sweep_extra(dev, steps):
+    """BASELINE config [4] (tensor-pipe utilisation against width / depth / batch), a few points of tools/sweep.py under the
+    bench's clock: full training step through wire_b200.Trainer on random coordinates, mixed16."""
+    import wire_b200
+    peaks, _ = load_peaks()
+    out = []
+    for hidden, H, n in ((128, 2, 1 << 18), (512, 2, 1 << 18), (1024, 2, 1 << 18), (300, 5, 1 << 18), (300, 2, 1 << 16), (300, 2, 1 << 22)):
+        torch.manual_seed(0)
+        model = wire_b200.get_INR(nonlin="wire", in_features=2, hidden_features=hidden, hidden_layers=H, out_features=3,
+                                  first_omega_0=7.0, hidden_omega_0=7.0, scale=6.0).to(dev)
+        tr = wire_b200.Trainer(model, lr=LR)
+        coords = torch.rand(1, n, 2, device=dev) * 2 - 1
+        target = torch.rand(1, n, 3, device=dev)
+        for _ in range(3):
+            tr.step(coords, target)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tr.step(coords, target)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        M = model.width
+        tf = flop_per_coord(M, H, 2, 3) * n / (ms * 1e-3) / 1e12
+        out.append({"hidden_features": hidden, "M": M, "H": H, "coords": n, "ms_per_step": ms, "coords_per_s": n / (ms * 1e-3),
+                    "algorithmic_tflops": tf, "frac_of_measured_bf16_burst": tf / peaks["bf16_tflops"]})
+        tr.close()
+        del tr, model, coords, target
+        torch.cuda.empty_cache()
+    return out
 
 
 def sisr_extra(dev, steps):
