@@ -281,6 +281,17 @@ int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, cons
 /* RealGaborLayer (modules/wire.py:6-42; not used by INR): the fused activation y = cos(omega_0 f) exp(-(scale_0 s)^2) of the
  * two real Linears' outputs f = freqs(x), s = scale(x) (modules/wire.py:38-42), and its derivative w.r.t. f and s. */
 int wire_real_gabor_forward(const float* f, const float* s, int64_t count, float omega0, float scale0, float* y, void* stream);
+/* The whole RealGaborLayer.forward (modules/wire.py:29-42) and its autograd on FP32 FMAs: x [n][K], weights [M][K] row-major as
+ * nn.Linear stores them, biases [M] (may be NULL).  forward: y [n][M]; f_save / s_save [n][M] = the two Linears' outputs, kept for
+ * the backward pass (may be NULL under no_grad).  backward: OVERWRITES the four parameter gradients (g_b_* may be NULL) and, when
+ * non-NULL, grad_x [n][K]; scratch_gf / scratch_gs are [n][M] work buffers. */
+int wire_real_gabor_layer_forward(const float* x, int64_t n, int32_t K, int32_t M, const float* w_freqs, const float* b_freqs,
+                                  const float* w_scale, const float* b_scale, float omega0, float scale0, float* y, float* f_save,
+                                  float* s_save, void* stream);
+int wire_real_gabor_layer_backward(const float* x, const float* f_save, const float* s_save, const float* grad_y, int64_t n, int32_t K,
+                                   int32_t M, const float* w_freqs, const float* w_scale, float omega0, float scale0, float* grad_x,
+                                   float* g_w_freqs, float* g_b_freqs, float* g_w_scale, float* g_b_scale, float* scratch_gf,
+                                   float* scratch_gs, void* stream);
 int wire_real_gabor_backward(const float* f, const float* s, const float* grad_y, int64_t count, float omega0, float scale0,
                              float* grad_f, float* grad_s, void* stream);
 

@@ -102,6 +102,10 @@ SIGNATURES = {
     "wire_gabor_scalar_grads": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
     "wire_real_gabor_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "wire_real_gabor_layer_forward": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "wire_real_gabor_layer_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_float,
+                                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "wire_real_gabor_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "wire_avgpool_mse_loss_grad": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }

@@ -1573,6 +1573,51 @@ int wire_gabor_scalar_grads(int32_t is_first, int32_t two_d, int32_t width, cons
   return 0;
 }
 
+int wire_real_gabor_layer_forward(const float* x, int64_t n, int32_t K, int32_t M, const float* w_freqs, const float* b_freqs,
+                                  const float* w_scale, const float* b_scale, float omega0, float scale0, float* y, float* f_save,
+                                  float* s_save, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (n <= 0) return 0;
+  if (!x || !w_freqs || !w_scale || !y) return fail("null argument");
+  if (K < 1 || M < 1) return fail("bad shape K=%d M=%d", K, M);
+  ProfScope prof(K_LAYER_MISC, st);
+  dim3 grid(unsigned((n + 63) / 64), unsigned((M + 63) / 64));
+  real_gabor_layer_fwd_kernel<<<grid, 256, 0, st>>>(x, int(n), K, M, w_freqs, b_freqs, w_scale, b_scale, omega0, scale0, y, f_save, s_save);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int wire_real_gabor_layer_backward(const float* x, const float* f_save, const float* s_save, const float* grad_y, int64_t n, int32_t K,
+                                   int32_t M, const float* w_freqs, const float* w_scale, float omega0, float scale0, float* grad_x,
+                                   float* g_w_freqs, float* g_b_freqs, float* g_w_scale, float* g_b_scale, float* scratch_gf,
+                                   float* scratch_gs, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(require_device());
+  if (!x || !f_save || !s_save || !grad_y || !w_freqs || !w_scale || !g_w_freqs || !g_w_scale || !scratch_gf || !scratch_gs)
+    return fail("null argument");
+  if (K < 1 || M < 1) return fail("bad shape K=%d M=%d", K, M);
+  TRY(zero(g_w_freqs, size_t(M) * K, st)); TRY(zero(g_w_scale, size_t(M) * K, st));
+  TRY(zero(g_b_freqs, size_t(M), st)); TRY(zero(g_b_scale, size_t(M), st));
+  if (n <= 0) return 0;
+  ProfScope prof(K_LAYER_MISC, st, grad_x ? 4 : 3);
+  real_gabor_bwd_kernel<<<grid_for(n * M), 256, 0, st>>>(f_save, s_save, grad_y, n * int64_t(M), omega0, scale0, scratch_gf, scratch_gs);
+  if (grad_x) {
+    dim3 gd(unsigned((n + 63) / 64), unsigned((K + 63) / 64));
+    real_gabor_layer_dgrad_kernel<<<gd, 256, 0, st>>>(scratch_gf, scratch_gs, int(n), K, M, w_freqs, w_scale, grad_x);
+  }
+  dim3 gw(unsigned((M + 63) / 64), unsigned((K + 63) / 64), 1);
+  int splits = (4 * g_sm_count) / int(gw.x * gw.y);
+  if (splits < 1) splits = 1;
+  int rps = int((n + splits - 1) / splits);
+  rps = (rps + 15) / 16 * 16;
+  gw.z = unsigned((n + rps - 1) / rps);
+  real_gabor_layer_wgrad_kernel<<<gw, 256, 0, st>>>(scratch_gf, x, int(n), K, M, rps, g_w_freqs, g_b_freqs);
+  real_gabor_layer_wgrad_kernel<<<gw, 256, 0, st>>>(scratch_gs, x, int(n), K, M, rps, g_w_scale, g_b_scale);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
 int wire_radon_forward(const float* image, int32_t nimg, int32_t H, int32_t W, const float* angles_deg, int32_t nangles, float* sinogram,
                        void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

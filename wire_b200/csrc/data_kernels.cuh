@@ -243,6 +243,151 @@ __global__ void real_gabor_bwd_kernel(const float* __restrict__ f, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// RealGaborLayer as a whole (modules/wire.py:29-42): both real Linears and the activation on FP32 FMAs.  The class is not
+// part of any INR, so these are plain 64 x 64 shared-memory tiles (16 x 16 threads, 4 x 4 outputs each), not tcgen05 GEMMs.
+//   forward : f = x Wf^T + bf, s = x Ws^T + bs, y = cos(omega f) exp(-(scale s)^2)       [n, K] x [M, K]^T -> [n, M]
+//   dgrad   : g_x = g_f Wf + g_s Ws                                                        [n, M] x [M, K]   -> [n, K]
+//   wgrad   : g_W = g^T x, g_b = sum_n g (split over n, fp32 atomics into zeroed buffers)  [n, M]^T x [n, K] -> [M, K]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) real_gabor_layer_fwd_kernel(const float* __restrict__ x, int n, int K, int M,
+                                                                    const float* __restrict__ Wf, const float* __restrict__ bf,
+                                                                    const float* __restrict__ Ws, const float* __restrict__ bs,
+                                                                    float omega, float s0, float* __restrict__ y,
+                                                                    float* __restrict__ f_save, float* __restrict__ s_save) {
+  __shared__ float Xs[16][65], Fs[16][65], Ss[16][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  float af[4][4] = {}, as[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 256 + tid, rr = idx >> 4, kk = idx & 15;   // 64 rows (or features) x 16 k
+      const bool kok = k0 + kk < K;
+      Xs[kk][rr] = (kok && r0 + rr < n) ? x[size_t(r0 + rr) * K + k0 + kk] : 0.f;
+      Fs[kk][rr] = (kok && j0 + rr < M) ? Wf[size_t(j0 + rr) * K + k0 + kk] : 0.f;
+      Ss[kk][rr] = (kok && j0 + rr < M) ? Ws[size_t(j0 + rr) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float xv[4], fv[4], sv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xv[i] = Xs[kk][ty * 4 + i]; fv[i] = Fs[kk][tx * 4 + i]; sv[i] = Ss[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { af[i][j] = fmaf(xv[i], fv[j], af[i][j]); as[i][j] = fmaf(xv[i], sv[j], as[i][j]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = j0 + tx * 4 + j;
+      if (c >= M) continue;
+      const float f = af[i][j] + (bf ? __ldg(bf + c) : 0.f), sc = as[i][j] + (bs ? __ldg(bs + c) : 0.f);
+      const float t = s0 * sc;
+      y[size_t(r) * M + c] = cosf(omega * f) * expf(-(t * t));
+      if (f_save) f_save[size_t(r) * M + c] = f;
+      if (s_save) s_save[size_t(r) * M + c] = sc;
+    }
+  }
+}
+// g_x[n][k] = sum_j g_f[n][j] Wf[j][k] + g_s[n][j] Ws[j][k]
+__global__ void __launch_bounds__(256) real_gabor_layer_dgrad_kernel(const float* __restrict__ gf, const float* __restrict__ gs, int n, int K, int M,
+                                                                      const float* __restrict__ Wf, const float* __restrict__ Ws,
+                                                                      float* __restrict__ gx) {
+  __shared__ float Gf[16][65], Gs[16][65], Wa[16][65], Wb[16][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int j0 = 0; j0 < M; j0 += 16) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 256 + tid;
+      const int rr = idx >> 4, jj = idx & 15;          // g tiles: 64 rows x 16 j (j contiguous in memory)
+      const bool jok = j0 + jj < M;
+      Gf[jj][rr] = (jok && r0 + rr < n) ? gf[size_t(r0 + rr) * M + j0 + jj] : 0.f;
+      Gs[jj][rr] = (jok && r0 + rr < n) ? gs[size_t(r0 + rr) * M + j0 + jj] : 0.f;
+      const int j2 = idx >> 6, kk = idx & 63;          // weight tiles: 16 j x 64 k (k contiguous in memory)
+      const bool wok = j0 + j2 < M && k0 + kk < K;
+      Wa[j2][kk] = wok ? Wf[size_t(j0 + j2) * K + k0 + kk] : 0.f;
+      Wb[j2][kk] = wok ? Ws[size_t(j0 + j2) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      float a[4], b[4], wa[4], wb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Gf[jj][ty * 4 + i]; b[i] = Gs[jj][ty * 4 + i]; wa[i] = Wa[jj][tx * 4 + i]; wb[i] = Wb[jj][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], wa[j], fmaf(b[i], wb[j], acc[i][j]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) gx[size_t(r) * K + k] = acc[i][j];
+    }
+  }
+}
+// g_W[j][k] += sum_n g[n][j] x[n][k] over this block's row range; g_b[j] += sum_n g[n][j] (by the blocks of the first k tile)
+__global__ void __launch_bounds__(256) real_gabor_layer_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x, int n, int K, int M,
+                                                                      int rows_per_split, float* __restrict__ gW, float* __restrict__ gb) {
+  __shared__ float Gt[16][65], Xt[16][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int j0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int n0 = blockIdx.z * rows_per_split;
+  const int n1 = min(n, n0 + rows_per_split);
+  float acc[4][4] = {};
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r0 = n0; r0 < n1; r0 += 16) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 256 + tid, rr = idx >> 6, cc = idx & 63;   // 16 rows x 64 columns (columns contiguous in memory)
+      const bool rok = r0 + rr < n1;
+      Gt[rr][cc] = (rok && j0 + cc < M) ? g[size_t(r0 + rr) * M + j0 + cc] : 0.f;
+      Xt[rr][cc] = (rok && k0 + cc < K) ? x[size_t(r0 + rr) * K + k0 + cc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      float gv[4], xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { gv[i] = Gt[rr][ty * 4 + i]; xv[i] = Xt[rr][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bsum[i] += gv[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + ty * 4 + i;
+    if (j >= M) continue;
+    if (gb && blockIdx.y == 0 && tx == 0) atomicAdd(gb + j, bsum[i]);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int k = k0 + tx * 4 + jj;
+      if (k < K) atomicAdd(gW + size_t(j) * K + k, acc[i][jj]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Radon forward operator of the CT driver (modules/lin_inverse.py:19-40, wire_ct.py:126-128): every angle rotates the image
 // about its centre (kornia.geometry.rotate: bilinear, zeros outside, align_corners=True, centre ((W-1)/2, (H-1)/2), positive
 // angle = counter-clockwise with the origin at the top-left pixel) and sums over the rows:

@@ -465,3 +465,58 @@ class RealGaborFn(torch.autograd.Function):
 
 def real_gabor(f, s, omega0, scale0):
     return RealGaborFn.apply(f, s, omega0, scale0)
+
+
+class RealGaborLayerFn(torch.autograd.Function):
+    """The whole ``RealGaborLayer.forward`` (modules/wire.py:29-42): both real Linears and the activation in the kernels of this
+    repo (C ABI ``wire_real_gabor_layer_forward`` / ``_backward``, FP32 FMAs) — no library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w_freqs, b_freqs, w_scale, b_scale, omega0: float, scale0: float):
+        lib = _lib.load()
+        xc = _require_cuda(x, "layer input", torch.float32)
+        wf = _require_cuda(w_freqs, "freqs.weight", torch.float32)
+        ws = _require_cuda(w_scale, "scale.weight", torch.float32)
+        bf = None if b_freqs is None else _require_cuda(b_freqs, "freqs.bias", torch.float32)
+        bs = None if b_scale is None else _require_cuda(b_scale, "scale.bias", torch.float32)
+        M, K = wf.shape
+        if tuple(ws.shape) != (M, K) or xc.shape[-1] != K:
+            raise WireB200Error(f"RealGaborLayer shapes do not match: x {tuple(xc.shape)}, freqs {tuple(wf.shape)}, scale {tuple(ws.shape)}")
+        flat = xc.reshape(-1, K)
+        n = flat.shape[0]
+        training = any(ctx.needs_input_grad)
+        y = torch.empty((n, M), dtype=torch.float32, device=flat.device)
+        f = torch.empty_like(y) if training else None
+        sv = torch.empty_like(y) if training else None
+        with torch.cuda.device(flat.device):
+            check(lib.wire_real_gabor_layer_forward(flat.data_ptr(), n, K, M, wf.data_ptr(), _ptr(bf), ws.data_ptr(), _ptr(bs),
+                                                    float(omega0), float(scale0), y.data_ptr(), _ptr(f), _ptr(sv), _stream()),
+                  "wire_real_gabor_layer_forward")
+        if training:
+            ctx.save_for_backward(flat, f, sv, wf, ws)
+            ctx.meta = (n, K, M, float(omega0), float(scale0), x.shape, b_freqs is not None, b_scale is not None)
+        return y.reshape(*x.shape[:-1], M)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        lib = _lib.load()
+        flat, f, sv, wf, ws = ctx.saved_tensors
+        n, K, M, omega0, scale0, x_shape, has_bf, has_bs = ctx.meta
+        gy = _require_cuda(grad_y, "grad_y", torch.float32).reshape(n, M)
+        gx = torch.empty_like(flat) if ctx.needs_input_grad[0] else None
+        gwf, gws = torch.empty_like(wf), torch.empty_like(ws)
+        gbf = torch.empty(M, dtype=torch.float32, device=flat.device)
+        gbs = torch.empty(M, dtype=torch.float32, device=flat.device)
+        sf, ss = torch.empty_like(f), torch.empty_like(sv)
+        with torch.cuda.device(flat.device):
+            check(lib.wire_real_gabor_layer_backward(flat.data_ptr(), f.data_ptr(), sv.data_ptr(), gy.data_ptr(), n, K, M, wf.data_ptr(),
+                                                     ws.data_ptr(), omega0, scale0, _ptr(gx), gwf.data_ptr(), gbf.data_ptr(),
+                                                     gws.data_ptr(), gbs.data_ptr(), sf.data_ptr(), ss.data_ptr(), _stream()),
+                  "wire_real_gabor_layer_backward")
+        if gx is not None:
+            gx = gx.reshape(x_shape)
+        return gx, gwf, (gbf if has_bf else None), gws, (gbs if has_bs else None), None, None
+
+
+def real_gabor_layer(x, w_freqs, b_freqs, w_scale, b_scale, omega0, scale0):
+    return RealGaborLayerFn.apply(x, w_freqs, b_freqs, w_scale, b_scale, omega0, scale0)

@@ -74,7 +74,8 @@ class ComplexGaborLayer(_GaborBase):
 class RealGaborLayer(nn.Module):
     """modules/wire.py:6-42 — real Gabor layer ``cos(omega_0 freqs(x)) * exp(-(scale_0 scale(x))^2)`` (not used by ``INR``).
     Same constructor and parameter names (``freqs``, ``scale``; ``omega_0`` / ``scale_0`` are plain floats, as in the
-    reference); the two real Linears are library GEMMs, the activation and its derivative one fused CUDA kernel each."""
+    reference).  ``freqs`` / ``scale`` are ``nn.Linear`` modules only as parameter containers (state_dict keys): the two
+    Linears, the activation and the whole backward pass run in this repo's FP32 kernels (``functional.real_gabor_layer``)."""
 
     def __init__(self, in_features, out_features, bias=True, is_first=False, omega0=10.0, sigma0=10.0, trainable=False):
         super().__init__()
@@ -88,7 +89,8 @@ class RealGaborLayer(nn.Module):
     def forward(self, input):
         if not input.is_cuda:
             raise F.WireB200Error("RealGaborLayer input must be a CUDA tensor: wire_b200 has no CPU path")
-        return F.real_gabor(self.freqs(input), self.scale(input), self.omega_0, self.scale_0)
+        return F.real_gabor_layer(input, self.freqs.weight, self.freqs.bias, self.scale.weight, self.scale.bias,
+                                  self.omega_0, self.scale_0)
 
 
 class FinalLinear(nn.Linear):
