@@ -40,9 +40,10 @@ extern "C" {
  * FP32    : FP32 FMAs on the CUDA cores (precision yardstick; same GPU, not a fallback).
  * MIXED16 : whole-network path with 16-bit tensors in HBM -- activations and forward weights FP16 (the same 11-bit
  *           significand as TF32), gradients and dgrad/wgrad operands BF16 (FP32's exponent range, so no loss scaling) --
- *           FP32 accumulate in TMEM; half the activation traffic and twice the tensor-core rate of TF32.  Falls back to
- *           the TF32 kernels for shapes it does not cover (in_features > 3, out_features > 4) and for the single-layer
- *           entry points. */
+ *           FP32 accumulate in TMEM; half the activation traffic and twice the tensor-core rate of TF32.  The whole-network
+ *           calls fall back to the TF32 kernels for shapes it does not cover (in_features > 3, out_features > 4); the
+ *           single-layer entry points run the 16-bit kernels for hidden layers (caller tensors stay fp32 and are converted on
+ *           the way in and out) and FP32 / TF32 kernels for the first layer and the stand-alone final Linear. */
 enum { WIRE_PRECISION_TF32 = 0, WIRE_PRECISION_FP32 = 1, WIRE_PRECISION_MIXED16 = 2 };
 
 typedef struct wire_net_desc {

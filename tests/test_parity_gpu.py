@@ -24,8 +24,7 @@ TOL = {
     # gradients from identical inputs): tf32 <= 2.5e-3, fp32 <= 5.5e-7.
     "tf32": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=7.5e-3, out=5.5e-3, grad=1.15e-2, out_w20=8.9e-2, grad_w20=1.83e-1),
     "fp32": dict(layer=2e-6, layer_w20=1e-4, layer_bwd=1.7e-6, out=5.2e-6, grad=1.1e-5, out_w20=5.8e-5, grad_w20=1.3e-4),
-    # the single-layer API runs the TF32 kernels under mixed16 (the 16-bit kernels are checked one by one from identical
-    # inputs in tests/test_kernel_parity_gpu.py)
+    # (the single-layer API runs the 16-bit kernels for hidden layers, FP32 math for the first layer)
     "mixed16": dict(layer=1.9e-3, layer_w20=5e-3, layer_bwd=7.5e-3, out=5.5e-3, grad=2e-2, out_w20=8.9e-2, grad_w20=1.77e-1),
 }
 
@@ -76,10 +75,11 @@ def test_net_forward_backward_vs_golden(name, precision):
     assert torch.all(m.net[last].bias.grad.imag == 0)  # exact zero, as in the reference
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "mixed16"])
 @pytest.mark.parametrize("name", ["wire_small", "wire2d_small", "wire_odd_width", "wire_occ_small"])
 def test_per_layer_from_identical_inputs(name, precision):
-    """model.net[i](x) on the reference's own layer inputs: the north-star per-layer tolerance."""
+    """model.net[i](x) on the reference's own layer inputs: the north-star per-layer tolerance.  Under mixed16 the hidden layers
+    run the 16-bit kernels (tc_rows16 GABOR_FWD / PLAIN, OP16 tc_wgrad) through the single-layer entry points as well."""
     c = util.load_golden(name)
     g = c["g"]
     tol = TOL[precision]

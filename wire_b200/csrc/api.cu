@@ -221,11 +221,14 @@ int net_precision(const wire_net_desc* d) {
   if (d->precision == WIRE_PRECISION_MIXED16 && (d->in_features > 3 || d->out_features > 4)) return WIRE_PRECISION_TF32;
   return d->precision;
 }
+// single-layer entry points: a hidden layer under MIXED16 runs the 16-bit kernels (layer16_ok); everything else that asks for
+// MIXED16 (the first layer, the stand-alone final Linear) runs the 32-bit-operand kernels
 wire_net_desc layer_desc(const wire_net_desc* d) {
   wire_net_desc dd = *d;
   if (dd.precision == WIRE_PRECISION_MIXED16) dd.precision = WIRE_PRECISION_TF32;
   return dd;
 }
+bool layer16_ok(const wire_net_desc* d, int is_first) { return d->precision == WIRE_PRECISION_MIXED16 && !is_first; }
 using sm100_host::kElemBF16;
 using sm100_host::kElemF16;
 using sm100_host::kElemF32;
@@ -391,15 +394,16 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
 
 // elem: element type of the packed matrix (FP32/TF32 kernels: kElemF32; mixed16: FP16 forward, BF16 dgrad)
 int run_pack(const float* W1, const float* W2, int M_out, int K_in, int mode, const Blocking& blk, int k0_pad,
-             int k_pad_total, float* B, int precision, cudaStream_t st, int elem = kElemF32) {
+             int k_pad_total, float* B, int precision, cudaStream_t st, int elem = kElemF32, int pair_perm = 1) {
   const int total = blk.n_blocks * blk.nb * k_pad_total;
   const int grid = (total + 255) / 256;
   ProfScope prof(K_PACK, st);
-  // 16-bit matrices feed tc_rows16_kernel, whose epilogues expect pair-transposed accumulator columns
+  // 16-bit matrices feed tc_rows16_kernel, whose Gabor epilogues expect pair-transposed accumulator columns (pair_perm; the
+  // plain epilogue of the single-layer dgrad keeps the natural order)
   if (elem == kElemF16)
-    pack_weights_kernel<1><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0, 1);
+    pack_weights_kernel<1><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0, pair_perm);
   else if (elem == kElemBF16)
-    pack_weights_kernel<2><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0, 1);
+    pack_weights_kernel<2><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B, 0, pair_perm);
   else
     pack_weights_kernel<0><<<grid, 256, 0, st>>>(W1, W2, M_out, K_in, mode, blk.n_blocks, blk.nb, blk.nbh, k0_pad, k_pad_total, B,
                                                 precision == WIRE_PRECISION_TF32, 0);
@@ -1135,6 +1139,25 @@ int copy2d(const float* src, int sp, float* dst, int dp, int64_t n, int cols, in
   return 0;
 }
 // element-wise Gabor backward on caller tensors (per-layer API)
+// hidden-layer Gabor backward on caller tensors with BF16 outputs (single-layer API under mixed16: g_z feeds the 16-bit GEMMs)
+__global__ void gabor_bwd_ew16_kernel(const float* __restrict__ gy, const float* __restrict__ z, const float* __restrict__ w, int64_t n,
+                                      int M, const float* __restrict__ omega_p, const float* __restrict__ scale_p,
+                                      __nv_bfloat16* __restrict__ g1, __nv_bfloat16* __restrict__ g2, int g_pitch) {
+  const float omega = __ldg(omega_p), s = __ldg(scale_p), s2 = s * s;
+  const int64_t total = n * M;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / M;
+    const int k = int(i % M);
+    const float gr = gy[i * 2], gi = gy[i * 2 + 1];
+    const float zr = z[i * 2], zi = z[i * 2 + 1];
+    const float wr = w ? w[i * 2] : 0.f, wi = w ? w[i * 2 + 1] : 0.f;
+    float yr, yi, gzr, gzi;
+    gabor_fwd<true>(zr, zi, omega, s2, s2 * (wr * wr + wi * wi), yr, yi);
+    const float pr = gabor_bwd(yr, yi, zr, zi, gr, gi, omega, s2, gzr, gzi);
+    *reinterpret_cast<__nv_bfloat162*>(g1 + r * g_pitch + 2 * k) = __floats2bfloat162_rn(gzr, gzi);
+    if (w) *reinterpret_cast<__nv_bfloat162*>(g2 + r * g_pitch + 2 * k) = __floats2bfloat162_rn(-2.0f * s2 * pr * wr, -2.0f * s2 * pr * wi);
+  }
+}
 template <bool FAST>
 __global__ void gabor_bwd_ew_kernel(const float* __restrict__ gy, const float* __restrict__ z, const float* __restrict__ w, int64_t n,
                                     int M, int is_first, const float* __restrict__ omega_p, const float* __restrict__ scale_p,
@@ -1172,6 +1195,109 @@ __global__ void gabor_bwd_ew_kernel(const float* __restrict__ gy, const float* _
 }
 }  // namespace
 
+namespace {
+int grid_rows(int64_t total) { const int64_t g = (total + 255) / 256; return int(g > 1184 * 8 ? 1184 * 8 : (g < 1 ? 1 : g)); }
+int to16(const float* src, int64_t n, int cols, void* dst, int pitch, int elem, cudaStream_t st) {
+  ProfScope prof(K_LAYER_MISC, st);
+  if (elem == kElemF16) to16_rows_kernel<1><<<grid_rows(n * cols), 256, 0, st>>>(src, n, cols, dst, pitch);
+  else to16_rows_kernel<2><<<grid_rows(n * cols), 256, 0, st>>>(src, n, cols, dst, pitch);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+int from16(const void* src, int pitch, int64_t n, int cols, float* dst, int elem, cudaStream_t st) {
+  ProfScope prof(K_LAYER_MISC, st);
+  if (elem == kElemF16) read_rows_kernel<1><<<grid_rows(n * cols), 256, 0, st>>>(src, pitch, n, cols, dst);
+  else read_rows_kernel<2><<<grid_rows(n * cols), 256, 0, st>>>(src, pitch, n, cols, dst);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+// One hidden layer on the 16-bit kernels of the mixed16 path (tc_rows16 GABOR_FWD; FP16 operands, FP16 y / z / w tiles): the
+// caller's fp32 tensors are converted on the way in and out.  Same workspace layout as the 32-bit route (16-bit rows fit).
+int layer_forward16(const wire_net_desc* d, int K, const wire_layer_params* p, const float* x, int64_t n, float* y, float* z_save,
+                    float* w_save, void* workspace, const LayerLayout& L, cudaStream_t st) {
+  const int M = d->width;
+  const bool training = z_save != nullptr;
+  int mask = 1;
+  if (training) { mask |= 2; if (d->two_d) mask |= 4; }
+  Blocking blk;
+  if (!job_blocking(d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD, 2 * M, mask, false, blk, false, true)) return fail("no tile configuration for width %d", M);
+  const int k_pad = round_up(2 * K, 64);
+  void* x16 = at(workspace, L.off_x);
+  TRY(to16(x, n, 2 * K, x16, L.P_in, kElemF16, st));
+  float* B = at(workspace, L.off_b);
+  TRY(run_pack(p->weight, d->two_d ? p->weight2 : nullptr, M, K, 0, blk, k_pad, k_pad, B, WIRE_PRECISION_MIXED16, st, kElemF16));
+  RowsJob J;
+  memset(&J, 0, sizeof(J));
+  J.mode = d->two_d ? MODE_GABOR2D_FWD : MODE_GABOR_FWD;
+  J.a_elem = kElemF16; J.b_elem = kElemF16;
+  J.a[0] = static_cast<const float*>(x16); J.a_pitch[0] = L.P_in; J.k_cols[0] = 2 * K;
+  J.b = B; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = k_pad; J.k0_pad = k_pad;
+  J.blk = blk;
+  int slot = 0;
+  J.o[slot] = at(workspace, L.off_y); J.o_half[slot] = kElemF16; J.o_pitch[slot++] = L.P_out;
+  if (mask & 2) { J.o[slot] = at(workspace, L.off_z); J.o_half[slot] = kElemF16; J.o_pitch[slot++] = L.P_out; }
+  if (mask & 4) { J.o[slot] = at(workspace, L.off_w); J.o_half[slot] = kElemF16; J.o_pitch[slot++] = L.P_out; }
+  J.store_mask = mask;
+  J.e = base_epi(n, 2 * M, WIRE_PRECISION_MIXED16);
+  J.e.round_out0 = 0;
+  J.e.z_half = 1;
+  J.e.bias = p->bias; J.e.bias2 = p->bias2; J.e.omega = p->omega0; J.e.scale = p->scale0;
+  TRY(run_rows(J, WIRE_PRECISION_MIXED16, st));
+  TRY(from16(at(workspace, L.off_y), L.P_out, n, 2 * M, y, kElemF16, st));
+  if (z_save) TRY(from16(at(workspace, L.off_z), L.P_out, n, 2 * M, z_save, kElemF16, st));
+  if (w_save && d->two_d) TRY(from16(at(workspace, L.off_w), L.P_out, n, 2 * M, w_save, kElemF16, st));
+  return 0;
+}
+
+// ... and its backward: Gabor backward of the caller's saved z / w (fp32 math, BF16 g_z / g_w), OP16 tc_wgrad (FP16 x converted
+// to BF16 in shared memory, BF16 g), tc_rows16 PLAIN dgrad with BF16 operands
+int layer_backward16(const wire_net_desc* d, int K, const wire_layer_params* p, const float* x, const float* z_save, const float* w_save,
+                     const float* grad_y, int64_t n, float* grad_x, const wire_layer_grads* g, void* workspace, const LayerLayout& L,
+                     cudaStream_t st) {
+  const int M = d->width;
+  __nv_bfloat16* g1 = reinterpret_cast<__nv_bfloat16*>(at(workspace, L.off_g1));
+  __nv_bfloat16* g2 = d->two_d ? reinterpret_cast<__nv_bfloat16*>(at(workspace, L.off_g2)) : nullptr;
+  const int g_pitch = L.P_out;
+  {
+    ProfScope prof(K_LAYER_MISC, st);
+    gabor_bwd_ew16_kernel<<<grid_rows(n * M), 256, 0, st>>>(grad_y, z_save, d->two_d ? w_save : nullptr, n, M, p->omega0, p->scale0, g1, g2, g_pitch);
+    CU_OK(cudaGetLastError());
+  }
+  void* x16 = at(workspace, L.off_x);
+  TRY(to16(x, n, 2 * K, x16, L.P_in, kElemF16, st));
+  set_column16_kernel<<<int((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint16_t*>(x16), L.P_in, n, 2 * K, uint16_t(0x3C00));  // FP16 1.0
+  CU_OK(cudaGetLastError());
+  if (g->weight)
+    TRY(run_wgrad(static_cast<const float*>(x16), L.P_in, K, reinterpret_cast<const float*>(g1), reinterpret_cast<const float*>(g2), g_pitch, M, n,
+                  g->weight, g->bias, g->weight2, g->bias2, WIRE_PRECISION_MIXED16, st, nullptr, kElemF16, kElemBF16));
+  if (grad_x) {
+    Blocking blk;
+    if (!job_blocking(MODE_PLAIN, 2 * K, 1, false, blk, false, true)) return fail("no tile configuration");
+    float* B = at(workspace, L.off_b);
+    const int k_pad_out = round_up(2 * M, 64);
+    const int kparts = d->two_d ? 2 : 1;
+    TRY(run_pack(p->weight, d->two_d ? p->weight2 : nullptr, M, K, 1, blk, k_pad_out, kparts * k_pad_out, B, WIRE_PRECISION_MIXED16, st,
+                 kElemBF16, /*pair_perm=*/0));
+    RowsJob J;
+    memset(&J, 0, sizeof(J));
+    J.mode = MODE_PLAIN;
+    J.a_elem = kElemBF16; J.b_elem = kElemBF16;
+    J.a[0] = reinterpret_cast<const float*>(g1); J.a_pitch[0] = g_pitch; J.k_cols[0] = 2 * M;
+    if (d->two_d) { J.a[1] = reinterpret_cast<const float*>(g2); J.a_pitch[1] = g_pitch; J.k_cols[1] = 2 * M; }
+    J.b = B; J.b_rows = blk.n_blocks * blk.nb; J.b_pitch = kparts * k_pad_out; J.k0_pad = k_pad_out;
+    J.blk = blk;
+    J.o[0] = at(workspace, L.off_gx); J.o_pitch[0] = L.P_in; J.o_half[0] = kElemBF16;
+    J.store_mask = 1;
+    J.e = base_epi(n, 2 * K, WIRE_PRECISION_MIXED16);
+    J.e.round_out0 = 0;
+    TRY(run_rows(J, WIRE_PRECISION_MIXED16, st));
+    TRY(from16(at(workspace, L.off_gx), L.P_in, n, 2 * K, grad_x, kElemBF16, st));
+  }
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 size_t wire_gabor_layer_workspace_bytes(const wire_net_desc* d, int32_t is_first, int32_t in_features, int64_t n) {
@@ -1198,6 +1324,7 @@ int wire_gabor_layer_forward(const wire_net_desc* d_in, int32_t is_first, int32_
   LayerLayout L;
   make_layer_layout(d, in_features, n, L);
   if (!workspace || workspace_bytes < L.total) return fail("layer workspace too small: %zu < %zu", workspace_bytes, L.total);
+  if (layer16_ok(d_in, is_first)) return layer_forward16(d_in, in_features, p, x, n, y, z_save, w_save, workspace, L, st);
   const int tf32 = d->precision == WIRE_PRECISION_TF32;
   float* xp = at(workspace, L.off_x);
   TRY(copy2d(x, 2 * in_features, xp, L.P_in, n, 2 * in_features, tf32, st));
@@ -1246,6 +1373,10 @@ int wire_gabor_layer_backward(const wire_net_desc* d_in, int32_t is_first, int32
   LayerLayout L;
   make_layer_layout(d, in_features, n, L);
   if (!workspace || workspace_bytes < L.total) return fail("layer workspace too small: %zu < %zu", workspace_bytes, L.total);
+  if (layer16_ok(d_in, is_first)) {
+    if (d->two_d && !w_save) return fail("wire2d layer without its saved scale_orth pre-activation");
+    return layer_backward16(d_in, in_features, p, x, z_save, w_save, grad_y, n, grad_x, g, workspace, L, st);
+  }
   const int tf32 = d->precision == WIRE_PRECISION_TF32;
   float* g1 = at(workspace, L.off_g1);
   float* g2 = d->two_d ? at(workspace, L.off_g2) : nullptr;

@@ -362,6 +362,18 @@ __global__ void set_column16_kernel(uint16_t* __restrict__ dst, int pitch, int64
     dst[r * pitch + col] = bits;
 }
 
+// dense fp32 [n][cols] -> pitched 16-bit rows (the single-layer entry points under mixed16: caller tensors are fp32)
+template <int ELEM>  // 1 = f16, 2 = bf16
+__global__ void to16_rows_kernel(const float* __restrict__ src, int64_t n, int cols, void* __restrict__ dst, int dst_pitch) {
+  const int64_t total = n * cols;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = int(i % cols);
+    if constexpr (ELEM == 1) reinterpret_cast<__half*>(dst)[r * dst_pitch + c] = __float2half_rn(src[i]);
+    else reinterpret_cast<__nv_bfloat16*>(dst)[r * dst_pitch + c] = __float2bfloat16_rn(src[i]);
+  }
+}
+
 // workspace tensor (fp32, FP16 or BF16, row pitch in elements) -> dense fp32 [n][cols] (wire_net_workspace_read)
 template <int ELEM>  // sm100_host::ElemType: 0 = f32, 1 = f16, 2 = bf16
 __global__ void read_rows_kernel(const void* __restrict__ src, int src_pitch, int64_t n, int cols, float* __restrict__ dst) {
