@@ -453,13 +453,24 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
   // CTA pair (256 x-columns per tile) or single CTAs (128)?  Measured equal at M = 212 (0.108 vs 0.110 ms), so on the 16-bit
   // path take whichever pads the 2K+1 x-columns less: at the SISR width (2K+1 = 257) pairs would spend half of their tiles
   // on the single "ones" column (2 x 256 column slots against 3 x 128).
+  // The "ones" column (bias gradient for free) costs a whole extra x tile when 2K is a multiple of the tile width (wire2d at the
+  // SISR width: 257 columns = 3 tiles of 128 instead of 2): the converter warps then sum the bias gradient from the g tiles
+  // in shared memory instead (WgradParams::bias_sum; WIRE_B200_BIAS_SUM=0 keeps the ones column)
+  const char* bs_env = getenv("WIRE_B200_BIAS_SUM");
+  const bool bias_sum_on = !(bs_env && bs_env[0] == '0');
+  P.bias_sum = (op16 && P.x_conv && bias_sum_on && (2 * k_in) % 128 == 0) ? 1 : 0;
+  {
+    const char* e = getenv("WIRE_B200_WGRAD_DUAL");   // =0: one work item per g tensor (A/B runs)
+    P.dual = (e && e[0] == '0') ? 0 : 1;               // a request; wgrad_configure decides (pair, bias_sum, two 256-column tensors)
+  }
   int cl = cluster_size();
   if (op16 && cl == 2) {
-    const int xc = 2 * k_in + 1;
+    const int xc = 2 * k_in + (P.bias_sum ? 0 : 1);
     if ((xc + 127) / 128 * 128 < (xc + 255) / 256 * 256) cl = 1;
   }
   const size_t smem = wgrad_configure(P, g_sm_count, cl, use_gen, op16);
   if (!smem) return fail("wgrad configuration does not fit shared memory");
+  if (const char* e = getenv("WIRE_B200_WGRAD_SPLITS")) P.splits = atoi(e) > 0 ? atoi(e) : P.splits;   // experiments
   if (use_gen) {
     P.coords = gen->coords; P.in_features = gen->in_features; P.w0 = gen->w0; P.b0 = gen->b0; P.w0b = gen->w0b; P.b0b = gen->b0b;
     P.gen_omega = gen->omega; P.gen_scale = gen->scale; P.gen_two_d = gen->two_d;
@@ -467,7 +478,7 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
   }
   bool ok;
   if (op16) {
-    ok = sm100_host::make_tmap_2d_t(&P.x_map, x, n, 2 * k_in + 1, x_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, x_elem);
+    ok = sm100_host::make_tmap_2d_t(&P.x_map, x, n, 2 * k_in + (P.bias_sum ? 0 : 1), x_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, x_elem);
     ok &= sm100_host::make_tmap_2d_t(&P.g_map[0], g1, n, 2 * m_out, g_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, g_elem);
     ok &= sm100_host::make_tmap_2d_t(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, kWgradKC16, 64, CU_TENSOR_MAP_SWIZZLE_128B, g_elem);
   } else {
@@ -476,7 +487,33 @@ int run_wgrad(const float* x, int x_pitch, int k_in, const float* g1, const floa
     ok &= sm100_host::make_tmap_2d(&P.g_map[1], g2 ? g2 : g1, n, 2 * m_out, g_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   }
   if (!ok) return fail("cuTensorMapEncodeTiled failed for wgrad");
+  // WIRE_B200_WGRAD_CLK=1 (eager launches only, never under graph capture): per-CTA clock64 stamps of the kernel's phases
+  static unsigned long long* clk_dev = nullptr;
+  const bool clk = getenv("WIRE_B200_WGRAD_CLK") != nullptr;
+  if (clk) {
+    if (!clk_dev) CU_OK(cudaMalloc(&clk_dev, 1024 * 8 * sizeof(unsigned long long)));
+    CU_OK(cudaMemsetAsync(clk_dev, 0, 1024 * 8 * sizeof(unsigned long long), st));
+    P.dbg = clk_dev;
+  }
   CU_OK(launch_wgrad(P, smem, st, use_gen, op16));
+  if (clk) {
+    static unsigned long long h[1024 * 8];
+    CU_OK(cudaStreamSynchronize(st));
+    CU_OK(cudaMemcpy(h, clk_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    double s[4] = {0, 0, 0, 0}; int nb = 0; unsigned long long t_min = ~0ull, t_max = 0;
+    for (int b = 0; b < 1024; ++b) {
+      const unsigned long long* t = h + b * 8;
+      if (!t[0] || !t[4]) continue;
+      ++nb;
+      for (int k = 0; k < 4; ++k) s[k] += double(t[k + 1] - t[k]);
+      t_min = t[0] < t_min ? t[0] : t_min; t_max = t[4] > t_max ? t[4] : t_max;
+    }
+    const int cps_h = ((int(n) + 63) / 64 + P.splits - 1) / P.splits;
+    if (nb) fprintf(stderr, "[wgrad clk] splits %d chunks/split %d k-loop cycles/chunk %.0f stage bytes/cta %zu stages %d\n", P.splits, cps_h, s[1] / nb / cps_h,
+                    (smem - 1024) / P.stages, P.stages);
+    if (nb) fprintf(stderr, "[wgrad clk] ctas %d  setup+wait %.0f  k-loop %.0f  epilogue %.0f  teardown %.0f  (mean cycles; per-SM clocks, first start to last end %llu)\n",
+                    nb, s[0] / nb, s[1] / nb, s[2] / nb, s[3] / nb, t_max - t_min);
+  }
   return 0;
 }
 
@@ -486,20 +523,26 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
   if (y_elem == kElemF16) {  // mixed16 whole-network path: FP16 activations
     if (z_out || w_out || (y_pitch % 4)) return fail("FP16 first layer: unsupported call");
     if (in_f > 3 || (y_pitch % 8)) return fail("FP16 first layer: unsupported shape");
-    // persistent blocks: 8 per SM, each owns a contiguous row range (the weight table is built once per block)
+    // exactly one wave of persistent blocks, each owns a contiguous row range; a block is as many whole passes over the quads
+    // of a row as fit 256 threads (M = 212: 53 quads x 4 row slots = 212 threads -> 224)
     const int nq = (d->width + 3) / 4;
-    const size_t smem = size_t(d->two_d ? 8 : 4) * nq * 16;
-    int nblk = 8 * g_sm_count;
+    const int qpp = nq < kFirstFwd16Threads ? nq : kFirstFwd16Threads;
+    const int threads = round_up((kFirstFwd16Threads / qpp) * qpp, 32);
+    const size_t smem = 0;
+    int per_sm = 1;
+    if (d->two_d) CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_fwd16_kernel<true>, threads, smem));
+    else CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_fwd16_kernel<false>, threads, smem));
+    int nblk = (per_sm < 1 ? 1 : per_sm) * g_sm_count;
     if (int64_t(nblk) * 32 > n) nblk = int((n + 31) / 32);
     const int rpb = int((n + nblk - 1) / nblk);
     const int grid = int((n + rpb - 1) / rpb);
     ProfScope prof(K_FIRST_FWD, st);
     const float* nul = nullptr;
     if (d->two_d)
-      CU_OK(launch_pdl(first_fwd16_kernel<true>, dim3(grid), dim3(256), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, p.weight2,
+      CU_OK(launch_pdl(first_fwd16_kernel<true>, dim3(grid), dim3(threads), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, p.weight2,
                        p.bias2, p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb));
     else
-      CU_OK(launch_pdl(first_fwd16_kernel<false>, dim3(grid), dim3(256), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, nul, nul,
+      CU_OK(launch_pdl(first_fwd16_kernel<false>, dim3(grid), dim3(threads), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, nul, nul,
                        p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb));
     return 0;
   }
@@ -681,7 +724,38 @@ int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t 
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
   ProfScope prof(K_FIRST_WGRAD, st);
   if (g_elem == kElemBF16) {
-    if (in_f <= 3 && M <= 256 && (g_pitch % 8) == 0) {
+    const char* fs_env = getenv("WIRE_B200_FWGRAD_STREAM");   // =0: the register-pipelined kernel (A/B runs)
+    const bool stream_on = !(fs_env && fs_env[0] == '0');
+    const bool aligned = ((reinterpret_cast<uintptr_t>(gz0) | reinterpret_cast<uintptr_t>(coords)) & 15) == 0;
+    if (stream_on && aligned && in_f >= 1 && in_f <= 3 && M <= 256 && (g_pitch % 8) == 0 && g_pitch <= 256) {
+      // streamed variant: bulk copies into a shared-memory ring, one block per SM, reversed sweep (simt16_kernels.cuh)
+      const uint32_t stage_bytes = fw16s_stage_bytes(g_pitch);
+      int stages = int((200u * 1024u) / stage_bytes);
+      stages = stages > 8 ? 8 : stages;
+      size_t smem = size_t(stages) * stage_bytes;
+      smem = (smem < 65536 ? 65536 : smem) + 128;   // the block reduction parks 16 x 32 x 32 partial sums in the ring
+      const int n_chunks = int((n + kFw16sRows - 1) / kFw16sRows);
+      auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 256);
+        if (e != cudaSuccess) return e;
+        return launch_pdl(kern, dim3(n_chunks < g_sm_count ? n_chunks : g_sm_count), dim3(kFw16sThreads), smem, st,
+                          reinterpret_cast<const __nv_bfloat16*>(gz0), g_pitch, coords, int(n), M, gW, gb, stages);
+      };
+      const int lpr = g_pitch <= 64 ? 8 : (g_pitch <= 128 ? 16 : 32);   // lanes per row (16-byte octets)
+      cudaError_t e = cudaErrorInvalidValue;
+      switch (in_f * 100 + lpr) {
+        case 108: e = launch(first_wgrad16s_kernel<1, 8>); break;
+        case 116: e = launch(first_wgrad16s_kernel<1, 16>); break;
+        case 132: e = launch(first_wgrad16s_kernel<1, 32>); break;
+        case 208: e = launch(first_wgrad16s_kernel<2, 8>); break;
+        case 216: e = launch(first_wgrad16s_kernel<2, 16>); break;
+        case 232: e = launch(first_wgrad16s_kernel<2, 32>); break;
+        case 308: e = launch(first_wgrad16s_kernel<3, 8>); break;
+        case 316: e = launch(first_wgrad16s_kernel<3, 16>); break;
+        case 332: e = launch(first_wgrad16s_kernel<3, 32>); break;
+      }
+      CU_OK(e);
+    } else if (in_f <= 3 && M <= 256 && (g_pitch % 8) == 0) {
       const int nblk = int(n < int64_t(2 * g_sm_count) * 256 ? (n + 255) / 256 : 2 * g_sm_count);
       const int rpb = int((n + nblk - 1) / nblk);
       CU_OK(launch_pdl(first_wgrad16_kernel, dim3(int((n + rpb - 1) / rpb)), dim3(kFirstWgrad16Threads), 0, st,

@@ -19,84 +19,103 @@
 namespace wire {
 
 // ---------------------------------------------------------------------------------------------
-// first layer forward.  Work item = (row, quad of 4 complex features) dealt round-robin to the threads of a block
-// (every lane busy whatever M is); the per-feature {w0[0..2], b0} table and the block's coordinates sit in smem;
-// one 16-byte store (8 halves) per item.  y: FP16 [n][y_pitch]; columns >= 2M (the "ones" column) are not touched.
+// first layer forward.  y: FP16 [n][y_pitch]; columns >= 2M (the "ones" column) are not touched.
+// A thread OWNS one quad of 4 complex features (its {w0[0..2], b0} rows live in registers as packed pairs) and walks the
+// rows of its block's range: slot s = threadIdx / nq takes rows s, s + slots, ...; the lanes of a warp are consecutive quads
+// of (mostly) one row, so the 16-byte stores of a warp are contiguous.  The block's coordinates are staged once in shared
+// memory as float4.  Per item that leaves one broadcast LDS.128, the packed math, 12 MUFU and one STG.128.
+// (The previous version dealt (row, quad) items round-robin and re-read the quad's table from shared memory for every item:
+// 107 instructions per item, 12 of them register moves pairing the halves of two LDS.128, 3 dependent global loads for the
+// coordinates; ncu r02: issue slots 66 % busy, XU 60 %, 73 us.  The XU floor of this stage is 37 us.)
 // ---------------------------------------------------------------------------------------------
-// Persistent blocks (a few per SM) own a contiguous row range, so the table is built once per block.
+constexpr int kFirstFwd16Threads = 256;
+constexpr int kFirstFwd16MaxRows = 512;   // rows per block (coordinates staged in 8 KB of shared memory)
 template <bool TWO_D>
-__global__ void __launch_bounds__(256) first_fwd16_kernel(const float* __restrict__ coords, int n, int in_f, int M,
+__global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const float* __restrict__ coords, int n, int in_f, int M,
                                                            const float* __restrict__ W0, const float* __restrict__ b0,
                                                            const float* __restrict__ W0b, const float* __restrict__ b0b,
                                                            const float* __restrict__ omega_p, const float* __restrict__ scale_p,
                                                            __half* __restrict__ y, int y_pitch, int rows_per_block) {
-  extern __shared__ __align__(16) float4 fsm[];
+  __shared__ __align__(16) float4 cs[kFirstFwd16MaxRows];
   const int nq = (M + 3) >> 2;
-  // table entry of feature k = 4q + f sits at [f * nq + q]: the lanes of a warp (consecutive q) then read consecutive
-  // float4 (the [q][f] order made every LDS.128 a 4-way bank conflict: 21.6 M conflicts, smem wavefronts bound the kernel)
-  float4* tab = fsm;            // [4][nq]
-  float4* tab2 = fsm + 4 * nq;  // [4][nq] (wire2d scale_orth)
   const int row0 = blockIdx.x * rows_per_block;
   int rows = n - row0;
   rows = rows > rows_per_block ? rows_per_block : rows;
   sm100::pdl_trigger();
   if (rows <= 0) return;
-  for (int k = threadIdx.x; k < 4 * nq; k += blockDim.x) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t;
-    if (k < M) {
-      t.x = W0[size_t(k) * in_f];
-      if (in_f > 1) t.y = W0[size_t(k) * in_f + 1];
-      if (in_f > 2) t.z = W0[size_t(k) * in_f + 2];
-      t.w = b0[k];
-      if constexpr (TWO_D) {
-        t2.x = W0b[size_t(k) * in_f];
-        if (in_f > 1) t2.y = W0b[size_t(k) * in_f + 1];
-        if (in_f > 2) t2.z = W0b[size_t(k) * in_f + 2];
-        t2.w = b0b[k];
-      }
-    }
-    tab[(k & 3) * nq + (k >> 2)] = t;
-    if constexpr (TWO_D) tab2[(k & 3) * nq + (k >> 2)] = t2;
-  }
-  __syncthreads();
-  sm100::pdl_wait();  // parameters only above; coords and the y buffer (still read by last step's kernels) below
+  // quads per pass and row slots: nq <= blockDim (every driver): one pass covers all quads, blockDim / nq rows at a time
+  const int qpp = nq < int(blockDim.x) ? nq : int(blockDim.x);
+  const int slots = int(blockDim.x) / qpp;
+  const int qi = int(threadIdx.x) % qpp, slot = int(threadIdx.x) / qpp;
   const GaborConst2 G2 = make_gabor_const2(make_gabor_const(__ldg(omega_p), __ldg(scale_p)));
-  const int items = rows * nq;
-  // (r, q) of this thread's first item and the per-step increment, without a division in the loop
-  int r = int(threadIdx.x) / nq, q = int(threadIdx.x) - r * nq;
-  const int dr = int(blockDim.x) / nq, dq = int(blockDim.x) - dr * nq;
-  for (int item = threadIdx.x; item < items; item += blockDim.x) {
-    // the ~nq threads that share a row hit the same L1 line
-    const float* cp = coords + size_t(row0 + r) * in_f;
-    const f2 c0p = f2_bcast(__ldg(cp)), c1p = f2_bcast(in_f > 1 ? __ldg(cp + 1) : 0.f), c2p = f2_bcast(in_f > 2 ? __ldg(cp + 2) : 0.f);
-    // two feature pairs (f = 0,1 and 2,3), packed FP32 math (f32x2.cuh)
-    uint32_t pp[4];
+  bool waited = false;
+  for (int qb = 0; qb < nq; qb += qpp) {   // (block-uniform trip count: the loop body synchronises)
+    const int q = qb + qi;
+    const bool active = q < nq && slot < slots;   // threads beyond slots * qpp idle (blockDim is not a multiple of nq)
+    // this quad's table: pair h = features (4q + 2h, 4q + 2h + 1); parameters only, so before the dependency wait
+    f2 wx[2], wy[2], wz[2], wb[2], vx[2], vy[2], vz[2], vb[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float4 ta = tab[(2 * h) * nq + q], tb = tab[(2 * h + 1) * nq + q];
-      const f2 z = f2_fma(c0p, f2_make(ta.x, tb.x), f2_fma(c1p, f2_make(ta.y, tb.y), f2_fma(c2p, f2_make(ta.z, tb.z), f2_make(ta.w, tb.w))));
-      f2 wn = 0ull;
-      if constexpr (TWO_D) {
-        const float4 ua = tab2[(2 * h) * nq + q], ub = tab2[(2 * h + 1) * nq + q];
-        const f2 w = f2_fma(c0p, f2_make(ua.x, ub.x), f2_fma(c1p, f2_make(ua.y, ub.y), f2_fma(c2p, f2_make(ua.z, ub.z), f2_make(ua.w, ub.w))));
-        wn = f2_mul(w, w);
-      }
-      f2 yr, yi;
-      gabor_real_x2(G2, z, wn, yr, yi);
-      pp[2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
-      pp[2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
-    }
-    __half* dst = y + size_t(row0 + r) * y_pitch + 8 * q;
-    if (4 * q + 3 < M) {
-      __stcs(reinterpret_cast<uint4*>(dst), make_uint4(pp[0], pp[1], pp[2], pp[3]));
-    } else {  // ragged last quad: only the valid features (the ones column follows them)
-      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+      float t[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, u[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int f = 0; f < 4; ++f)
-        if (4 * q + f < M) d32[f] = pp[f];
+      for (int e = 0; e < 2; ++e) {
+        const int k = 4 * q + 2 * h + e;
+        if (k < M) {
+          t[e][0] = __ldg(W0 + size_t(k) * in_f);
+          if (in_f > 1) t[e][1] = __ldg(W0 + size_t(k) * in_f + 1);
+          if (in_f > 2) t[e][2] = __ldg(W0 + size_t(k) * in_f + 2);
+          t[e][3] = __ldg(b0 + k);
+          if constexpr (TWO_D) {
+            u[e][0] = __ldg(W0b + size_t(k) * in_f);
+            if (in_f > 1) u[e][1] = __ldg(W0b + size_t(k) * in_f + 1);
+            if (in_f > 2) u[e][2] = __ldg(W0b + size_t(k) * in_f + 2);
+            u[e][3] = __ldg(b0b + k);
+          }
+        }
+      }
+      wx[h] = f2_make(t[0][0], t[1][0]); wy[h] = f2_make(t[0][1], t[1][1]); wz[h] = f2_make(t[0][2], t[1][2]); wb[h] = f2_make(t[0][3], t[1][3]);
+      vx[h] = f2_make(u[0][0], u[1][0]); vy[h] = f2_make(u[0][1], u[1][1]); vz[h] = f2_make(u[0][2], u[1][2]); vb[h] = f2_make(u[0][3], u[1][3]);
     }
-    r += dr; q += dq;
-    if (q >= nq) { q -= nq; ++r; }
+    if (!waited) { sm100::pdl_wait(); waited = true; }   // coords and the y buffer (still read by last step's kernels) below
+    const bool full = 4 * q + 3 < M;
+    for (int c0r = 0; c0r < rows; c0r += kFirstFwd16MaxRows) {   // the block's rows, kFirstFwd16MaxRows staged at a time
+      const int crow = rows - c0r < kFirstFwd16MaxRows ? rows - c0r : kFirstFwd16MaxRows;
+      __syncthreads();   // everyone is done with the previous staging
+      for (int r = threadIdx.x; r < crow; r += blockDim.x) {
+        const float* cp = coords + size_t(row0 + c0r + r) * in_f;
+        cs[r] = make_float4(__ldg(cp), in_f > 1 ? __ldg(cp + 1) : 0.f, in_f > 2 ? __ldg(cp + 2) : 0.f, 0.f);
+      }
+      __syncthreads();
+      if (!active) continue;
+      __half* dst = y + size_t(row0 + c0r + slot) * y_pitch + 8 * q;
+      const size_t dstep = size_t(slots) * y_pitch;
+      for (int r = slot; r < crow; r += slots, dst += dstep) {
+        const float4 c = cs[r];
+        const f2 c0 = f2_bcast(c.x), c1 = f2_bcast(c.y), c2 = f2_bcast(c.z);
+        uint32_t pp[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const f2 z = f2_fma(c0, wx[h], f2_fma(c1, wy[h], f2_fma(c2, wz[h], wb[h])));
+          f2 wn = 0ull;
+          if constexpr (TWO_D) {
+            const f2 w = f2_fma(c0, vx[h], f2_fma(c1, vy[h], f2_fma(c2, vz[h], vb[h])));
+            wn = f2_mul(w, w);
+          }
+          f2 yr, yi;
+          gabor_real_x2(G2, z, wn, yr, yi);
+          pp[2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
+          pp[2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
+        }
+        if (full) {
+          __stcs(reinterpret_cast<uint4*>(dst), make_uint4(pp[0], pp[1], pp[2], pp[3]));
+        } else {  // ragged last quad: only the valid features (the ones column follows them)
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            if (4 * q + f < M) d32[f] = pp[f];
+        }
+      }
+    }
   }
 }
 
@@ -438,6 +457,160 @@ __global__ void __launch_bounds__(kFirstWgrad16Threads) first_wgrad16_kernel(con
     if (j < M) {
       if (d < 3) { if (d < in_f) atomicAdd(gW0 + size_t(j) * in_f + d, red[l][v]); }
       else atomicAdd(gb0 + j, red[l][v]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same sums, streamed: first_wgrad16_kernel keeps its loads in registers (4 rows per thread, load -> use in the same
+// iteration), so every block iteration pays one full memory round trip and the kernel ran at 2.2 TB/s (ncu r02:
+// long_scoreboard 9.7 warps per issue cycle).  g_z0 rows are contiguous (row pitch = g_pitch), so here ONE producer lane moves
+// 64-row chunks (27 KB at M = 212) with 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a ring of `stages`
+// shared-memory buffers — up to ~190 KB in flight per SM whatever the compute warps do — and 16 compute warps sum them from
+// shared memory with packed FFMA2.  One block per SM; chunks are dealt round-robin FROM THE LAST ROW TO THE FIRST: the
+// first-layer dgrad kernel in front of this one wrote g_z0 (113 MB, less than the 126 MB L2) in ascending row order, so the
+// rows it wrote last are still in L2 when this kernel starts there.
+// Requires M <= 256, in_f <= 3, g_pitch % 8 == 0, 16-byte aligned gz0 / coords.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFw16sRows = 64;                     // rows per chunk
+constexpr int kFw16sWarps = 16;                    // compute warps
+constexpr int kFw16sThreads = 32 * (kFw16sWarps + 1);
+__host__ __device__ inline uint32_t fw16s_stage_bytes(int g_pitch) {
+  return (uint32_t(kFw16sRows) * uint32_t(g_pitch) * 2u + uint32_t(kFw16sRows) * 16u + 127u) & ~127u;  // g rows | coords (<= 4 floats a row)
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(sm100::kEvictFirst) : "memory");
+}
+template <int IN_F, int LPR>   // input features (1..3); lanes per g_z0 row (8 / 16 / 32: narrow rows are packed 4 / 2 to a warp)
+__global__ void __launch_bounds__(kFw16sThreads, 1) first_wgrad16s_kernel(const __nv_bfloat16* __restrict__ gz0, int g_pitch,
+                                                                           const float* __restrict__ coords, int n, int M,
+                                                                           float* __restrict__ gW0, float* __restrict__ gb0, int stages) {
+  constexpr int in_f = IN_F;
+  using namespace sm100;
+  extern __shared__ __align__(128) uint8_t fwsm[];
+  __shared__ __align__(8) uint64_t bar_full[8];
+  __shared__ __align__(8) uint64_t bar_empty[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t pad = ((smem_u32(fwsm) + 127u) & ~127u) - smem_u32(fwsm);
+  uint8_t* sm = fwsm + pad;
+  const uint32_t stage_bytes = fw16s_stage_bytes(g_pitch);
+  const uint32_t g_bytes_row = uint32_t(g_pitch) * 2u;
+  const uint32_t c_off = uint32_t(kFw16sRows) * g_bytes_row;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), kFw16sWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  const int n_chunks = (n + kFw16sRows - 1) / kFw16sRows;
+  // chunk of iteration i: the sweep runs from the last chunk to the first, all blocks side by side
+  const int n_mine = (n_chunks - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  auto chunk_of = [&](int i) { return n_chunks - 1 - (i * int(gridDim.x) + int(blockIdx.x)); };
+
+  if (warp == kFw16sWarps) {
+    // ===================== producer warp =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_mine; ++i) {
+      const int r0 = chunk_of(i) * kFw16sRows;
+      const int rows = n - r0 < kFw16sRows ? n - r0 : kFw16sRows;
+      if (lane == 0) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+      __syncwarp();
+      uint8_t* dst = sm + size_t(stage) * stage_bytes;
+      const uint32_t cbytes = uint32_t(rows) * uint32_t(in_f) * 4u;
+      const bool c_bulk = (cbytes & 15u) == 0;  // r0 is a multiple of 64 rows, so the source offset is 16-byte aligned
+      if (!c_bulk) {  // ragged last chunk: plain copies, published by lane 0's arrive below
+        float* cs = reinterpret_cast<float*>(dst + c_off);
+        for (int k = lane; k < rows * in_f; k += 32) cs[k] = __ldg(coords + size_t(r0) * in_f + k);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const uint32_t bar = smem_u32(&bar_full[stage]);
+        const uint32_t gbytes = uint32_t(rows) * g_bytes_row;
+        mbar_expect_tx(bar, gbytes + (c_bulk ? cbytes : 0u));
+        bulk_load_1d(smem_u32(dst), gz0 + size_t(r0) * g_pitch, gbytes, bar);
+        if (c_bulk) bulk_load_1d(smem_u32(dst + c_off), coords + size_t(r0) * in_f, cbytes, bar);
+      }
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    return;
+  }
+
+  // ===================== compute warps =====================
+  // lane = octet of 8 features (one 16-byte shared load), narrow rows packed two or four to a warp; acc[h][d] is the
+  // {feature 2h, feature 2h+1} pair of sums against (c0, c1, c2, 1)
+  constexpr int lpr = LPR, rpw = 32 / LPR;
+  const int oct = lane % lpr, rsub = lane / lpr;
+  // lanes past the end of a row (g_pitch = 216: octets 27..31) read octet 0 instead and their sums are dropped by the j < M test of
+  // the reduction: no predicate inside the loop.  (A first version guarded the accumulation with `if (col_ok)`: the compiler then
+  // kept two copies of the 32 accumulators and the loop was 66 instructions per row, 24 of them moves; ncu: issue-bound, 22 M
+  // warp instructions for 113 MB.)
+  const uint32_t oct_off = 16u * uint32_t(8 * oct < g_pitch ? oct : 0);
+  f2 acc[4][4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) acc[h][d] = 0ull;
+  auto add_row = [&](const uint8_t* src, const float* cs, int r) {
+    const uint4 g = *reinterpret_cast<const uint4*>(src + uint32_t(r) * g_bytes_row + oct_off);
+    const f2 c0 = f2_bcast(cs[r * in_f]);
+    const f2 c1 = f2_bcast(in_f > 1 ? cs[r * in_f + (in_f > 1 ? 1 : 0)] : 0.f);
+    const f2 c2 = f2_bcast(in_f > 2 ? cs[r * in_f + (in_f > 2 ? 2 : 0)] : 0.f);
+    const uint32_t pk[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const f2 v = f2_bits(pk[h] << 16, pk[h] & 0xffff0000u);  // BF16 pair -> {float, float}
+      acc[h][0] = f2_fma(v, c0, acc[h][0]);
+      if (in_f > 1) acc[h][1] = f2_fma(v, c1, acc[h][1]);
+      if (in_f > 2) acc[h][2] = f2_fma(v, c2, acc[h][2]);
+      acc[h][3] = f2_add(v, acc[h][3]);
+    }
+  };
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < n_mine; ++i) {
+    const int r0 = chunk_of(i) * kFw16sRows;
+    const int rows = n - r0 < kFw16sRows ? n - r0 : kFw16sRows;
+    const uint8_t* src = sm + size_t(stage) * stage_bytes;
+    const float* cs = reinterpret_cast<const float*>(src + c_off);
+    mbar_wait(smem_u32(&bar_full[stage]), phase);
+    if (rows == kFw16sRows) {   // whole chunk: straight-line, all rows of this warp in flight together
+#pragma unroll
+      for (int u = 0; u < kFw16sRows / (kFw16sWarps * rpw); ++u) add_row(src, cs, warp * rpw + rsub + u * kFw16sWarps * rpw);
+    } else {                    // ragged last chunk
+      for (int r = warp * rpw + rsub; r < rows; r += kFw16sWarps * rpw) add_row(src, cs, r);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
+    if (++stage == stages) { stage = 0; phase ^= 1; }
+  }
+  // Block reduction without shared-memory atomics (float atomicAdd on shared memory is a compare-and-swap loop: 32 of them per
+  // thread with 16 warps contending cost more than the whole streaming part).  Every compute warp has consumed all its chunks,
+  // so every bulk copy has landed and the ring is free: warp w parks its 32 x 32 partial sums there as part[w][v][lane].
+  float* part = reinterpret_cast<float*>(sm);
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kFw16sWarps) : "memory");
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      part[(warp * 32 + 4 * (2 * h) + d) * 32 + lane] = f2_lo(acc[h][d]);
+      part[(warp * 32 + 4 * (2 * h + 1) + d) * 32 + lane] = f2_hi(acc[h][d]);
+    }
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kFw16sWarps) : "memory");
+  for (int i = threadIdx.x; i < 32 * 32; i += 32 * kFw16sWarps) {
+    const int v = i >> 5, l = i & 31, f = v >> 2, d = v & 3;   // l = octet, v = (feature of the octet, which sum)
+    const int j = 8 * l + f;
+    if (l < lpr && j < M && (d == 3 || d < in_f)) {
+      float sum = 0.f;
+      for (int w = 0; w < kFw16sWarps; ++w)
+        for (int rs = 0; rs < rpw; ++rs) sum += part[(w * 32 + v) * 32 + l + rs * lpr];
+      if (d < 3) atomicAdd(gW0 + size_t(j) * in_f + d, sum);
+      else atomicAdd(gb0 + j, sum);
     }
   }
 }

@@ -300,7 +300,7 @@ inline cudaError_t launch_rows16(int mode, const RowsParams& P, size_t smem, int
 
 // wgrad: choose column blocking, K splits (to fill the machine) and pipeline depth
 inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, bool gen = false, bool op16 = false) {
-  const int x_cols = 2 * P.k_in + 1;
+  const int x_cols = 2 * P.k_in + (P.bias_sum ? 0 : 1);   // bias_sum: no "ones" column in the x tiles
   P.cluster = cluster;
   P.m_tiles = (x_cols + 128 * cluster - 1) / (128 * cluster);
   // a pair splits every MMA piece in block-aligned halves (blocks: 32 columns, or 64 for 16-bit operands); the
@@ -311,9 +311,15 @@ inline size_t wgrad_configure(WgradParams& P, int sm_count, int cluster = 2, boo
   const int gran = cluster == 2 ? (op16 ? blk_cols : 2 * blk_cols) : blk_cols;
   const int nb_max = op16 ? 512 : 448;
   const int gpad = round_up(P.g_cols, gran);
-  P.n_blocks = (gpad + nb_max - 1) / nb_max;
-  P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran);
-  if (P.nb > nb_max) { P.n_blocks += 1; P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran); }
+  // dual (tc_wgrad.cuh): both g tensors of a wire2d layer in one work item when each pads to exactly one 256-column MMA piece
+  P.dual = (op16 && cluster == 2 && P.bias_sum && P.n_g == 2 && round_up(P.g_cols, 64) == 256 && P.dual) ? 1 : 0;
+  if (P.dual) {
+    P.n_g = 1; P.n_blocks = 1; P.nb = 512;
+  } else {
+    P.n_blocks = (gpad + nb_max - 1) / nb_max;
+    P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran);
+    if (P.nb > nb_max) { P.n_blocks += 1; P.nb = round_up((gpad + P.n_blocks - 1) / P.n_blocks, gran); }
+  }
   const int base = P.m_tiles * P.n_blocks * P.n_g;
   int splits = (sm_count / cluster) / base;
   if (splits < 1) splits = 1;

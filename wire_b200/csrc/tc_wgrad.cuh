@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "f32x2.cuh"
 #include "gabor_math.cuh"
 #include "sm100.cuh"
 
@@ -46,6 +47,12 @@ struct WgradParams {
   float* gW[2];  // [M][K][2] fp32, accumulated
   float* gB[2];  // [M][2]
   int x_fmt, g_fmt;  // OP16 kernels: operand formats of x and g in HBM (sm100::kFmtF16 / kFmtBF16)
+  int bias_sum;      // OP16 + x_conv: the x tiles do NOT include the "ones" column (2K is a multiple of the tile width, so column 2K
+                     // would cost a whole extra tile: wire2d at M = 128 runs 3 x-tiles of 128 instead of one pair tile of 256 for
+                     // it); the bias gradient g_b = sum_n g is summed by the converter warps from the g tiles in shared memory
+  int dual;          // bias_sum + pair + two g tensors of <= 256 padded columns (wire2d: g_z and g_w): ONE work item carries both
+                     // (MMA piece 1 = g_map[0], piece 2 = g_map[1], all 512 TMEM columns), so the x tile is staged and converted
+                     // once for both and a CTA ingests 48 KB per 1024 cycles of MMA work instead of 32 KB per 512
   int x_conv;        // OP16: x is stored FP16 but g is BF16.  kind::f16 cannot mix the two (illegal instruction on
                      // sm_100a, profiles/r01_probe16.log), so the four epilogue warps -- idle during the K loop --
                      // convert each landed x tile FP16 -> BF16 in place in shared memory (element-wise, so the swizzle
@@ -84,6 +91,7 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
   __shared__ __align__(8) uint64_t bar_empty[8];
   __shared__ __align__(8) uint64_t bar_tmem_full;
   __shared__ __align__(8) uint64_t bar_x[8];  // x_conv: this CTA's x tile has landed (own barrier; converters wait on it)
+  __shared__ __align__(8) uint64_t bar_g[8];  // bias_sum: this CTA's g tile has landed (own barrier; the converters sum its columns)
   __shared__ uint32_t tmem_slot;
 
   constexpr int C = PAIR ? 2 : 1;
@@ -92,6 +100,8 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
   // warps issue it (18 us fixed per launch with four, profiles/r01: 12.9 k cycles)
   constexpr int kEpiW = OP16 ? kWgradEpi16Warps : 4;
   const bool conv = OP16 && P.x_conv;
+  const bool bsum = conv && P.bias_sum;
+  const bool dual = PAIR && bsum && P.dual;
   unsigned long long* dbg = P.dbg ? P.dbg + size_t(blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 64) dbg[0] = clock64();
   const int warp = threadIdx.x >> 5;
@@ -146,9 +156,11 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : (conv ? 1 + kEpiW * C : 1));
+      // bias_sum: x and g both land on this CTA's own barriers; the MMA's barrier only counts the converter warps' arrivals
+      mbar_init(smem_u32(&bar_full[s]), GEN ? 1 + kWgradGenWarps * C : (bsum ? kEpiW * C : (conv ? 1 + kEpiW * C : 1)));
       mbar_init(smem_u32(&bar_empty[s]), 1);
       mbar_init(smem_u32(&bar_x[s]), 1);
+      mbar_init(smem_u32(&bar_g[s]), 1);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
     fence_barrier_init();
@@ -183,7 +195,20 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
             mbar_expect_tx(xb, a_bytes);
             for (int b = 0; b < kXBlocks; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, xb, x_col0 + b * kBlkCols, r0);
           }
-          if (!PAIR) {
+          if (bsum) {  // g tile on this CTA's own barrier (the same blocks as below)
+            const uint32_t gb = smem_u32(&bar_g[stage]);
+            mbar_expect_tx(gb, b_bytes);
+            if (!PAIR) {
+              for (int b = 0; b < nbb_cta; ++b) tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], gb, nblk * P.nb + b * kBlkCols, r0);
+            } else {
+              for (int b = 0; b < pb1; ++b)
+                tma_load_2d(a_dst + a_bytes + b * blk_bytes, &P.g_map[gi], gb, nblk * P.nb + crank * (n1 / 2) + b * kBlkCols, r0);
+              // piece 2: the second half of the same tensor, or (dual) this CTA's half of the second tensor
+              for (int b = 0; b < pb2; ++b)
+                tma_load_2d(a_dst + a_bytes + (pb1 + b) * blk_bytes, &P.g_map[dual ? 1 : gi], gb,
+                            (dual ? 0 : nblk * P.nb + n1) + crank * (n2 / 2) + b * kBlkCols, r0);
+            }
+          } else if (!PAIR) {
             mbar_expect_tx(full_own, tx_bytes);
             if (!GEN && !conv) for (int b = 0; b < kXBlocks; ++b) tma_load_2d(a_dst + b * blk_bytes, &P.x_map, full_own, x_col0 + b * kBlkCols, r0);
             for (int b = 0; b < nbb_cta; ++b)
@@ -320,34 +345,101 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
     } else {
       if (conv) {
         // ===================== x converters (epilogue warps, during the K loop) =====================
-        // warp b converts slice b (16 KB / kEpiW = 16-byte pieces per lane) of every landed x tile FP16 -> BF16 in place
-        const int b = warp - 2;
-        constexpr int kPieces = 16384 / kEpiW / 512;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int i = 0; i < n_chunks; ++i) {
-          mbar_wait(smem_u32(&bar_x[stage]), phase);
-          const uint32_t blk = smem_base + stage * stage_bytes + b * (16384 / kEpiW);
-#pragma unroll
-          for (int j = 0; j < kPieces; ++j) {
-            const uint32_t addr = blk + (j * 32 + lane) * 16;
-            uint32_t h[4];
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr) : "memory");
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[k]));
-              const __nv_bfloat162 t = __floats2bfloat162_rn(f.x, f.y);
-              h[k] = *reinterpret_cast<const uint32_t*>(&t);
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-          }
+        // warp b converts slice b (16 KB / kEpiW = 16-byte pieces per lane) of every landed x tile FP16 -> BF16 in place.
+        // bias_sum: the same warps add up the columns of this CTA's g tile (only the CTAs of the first x tile: every x tile
+        // sees the same g).  Thread -> one 16-byte piece (8 BF16 columns) `pc` of the tile's rows rb, rb + rpp, ...: four
+        // shared loads in flight, then two integer ops and one packed add per column pair, FP32 sums in 8 registers for the
+        // whole kernel.  (A first version summed 32-bit words with per-item index arithmetic: 2 440 cycles per chunk against
+        // 1 540 without it, profiles/r02_probe_wgrad_variants.log.)
+        const int ctid = (warp - 2) * 32 + lane;
+        const bool do_sum = bsum && mt == 0;
+        const int ppr = nbb_cta * 8;                 // 16-byte pieces per tile row
+        const int rpp = (32 * kEpiW) / ppr;          // rows per pass of the converter threads
+        const bool sum_thread = do_sum && ctid < rpp * ppr;
+        const int pc = ctid % ppr, rb = ctid / ppr;
+        const uint32_t piece_off = uint32_t(pc >> 3) * blk_bytes;
+        f2 bacc[4] = {0ull, 0ull, 0ull, 0ull};
+        auto x_done = [&](int stage, uint32_t phase) {
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          if (bsum) {
+            mbar_wait(smem_u32(&bar_g[stage]), phase);   // every converter warp waits: its arrival below also vouches for the g tile
+            if (sum_thread) {
+              const uint32_t gbase = smem_base + stage * stage_bytes + a_bytes + piece_off;
+              for (int r4 = rb; r4 < kKC; r4 += 4 * rpp) {
+                uint32_t v[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t r = uint32_t(r4 + j * rpp);
+                  if (r < uint32_t(kKC)) {
+                    // SW128: 16-byte chunk (pc % 8) of row r sits at chunk position (pc % 8) ^ (r % 8)
+                    const uint32_t addr = gbase + r * 128 + (((uint32_t(pc) & 7u) ^ (r & 7u)) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3]) : "r"(addr) : "memory");
+                  } else {
+                    v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0u;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) bacc[k] = f2_add(bacc[k], f2_bits(v[j][k] << 16, v[j][k] & 0xffff0000u));
+              }
+            }
+          }
           __syncwarp();
           if (lane == 0) {
             const uint32_t full_own = smem_u32(&bar_full[stage]);
             if (PAIR) mbar_arrive_cluster(full_own & kPeerBitMask); else mbar_arrive(full_own);
           }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        const int b = warp - 2;
+        constexpr int kPieces = 16384 / kEpiW / 512;
+        for (int i = 0; i < n_chunks; ++i) {
+          mbar_wait(smem_u32(&bar_x[stage]), phase);
+          const uint32_t blk = smem_base + stage * stage_bytes + b * (16384 / kEpiW);
+          uint32_t h[kPieces][4];
+#pragma unroll
+          for (int j = 0; j < kPieces; ++j) {
+            const uint32_t addr = blk + (j * 32 + lane) * 16;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[j][0]), "=r"(h[j][1]), "=r"(h[j][2]), "=r"(h[j][3]) : "r"(addr) : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < kPieces; ++j) {
+            const uint32_t addr = blk + (j * 32 + lane) * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[j][k]));
+              const __nv_bfloat162 t = __floats2bfloat162_rn(f.x, f.y);
+              h[j][k] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[j][0]), "r"(h[j][1]), "r"(h[j][2]), "r"(h[j][3]) : "memory");
+          }
+          x_done(stage, phase);
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        if (sum_thread) {
+          // column 8 pc + e of this CTA's staged blocks -> real column of g.  Single CTA: block-contiguous; pair: this CTA's half of
+          // each MMA piece (a half that ends inside a block loaded the whole block: only the columns of the half are this CTA's to
+          // count); dual: piece 2 is the second tensor
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float val = (e & 1) ? f2_hi(bacc[e >> 1]) : f2_lo(bacc[e >> 1]);
+            int col = 8 * pc + e, gcol;
+            bool own = true;
+            float* gB = P.gB[gi];
+            int limit = nblk * P.nb + nvalid;
+            if (!PAIR) gcol = nblk * P.nb + col;
+            else if (col < pb1 * kBlkCols) {
+              own = col < n1 / 2; gcol = nblk * P.nb + crank * (n1 / 2) + col;
+              if (dual) limit = P.g_cols;
+            } else {
+              col -= pb1 * kBlkCols; own = col < n2 / 2;
+              if (dual) { gB = P.gB[1]; gcol = crank * (n2 / 2) + col; limit = P.g_cols; }
+              else gcol = nblk * P.nb + n1 + crank * (n2 / 2) + col;
+            }
+            if (own && gcol < limit) atomicAdd(gB + gcol, val);
+          }
         }
       }
       const int q = warp & 3;
@@ -356,7 +448,7 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
       const int two_k = 2 * P.k_in;
       float* gW = P.gW[gi];
       float* gB = P.gB[gi];
-      const int nchunks = (nvalid + 31) / 32;
+      const int nchunks = dual ? 16 : (nvalid + 31) / 32;   // dual: TMEM columns [0, 256) = first tensor, [256, 512) = second
       mbar_wait(smem_u32(&bar_tmem_full), 0);
       tc_fence_after();
       if (dbg && threadIdx.x == 64) dbg[2] = clock64();
@@ -366,14 +458,15 @@ __global__ void __launch_bounds__(wgrad_threads(GEN, OP16), 1) tc_wgrad_kernel(c
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + ch * 32, raw);
         tmem_wait_ld();
-        const int r0 = nblk * P.nb + ch * 32;
+        const bool second = dual && ch >= 8;
+        const int r0 = second ? (ch - 8) * 32 : nblk * P.nb + ch * 32;
         // all 16 lane-pair exchanges first (independent shuffles in flight together), then straight-line reductions:
         // the per-element branches of the first version serialised shuffle -> branch -> address -> red (80 cycles each)
         float other[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) other[i] = __shfl_xor_sync(0xffffffffu, __uint_as_float(raw[2 * i + 1]), 1);
         if (c < two_k) {
-          float* dst = gW + size_t(r0 >> 1) * two_k + c;
+          float* dst = (second ? P.gW[1] : gW) + size_t(r0 >> 1) * two_k + c;
           const int n_ok = (P.g_cols - r0 + 1) >> 1;  // complex outputs of this chunk inside the matrix (warp-uniform)
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
