@@ -89,10 +89,8 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
       if (!active) continue;
       __half* dst = y + size_t(row0 + c0r + slot) * y_pitch + 8 * q;
       const size_t dstep = size_t(slots) * y_pitch;
-      for (int r = slot; r < crow; r += slots, dst += dstep) {
-        const float4 c = cs[r];
+      auto item = [&](const float4 c, uint32_t (&pp)[4]) {
         const f2 c0 = f2_bcast(c.x), c1 = f2_bcast(c.y), c2 = f2_bcast(c.z);
-        uint32_t pp[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const f2 z = f2_fma(c0, wx[h], f2_fma(c1, wy[h], f2_fma(c2, wz[h], wb[h])));
@@ -106,14 +104,23 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
           pp[2 * h] = pack_f16(f2_lo(yr), f2_lo(yi));
           pp[2 * h + 1] = pack_f16(f2_hi(yr), f2_hi(yi));
         }
+      };
+      auto store = [&](__half* d, const uint32_t (&pp)[4]) {
         if (full) {
-          __stcs(reinterpret_cast<uint4*>(dst), make_uint4(pp[0], pp[1], pp[2], pp[3]));
+          __stcs(reinterpret_cast<uint4*>(d), make_uint4(pp[0], pp[1], pp[2], pp[3]));
         } else {  // ragged last quad: only the valid features (the ones column follows them)
-          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
 #pragma unroll
           for (int f = 0; f < 4; ++f)
             if (4 * q + f < M) d32[f] = pp[f];
         }
+      };
+      // (two rows per iteration -- 24 MUFU in flight per thread -- measured equal: 85.8 vs 81.8 us on a 3 % slower box)
+      int r = slot;
+      for (; r < crow; r += slots, dst += dstep) {
+        uint32_t pp[4];
+        item(cs[r], pp);
+        store(dst, pp);
       }
     }
   }
