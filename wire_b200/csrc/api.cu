@@ -149,6 +149,12 @@ int cluster_size() {
   return c;
 }
 
+// WIRE_B200_SECTOR_ALIGN=0: stored tensors end at column 2M again (A/B runs; see run_rows_job)
+bool store_sector_align() {
+  const char* e = getenv("WIRE_B200_SECTOR_ALIGN");
+  return !(e && e[0] == '0');
+}
+
 constexpr int64_t kInferChunk = 1 << 19;  // rows per pass when nothing has to be kept for backward
 constexpr int kRowsPerBlock = 64;
 
@@ -372,9 +378,17 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
     if (J.store_mask & (1 << bit)) {
       P.o_fmt[nslot] = J.o_half[nslot];
       if (op16 && !J.o_half[nslot]) return fail("16-bit row-tile kernels store 16-bit tensors only");
-      if (J.o_half[nslot])  // 16-bit tiles: dense for the TF32 kernels' saved z, 64 B swizzle for the 16-bit kernels
-        ok &= sm100_host::make_tmap_2d_t(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32,
+      if (J.o_half[nslot]) {  // 16-bit tiles: dense for the TF32 kernels' saved z, 64 B swizzle for the 16-bit kernels
+        // 16-bit kernels: the stored width is rounded up to whole 32-byte sectors (16 columns) when the row pitch has room.  A row
+        // that ends inside a sector (2M = 424 columns = 848 B = 26.5 sectors) makes every row's last sector a read-modify-write in
+        // DRAM: measured +45 % time on the store stream (tools/tma_probe: 73.8 us per 222 MB tensor against 49.6-51.3 us with 416 /
+        // 448 columns, profiles/r02_probe_tma_valid_cols.log).  The extra columns carry the epilogue's values of the zero-padded
+        // features (z = 0, y = gabor(0) = 1 + 0j -- column 2M of a y tensor is the wgrad's "ones" column and is forced to 1.0).
+        int store_cols = J.e.n_cols;
+        if (op16 && store_sector_align()) { const int r = round_up(J.e.n_cols, 16); if (r <= J.o_pitch[nslot]) store_cols = r; }
+        ok &= sm100_host::make_tmap_2d_t(&P.o_map[nslot], J.o[nslot], J.e.n_rows, store_cols, J.o_pitch[nslot], 32, 32,
                                          op16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, J.o_half[nslot]);
+      }
       else
         ok &= sm100_host::make_tmap_2d(&P.o_map[nslot], J.o[nslot], J.e.n_rows, J.e.n_cols, J.o_pitch[nslot], 32, 32);
       ++nslot;
@@ -540,10 +554,10 @@ int run_first_fwd(const wire_net_desc* d, const wire_layer_params& p, const floa
     const float* nul = nullptr;
     if (d->two_d)
       CU_OK(launch_pdl(first_fwd16_kernel<true>, dim3(grid), dim3(threads), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, p.weight2,
-                       p.bias2, p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb));
+                       p.bias2, p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb, store_sector_align() ? 1 : 0));
     else
       CU_OK(launch_pdl(first_fwd16_kernel<false>, dim3(grid), dim3(threads), smem, st, coords, int(n), in_f, int(d->width), p.weight, p.bias, nul, nul,
-                       p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb));
+                       p.omega0, p.scale0, reinterpret_cast<__half*>(y), y_pitch, rpb, store_sector_align() ? 1 : 0));
     return 0;
   }
   const int grid = int((n + kRowsPerBlock - 1) / kRowsPerBlock);
@@ -626,8 +640,11 @@ int run_top_bwd(const wire_net_desc* d, const float* g_out, int64_t n, const flo
       }
       bool ok = sm100_host::make_tmap_2d_t(&T.z_map[0], z, n, g_pitch, zw_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemF16);
       ok &= sm100_host::make_tmap_2d_t(&T.z_map[1], w ? w : z, n, g_pitch, zw_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemF16);
-      ok &= sm100_host::make_tmap_2d_t(&T.g_map[0], gz, n, 2 * d->width, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
-      ok &= sm100_host::make_tmap_2d_t(&T.g_map[1], gw ? gw : gz, n, 2 * d->width, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
+      // stored width: whole 32-byte sectors (see run_rows_job); the threads of the padded features store zeros there
+      T.store_cols = 2 * d->width;
+      if (store_sector_align() && round_up(2 * d->width, 16) <= g_pitch) T.store_cols = round_up(2 * d->width, 16);
+      ok &= sm100_host::make_tmap_2d_t(&T.g_map[0], gz, n, T.store_cols, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
+      ok &= sm100_host::make_tmap_2d_t(&T.g_map[1], gw ? gw : gz, n, T.store_cols, g_pitch, kTopRows, T.bw, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16);
       if (!ok) return fail("cuTensorMapEncodeTiled failed for top_bwd16");
       const int threads = round_up(d->width, 32) + 32;  // compute warps + the I/O warp
       const int n_tiles = int((n + kTopRows - 1) / kTopRows);

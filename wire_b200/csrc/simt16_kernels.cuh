@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
                                                            const float* __restrict__ W0, const float* __restrict__ b0,
                                                            const float* __restrict__ W0b, const float* __restrict__ b0b,
                                                            const float* __restrict__ omega_p, const float* __restrict__ scale_p,
-                                                           __half* __restrict__ y, int y_pitch, int rows_per_block) {
+                                                           __half* __restrict__ y, int y_pitch, int rows_per_block, int sector_tail) {
   __shared__ __align__(16) float4 cs[kFirstFwd16MaxRows];
   const int nq = (M + 3) >> 2;
   const int row0 = blockIdx.x * rows_per_block;
@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
       if (!active) continue;
       __half* dst = y + size_t(row0 + c0r + slot) * y_pitch + 8 * q;
       const size_t dstep = size_t(slots) * y_pitch;
+      // A row of 2M columns that ends inside a 32-byte sector makes that sector a read-modify-write in DRAM for every row (see
+      // run_rows_job in api.cu): the thread of the row's last quad completes it with column 2M = 1.0 (what that column holds
+      // anyway: the wgrad's "ones" column) and zeros.  tail_words: 32-bit words from column 2M to the sector boundary.
+      const int tail_cols = ((2 * M + 15) & ~15) - 2 * M;
+      const int tail_words = (sector_tail && q == nq - 1 && 2 * M + tail_cols <= y_pitch) ? tail_cols / 2 : 0;
       auto item = [&](const float4 c, uint32_t (&pp)[4]) {
         const f2 c0 = f2_bcast(c.x), c1 = f2_bcast(c.y), c2 = f2_bcast(c.z);
 #pragma unroll
@@ -121,6 +126,15 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
         uint32_t pp[4];
         item(cs[r], pp);
         store(dst, pp);
+        if (tail_words > 0) {   // last quad of the row: the "ones" column and zeros up to the end of the 32-byte sector
+          uint32_t* t32 = reinterpret_cast<uint32_t*>(y + size_t(row0 + c0r + r) * y_pitch + 2 * M);
+          if (tail_words == 4 && (M & 3) == 0) {
+            __stcs(reinterpret_cast<uint4*>(t32), make_uint4(0x00003C00u, 0u, 0u, 0u));
+          } else {
+            t32[0] = 0x00003C00u;
+            for (int i = 1; i < tail_words; ++i) t32[i] = 0u;
+          }
+        }
       }
     }
   }
@@ -162,6 +176,7 @@ struct TopBwd16Params {
   float* gs_omega;
   float* gs_scale;
   int in_depth, out_depth;  // ring depths (<= kTopIn / kTopOut)
+  int store_cols;           // columns of g_z / g_w that leave (2M rounded up to whole 32-byte sectors when the pitch allows)
 };
 
 // Block = W compute warps (thread k owns complex feature k) + one I/O warp.  No block-wide barrier in the loop: tiles
@@ -291,7 +306,9 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
   float bsum = 0.f;
   f2 s_om = 0ull, s_sc = 0ull;  // SCAL: sum Im(conj(z) p), sum (|z|^2 + |w|^2) Re p over this thread's feature
   // byte offset of this thread's (re, im) pair inside a tile: box b holds columns [b*bw, (b+1)*bw) as a dense [rows][bw] block
-  const int col = active ? 2 * k : 0;
+  // threads of the zero-padded features up to the stored width write their (zero) results; the rest alias feature 0's slot and never store
+  const bool st_ok = 2 * k < P.store_cols;
+  const int col = st_ok ? 2 * k : 0;
   const int bi = col / P.bw;
   const uint32_t row_bytes = uint32_t(P.bw) * 2;
   const uint32_t off0 = uint32_t(bi) * box_bytes + uint32_t(col - bi * P.bw) * 2;
@@ -345,17 +362,17 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
       } else {
         pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gyr, gyi, gzr, gzi);
       }
-      // (lanes past the last feature alias feature 0's slot: they compute on it but must not store)
-      if (active) {
-        *reinterpret_cast<uint32_t*>(zout + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gzr), f2_lo(gzi));
-        *reinterpret_cast<uint32_t*>(zout + (2 * rp + 1) * row_bytes) = pack_bf16(f2_hi(gzr), f2_hi(gzi));
+      // (lanes past the stored width alias feature 0's slot: they compute on it but must not store)
+      if (st_ok) {   // (padded features: literal zeros, whatever the z tile held in their columns)
+        *reinterpret_cast<uint32_t*>(zout + (2 * rp) * row_bytes) = active ? pack_bf16(f2_lo(gzr), f2_lo(gzi)) : 0u;
+        *reinterpret_cast<uint32_t*>(zout + (2 * rp + 1) * row_bytes) = active ? pack_bf16(f2_hi(gzr), f2_hi(gzi)) : 0u;
       }
       if constexpr (TWO_D) {
         const f2 t = f2_mul(G2.m2s2, pr);
         const f2 gwr = f2_mul(t, wre), gwi = f2_mul(t, wim);
-        if (active) {
-          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gwr), f2_lo(gwi));
-          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp + 1) * row_bytes) = pack_bf16(f2_hi(gwr), f2_hi(gwi));
+        if (st_ok) {
+          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp) * row_bytes) = active ? pack_bf16(f2_lo(gwr), f2_lo(gwi)) : 0u;
+          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp + 1) * row_bytes) = active ? pack_bf16(f2_hi(gwr), f2_hi(gwi)) : 0u;
         }
       }
 #pragma unroll

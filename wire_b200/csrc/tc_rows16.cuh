@@ -471,6 +471,14 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
               pz[4 * g + 2 * h + 1] = pack_f16(f2_hi(zr), f2_hi(zi));
             }
           }
+          if (st0 && c <= E.n_cols && c + kChunk > E.n_cols) {
+            // the chunk that holds column 2M: the stored width is rounded up to a whole 32-byte sector (api.cu: run_rows_job), so this
+            // store overwrites the "ones" column of the y tensor.  The zero-padded feature M gives y = gabor(0) = 1 + 0j there
+            // anyway; written explicitly so that the wgrad's bias row does not hang on ex2(0) * cos(0) being exactly 1
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c + 2 * i == E.n_cols) py[i] = 0x00003C00u;   // FP16 (1.0, 0.0)
+          }
           if (n_out > 0) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
