@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
       // anyway: the wgrad's "ones" column) and zeros.  tail_words: 32-bit words from column 2M to the sector boundary.
       const int tail_cols = ((2 * M + 15) & ~15) - 2 * M;
       const int tail_words = (sector_tail && q == nq - 1 && 2 * M + tail_cols <= y_pitch) ? tail_cols / 2 : 0;
+      const bool tail_vec = tail_words == 4 && (M & 3) == 0;
       auto item = [&](const float4 c, uint32_t (&pp)[4]) {
         const f2 c0 = f2_bcast(c.x), c1 = f2_bcast(c.y), c2 = f2_bcast(c.z);
 #pragma unroll
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(kFirstFwd16Threads) first_fwd16_kernel(const f
         item(cs[r], pp);
         store(dst, pp);
         if (tail_words > 0) {   // last quad of the row: the "ones" column and zeros up to the end of the 32-byte sector
-          uint32_t* t32 = reinterpret_cast<uint32_t*>(y + size_t(row0 + c0r + r) * y_pitch + 2 * M);
-          if (tail_words == 4 && (M & 3) == 0) {
+          uint32_t* t32 = reinterpret_cast<uint32_t*>(dst + (2 * M - 8 * q));
+          if (tail_vec) {
             __stcs(reinterpret_cast<uint4*>(t32), make_uint4(0x00003C00u, 0u, 0u, 0u));
           } else {
             t32[0] = 0x00003C00u;
