@@ -510,7 +510,10 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src,
 template <int IN_F, int LPR>   // input features (1..3); lanes per g_z0 row (8 / 16 / 32: narrow rows are packed 4 / 2 to a warp)
 __global__ void __launch_bounds__(kFw16sThreads, 1) first_wgrad16s_kernel(const __nv_bfloat16* __restrict__ gz0, int g_pitch,
                                                                            const float* __restrict__ coords, int n, int M,
-                                                                           float* __restrict__ gW0, float* __restrict__ gb0, int stages) {
+                                                                           float* __restrict__ gW0, float* __restrict__ gb0, int stages,
+                                                                           const __grid_constant__ CUtensorMap g_map, int use_tma) {
+  // use_tma: the g_z0 chunk arrives as ONE 2-D tensor box {g_pitch columns, 64 rows} (rows past n are zero fill) instead of a 1-D
+  // bulk copy: the 1-D copies streamed at 11.4 B/clk per SM whatever was in flight (ncu, cold L2: 3.2 TB/s at both row widths)
   constexpr int in_f = IN_F;
   using namespace sm100;
   extern __shared__ __align__(128) uint8_t fwsm[];
@@ -557,8 +560,13 @@ __global__ void __launch_bounds__(kFw16sThreads, 1) first_wgrad16s_kernel(const 
       if (lane == 0) {
         const uint32_t bar = smem_u32(&bar_full[stage]);
         const uint32_t gbytes = uint32_t(rows) * g_bytes_row;
-        mbar_expect_tx(bar, gbytes + (c_bulk ? cbytes : 0u));
-        bulk_load_1d(smem_u32(dst), gz0 + size_t(r0) * g_pitch, gbytes, bar);
+        if (use_tma) {
+          mbar_expect_tx(bar, uint32_t(kFw16sRows) * g_bytes_row + (c_bulk ? cbytes : 0u));   // a box counts whole, zero fill included
+          tma_load_2d_hint(smem_u32(dst), &g_map, bar, 0, r0, kEvictFirst);
+        } else {
+          mbar_expect_tx(bar, gbytes + (c_bulk ? cbytes : 0u));
+          bulk_load_1d(smem_u32(dst), gz0 + size_t(r0) * g_pitch, gbytes, bar);
+        }
         if (c_bulk) bulk_load_1d(smem_u32(dst + c_off), coords + size_t(r0) * in_f, cbytes, bar);
       }
       if (++stage == stages) { stage = 0; phase ^= 1; }
