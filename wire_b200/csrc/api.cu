@@ -747,24 +747,25 @@ int run_first_wgrad(const float* gz0, int g_pitch, const float* coords, int64_t 
     // (below ~64 k rows the ring's set-up and the block reduction cost more than the streaming saves: 21 vs 15 us at 25 k rows)
     if (stream_on && n >= 65536 && aligned && in_f >= 1 && in_f <= 3 && M <= 256 && (g_pitch % 8) == 0 && g_pitch <= 256) {
       // streamed variant: bulk copies into a shared-memory ring, one block per SM, reversed sweep (simt16_kernels.cuh)
-      const uint32_t stage_bytes = fw16s_stage_bytes(g_pitch);
-      int stages = int((200u * 1024u) / stage_bytes);
+      const int lpr = g_pitch <= 64 ? 8 : (g_pitch <= 128 ? 16 : 32);   // lanes per row (16-byte octets)
+      const int chunk_rows = fw16s_rows(lpr);
+      const uint32_t stage_bytes = fw16s_stage_bytes(g_pitch, chunk_rows);
+      int stages = int((210u * 1024u) / stage_bytes);
       stages = stages > 8 ? 8 : stages;
       size_t smem = size_t(stages) * stage_bytes;
       smem = (smem < 65536 ? 65536 : smem) + 128;   // the block reduction parks 16 x 32 x 32 partial sums in the ring
-      const int n_chunks = int((n + kFw16sRows - 1) / kFw16sRows);
+      const int n_chunks = int((n + chunk_rows - 1) / chunk_rows);
       CUtensorMap g_map;
       const char* b1 = getenv("WIRE_B200_FWGRAD_BULK1D");   // =1: 1-D bulk copies instead of the tensor box (A/B runs)
       const int use_tma = !(b1 && b1[0] == '1');
-      if (!sm100_host::make_tmap_2d_t(&g_map, gz0, n, g_pitch, g_pitch, kFw16sRows, g_pitch, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16))
+      if (!sm100_host::make_tmap_2d_t(&g_map, gz0, n, g_pitch, g_pitch, chunk_rows, g_pitch, CU_TENSOR_MAP_SWIZZLE_NONE, kElemBF16))
         return fail("cuTensorMapEncodeTiled failed for first_wgrad16s");
       auto launch = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 256);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
         if (e != cudaSuccess) return e;
         return launch_pdl(kern, dim3(n_chunks < g_sm_count ? n_chunks : g_sm_count), dim3(kFw16sThreads), smem, st,
                           reinterpret_cast<const __nv_bfloat16*>(gz0), g_pitch, coords, int(n), M, gW, gb, stages, g_map, use_tma);
       };
-      const int lpr = g_pitch <= 64 ? 8 : (g_pitch <= 128 ? 16 : 32);   // lanes per row (16-byte octets)
       cudaError_t e = cudaErrorInvalidValue;
       switch (in_f * 100 + lpr) {
         case 108: e = launch(first_wgrad16s_kernel<1, 8>); break;

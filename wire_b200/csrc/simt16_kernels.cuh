@@ -497,11 +497,15 @@ __global__ void __launch_bounds__(kFirstWgrad16Threads) first_wgrad16_kernel(con
 // rows it wrote last are still in L2 when this kernel starts there.
 // Requires M <= 256, in_f <= 3, g_pitch % 8 == 0, 16-byte aligned gz0 / coords.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFw16sRows = 64;                     // rows per chunk
+// rows per chunk: 128 for full-width rows (lanes per row = 32), 256 for narrow rows (wire2d at the SISR width: 256-byte rows).  With 64
+// the per-chunk bookkeeping (barrier wait, arrive, loop) was half of the instructions and the kernel, not the copies, set the time:
+// 43 -> 37.5 us at 512^2, 199 -> 138 us for the two launches of the SISR step; the copy skeleton alone streams at 4.8-5.6 TB/s
+// (tools/stream_probe, profiles/r02_probe_stream.log)
+__host__ __device__ constexpr int fw16s_rows(int lpr) { return lpr == 32 ? 128 : 256; }
 constexpr int kFw16sWarps = 16;                    // compute warps
 constexpr int kFw16sThreads = 32 * (kFw16sWarps + 1);
-__host__ __device__ inline uint32_t fw16s_stage_bytes(int g_pitch) {
-  return (uint32_t(kFw16sRows) * uint32_t(g_pitch) * 2u + uint32_t(kFw16sRows) * 16u + 127u) & ~127u;  // g rows | coords (<= 4 floats a row)
+__host__ __device__ inline uint32_t fw16s_stage_bytes(int g_pitch, int rows) {
+  return (uint32_t(rows) * uint32_t(g_pitch) * 2u + uint32_t(rows) * 16u + 127u) & ~127u;  // g rows | coords (<= 4 floats a row)
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -522,7 +526,8 @@ __global__ void __launch_bounds__(kFw16sThreads, 1) first_wgrad16s_kernel(const 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t pad = ((smem_u32(fwsm) + 127u) & ~127u) - smem_u32(fwsm);
   uint8_t* sm = fwsm + pad;
-  const uint32_t stage_bytes = fw16s_stage_bytes(g_pitch);
+  constexpr int kFw16sRows = fw16s_rows(LPR);
+  const uint32_t stage_bytes = fw16s_stage_bytes(g_pitch, kFw16sRows);
   const uint32_t g_bytes_row = uint32_t(g_pitch) * 2u;
   const uint32_t c_off = uint32_t(kFw16sRows) * g_bytes_row;
   if (threadIdx.x == 0) {
