@@ -16,6 +16,7 @@ struct Params {
   int n_tiles, do_load, store_mode;   // store_mode: 0 none, 1 = 64-byte rows (2 x 14 x 4 boxes of 2 KB), 2 = 128-byte rows (2 x 7 x 4 boxes of 4 KB)
   int n_store;                    // tensors stored (1 or 2)
   int vc;                         // valid columns
+  int tile_major;
   uint8_t* o_ptr[2];              // store modes 3 / 4: the same tiles leave through LDS.128 + coalesced st.global.v4 (3: 64-byte rows, 8 rows per
                                   // warp instruction; 4: 128-byte rows, 4 rows per instruction) instead of TMA stores
 };
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(64 + 512, 1) probe_kernel(const __grid_constan
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
           const uint32_t bar = smem_u32(&bar_full[stage]);
           mbar_expect_tx(bar, kStageBytes);
-          tma_load_2d(base + stage * kStageBytes, &P.a_map, bar, (s % 7) * 64, t * 128);
+          if (P.tile_major) tma_load_2d(base + stage * kStageBytes, &P.a_map, bar, 0, (t * 7 + (s % 7)) * 128);
+          else tma_load_2d(base + stage * kStageBytes, &P.a_map, bar, (s % 7) * 64, t * 128);
           tma_load_2d(base + stage * kStageBytes + 16384, &P.b_map, bar, (s % 7) * 64, (s / 7) * 224);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -89,7 +91,10 @@ __global__ void __launch_bounds__(64 + 512, 1) probe_kernel(const __grid_constan
         if (P.store_mode == 1) {
           for (int ch = part; ch < 14; ch += 4) {
             tma_store_wait_read<0>();
-            for (int s = 0; s < P.n_store; ++s) tma_store_2d(&P.o32[s], tile + s * 2048, ch * 32, row);
+            for (int s = 0; s < P.n_store; ++s) {
+              if (P.tile_major) tma_store_2d(&P.o32[s], tile + s * 2048, (ch & 1) * 32, (t * 7 + (ch >> 1)) * 128 + q * 32);
+              else tma_store_2d(&P.o32[s], tile + s * 2048, ch * 32, row);
+            }
             tma_store_commit();
           }
         } else {
@@ -111,20 +116,24 @@ int main(int argc, char** argv) {
   const int N = 262144, W = 448;
   const int VC = argc > 1 ? atoi(argv[1]) : 424;   // valid (written) columns per row
   const int only = argc > 2 ? atoi(argv[2]) : -1;  // run only this store mode
+  const int tile_major = argc > 3 ? atoi(argv[3]) : 0;   // 1: activations stored as [row tile][k block of 64 cols][128 rows][64 cols]: every box is contiguous
   void *a, *b, *o0, *o1;
   cudaMalloc(&a, size_t(N) * W * 2); cudaMalloc(&o0, size_t(N) * W * 2); cudaMalloc(&o1, size_t(N) * W * 2); cudaMalloc(&b, size_t(W) * W * 2);
   cudaMemset(a, 0, size_t(N) * W * 2); cudaMemset(b, 0, size_t(W) * W * 2);
   Params P;
-  bool ok = sm100_host::make_tmap_2d_t(&P.a_map, a, N, W, W, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B, sm100_host::kElemF16);
+  P.tile_major = tile_major;
+  bool ok = tile_major ? sm100_host::make_tmap_2d_t(&P.a_map, a, size_t(N) * 7, 64, 64, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B, sm100_host::kElemF16)
+                       : sm100_host::make_tmap_2d_t(&P.a_map, a, N, W, W, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B, sm100_host::kElemF16);
   ok &= sm100_host::make_tmap_2d_t(&P.b_map, b, W, W, W, 112, 64, CU_TENSOR_MAP_SWIZZLE_128B, sm100_host::kElemF16);
   void* o[2] = {o0, o1};
   for (int s = 0; s < 2; ++s) {
-    ok &= sm100_host::make_tmap_2d_t(&P.o32[s], o[s], N, VC, W, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, sm100_host::kElemF16);
+    if (tile_major) ok &= sm100_host::make_tmap_2d_t(&P.o32[s], o[s], size_t(N) * 7, 64, 64, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, sm100_host::kElemF16);
+    else ok &= sm100_host::make_tmap_2d_t(&P.o32[s], o[s], N, VC, W, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, sm100_host::kElemF16);
     ok &= sm100_host::make_tmap_2d_t(&P.o64[s], o[s], N, VC, W, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B, sm100_host::kElemF16);
   }
   if (!ok) { printf("tensor map failed\n"); return 1; }
   P.n_tiles = N / 128; P.vc = VC;
-  printf("valid columns %d of %d\n", VC, W);
+  printf("valid columns %d of %d%s\n", VC, W, tile_major ? "  TILE-MAJOR activations (mode 1 only)" : "");
   P.o_ptr[0] = (uint8_t*)o0; P.o_ptr[1] = (uint8_t*)o1;
   const size_t smem = kStages * kStageBytes + 16 * 4096 + 1024;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
