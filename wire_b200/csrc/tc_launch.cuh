@@ -222,7 +222,7 @@ inline size_t rows16_configure(RowsParams& P, int nb, int nbh, int store_mask, i
   return stages * stage + staging + pbytes + 1024;
 }
 
-template <int MODE, bool PAIR, bool FUSE, bool SCAL = false>
+template <int MODE, bool PAIR, int FUSE, bool SCAL = false>
 inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   static bool attr_set_dev[kMaxDevices] = {};
   static int max_clusters_dev[kMaxDevices] = {};
@@ -268,7 +268,7 @@ inline cudaError_t launch_rows16_p(const RowsParams& P, size_t smem, int sm_coun
   add_pdl_attr(attr, cfg.numAttrs);
   return cudaLaunchKernelEx(&cfg, tc_rows16_kernel<MODE, PAIR, FUSE, SCAL>, P);
 }
-template <int MODE, bool FUSE = false>
+template <int MODE, int FUSE = 0>
 inline cudaError_t launch_rows16_mode(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   return P.cluster == 2 ? launch_rows16_p<MODE, true, FUSE>(P, smem, sm_count, st) : launch_rows16_p<MODE, false, FUSE>(P, smem, sm_count, st);
 }
@@ -277,7 +277,7 @@ template <int MODE>
 inline cudaError_t launch_rows16_bwd(const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   if (P.e.g_omega || P.e.g_scale) {
     if (P.cluster != 2) return cudaErrorNotSupported;
-    return launch_rows16_p<MODE, true, false, true>(P, smem, sm_count, st);
+    return launch_rows16_p<MODE, true, 0, true>(P, smem, sm_count, st);
   }
   return launch_rows16_mode<MODE>(P, smem, sm_count, st);
 }
@@ -286,10 +286,16 @@ inline cudaError_t launch_rows16_bwd(const RowsParams& P, size_t smem, int sm_co
 inline cudaError_t launch_rows16(int mode, const RowsParams& P, size_t smem, int sm_count, cudaStream_t st) {
   if (P.e.n_rows <= 0) return cudaSuccess;
   const bool fuse = P.e.fuse_final != 0;
+  const char* f4 = getenv("WIRE_B200_FUSE4");   // =1: the four-output epilogue whatever the output count (A/B runs)
+  const bool three = P.e.out_features <= 3 && !(f4 && f4[0] == '1');
   switch (mode) {
     case MODE_PLAIN: return launch_rows16_mode<MODE_PLAIN>(P, smem, sm_count, st);
-    case MODE_GABOR_FWD: return fuse ? launch_rows16_mode<MODE_GABOR_FWD, true>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR_FWD>(P, smem, sm_count, st);
-    case MODE_GABOR2D_FWD: return fuse ? launch_rows16_mode<MODE_GABOR2D_FWD, true>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st);
+    case MODE_GABOR_FWD:
+      if (!fuse) return launch_rows16_mode<MODE_GABOR_FWD>(P, smem, sm_count, st);
+      return three ? launch_rows16_mode<MODE_GABOR_FWD, 3>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR_FWD, 4>(P, smem, sm_count, st);
+    case MODE_GABOR2D_FWD:
+      if (!fuse) return launch_rows16_mode<MODE_GABOR2D_FWD>(P, smem, sm_count, st);
+      return three ? launch_rows16_mode<MODE_GABOR2D_FWD, 3>(P, smem, sm_count, st) : launch_rows16_mode<MODE_GABOR2D_FWD, 4>(P, smem, sm_count, st);
     case MODE_GABOR_BWD: return launch_rows16_bwd<MODE_GABOR_BWD>(P, smem, sm_count, st);
     case MODE_GABOR2D_BWD: return launch_rows16_bwd<MODE_GABOR2D_BWD>(P, smem, sm_count, st);
     case MODE_FIRST_BWD: return launch_rows16_bwd<MODE_FIRST_BWD>(P, smem, sm_count, st);

@@ -69,7 +69,9 @@ __device__ __forceinline__ void gabor16(const GaborConst& g, float zr, float zi,
 // FUSE: the final Linear (.real) is accumulated in this epilogue (GABOR_FWD / GABOR2D_FWD only)
 // SCAL: backward modes only -- the gradients of the epilogue layer's own omega_0 / scale_0 are accumulated on the way
 //       (per-thread partial sums over everything the thread touches, one warp reduction + two atomics per warp at the end)
-template <int MODE, bool PAIR, bool FUSE = false, bool SCAL = false>
+// FUSE: 0 = the layer's y is stored; 3 / 4 = the final Linear (up to 3 / 4 real outputs) is applied in the epilogue instead: with three
+// outputs (every image driver) the weight table is 12 floats per feature pair and a pair costs 6 packed FMAs + 3 LDS.128, not 8 + 4
+template <int MODE, bool PAIR, int FUSE = 0, bool SCAL = false>
 __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __grid_constant__ RowsParams P) {
   using namespace sm100;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -145,7 +147,17 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
       params[i] = l < E.n_cols ? E.bias[l] : 0.f;
       if constexpr (k2D) params[P.param_cols + i] = l < E.n_cols ? E.bias2[l] : 0.f;
     }
-    if constexpr (FUSE) {
+    if constexpr (FUSE == 3) {
+      // pair P = features (2P, 2P+1): float4 {wr0A,wr0B,wr1A,wr1B} {wr2A,wr2B,-wi0A,-wi0B} {-wi1A,-wi1B,-wi2A,-wi2B}
+      float* wf = params + (k2D ? 2 : 1) * P.param_cols;
+      for (int i = threadIdx.x; i < (P.param_cols >> 2) * 12; i += blockDim.x) {
+        const int pr = i / 12, j = i - pr * 12;
+        const int slot = j >> 1, o = slot % 3, im = slot / 3, k = 2 * pr + (j & 1);
+        float v = 0.f;
+        if (k < n_feat && o < E.out_features) v = E.wf[(size_t(o) * n_feat + k) * 2 + im];
+        wf[i] = im ? -v : v;
+      }
+    } else if constexpr (FUSE != 0) {
       float* wf = params + (k2D ? 2 : 1) * P.param_cols;
       for (int i = threadIdx.x; i < (P.param_cols >> 2) * 16; i += blockDim.x) {
         const int pr = i >> 4, qd = (i >> 2) & 3, e = i & 3;
@@ -457,7 +469,13 @@ __global__ void __launch_bounds__(kRows16Threads, 1) tc_rows16_kernel(const __gr
               const f2 zi = f2_add(f2_bits(raw[8 * g + 4 * h + 2], raw[8 * g + 4 * h + 3]), f2_make(b.z, b.w));
               f2 yr, yi;
               gabor_x2(G2, zr, zi, k2D ? wn[2 * g + h] : 0ull, yr, yi);
-              if constexpr (FUSE) {
+              if constexpr (FUSE == 3) {
+                const float4* wq = s_wf + ((c >> 2) + 2 * g + h) * 3;
+                const float4 w0 = wq[0], w1 = wq[1], w2 = wq[2];
+                facc2[0] = f2_fma(yr, f2_make(w0.x, w0.y), f2_fma(yi, f2_make(w1.z, w1.w), facc2[0]));
+                facc2[1] = f2_fma(yr, f2_make(w0.z, w0.w), f2_fma(yi, f2_make(w2.x, w2.y), facc2[1]));
+                facc2[2] = f2_fma(yr, f2_make(w1.x, w1.y), f2_fma(yi, f2_make(w2.z, w2.w), facc2[2]));
+              } else if constexpr (FUSE != 0) {
                 const float4* wq = s_wf + ((c >> 2) + 2 * g + h) * 4;
                 const float4 w0 = wq[0], w1 = wq[1], w2 = wq[2], w3 = wq[3];
                 facc2[0] = f2_fma(yr, f2_make(w0.x, w0.y), f2_fma(yi, f2_make(w2.x, w2.y), facc2[0]));
