@@ -44,13 +44,26 @@ __device__ __forceinline__ GaborConst2 make_gabor_const2(const GaborConst& g) {
 }
 
 // y = exp(j w z - s2 (|z|^2 + wnorm)) for two features at once (zr, zi, wnorm, yr, yi are {feature A, feature B} pairs).
-// 11 packed FP32 instructions + 6 MUFU per pair (scalar: 14 + 3 per feature).
+// 7 packed FP32 instructions + 6 MUFU (+ 2 FMUL.RZ inside sin / cos.approx) per pair (scalar: 14 + 3 per feature).
+// Phase: sin.approx / cos.approx are a multiply by 1/2pi (round toward zero) and a MUFU that takes the fraction of a turn itself, so
+// the phase w Re z goes in as it is.  Measured (tools/sincos_probe, profiles/r02_probe_sincos.log): max |error| 1.0e-5 for
+// |w Re z| <= 100 (every driver: omega_0 <= 20), 1.4e-4 up to 1000 -- against the 4.9e-4 of the FP16 the result is stored in.  The
+// explicit reduction this replaces (u = z w/2pi; k = rint(u) by the magic constant; r = (u - k) 2pi: four more packed
+// instructions per pair) was 3x more accurate at every range and bought nothing at 16-bit storage; -DWIRE_B200_EXPLICIT_TURNS
+// brings it back.
+__device__ __forceinline__ f2 gabor_phase_x2(const GaborConst2& c, f2 zr) {
+#ifdef WIRE_B200_EXPLICIT_TURNS
+  const f2 u = f2_mul(zr, c.c_turn);
+  const f2 k = f2_add(f2_add(u, c.magic), c.nmagic);  // rint(u) for |u| < 2^22
+  return f2_mul(f2_fma(k, c.none, u), c.two_pi);      // (u - rint(u)) is exact
+#else
+  return f2_mul(zr, c.omega);
+#endif
+}
 __device__ __forceinline__ void gabor_x2(const GaborConst2& c, f2 zr, f2 zi, f2 wnorm, f2& yr, f2& yi) {
   const f2 t = f2_fma(zi, zi, f2_fma(zr, zr, wnorm));
   const f2 arg = f2_fma(c.c_t, t, f2_mul(c.c_zi, zi));
-  const f2 u = f2_mul(zr, c.c_turn);
-  const f2 k = f2_add(f2_add(u, c.magic), c.nmagic);  // rint(u) for |u| < 2^22
-  const f2 r = f2_mul(f2_fma(k, c.none, u), c.two_pi);  // (u - rint(u)) is exact
+  const f2 r = gabor_phase_x2(c, zr);
   const f2 m = f2_make(ex2_ftz(f2_lo(arg)), ex2_ftz(f2_hi(arg)));
   const f2 cs = f2_make(cos_ftz(f2_lo(r)), cos_ftz(f2_hi(r)));
   const f2 sn = f2_make(sin_ftz(f2_lo(r)), sin_ftz(f2_hi(r)));
@@ -61,9 +74,7 @@ __device__ __forceinline__ void gabor_x2(const GaborConst2& c, f2 zr, f2 zi, f2 
 __device__ __forceinline__ void gabor_real_x2(const GaborConst2& c, f2 z, f2 wnorm, f2& yr, f2& yi) {
   const f2 t = f2_fma(z, z, wnorm);
   const f2 arg = f2_mul(c.c_t, t);
-  const f2 u = f2_mul(z, c.c_turn);
-  const f2 k = f2_add(f2_add(u, c.magic), c.nmagic);
-  const f2 r = f2_mul(f2_fma(k, c.none, u), c.two_pi);
+  const f2 r = gabor_phase_x2(c, z);
   const f2 m = f2_make(ex2_ftz(f2_lo(arg)), ex2_ftz(f2_hi(arg)));
   const f2 cs = f2_make(cos_ftz(f2_lo(r)), cos_ftz(f2_hi(r)));
   const f2 sn = f2_make(sin_ftz(f2_lo(r)), sin_ftz(f2_hi(r)));
