@@ -39,7 +39,7 @@ __device__ __forceinline__ void exp_cis(float mag_arg, float phase, float& yr, f
   }
 }
 
-// ---- branch-free FTZ fast path (TF32 mode): phase reduced in turns (u - rint(u) is exact), magnitude via ex2 ----
+// ---- branch-free FTZ fast path (TF32 mode): magnitude via ex2, phase via sin / cos.approx ----
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -63,9 +63,15 @@ __device__ __forceinline__ GaborConst make_gabor_const(float omega, float scale)
 __device__ __forceinline__ void gabor_fast(const GaborConst& g, float zr, float zi, float wnorm, float& yr, float& yi) {
   const float t = fmaf(zi, zi, fmaf(zr, zr, wnorm));
   const float m = ex2_ftz(fmaf(g.c_t, t, g.c_zi * zi));
+  // the phase goes in as it is: sin / cos.approx multiply by 1/2pi and the MUFU takes the fraction of a turn (f32x2.cuh:
+  // gabor_phase_x2; tools/sincos_probe: 1e-5 up to |w Re z| = 100).  The explicit reduction it replaces cost a FRND on the XU pipe.
+#ifdef WIRE_B200_EXPLICIT_TURNS
   float u = zr * g.c_turn;
   u -= rintf(u);
   const float r = u * 6.283185307179586f;
+#else
+  const float r = zr * g.omega;
+#endif
   yr = m * cos_ftz(r);
   yi = m * sin_ftz(r);
 }
