@@ -364,16 +364,18 @@ __global__ void __launch_bounds__(MAXT) top_bwd16_kernel(const __grid_constant__
         pr = gabor_bwd_x2(G2, yr, yi, zr, zi, gyr, gyi, gzr, gzi);
       }
       // (lanes past the stored width alias feature 0's slot: they compute on it but must not store)
-      if (st_ok) {   // (padded features: literal zeros, whatever the z tile held in their columns)
-        *reinterpret_cast<uint32_t*>(zout + (2 * rp) * row_bytes) = active ? pack_bf16(f2_lo(gzr), f2_lo(gzi)) : 0u;
-        *reinterpret_cast<uint32_t*>(zout + (2 * rp + 1) * row_bytes) = active ? pack_bf16(f2_hi(gzr), f2_hi(gzi)) : 0u;
+      // (padded features up to the stored width: their weights are zero, so p = 0 and g_z = 0 * z; z there is the exact 0 the
+      // forward kernel stored for the zero-padded feature -- the same stored-width rule on both sides, api.cu: run_rows_job)
+      if (st_ok) {
+        *reinterpret_cast<uint32_t*>(zout + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gzr), f2_lo(gzi));
+        *reinterpret_cast<uint32_t*>(zout + (2 * rp + 1) * row_bytes) = pack_bf16(f2_hi(gzr), f2_hi(gzi));
       }
       if constexpr (TWO_D) {
         const f2 t = f2_mul(G2.m2s2, pr);
         const f2 gwr = f2_mul(t, wre), gwi = f2_mul(t, wim);
         if (st_ok) {
-          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp) * row_bytes) = active ? pack_bf16(f2_lo(gwr), f2_lo(gwi)) : 0u;
-          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp + 1) * row_bytes) = active ? pack_bf16(f2_hi(gwr), f2_hi(gwi)) : 0u;
+          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp) * row_bytes) = pack_bf16(f2_lo(gwr), f2_lo(gwi));
+          *reinterpret_cast<uint32_t*>(zout + tile_bytes + (2 * rp + 1) * row_bytes) = pack_bf16(f2_hi(gwr), f2_hi(gwi));
         }
       }
 #pragma unroll
