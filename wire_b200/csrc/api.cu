@@ -385,7 +385,8 @@ int run_rows(const RowsJob& J, int precision, cudaStream_t st) {
         // 448 columns, profiles/r02_probe_tma_valid_cols.log).  The extra columns carry the epilogue's values of the zero-padded
         // features (z = 0, y = gabor(0) = 1 + 0j -- column 2M of a y tensor is the wgrad's "ones" column and is forced to 1.0).
         int store_cols = J.e.n_cols;
-        if (op16 && store_sector_align()) { const int r = round_up(J.e.n_cols, 16); if (r <= J.o_pitch[nslot]) store_cols = r; }
+        // (the TF32 kernels' FP16 saved-z tiles follow the same rule: their parameter tables are zero padded as well)
+        if (store_sector_align()) { const int r = round_up(J.e.n_cols, 16); if (r <= J.o_pitch[nslot]) store_cols = r; }
         ok &= sm100_host::make_tmap_2d_t(&P.o_map[nslot], J.o[nslot], J.e.n_rows, store_cols, J.o_pitch[nslot], 32, 32,
                                          op16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, J.o_half[nslot]);
       }
